@@ -1,0 +1,25 @@
+"""Stateful scalar schedules (reference: ``deep_rl/utils/schedule.py:7-31``).  A
+``LinearSchedule`` advances on EVERY call (schedule.py:28-31), so e.g. the PER beta moves once
+per gradient update (DQN_agent.py:125)."""
+
+
+class ConstantSchedule:
+    def __init__(self, val):
+        self.val = val
+
+    def __call__(self, steps=1):
+        return self.val
+
+
+class LinearSchedule:
+    def __init__(self, start, end=None, steps=None):
+        if end is None:
+            end, steps = start, 1
+        self.inc = (end - start) / float(steps)
+        self.current, self.end = start, end
+        self.bound = min if end > start else max
+
+    def __call__(self, steps=1):
+        now = self.current
+        self.current = self.bound(now + self.inc * steps, self.end)
+        return now
