@@ -131,3 +131,23 @@ def ppo_update(sd, actor_keys, critic_keys, actor_opt, critic_opt, states, actio
             vl.backward()
             critic_opt.step()
     return adv
+
+
+def a2c_update(sd, params, opt, states, actions, rewards, masks, discount, tau, entropy_weight,
+               value_loss_weight, gradient_clip, gate=torch.tanh):
+    """A2C_agent.py:22-64 for one rollout whose env interaction is given: ``states`` (T+1,N,obs),
+    ``actions`` (T,N), ``rewards``/``masks`` (T,N,1).  Forward passes keep their graphs, GAE runs on
+    detached values, one backward + clip + optimizer step.  Returns (adv, ret) for inspection."""
+    T = actions.shape[0]
+    preds = [nets.categorical_actor_critic(sd, states[t], actions[t], gate) for t in range(T)]
+    last = nets.categorical_actor_critic(sd, states[T], actions[T - 1], gate)
+    v = torch.stack([p["v"] for p in preds] + [last["v"]])
+    adv, ret = losses.gae(rewards, masks, v.detach(), discount, tau)
+    cat = lambda k: torch.cat([p[k] for p in preds], dim=0)
+    loss = losses.a2c_loss(cat("log_pi_a"), cat("v"), ret.reshape(-1, 1), adv.reshape(-1, 1), cat("entropy"),
+                           entropy_weight, value_loss_weight)
+    opt.zero_grad()
+    loss.backward()
+    clip_grad_norm(params, gradient_clip)
+    opt.step()
+    return adv, ret

@@ -49,3 +49,14 @@ def gaussian_actor_critic(sd, obs, action, gate=torch.tanh):            # networ
     dist = torch.distributions.Normal(mean, F.softplus(sd["std"]))
     return dict(log_pi_a=dist.log_prob(action).sum(-1).unsqueeze(-1),
                 entropy=dist.entropy().sum(-1).unsqueeze(-1), mean=mean, v=v)
+
+
+def categorical_actor_critic(sd, obs, action=None, gate=torch.tanh):   # network_heads.py:239-255 (shared phi_body)
+    phi = fc_body(sd, obs, "phi_body.", gate)
+    logits = F.linear(phi, sd["fc_action.weight"], sd["fc_action.bias"])
+    v = F.linear(phi, sd["fc_critic.weight"], sd["fc_critic.bias"])
+    dist = torch.distributions.Categorical(logits=logits)
+    if action is None:
+        action = dist.sample()
+    return dict(action=action, log_pi_a=dist.log_prob(action).unsqueeze(-1),
+                entropy=dist.entropy().unsqueeze(-1), v=v)
