@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- gradient-updates/s of the DQN hot path (BASELINE.json metric) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b2rl|reference] [--workload dqn|per|c51|qr]
+
+A "step" is ONE gradient update of ``DQNAgent.step`` (DQN_agent.py:101-138) at batch 512: the 4 env transitions
+that ``sgd_update_frequency = 4`` implies are fed to the ring, a batch is sampled from a 1M-transition ring of
+84x84 uint8 frames (7.06 GB, larger than L2, random indices every step), target / online NatureConvBody forward,
+fused loss, backward, global-norm clip, RMSprop(centered) step.  Weights are random-init, frames synthetic.
+
+  value      whole-job updates/s with the env transitions already in HBM (graph replays back to back)
+  e2e        same metric through host buffers: per step the 4 transitions are copied host->device from pinned
+             memory inside the timed region and the loss is read back device->host
+  roofline   the replay gather kernel (HBM-bound): algorithmic bytes per launch / CUDA-event time per launch
+  cpu_baseline / --impl reference   the oracle port of the reference's CPU path (oracle/agents.py, torch-CPU)
+             timed on the host cores for a bounded number of updates (the reference is pure Python; there is no
+             oracle/_ref binary -- /root/reference does not exist on the GPU box)
+
+Multi-GPU: launched by torchrun, one rank per GPU; each rank owns a replay shard and a full batch-512 update,
+gradients are all-reduced (NCCL) every step: weak scaling, value = ranks x updates/s.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B, HIST, FRAME, CAP, ACTIONS = 512, 4, 84 * 84, 1_000_000, 4
+# per sampled transition read 5 unique frames, write 2 x 4 frames in the output dtype
+ALGO_BYTES_U8 = 5 * FRAME + 2 * 4 * FRAME                 # 91 728 B / sample, uint8 -> uint8 stacks
+ALGO_BYTES_BF16 = 5 * FRAME + 2 * 4 * FRAME * 2           # fused gather -> normalize -> bf16 NHWC (what the step uses)
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.stop, self.index = [], threading.Event(), index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=5)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------------- product arm
+def synthetic_ring(rl, replay_cls, device, seed, capacity=CAP):
+    """SURVEY 8d synthetic inputs, generated on the device in chunks."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    frames = torch.empty((capacity, FRAME), dtype=torch.uint8, device=device)
+    step = 50_000
+    for s in range(0, capacity, step):
+        n = min(step, capacity - s)
+        frames[s:s + n] = torch.randint(0, 256, (n, FRAME), dtype=torch.uint8, device=device, generator=g)
+    action = torch.randint(0, ACTIONS, (capacity,), device=device, generator=g).int()
+    u = torch.rand(capacity, device=device, generator=g)
+    reward = torch.where(u < 0.05, -1.0, torch.where(u > 0.95, 1.0, 0.0)).double()
+    mask = (torch.rand(capacity, device=device, generator=g) > 1e-3).int()
+    rp = replay_cls(capacity, B, n_step=1, discount=0.99, history_length=HIST, device=device, seed=seed)
+    rp.item_shape, rp.item_dtype = (84, 84), np.dtype(np.uint8)
+    if replay_cls.__name__ == "PrioritizedReplay":
+        pr = (torch.randn(capacity, device=device, generator=g).abs() + 0.01).sqrt()
+        rp.load_synthetic(frames, action, reward, mask, pos=123_457, priorities=pr)
+    else:
+        rp.load_synthetic(frames, action, reward, mask, pos=123_457)
+    return rp
+
+
+def build_learner(rl, workload, device, rank, world):
+    from deeprl_b200.learner import GraphedDQNLearner
+    torch.manual_seed(0)                                   # identical initial parameters on every rank
+    body = lambda: rl.NatureConvBody(in_channels=HIST)
+    if workload in ("dqn", "per"):
+        mk = (lambda: rl.DuelingNet(ACTIONS, body())) if workload == "per" else (lambda: rl.VanillaNet(ACTIONS, body()))
+        topt = lambda p: torch.optim.RMSprop(p, lr=0.00025, alpha=0.95, eps=0.01, centered=True)     # examples.py:67-68
+        kind = "dqn"
+    elif workload == "c51":
+        mk = lambda: rl.CategoricalNet(ACTIONS, 51, body())
+        topt = lambda p: torch.optim.Adam(p, lr=0.00025, eps=0.01 / 32)                               # examples.py:204
+        kind = "c51"
+    else:
+        mk = lambda: rl.QuantileNet(ACTIONS, 200, body())
+        topt = lambda p: torch.optim.Adam(p, lr=0.00005, eps=0.01 / 32)                               # examples.py:139
+        kind = "qr"
+    net, tgt = mk(), mk()
+    tgt.load_state_dict(net.state_dict())
+    net = net.to(memory_format=torch.channels_last)
+    tgt = tgt.to(memory_format=torch.channels_last)
+    opt = rl.ops.FlatOptimizer.from_torch(topt(net.parameters()))
+    replay_cls = rl.PrioritizedReplay if workload == "per" else rl.UniformReplay
+    rp = synthetic_ring(rl, replay_cls, device, seed=rank)
+    return GraphedDQNLearner(net, tgt, opt, rp, kind=kind, double_q=(workload == "per"), gradient_clip=5.0,
+                             feeds_per_update=4, compute_dtype=torch.bfloat16, world_size=world,
+                             target_sync_every=0)
+
+
+def time_gather_kernel(rl, rp, iters=200):
+    """CUDA-event time per launch of the replay gather kernel alone (random indices into a 7 GB ring: every launch
+    misses L2), for the two variants: raw uint8 stacks (SURVEY 8d accounting) and the fused bf16-NHWC one the step uses."""
+    res = {}
+    for name, fn in (("u8", lambda: rp.gather(bufs_u8["idx"], B, bufs_u8)),
+                     ("bf16_nhwc", lambda: rp.gather(bufs_bf["idx"], B, bufs_bf, torch.bfloat16, rp.lut(1 / 255.0), True))):
+        bufs_u8 = rp._buffers(B, torch.uint8, False, tag=7)
+        bufs_bf = rp._buffers(B, torch.bfloat16, True, tag=7)
+        idxs = [torch.randint(8, CAP - 8, (B,), device=rp.device) for _ in range(iters)]
+        idxs = [torch.where((i > 123_440) & (i < 123_470), i + 100, i) for i in idxs]        # keep clear of the ring seam
+        for i in idxs[:5]:
+            bufs_u8["idx"].copy_(i), bufs_bf["idx"].copy_(i)
+            fn()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for i, (a, b) in zip(idxs, ev):
+            bufs_u8["idx"].copy_(i), bufs_bf["idx"].copy_(i)
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        ms = sorted(a.elapsed_time(b) for a, b in ev)
+        res[name] = float(np.mean(ms[len(ms) // 10: -len(ms) // 10 or None]))
+    return res
+
+
+def run_b2rl(args):
+    import torch.distributed as dist
+    import deeprl_b200 as rl
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    rl.select_device(local)
+    rl.Config.COMPUTE_DTYPE = torch.bfloat16
+    torch.backends.cudnn.benchmark = True
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    learner = build_learner(rl, args.workload, dev, rank, world)
+    if world > 1:                                          # parameters identical on every rank
+        dist.broadcast(learner.opt.flat, 0)
+        learner.tgt.load_state_dict(learner.net.state_dict())
+    learner.capture(warmup=3, with_h2d=False)
+    K, W = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM
+    for _ in range(W):
+        learner.update()
+    rl._lib.reset_launch_count()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        t0.record()
+        for _ in range(K):
+            learner.update()
+        t1.record()
+        barrier()
+    ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+    loss_value = float(learner.loss)
+
+    # ---- launches of OUR kernels per update (count one eager update; graph replays do not pass through the C ABI)
+    rl._lib.reset_launch_count()
+    learner._main(), learner._allreduce(), learner._opt()
+    torch.cuda.synchronize()
+    launches_per_update = rl._lib.launch_count()
+
+    # ---- e2e: host buffers in, loss out, every step
+    learner.capture(warmup=1, with_h2d=True)
+    rng = np.random.RandomState(rank)
+    host = [(rng.randint(0, 256, (4, FRAME)).astype(np.uint8), rng.randint(0, ACTIONS, 4).astype(np.int32),
+             rng.choice([-1.0, 0.0, 1.0], 4), (rng.rand(4) > 1e-3).astype(np.int32)) for _ in range(16)]
+    for i in range(W):
+        learner.update_from_host(*host[i % 16], beta=0.4)
+    barrier()
+    wall0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        last = learner.update_from_host(*host[i % 16], beta=0.4 + 0.6 * i / K)
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    # ---- roofline of the replay gather kernel, timed alone (burst peak applies)
+    gt = time_gather_kernel(rl, learner.replay)
+    hbm = pk.get("hbm_gbs", 6650.0)
+    ach = B * ALGO_BYTES_BF16 / (gt["bf16_nhwc"] * 1e-3) / 1e9
+    ach_u8 = B * ALGO_BYTES_U8 / (gt["u8"] * 1e-3) / 1e9
+    roof = dict(bound="hbm", kernel="gather_cvt_kernel<bf16, NHWC> (fused gather->normalize, as used by the step)",
+                achieved=round(ach, 1), peak=hbm, unit="GB/s", frac=round(ach / hbm, 4),
+                peak_source="MEASURED_PEAKS.json hbm_gbs (burst)" if "hbm_gbs" in pk else "fallback 6650",
+                us_per_launch=round(gt["bf16_nhwc"] * 1e3, 2), algorithmic_bytes_per_launch=B * ALGO_BYTES_BF16,
+                traffic=None,
+                raw_u8_variant=dict(kernel="gather_raw_tma_kernel (uint8 stacks, SURVEY 8d: 91 728 B/sample)",
+                                    achieved=round(ach_u8, 1), frac=round(ach_u8 / hbm, 4),
+                                    us_per_launch=round(gt["u8"] * 1e3, 2), algorithmic_bytes_per_launch=B * ALGO_BYTES_U8))
+    cpu = cpu_baseline(args.workload, seconds=20.0)
+    value = world * K / (ms_total * 1e-3)
+    e2e = world * K / (e2e_ms * 1e-3)
+    flops = 34.9e9 if args.workload == "dqn" else None
+    line = dict(
+        metric="gradient-updates/sec (DQN batch 512, 84x84x4 synthetic)", value=round(value, 1), unit="updates/s",
+        n_gpus=world, steps=K, warmup=W, ms_per_step=round(ms_total / K, 4), higher_is_better=True, scaling="weak",
+        vs_baseline=None, dtype="bf16", data="synthetic",
+        config=dict(workload={"dqn": "DQN synthetic 84x84x4 uint8 frames, 1M-transition uniform Replay, batch 512, NatureConvBody, 1 B200 (BASELINE configs[1])",
+                              "per": "Prioritized Dueling Double-DQN, 1M sum-tree PrioritizedReplay, batch 512 (BASELINE configs[2])",
+                              "c51": "C51 51 atoms, batch 512 (BASELINE configs[4])", "qr": "QR-DQN 200 quantiles, batch 512 (BASELINE configs[4])"}[args.workload],
+                    batch=B, replay_capacity=CAP, replay_bytes=CAP * FRAME, actions=ACTIONS, feeds_per_update=4,
+                    l2_policy="inputs larger than L2: 7.06 GB ring, fresh random indices every step",
+                    parallelism="dp%d (rank-local replay shard, NCCL all-reduce of 6.7 MB fp32 gradients per step)" % world,
+                    dense="cuDNN/cuBLAS bf16 (fp32 accumulate, fp32 master weights)", cuda_graph=True),
+        e2e=dict(value=round(e2e, 1), unit="updates/s", h2d_bytes_per_step=learner.h2d_bytes, d2h_bytes_per_step=4,
+                 ms_per_step=round(e2e_ms / K, 4)),
+        gpu_launches=int(launches_per_update * K), gpu_launches_per_step=int(launches_per_update),
+        clocks=clocks.summary(), roofline=roof, cpu_baseline=cpu, loss=loss_value, last_e2e_loss=last,
+        tensor_frac_of_sustained=(round(flops * value / world / (pk.get("bf16_tflops_sustained", 1447.2) * 1e12), 4) if flops else None),
+    )
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------- CPU arm (oracle port)
+def make_cpu_agent(workload, capacity=20_000):
+    """The reference's CPU path as restated in oracle/ (pinned against the reference by tests/test_oracle_golden.py):
+    python-list replay with per-sample np.array stacking, float64 ImageNormalizer, torch-CPU networks, torch.optim."""
+    from oracle import agents, nets  # noqa: F401
+    from oracle.replay import PrioritizedReplay, UniformReplay
+    import deeprl_b200 as rl
+    rl.select_device(-1)
+    torch.manual_seed(0)
+    body = rl.NatureConvBody(in_channels=HIST)
+    if workload == "per":
+        net, head = rl.DuelingNet(ACTIONS, body), "dueling"
+    elif workload == "c51":
+        net, head = rl.CategoricalNet(ACTIONS, 51, body), "categorical"
+    elif workload == "qr":
+        net, head = rl.QuantileNet(ACTIONS, 200, body), "quantile"
+    else:
+        net, head = rl.VanillaNet(ACTIONS, body), "vanilla"
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    if workload in ("dqn", "per"):
+        opt = lambda p: torch.optim.RMSprop(p, lr=0.00025, alpha=0.95, eps=0.01, centered=True)
+    else:
+        opt = lambda p: torch.optim.Adam(p, lr=0.00025, eps=0.01 / 32)
+    orc = agents.DQNFamilyOracle(sd, head, "nature", ACTIONS, opt, 0.99, 1, double_q=(workload == "per"), gradient_clip=5,
+                                 state_coef=1.0 / 255, atoms=np.linspace(-10, 10, 51) if workload == "c51" else None,
+                                 v_min=-10, v_max=10, num_quantiles=200 if workload == "qr" else None,
+                                 replay_beta=lambda: 0.4)
+    cls = PrioritizedReplay if workload == "per" else UniformReplay
+    rp = cls(capacity, B, 1, 0.99, HIST)
+    rng = np.random.RandomState(0)
+    for i in range(capacity):
+        rp.feed(dict(state=[rng.randint(0, 256, (84, 84)).astype(np.uint8)], action=[int(rng.randint(ACTIONS))],
+                     reward=[float(rng.choice([-1.0, 0.0, 1.0], p=[0.05, 0.9, 0.05]))], mask=[int(rng.rand() > 1e-3)]))
+    return orc, rp, rng
+
+
+def cpu_step(orc, rp, rng, workload):
+    for _ in range(4):                                     # the 4 feeds per update (sgd_update_frequency)
+        rp.feed(dict(state=[rng.randint(0, 256, (84, 84)).astype(np.uint8)], action=[int(rng.randint(ACTIONS))],
+                     reward=[0.0], mask=[1]))
+    if workload == "per":
+        tr = rp.sample()
+        orc.update(tr, rp)
+    else:
+        tr, _, _ = rp.sample()
+        orc.update(tr)
+
+
+def cpu_baseline(workload, seconds=20.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    orc, rp, rng = make_cpu_agent(workload)
+    cpu_step(orc, rp, rng, workload)                       # warm-up
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds and n < 200:
+        cpu_step(orc, rp, rng, workload)
+        n += 1
+    dt = time.perf_counter() - t0
+    return dict(value=round(n / dt, 4), unit="updates/s", cores=cores, kind="port",
+                sample="%d full batch-512 updates (4 feeds + sample + fwd/bwd + clip + optimizer) of the oracle port of the "
+                       "reference's torch-CPU path, %d torch threads, replay capacity 20k (its sampling cost does not depend "
+                       "on capacity), %.1f s" % (n, cores, dt))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    orc, rp, rng = make_cpu_agent(args.workload)
+    W = max(1, min(args.warmup, 3))
+    for _ in range(W):
+        cpu_step(orc, rp, rng, args.workload)
+    t0 = time.perf_counter()
+    per = None
+    K = 0
+    budget = 180.0                                         # the whole run must end within a few minutes
+    while K < args.steps:
+        cpu_step(orc, rp, rng, args.workload)
+        K += 1
+        if time.perf_counter() - t0 > budget:
+            break
+    dt = time.perf_counter() - t0
+    v = K / dt
+    sample = "%d of the requested %d batch-512 updates (bounded to %.0f s of CPU work), %d torch threads" % (K, args.steps, budget, cores)
+    print(json.dumps(dict(
+        impl="reference", metric="gradient-updates/sec (DQN batch 512, 84x84x4 synthetic)", value=round(v, 4),
+        unit="updates/s", n_gpus=int(os.environ.get("WORLD_SIZE", "1")), steps=K, warmup=W, ms_per_step=round(1e3 / v, 2),
+        higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+        config=dict(workload="same as the b2rl arm: %s" % args.workload, batch=B, device="host CPU"),
+        cpu_baseline=dict(value=round(v, 4), unit="updates/s", cores=cores, kind="port", sample=sample),
+        e2e=dict(value=round(v, 4), unit="updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b2rl", choices=["b2rl", "reference"])
+    ap.add_argument("--workload", default="dqn", choices=["dqn", "per", "c51", "qr"])
+    a = ap.parse_args()
+    run_reference(a) if a.impl == "reference" else run_b2rl(a)

@@ -1,0 +1,130 @@
+"""PPO behind the reference's interface (``deep_rl/agent/PPO_agent.py:13-99``): rollout, GAE, advantage
+normalisation, ``optimization_epochs`` x minibatches of the clipped surrogate, KL-gated actor step (non-shared
+representation) or one clipped optimizer step (shared representation).
+
+CUDA device: GAE = ``b2rl_gae``, advantage normalisation = ``b2rl_normalize_advantage``, each minibatch's surrogate /
+value loss / approx-KL and their gradients = one ``b2rl_ppo_loss`` launch.  ``select_device(-1)``: torch statements
+(the reference's own CPU path; see A2C_agent.py docstring).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..component import Storage
+from ..utils import random_sample, tensor, to_np
+from .A2C_agent import compute_advantages
+from .BaseAgent import BaseAgent
+
+
+class PPOAgent(BaseAgent):
+    def __init__(self, config):
+        BaseAgent.__init__(self, config)
+        self.config = config
+        self.task = config.task_fn()
+        self.network = config.network_fn()
+        if config.shared_repr:
+            self.opt = config.optimizer_fn(self.network.parameters())
+        else:
+            self.actor_opt = config.actor_opt_fn(self.network.actor_params)
+            self.critic_opt = config.critic_opt_fn(self.network.critic_params)
+        self.total_steps = 0
+        self.states = self.task.reset()
+        self.states = config.state_normalizer(self.states)
+        if config.shared_repr:
+            self.lr_scheduler = torch.optim.lr_scheduler.LambdaLR(self.opt, lambda step: 1 - step / config.max_steps)
+        self.gae_exact = True
+        self.last_stats = None
+
+    def eval_step(self, state):
+        with torch.no_grad():
+            prediction = self.network(self.config.state_normalizer(state))
+        return to_np(prediction["action"])
+
+    def _rollout(self):
+        config = self.config
+        storage = Storage(config.rollout_length)
+        states = self.states
+        for _ in range(config.rollout_length):
+            with torch.no_grad():
+                prediction = self.network(states)
+            next_states, rewards, terminals, info = self.task.step(to_np(prediction["action"]))
+            self.record_online_return(info)
+            rewards = config.reward_normalizer(rewards)
+            next_states = config.state_normalizer(next_states)
+            storage.feed(prediction)
+            storage.feed({"reward": tensor(rewards).unsqueeze(-1), "mask": tensor(1 - terminals).unsqueeze(-1),
+                          "state": tensor(states)})
+            states = next_states
+            self.total_steps += config.num_workers
+        self.states = states
+        with torch.no_grad():
+            prediction = self.network(states)
+        storage.feed(prediction)
+        storage.placeholder()
+        compute_advantages(storage, config, prediction["v"], exact=self.gae_exact)
+        entries = storage.extract(["state", "action", "log_pi_a", "ret", "advantage"])
+        return type(entries)(*[x.detach().contiguous() for x in entries])
+
+    def _normalize(self, entries):
+        adv = entries.advantage
+        if adv.is_cuda:
+            ops.normalize_advantage_(adv)
+        else:
+            adv.copy_((adv - adv.mean()) / adv.std())
+
+    def _minibatch(self, entries, batch_indices):
+        config = self.config
+        batch_indices = tensor(batch_indices).long()
+        entry = type(entries)(*[x[batch_indices] for x in entries])
+        prediction = self.network(entry.state, entry.action)
+        if entry.state.is_cuda:
+            r = ops.ppo_loss_fused(prediction["log_pi_a"].detach(), prediction["entropy"].detach(), prediction["v"].detach(),
+                                   entry.log_pi_a, entry.advantage, entry.ret, config.ppo_ratio_clip, config.entropy_weight)
+            shape = prediction["v"].shape
+            g_lp, g_en, g_v = r["dlogp"].view(shape), r["dent"].view(shape), r["dv"].view(shape)
+            self.last_stats = r["out"]
+            if config.shared_repr:
+                self.opt.zero_grad()
+                torch.autograd.backward([prediction["log_pi_a"], prediction["entropy"], prediction["v"]], [g_lp, g_en, g_v])
+                nn.utils.clip_grad_norm_(self.network.parameters(), config.gradient_clip)
+                self.opt.step()
+            else:
+                approx_kl = r["out"][2]
+                if approx_kl <= 1.5 * config.target_kl:          # host decision, as PPO_agent.py:94
+                    self.actor_opt.zero_grad()
+                    torch.autograd.backward([prediction["log_pi_a"], prediction["entropy"]], [g_lp, g_en])
+                    self.actor_opt.step()
+                self.critic_opt.zero_grad()
+                prediction["v"].backward(g_v)
+                self.critic_opt.step()
+            return
+        ratio = (prediction["log_pi_a"] - entry.log_pi_a).exp()
+        obj = ratio * entry.advantage
+        obj_clipped = ratio.clamp(1.0 - config.ppo_ratio_clip, 1.0 + config.ppo_ratio_clip) * entry.advantage
+        policy_loss = -torch.min(obj, obj_clipped).mean() - config.entropy_weight * prediction["entropy"].mean()
+        value_loss = 0.5 * (entry.ret - prediction["v"]).pow(2).mean()
+        approx_kl = (entry.log_pi_a - prediction["log_pi_a"]).mean()
+        if config.shared_repr:
+            self.opt.zero_grad()
+            (policy_loss + value_loss).backward()
+            nn.utils.clip_grad_norm_(self.network.parameters(), config.gradient_clip)
+            self.opt.step()
+        else:
+            if approx_kl <= 1.5 * config.target_kl:
+                self.actor_opt.zero_grad()
+                policy_loss.backward()
+                self.actor_opt.step()
+            self.critic_opt.zero_grad()
+            value_loss.backward()
+            self.critic_opt.step()
+
+    def step(self):
+        config = self.config
+        entries = self._rollout()
+        self._normalize(entries)
+        if config.shared_repr:
+            self.lr_scheduler.step(self.total_steps)
+        for _ in range(config.optimization_epochs):
+            for batch_indices in random_sample(np.arange(entries.state.size(0)), config.mini_batch_size):
+                self._minibatch(entries, batch_indices)

@@ -1,0 +1,450 @@
+"""Replay store / sample path, resident in HBM, behind the reference's interface
+(``deep_rl/component/replay.py``: ``Storage``:20, ``UniformReplay``:57, ``PrioritizedReplay``:152,
+``ReplayWrapper``:199).
+
+What lives where
+* ``Storage`` (on-policy rollouts) keeps the reference's list-of-tensors design: it holds a handful
+  of device tensors per step and is not a bandwidth problem.
+* ``UniformReplay`` / ``PrioritizedReplay`` keep the ring in device memory: ``frames`` uint8
+  ``[capacity][row_bytes]`` (7.06 GB for 1M 84x84 frames), ``action`` int32, ``reward`` float64,
+  ``mask`` int32, and for PER the float64 sum tree.  ``feed`` stages the host items in pinned memory,
+  copies them once and runs the feed kernel; ``sample`` runs index selection + the TMA gather
+  kernel (``csrc/replay.cu``) and returns DEVICE tensors in a ``Transition`` namedtuple with the
+  reference's field names.  No CPU fallback exists: constructing a replay on a CPU device raises.
+* ``ReplayWrapper(replay_cls, replay_kwargs, async_=True)``: the reference's ``async`` keyword is a
+  reserved word since Python 3.7 (replay.py:205), hence ``async_`` (third positional argument, as
+  examples.py passes it).  ``async_=True`` keeps the reference's double-buffer semantics
+  (replay.py:246-254: the batch handed out was drawn BEFORE the previous ``update_priorities``)
+  with two device batch buffers filled on a side stream instead of a subprocess and a pipe.
+
+RNG: the reference draws indices with ``np.random.randint`` / ``random.uniform`` on the host.  In
+production mode the kernels draw from Philox4x32-10 on the device (seed = ``seed`` argument, counter in
+``ring_state[4]``); in parity mode ``sample(candidates=...)`` / ``sample(uniforms=..., fills=...)`` take
+the host stream so that results are bit-identical to the reference's (tests/test_replay_gpu.py).
+"""
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..utils.config import Config
+from ..utils.sum_tree import SumTree
+
+Transition = namedtuple("Transition", ["state", "action", "reward", "next_state", "mask"])
+PrioritizedTransition = namedtuple("Transition",
+                                   ["state", "action", "reward", "next_state", "mask", "sampling_prob", "idx"])
+
+
+class Storage:
+    """replay.py:20-54 -- per-rollout lists keyed by name; ``extract`` concatenates over time."""
+
+    def __init__(self, memory_size, keys=None):
+        if keys is None:
+            keys = []
+        keys = keys + ["state", "action", "reward", "mask", "v", "q", "pi", "log_pi", "entropy", "advantage", "ret",
+                       "q_a", "log_pi_a", "mean", "next_state"]
+        self.keys = keys
+        self.memory_size = memory_size
+        self.reset()
+
+    def feed(self, data):
+        for k, v in data.items():
+            if k not in self.keys:
+                raise RuntimeError("Undefined key")
+            getattr(self, k).append(v)
+
+    def placeholder(self):
+        for k in self.keys:
+            if len(getattr(self, k)) == 0:
+                setattr(self, k, [None] * self.memory_size)
+
+    def reset(self):
+        for key in self.keys:
+            setattr(self, key, [])
+        self.pos = 0
+        self._size = 0
+
+    def extract(self, keys):
+        data = [torch.cat(getattr(self, k)[:self.memory_size], dim=0) for k in keys]
+        return namedtuple("Entry", keys)(*data)
+
+
+class UniformReplay:
+    TransitionCLS = Transition
+
+    def __init__(self, memory_size, batch_size, n_step=1, discount=1, history_length=1, keys=None, device=None,
+                 seed=0, reference_feed_quirk=True):
+        self.device = _lib.require_cuda(device if device is not None else Config.DEVICE)
+        self.memory_size, self.batch_size = int(memory_size), int(batch_size)
+        self.n_step, self.discount, self.history_length = int(n_step), float(discount), int(history_length)
+        self.keys = ["state", "action", "reward", "mask"] + list(keys or [])
+        self.seed = int(seed)
+        self.quirk = bool(reference_feed_quirk)
+        self.pos = 0
+        self._size = 0
+        self.frames = None                     # allocated at first feed (shape / dtype come from the data)
+        dev = self.device
+        self.ring_state = torch.zeros(8, dtype=torch.int64, device=dev)
+        self.ring_state[2] = self.memory_size
+        self.action = torch.zeros(self.memory_size, dtype=torch.int32, device=dev)
+        self.reward = torch.zeros(self.memory_size, dtype=torch.float64, device=dev)
+        self.mask = torch.zeros(self.memory_size, dtype=torch.int32, device=dev)
+        self._status = torch.zeros(2, dtype=torch.int32, device=dev)
+        self._stage = None
+        self._lut_cache = {}
+        self._bufs = {}
+
+    # ------------------------------------------------------------------ storage
+    def _allocate(self, item):
+        item = np.asarray(item)
+        self.item_shape, self.item_dtype = tuple(item.shape), item.dtype
+        self.row_bytes = int(item.nbytes)
+        if self.row_bytes == 0:
+            raise ValueError("cannot store empty states")
+        self.frames = torch.empty((self.memory_size, self.row_bytes), dtype=torch.uint8, device=self.device)
+        self._torch_dtype = torch.from_numpy(np.zeros(1, self.item_dtype)).dtype
+
+    def _staging(self, n):
+        if self._stage is None or self._stage["n"] < n:
+            cap = max(n, 16)
+            pin = dict(pin_memory=True)
+            self._stage = dict(
+                n=cap,
+                hf=torch.empty((cap, self.row_bytes), dtype=torch.uint8, **pin), ha=torch.empty(cap, dtype=torch.int32, **pin),
+                hr=torch.empty(cap, dtype=torch.float64, **pin), hm=torch.empty(cap, dtype=torch.int32, **pin),
+                df=torch.empty((cap, self.row_bytes), dtype=torch.uint8, device=self.device),
+                da=torch.empty(cap, dtype=torch.int32, device=self.device),
+                dr=torch.empty(cap, dtype=torch.float64, device=self.device),
+                dm=torch.empty(cap, dtype=torch.int32, device=self.device))
+        return self._stage
+
+    def feed(self, data):
+        """replay.py:75-90.  ``data``: dict of equal-length sequences for state / action / reward / mask."""
+        for k in data:
+            if k not in self.keys:
+                raise RuntimeError("Undefined key")
+        states = data["state"]
+        n = len(states)
+        if n == 0:
+            return
+        if n > 1024:
+            for s in range(0, n, 1024):
+                self.feed({k: v[s:s + 1024] for k, v in data.items()})
+            return
+        if self.frames is None:
+            self._allocate(states[0])
+        st = self._staging(n)
+        arr = np.ascontiguousarray(np.asarray(states, dtype=self.item_dtype)).reshape(n, self.row_bytes // self.item_dtype.itemsize)
+        st["hf"][:n].numpy()[...] = arr.view(np.uint8).reshape(n, self.row_bytes)
+        st["ha"][:n].numpy()[...] = np.asarray(data["action"]).astype(np.int32).reshape(n)
+        st["hr"][:n].numpy()[...] = np.asarray(data["reward"], dtype=np.float64).reshape(n)
+        st["hm"][:n].numpy()[...] = np.asarray(data["mask"]).astype(np.int32).reshape(n)
+        for h, d in (("hf", "df"), ("ha", "da"), ("hr", "dr"), ("hm", "dm")):
+            st[d][:n].copy_(st[h][:n], non_blocking=True)
+        self.feed_device(st["df"], st["da"], st["dr"], st["dm"], n)
+        torch.cuda.current_stream().synchronize()       # the pinned staging buffers are reused by the next call
+
+    def feed_device(self, frames, action, reward, mask, n):
+        """Feed ``n`` items already staged on the device (uint8 rows, int32, float64, int32)."""
+        if self.frames is None:
+            raise RuntimeError("feed_device needs an allocated ring: call feed() once or allocate(item) first")
+        _lib.call("b2rl_replay_feed", _lib.ptr(self.frames), _lib.ptr(self.action), _lib.ptr(self.reward),
+                  _lib.ptr(self.mask), _lib.ptr(self.ring_state), self.row_bytes, _lib.ptr(frames), _lib.ptr(action),
+                  _lib.ptr(reward), _lib.ptr(mask), int(n), int(self.quirk), _lib.stream())
+        # host mirror of the cursor (replay.py:80-90)
+        pos, size = self.pos, self._size
+        for _ in range(n):
+            if pos >= size:
+                size += 1
+            pos = (pos + 1) % self.memory_size
+        self.pos, self._size = pos, size
+
+    def allocate(self, item):
+        if self.frames is None:
+            self._allocate(item)
+
+    def load_synthetic(self, frames, action, reward, mask, pos):
+        """Bulk-load a full ring from device tensors (bench / tests): ``frames`` uint8 [capacity, row_bytes]."""
+        assert frames.shape[0] == self.memory_size and frames.dtype == torch.uint8
+        self.row_bytes = int(frames.shape[1])
+        self.item_shape = getattr(self, "item_shape", (self.row_bytes,))
+        self.item_dtype = getattr(self, "item_dtype", np.dtype(np.uint8))
+        self._torch_dtype = torch.from_numpy(np.zeros(1, self.item_dtype)).dtype
+        self.frames = frames
+        self.action.copy_(action), self.reward.copy_(reward), self.mask.copy_(mask)
+        self.pos, self._size = int(pos), self.memory_size
+        self.ring_state[0], self.ring_state[1] = self.pos, self._size
+
+    def size(self):
+        return self._size
+
+    def full(self):
+        return self._size == self.memory_size
+
+    def valid_index(self, index):
+        """replay.py:105-110 (host arithmetic on the mirrored cursor; the kernels apply the same rule)."""
+        hl, n = self.history_length, self.n_step
+        if index - hl + 1 >= 0 and index + n < self.pos:
+            return True
+        if index - hl + 1 >= self.pos and index + n < self._size:
+            return True
+        return False
+
+    def compute_valid_indices(self):
+        """replay.py:69-73."""
+        hl, n = self.history_length, self.n_step
+        idx = list(range(hl - 1, self.pos - n)) + list(range(self.pos + hl - 1, self._size - n))
+        return np.asarray(idx)
+
+    # ------------------------------------------------------------------ sampling
+    def _buffers(self, B, out_dtype, channels_last, tag=0):
+        key = (B, out_dtype, channels_last, tag)
+        if key not in self._bufs:
+            dev, hl = self.device, self.history_length
+            if out_dtype == torch.uint8:
+                shape = (B, hl, self.row_bytes)
+            elif channels_last:
+                shape = (B, self.row_bytes, hl)
+            else:
+                shape = (B, hl, self.row_bytes)
+            self._bufs[key] = dict(
+                idx=torch.empty(B, dtype=torch.int64, device=dev),
+                state=torch.empty(shape, dtype=out_dtype, device=dev), next_state=torch.empty(shape, dtype=out_dtype, device=dev),
+                action=torch.empty(B, dtype=torch.int64, device=dev), reward=torch.empty(B, dtype=torch.float32, device=dev),
+                mask=torch.empty(B, dtype=torch.float32, device=dev),
+                tree_idx=torch.empty(B, dtype=torch.int64, device=dev), prob64=torch.empty(B, dtype=torch.float64, device=dev),
+                prob=torch.empty(B, dtype=torch.float32, device=dev))
+        return self._bufs[key]
+
+    def lut(self, scale=1.0 / 255):
+        """uint8 -> float table ``float32(float64(v) * scale)``: the reference's ImageNormalizer multiplies in
+        float64 and ``tensor()`` rounds once to float32 (normalizer.py:58-61, torch_utils.py:23)."""
+        if scale not in self._lut_cache:
+            t = (np.arange(256, dtype=np.float64) * scale).astype(np.float32)
+            self._lut_cache[scale] = torch.from_numpy(t).to(self.device)
+        return self._lut_cache[scale]
+
+    def select(self, B, idx_out, candidates=None):
+        n_cand = min(8192, max(2 * B, B + 256)) if candidates is None else min(8192, candidates.numel())
+        _lib.call("b2rl_replay_select_uniform", _lib.ptr(self.ring_state), _lib.ptr(candidates), int(n_cand), self.seed,
+                  self.history_length, self.n_step, int(B), _lib.ptr(idx_out), _lib.ptr(self._status), _lib.stream())
+
+    def gather(self, idx, B, bufs, out_dtype=torch.uint8, lut=None, channels_last=False):
+        _lib.call("b2rl_replay_gather", _lib.ptr(self.frames), _lib.ptr(self.action), _lib.ptr(self.reward),
+                  _lib.ptr(self.mask), self.memory_size, self.row_bytes, _lib.ptr(idx), int(B), self.history_length,
+                  self.n_step, self.discount, _lib.ptr(lut), _lib.DTYPE_CODE[out_dtype], int(bool(channels_last)),
+                  _lib.ptr(bufs["state"]), _lib.ptr(bufs["next_state"]), _lib.ptr(bufs["action"]), _lib.ptr(bufs["reward"]),
+                  _lib.ptr(bufs["mask"]), _lib.stream())
+
+    def _typed(self, raw, B):
+        """uint8 rows -> stored dtype and shape; the frame-stack axis disappears when history_length == 1."""
+        x = raw.view(self._torch_dtype) if self._torch_dtype != torch.uint8 else raw
+        shape = (B, self.history_length) + self.item_shape if self.history_length > 1 else (B,) + self.item_shape
+        return x.view(shape)
+
+    def sample(self, batch_size=None, candidates=None, check=True, tag=0):
+        """replay.py:92-103.  Returns ``Transition`` of device tensors: state / next_state in the stored dtype,
+        action int64, reward float32, mask float32.  ``candidates`` (int64 tensor / array) replaces the device
+        Philox stream by an ``np.random.randint(0, size)`` stream (parity mode)."""
+        B = self.batch_size if batch_size is None else int(batch_size)
+        if self._size == 0:
+            raise ValueError("cannot sample from an empty replay")
+        bufs = self._buffers(B, torch.uint8, False, tag)
+        if candidates is not None and not isinstance(candidates, torch.Tensor):
+            candidates = torch.as_tensor(np.asarray(candidates, dtype=np.int64), device=self.device)
+        self.select(B, bufs["idx"], candidates)
+        if check:
+            acc = int(self._status[0].item())
+            if acc < B:
+                raise RuntimeError("candidate stream exhausted: %d of %d valid indices found" % (acc, B))
+        self.gather(bufs["idx"], B, bufs)
+        return Transition(self._typed(bufs["state"], B), bufs["action"], bufs["reward"], self._typed(bufs["next_state"], B),
+                          bufs["mask"])
+
+    def sample_normalized(self, batch_size=None, out_dtype=torch.float32, scale=1.0 / 255, channels_last=False,
+                          candidates=None, tag=0):
+        """Fused gather -> normalize (``ImageNormalizer``) for uint8 frame rings: state / next_state come back
+        as ``out_dtype`` [B, history, H, W] (``channels_last`` -> torch channels_last memory format)."""
+        B = self.batch_size if batch_size is None else int(batch_size)
+        if self.item_dtype != np.uint8:
+            raise TypeError("sample_normalized is for uint8 frame rings")
+        bufs = self._buffers(B, out_dtype, channels_last, tag)
+        self.select(B, bufs["idx"], candidates)
+        self.gather(bufs["idx"], B, bufs, out_dtype, self.lut(scale), channels_last)
+        hw = self.item_shape[-2:] if len(self.item_shape) >= 2 else (self.row_bytes,)
+        hl = self.history_length
+
+        def view(x):
+            if channels_last:
+                return x.view((B,) + tuple(hw) + (hl,)).permute(0, 3, 1, 2)      # logical NCHW, NHWC in memory
+            return x.view((B, hl) + tuple(hw))
+
+        return Transition(view(bufs["state"]), bufs["action"], bufs["reward"], view(bufs["next_state"]), bufs["mask"])
+
+    def construct_transition(self, index):
+        """replay.py:112-140 for ONE index (inspection / tests): device gather of a batch of one."""
+        if not self.valid_index(index):
+            return None
+        bufs = self._buffers(1, torch.uint8, False, tag=-1)
+        bufs["idx"][0] = int(index)
+        self.gather(bufs["idx"], 1, bufs)
+        t = Transition(self._typed(bufs["state"], 1)[0].clone(), bufs["action"][0].clone(), bufs["reward"][0].clone(),
+                       self._typed(bufs["next_state"], 1)[0].clone(), bufs["mask"][0].clone())
+        return t
+
+    def update_priorities(self, info):
+        raise NotImplementedError
+
+    def close(self):
+        pass
+
+
+class PrioritizedReplay(UniformReplay):
+    TransitionCLS = PrioritizedTransition
+
+    def __init__(self, memory_size, batch_size, n_step=1, discount=1, history_length=1, keys=None, device=None,
+                 seed=0, reference_feed_quirk=True):
+        super().__init__(memory_size, batch_size, n_step, discount, history_length, keys, device, seed,
+                         reference_feed_quirk)
+        self.tree = SumTree(memory_size, self.device, ring_state=self.ring_state)
+        self.max_priority_dev = torch.ones(1, dtype=torch.float64, device=self.device)    # replay.py:158
+
+    @property
+    def max_priority(self):
+        return float(self.max_priority_dev.item())
+
+    def feed(self, data):
+        """replay.py:160-162 -- NOTE the reference adds ONE leaf per feed() call whatever the item count."""
+        super().feed(data)
+        if len(data["state"]):
+            self.tree.add_n(1, self.max_priority_dev)
+
+    def feed_device(self, frames, action, reward, mask, n, add_leaf=False):
+        super().feed_device(frames, action, reward, mask, n)
+        if add_leaf:
+            self.tree.add_n(1, self.max_priority_dev)
+
+    def load_synthetic(self, frames, action, reward, mask, pos, priorities=None):
+        super().load_synthetic(frames, action, reward, mask, pos)
+        cap = self.memory_size
+        leaves = torch.ones(cap, dtype=torch.float64, device=self.device) if priorities is None else priorities.double()
+        # initial state only: internal nodes = exact sums of their children, built level by level
+        t = self.tree.tree
+        t[cap - 1:] = leaves
+        depth = (cap - 1).bit_length()
+        for d in range(depth, -1, -1):
+            lo, hi = 2 ** d - 1, min(2 ** (d + 1) - 1, cap - 1)
+            if hi > lo:
+                idx = torch.arange(lo, hi, device=self.device)
+                t[idx] = t[2 * idx + 1] + t[2 * idx + 2]
+        self.ring_state[3] = self.pos
+        self.tree.n_entries = cap
+
+    def sample(self, batch_size=None, uniforms=None, fills=None, check=True, tag=0):
+        """replay.py:164-191 -> ``PrioritizedTransition`` (sampling_prob float32 = tensor(p / total), idx = TREE index)."""
+        B = self.batch_size if batch_size is None else int(batch_size)
+        bufs = self._buffers(B, torch.uint8, False, tag)
+        self._select_per(B, bufs, uniforms, fills, check)
+        self.gather(bufs["idx"], B, bufs)
+        return PrioritizedTransition(self._typed(bufs["state"], B), bufs["action"], bufs["reward"],
+                                     self._typed(bufs["next_state"], B), bufs["mask"], bufs["prob"], bufs["tree_idx"])
+
+    def _select_per(self, B, bufs, uniforms=None, fills=None, check=False):
+        as_dev = lambda x, dt: None if x is None else (x if isinstance(x, torch.Tensor) else torch.as_tensor(
+            np.asarray(x, dtype=dt), device=self.device))
+        self.tree.sample_batch(B, self.history_length, self.n_step, bufs["tree_idx"], bufs["idx"], bufs["prob64"],
+                               self._status, as_dev(uniforms, np.float64), as_dev(fills, np.int64), self.seed)
+        if check and int(self._status[0].item()) == 0:
+            raise IndexError("no valid transition among the stratified draws (random.choice on an empty list)")
+        bufs["prob"].copy_(bufs["prob64"])              # tensor(sampling_prob): float64 -> float32, one rounding
+
+    def sample_normalized(self, batch_size=None, out_dtype=torch.float32, scale=1.0 / 255, channels_last=False,
+                          uniforms=None, fills=None, tag=0):
+        B = self.batch_size if batch_size is None else int(batch_size)
+        bufs = self._buffers(B, out_dtype, channels_last, tag)
+        self._select_per(B, bufs, uniforms, fills)
+        self.gather(bufs["idx"], B, bufs, out_dtype, self.lut(scale), channels_last)
+        hw, hl = self.item_shape[-2:], self.history_length
+        view = (lambda x: x.view((B,) + tuple(hw) + (hl,)).permute(0, 3, 1, 2)) if channels_last else \
+            (lambda x: x.view((B, hl) + tuple(hw)))
+        return PrioritizedTransition(view(bufs["state"]), bufs["action"], bufs["reward"], view(bufs["next_state"]),
+                                     bufs["mask"], bufs["prob"], bufs["tree_idx"])
+
+    def update_priorities(self, info):
+        """replay.py:193-196.  ``info``: iterable of (tree_idx, priority) pairs (the reference's zip of numpy
+        arrays) or a pair of DEVICE tensors ``(idx int64 [B], priority float32 [B])`` (no host round trip)."""
+        if isinstance(info, tuple) and len(info) == 2 and isinstance(info[0], torch.Tensor):
+            idx, prio = info
+        else:
+            pairs = list(info)
+            if not pairs:
+                return
+            idx = torch.as_tensor(np.asarray([p[0] for p in pairs], dtype=np.int64), device=self.device)
+            prio = torch.as_tensor(np.asarray([p[1] for p in pairs], dtype=np.float32), device=self.device)
+        for s in range(0, idx.numel(), 1024):
+            self.tree.update_batch(idx[s:s + 1024].contiguous(), prio[s:s + 1024].contiguous(), self.max_priority_dev)
+
+
+class ReplayWrapper:
+    """replay.py:199-278.  ``ReplayWrapper(replay_cls, replay_kwargs, async_)``."""
+    FEED, SAMPLE, EXIT, UPDATE_PRIORITIES = 0, 1, 2, 3
+
+    def __init__(self, replay_cls, replay_kwargs, async_=True):
+        self.replay_cls, self.replay_kwargs = replay_cls, replay_kwargs
+        self.cache_len = 2
+        self.replay = replay_cls(**replay_kwargs)
+        self.async_ = bool(async_)
+        if not self.async_:
+            self.sample = self.replay.sample
+            self.feed = self.replay.feed
+            self.update_priorities = self.replay.update_priorities
+        else:
+            self._side = torch.cuda.Stream(device=self.replay.device)
+            self._ready = [None, None]
+            self._cache = [None, None]
+            self._cur = 0
+            self._primed = False
+
+    # async mode: every replay operation is ordered on the side stream, exactly like the reference's worker
+    # processes its pipe messages in order; the learner only waits on the event of the buffer it receives.
+    def _on_side(self, fn, *a, **k):
+        self._side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            return fn(*a, **k)
+
+    def _fill(self, slot):
+        with torch.cuda.stream(self._side):
+            self._cache[slot] = self.replay.sample(tag=slot, check=False)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            self._ready[slot] = ev
+
+    def feed(self, exp):
+        self._on_side(self.replay.feed, exp)
+
+    def sample(self):
+        self._side.wait_stream(torch.cuda.current_stream())
+        if not self._primed:                        # replay.py:227-234: both buffers are filled on first use
+            self._fill(0), self._fill(1)
+            self._primed = True
+        slot = self._cur
+        torch.cuda.current_stream().wait_event(self._ready[slot])
+        out = self._cache[slot]
+        self._cur = (self._cur + 1) % 2
+        self._fill(self._cur)                       # replay.py:253-254: refill the OTHER buffer right away
+        return out
+
+    def update_priorities(self, info):
+        self._on_side(self.replay.update_priorities, info)
+
+    def size(self):
+        return self.replay.size()
+
+    def full(self):
+        return self.replay.full()
+
+    def close(self):
+        if self.async_:
+            self._side.synchronize()
+        self.replay.close()

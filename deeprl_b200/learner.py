@@ -1,0 +1,164 @@
+"""CUDA-graph learner for the DQN family: one gradient update of ``DQNAgent.step`` (DQN_agent.py:101-138) --
+``sgd_update_frequency`` feeds, sample, target / online forward, fused loss, backward, [gradient all-reduce],
+fused clip + optimizer, PER priority update -- replayed as (at most two) captured graphs, with every scalar
+that changes between updates (ring cursor, Philox counter, PER beta, Adam step, max priority) living in device
+memory.  This is the throughput path of bench.py; ``DQNAgent`` without it runs the same kernels eagerly.
+
+Multi-GPU: one learner per rank, rank-local replay shard, parameters identical on every rank;
+gradients are summed with ONE NCCL all-reduce of the flat gradient arena between the two graphs and scaled by
+1 / world_size inside the clip kernel.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from .component.replay import PrioritizedReplay
+
+
+class GraphedDQNLearner:
+    def __init__(self, network, target_network, optimizer, replay, kind="dqn", discount=0.99, n_step=1, double_q=False,
+                 gradient_clip=5.0, feeds_per_update=4, compute_dtype=torch.bfloat16, state_scale=1.0 / 255,
+                 replay_eps=0.01, replay_alpha=0.5, categorical=(-10.0, 10.0), world_size=1, target_sync_every=10000):
+        self.net, self.tgt, self.opt, self.replay = network, target_network, optimizer, replay
+        self.kind, self.gamma_n, self.double_q = kind, discount ** n_step, double_q
+        self.clip, self.feeds = gradient_clip, feeds_per_update
+        self.dtype, self.scale = compute_dtype, state_scale
+        self.eps, self.alpha, self.cat = replay_eps, replay_alpha, categorical
+        self.world = world_size
+        self.per = isinstance(replay, PrioritizedReplay)
+        self.sync_every = target_sync_every
+        dev = replay.device
+        self.dev = dev
+        B = replay.batch_size
+        self.B = B
+        n = max(self.feeds, 1)
+        rb = replay.row_bytes
+        # pinned host staging for the env transitions of one update + device mirrors (one packed copy each)
+        self.h_frames = torch.zeros((n, rb), dtype=torch.uint8, pin_memory=True)
+        self.h_action = torch.zeros(n, dtype=torch.int32, pin_memory=True)
+        self.h_reward = torch.zeros(n, dtype=torch.float64, pin_memory=True)
+        self.h_mask = torch.ones(n, dtype=torch.int32, pin_memory=True)
+        self.d_frames = torch.zeros((n, rb), dtype=torch.uint8, device=dev)
+        self.d_action = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.d_reward = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.d_mask = torch.ones(n, dtype=torch.int32, device=dev)
+        self.h_beta = torch.full((1,), 0.4, dtype=torch.float32, pin_memory=True)
+        self.d_beta = torch.full((1,), 0.4, dtype=torch.float32, device=dev)
+        self.h_loss = torch.zeros(1, dtype=torch.float32, pin_memory=True)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.g_main = self.g_opt = None
+        self.updates = 0
+        self.with_h2d = False
+
+    # ------------------------------------------------------------------ the update, as eager code
+    def _h2d(self):
+        self.d_frames.copy_(self.h_frames, non_blocking=True)
+        self.d_action.copy_(self.h_action, non_blocking=True)
+        self.d_reward.copy_(self.h_reward, non_blocking=True)
+        self.d_mask.copy_(self.h_mask, non_blocking=True)
+        self.d_beta.copy_(self.h_beta, non_blocking=True)
+
+    def _main(self):
+        rp = self.replay
+        for j in range(self.feeds):                      # DQN_agent.py:104-112: one feed() per env transition
+            if self.per:
+                rp.feed_device(self.d_frames[j:j + 1], self.d_action[j:j + 1], self.d_reward[j:j + 1], self.d_mask[j:j + 1], 1,
+                               add_leaf=True)
+            else:
+                rp.feed_device(self.d_frames[j:j + 1], self.d_action[j:j + 1], self.d_reward[j:j + 1], self.d_mask[j:j + 1], 1)
+        cl = self.dtype == torch.bfloat16
+        t = rp.sample_normalized(out_dtype=self.dtype, scale=self.scale, channels_last=cl)
+        per = dict(is_prob=t.sampling_prob, eps=self.eps, alpha=self.alpha, beta_dev=self.d_beta) if self.per else {}
+        with torch.no_grad():
+            nxt_t = self.tgt(t.next_state)
+            nxt_o = self.net(t.next_state) if self.double_q else None
+        out = self.net(t.state)
+        if self.kind == "dqn":
+            head = out["q"]
+            r = ops.dqn_loss_fused(head.detach(), nxt_t["q"], nxt_o["q"] if nxt_o else None, t.action, t.reward, t.mask,
+                                   self.gamma_n, **per)
+            grad = r["dq"]
+        elif self.kind == "c51":
+            head = out["log_prob"]
+            r = ops.c51_loss_fused(head.detach(), nxt_t["prob"], nxt_o["prob"] if nxt_o else None, t.action, t.reward,
+                                   t.mask, self.gamma_n, self.cat[0], self.cat[1], **per)
+            grad = r["dlogp"]
+        else:
+            head = out["quantile"]
+            r = ops.qr_loss_fused(head.detach(), nxt_t["quantile"], t.action, t.reward, t.mask, self.gamma_n)
+            grad = r["dquant"]
+        if self.per:
+            rp.update_priorities((t.idx, r["priority"]))
+        self.opt.zero_grad()
+        head.backward(grad)
+        self.loss.copy_(r["loss"])
+
+    def _opt(self):
+        self.opt.step(max_norm=self.clip, grad_scale=1.0 / self.world)
+
+    # ------------------------------------------------------------------ capture / replay
+    def capture(self, warmup=3, with_h2d=False):
+        """Warm up eagerly on a side stream (cuDNN autotune, lazy allocations), then capture."""
+        self.with_h2d = with_h2d
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                if with_h2d:
+                    self._h2d()
+                self._main()
+                self._allreduce()
+                self._opt()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.g_main = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_main):
+            if with_h2d:
+                self._h2d()
+            self._main()
+            if self.world == 1:                          # single GPU: the whole update is ONE graph
+                self._opt()
+        if self.world > 1:                               # multi GPU: [sample..backward] | NCCL all-reduce | [clip+opt]
+            self.g_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_opt):
+                self._opt()
+        # host mirrors of the ring cursor advanced during warm-up / capture calls; re-derive from the device
+        st = self.replay.ring_state.cpu()
+        self.replay.pos, self.replay._size = int(st[0]), int(st[1])
+        self.launches_per_update = None
+        return self
+
+    def _allreduce(self):
+        if self.world > 1:
+            dist.all_reduce(self.opt.grad)
+
+    def update(self):
+        """One gradient update (graph replay).  Returns the device loss tensor (no sync)."""
+        self.g_main.replay()
+        if self.world > 1:
+            self._allreduce()
+            self.g_opt.replay()
+        self.updates += 1
+        if self.sync_every and self.updates % self.sync_every == 0:
+            self.tgt.load_state_dict(self.net.state_dict())        # DQN_agent.py:136-138
+        return self.loss
+
+    def update_from_host(self, frames, action, reward, mask, beta=None):
+        """End-to-end update through HOST buffers: the env transitions of this update are written to the pinned
+        staging area, copied host->device inside the captured graph, and the loss is read back."""
+        assert self.with_h2d, "capture(with_h2d=True) first"
+        self.h_frames.numpy()[...] = frames
+        self.h_action.numpy()[...] = action
+        self.h_reward.numpy()[...] = reward
+        self.h_mask.numpy()[...] = mask
+        if beta is not None:
+            self.h_beta[0] = beta
+        self.update()
+        self.h_loss.copy_(self.loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self.h_loss[0])
+
+    @property
+    def h2d_bytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.h_frames, self.h_action, self.h_reward, self.h_mask, self.h_beta))

@@ -1,0 +1,76 @@
+"""Feature extractors with the reference's module / parameter names
+(``deep_rl/network/network_bodies.py``: ``NatureConvBody``:10, ``FCBody``:50, ``DummyBody``:76), so that
+reference ``state_dict``s load unchanged (``body.conv1.weight`` ... ``body.fc4.bias``, ``layers.<i>``).
+
+``Config.COMPUTE_DTYPE`` selects the arithmetic of the dense contractions: ``torch.float32`` is the parity
+mode (TF32 off, results comparable with the reference at 1e-5), ``torch.bfloat16`` the throughput mode
+(bf16 operands, fp32 accumulation, fp32 master weights; inputs may arrive as channels_last bf16 straight from
+the fused replay gather).  The contractions themselves are plain library calls (cuDNN / cuBLAS) in this round.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..utils import Config
+from .network_utils import NoisyLinear, layer_init
+
+
+def _autocast():
+    on = Config.DEVICE.type == "cuda" and Config.COMPUTE_DTYPE == torch.bfloat16
+    return torch.autocast("cuda", dtype=torch.bfloat16, enabled=on)
+
+
+class NatureConvBody(nn.Module):
+    """conv(in,32,k8,s4) -> conv(32,64,k4,s2) -> conv(64,64,k3,s1) -> fc(3136,512), ReLU after each
+    (Mnih et al. 2015; network_bodies.py:10-33)."""
+
+    def __init__(self, in_channels=4, noisy_linear=False):
+        super().__init__()
+        self.feature_dim = 512
+        self.conv1 = layer_init(nn.Conv2d(in_channels, 32, kernel_size=8, stride=4))
+        self.conv2 = layer_init(nn.Conv2d(32, 64, kernel_size=4, stride=2))
+        self.conv3 = layer_init(nn.Conv2d(64, 64, kernel_size=3, stride=1))
+        self.fc4 = NoisyLinear(7 * 7 * 64, 512) if noisy_linear else layer_init(nn.Linear(7 * 7 * 64, 512))
+        self.noisy_linear = noisy_linear
+
+    def reset_noise(self):
+        if self.noisy_linear:
+            self.fc4.reset_noise()
+
+    def forward(self, x):
+        with _autocast():
+            y = F.relu(self.conv1(x))
+            y = F.relu(self.conv2(y))
+            y = F.relu(self.conv3(y))
+            y = y.reshape(y.size(0), -1)          # NCHW flatten order whatever the memory format
+            return F.relu(self.fc4(y))
+
+
+class FCBody(nn.Module):
+    def __init__(self, state_dim, hidden_units=(64, 64), gate=F.relu, noisy_linear=False):
+        super().__init__()
+        dims = (state_dim,) + tuple(hidden_units)
+        make = (lambda i, o: NoisyLinear(i, o)) if noisy_linear else (lambda i, o: layer_init(nn.Linear(i, o)))
+        self.layers = nn.ModuleList([make(i, o) for i, o in zip(dims[:-1], dims[1:])])
+        self.gate = gate
+        self.feature_dim = dims[-1]
+        self.noisy_linear = noisy_linear
+
+    def reset_noise(self):
+        if self.noisy_linear:
+            for layer in self.layers:
+                layer.reset_noise()
+
+    def forward(self, x):
+        for layer in self.layers:
+            x = self.gate(layer(x))
+        return x
+
+
+class DummyBody(nn.Module):
+    def __init__(self, state_dim):
+        super().__init__()
+        self.feature_dim = state_dim
+
+    def forward(self, x):
+        return x

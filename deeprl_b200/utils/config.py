@@ -27,6 +27,7 @@ _DEFAULTS = dict(
 
 class Config:
     DEVICE = torch.device("cpu")
+    COMPUTE_DTYPE = torch.float32      # torch.bfloat16 = throughput mode of the dense contractions (not in the reference)
     NOISY_LAYER_STD = 0.1
     DEFAULT_REPLAY = "replay"
     PRIORITIZED_REPLAY = "prioritized_replay"

@@ -1,0 +1,184 @@
+/* b2rl.h -- C ABI of libb2rl.so: the sm_100a hot path behind the DeepRL (ShangtongZhang/DeepRL) API.
+ *
+ * The reference has NO FFI / plugin layer: its seams are duck-typed Python factories on Config
+ * (SURVEY.md 8b).  This header is the boundary a maintainer binds with ctypes
+ * from the reference-side classes named beside each entry point.  Citations are file:line under
+ * /root/reference/deep_rl.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller (PyTorch caching
+ *     allocator in our host mirror) owns every buffer; the library allocates nothing on the hot path
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns at once;
+ *     all calls are CUDA-graph capturable (no host sync, no allocation)
+ *   - return value: 0 on success, negative b2rl_status on error; b2rl_last_error() gives the message
+ *     (thread-local).  Nothing throws across the boundary.
+ *   - "ring state" is a device int64[8]: [0]=pos [1]=size [2]=capacity [3]=tree write cursor
+ *     [4]=philox counter [5..7] reserved; device-resident so that feed/sample/update can be captured
+ *     in one CUDA graph
+ */
+#ifndef B2RL_H
+#define B2RL_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  B2RL_OK = 0,
+  B2RL_ERR_ARG = -1,      /* bad argument (null pointer, size out of range, unsupported shape) */
+  B2RL_ERR_CUDA = -2,     /* a CUDA runtime call / kernel launch failed */
+  B2RL_ERR_UNSUPPORTED = -3
+} b2rl_status;
+
+typedef enum { B2RL_U8 = 0, B2RL_F16 = 1, B2RL_BF16 = 2, B2RL_F32 = 3 } b2rl_dtype;
+
+int b2rl_version(void);
+const char* b2rl_last_error(void);
+/* number of kernels this library has launched since load / since the last reset (bench.py "gpu_launches") */
+int64_t b2rl_launch_count(void);
+void b2rl_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Replay ring -- UniformReplay.feed / valid_index / construct_transition / sample
+ * (component/replay.py:75-90, 105-110, 112-140, 92-103)
+ * frames: uint8 [capacity][row_bytes]  (row_bytes = 84*84 for Atari frames, 4*state_dim for f32 features)
+ * action: int32 [capacity]; reward: float64 [capacity] (the reference keeps python floats); mask: int32
+ * ------------------------------------------------------------------------------------------- */
+
+/* feed n items (staged on the device in new_*) at the ring cursor; updates ring_state[0..1].
+ * reference_quirk != 0 reproduces replay.py:87 (a multi-item feed into a FULL ring writes every item to
+ * the slot the call started at); 0 writes each item to its own slot. */
+int b2rl_replay_feed(uint8_t* frames, int32_t* action, double* reward, int32_t* mask, int64_t* ring_state,
+                     int64_t row_bytes, const uint8_t* new_frames, const int32_t* new_action,
+                     const double* new_reward, const int32_t* new_mask, int32_t n, int32_t reference_quirk,
+                     void* stream);
+
+/* choose B valid ring indices in candidate-stream order (replay.py:96-100).  candidates: int64 [n_cand] drawn
+ * like np.random.randint(0,size) (parity mode) or NULL -> Philox4x32-10 (seed, ring_state[4]) draws n_cand
+ * candidates on the device and advances the counter.  idx_out: int64 [B].  status_out: int32 [2] =
+ * {accepted (== B on success, < B if the stream ran dry), candidates consumed}. */
+int b2rl_replay_select_uniform(int64_t* ring_state, const int64_t* candidates, int32_t n_cand, uint64_t seed,
+                               int32_t history, int32_t n_step, int32_t B, int64_t* idx_out, int32_t* status_out,
+                               void* stream);
+
+/* construct_transition for B indices (replay.py:112-140): frame-stack gather + n-step return.
+ * state_out/next_out: [B][history][row_bytes] converted to out_dtype through `lut` (float32 [256]; NULL = raw
+ * copy, only with B2RL_U8).  channels_last != 0 writes [B][row_bytes][history] (NHWC for 84x84 frames).
+ * action_out int64 [B]; reward_out float32 [B] (float64 n-step sum rounded once, as tensor() does,
+ * utils/torch_utils.py:23); mask_out float32 [B].  Any *_out may be NULL to skip it. */
+int b2rl_replay_gather(const uint8_t* frames, const int32_t* action, const double* reward, const int32_t* mask,
+                       int64_t capacity, int64_t row_bytes, const int64_t* idx, int32_t B, int32_t history,
+                       int32_t n_step, double discount, const float* lut, int32_t out_dtype, int32_t channels_last,
+                       void* state_out, void* next_out, int64_t* action_out, float* reward_out, float* mask_out,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sum tree in HBM -- SumTree (utils/sum_tree.py:6-67) + PrioritizedReplay (component/replay.py:152-196)
+ * tree: float64 [2*capacity-1] array heap, leaves at [capacity-1, 2*capacity-2]; pending: uint8 [capacity]
+ * (the reference's pending_idx set, indexed by data index); max_priority: float64 [1] on the device.
+ * All arithmetic is sequential-order float64, bit-identical to the reference.
+ * ------------------------------------------------------------------------------------------- */
+
+/* n x SumTree.add(max_priority) at the tree write cursor ring_state[3] (replay.py:160-162, sum_tree.py:39-51). */
+int b2rl_sumtree_add(double* tree, uint8_t* pending, int64_t capacity, int64_t* ring_state, const double* max_priority,
+                     int32_t n, double* scratch /* 16*n bytes */, void* stream);
+
+/* PrioritizedReplay.sample index part (replay.py:167-186): stratified descents with s_i = seg*i +
+ * (seg*(i+1) - seg*i) * u_i (CPython random.uniform), sum_tree.py:23-33 descent rule, validity filter in batch
+ * order, back-fill.  uniforms: float64 [B] in [0,1) or NULL (Philox, 53-bit).  fills: int64 [B] positions for
+ * the back-fill draws (used modulo the current list length) or NULL (Philox).
+ * Outputs: tree_idx int64 [B], data_idx int64 [B], sampling_prob float64 [B] (= p / total), status int32[2] =
+ * {valid before back-fill, 0}. */
+int b2rl_sumtree_sample(const double* tree, uint8_t* pending, int64_t capacity, int64_t* ring_state,
+                        const double* uniforms, const int64_t* fills, uint64_t seed, int32_t history, int32_t n_step,
+                        int32_t B, int64_t* tree_idx_out, int64_t* data_idx_out, double* sampling_prob_out,
+                        int32_t* status_out, void* stream);
+
+/* SumTree.get(s) for B explicit prefix values (sum_tree.py:63-67): tree_idx_out int64 [B], priority_out float64 [B];
+ * marks the leaves pending. */
+int b2rl_sumtree_get(const double* tree, uint8_t* pending, int64_t capacity, const double* prefix, int32_t B,
+                     int64_t* tree_idx_out, double* priority_out, void* stream);
+
+/* PrioritizedReplay.update_priorities (replay.py:193-196): for i in batch order: max_priority = max(.., p_i);
+ * SumTree.update(tree_idx_i, p_i) honouring the pending guard (sum_tree.py:54-60).  priority: float32 [B]
+ * (to_np of an fp32 tensor, DQN_agent.py:121-123).  scratch: 16*B bytes. */
+int b2rl_sumtree_update(double* tree, uint8_t* pending, int64_t capacity, const int64_t* tree_idx,
+                        const float* priority, int32_t B, double* max_priority, void* scratch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused target/loss kernels.  Each computes the reference's per-sample loss tensor, the reduced scalar and
+ * dLoss/d(network output) in ONE launch.  is_prob (float32 [B], tensor(sampling_prob)) != NULL switches on
+ * the PER block of DQN_agent.py:120-127: priority = (|loss|+eps)^alpha ; w = (B*P+1e-6)^-beta / max ;
+ * loss *= w before reduce_loss.  priority_out float32 [B] may be NULL when is_prob is NULL.
+ * ------------------------------------------------------------------------------------------- */
+
+/* DQNAgent.compute_loss + reduce_loss (DQN_agent.py:78-99): delta = r + gamma_n*q_next*mask - q[a];
+ * loss = mean(0.5*(delta*w)^2).  q_next_online != NULL selects double-Q.  dq_out [B][A] receives dLoss/dq. */
+int b2rl_dqn_loss(const float* q, const float* q_next_target, const float* q_next_online, const int64_t* action,
+                  const float* reward, const float* mask, float gamma_n, int32_t B, int32_t A,
+                  const float* is_prob, float beta, float eps, float alpha,
+                  float* delta_out, float* priority_out, float* loss_out, float* dq_out,
+                  const float* beta_dev /* optional device scalar overriding beta (CUDA-graph replays) */, void* stream);
+
+/* CategoricalDQNAgent.compute_loss + reduce_loss (CategoricalDQN_agent.py:60-89).  log_prob [B][A][N] (online, s),
+ * prob_next_target / prob_next_online [B][A][N] (online NULL -> not double).  kl_out [B], loss_out [1] = mean,
+ * dlogp_out [B][A][N] = dLoss/dlog_prob.  target_prob_out [B][N] optional (NULL to skip). */
+int b2rl_c51_loss(const float* log_prob, const float* prob_next_target, const float* prob_next_online,
+                  const int64_t* action, const float* reward, const float* mask, float gamma_n, float v_min,
+                  float v_max, int32_t B, int32_t A, int32_t N, const float* is_prob, float beta, float eps,
+                  float alpha, float* kl_out, float* priority_out, float* loss_out, float* dlogp_out,
+                  float* target_prob_out, int32_t* counter /* int32 scratch [1], zero on first use */,
+                  const float* beta_dev /* optional device scalar overriding beta */, void* stream);
+
+/* QuantileRegressionDQNAgent.compute_loss + reduce_loss (QuantileRegressionDQN_agent.py:55-77).
+ * quantile / quantile_next [B][A][N].  vec_out [N] = the reference's per-TARGET-quantile vector, loss_out = its
+ * mean, dquant_out [B][A][N].  partial: float32 scratch [B][N]; counter: int32 scratch [1], zero on first use. */
+int b2rl_qr_loss(const float* quantile, const float* quantile_next, const int64_t* action, const float* reward,
+                 const float* mask, float gamma_n, float kappa, int32_t B, int32_t A, int32_t N, float* vec_out,
+                 float* loss_out, float* dquant_out, float* partial, int32_t* counter,
+                 const float* grad_weight /* float32 [N] = dLoss/dvec / B, or NULL for the mean (1/(B*N)); with
+                 partial == NULL only the gradient is computed */, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * On-policy: GAE backward recurrence (A2C_agent.py:43-53 == PPO_agent.py:51-61) and the losses.
+ * reward, mask: [T][N]; value: [T+1][N]; adv_out, ret_out: [T][N].
+ * mode 0 = sequential per env (bit-identical to the reference loop); mode 1 = warp segmented scan
+ * (same recurrence re-associated; <= 1e-5 relative).  use_gae == 0 gives adv = ret - v (A2C_agent.py:46-47).
+ * ------------------------------------------------------------------------------------------- */
+int b2rl_gae(const float* reward, const float* mask, const float* value, float discount, float tau, int32_t T,
+             int32_t N, int32_t use_gae, int32_t mode, float* adv_out, float* ret_out, void* stream);
+
+/* advantage normalisation of PPO_agent.py:66: (adv - mean) / std, unbiased std, no epsilon; in place, M elements. */
+int b2rl_normalize_advantage(float* adv, int32_t M, void* stream);
+
+/* PPO clipped surrogate for one minibatch of M rows (PPO_agent.py:77-86).  Inputs [M]: log_pi_a (new), entropy,
+ * v, old_log_pi_a, advantage, ret.  out[0]=policy_loss out[1]=value_loss out[2]=approx_kl.
+ * Gradients: dlogp_out, dent_out = d policy_loss / d(log_pi_a, entropy); dv_out = d value_loss / dv. */
+int b2rl_ppo_loss(const float* log_pi_a, const float* entropy, const float* v, const float* old_log_pi_a,
+                  const float* advantage, const float* ret, float clip, float entropy_weight, int32_t M, float* out,
+                  float* dlogp_out, float* dent_out, float* dv_out, void* stream);
+
+/* A2C objective (A2C_agent.py:55-62): -mean(logp*adv) - ew*mean(ent) + vw*0.5*mean((ret-v)^2) over M rows.
+ * out (float32 [4]) = {objective, policy_loss, value_loss, entropy_loss}. */
+int b2rl_a2c_loss(const float* log_pi_a, const float* entropy, const float* v, const float* advantage,
+                  const float* ret, float entropy_weight, float value_loss_weight, int32_t M, float* out,
+                  float* dlogp_out, float* dent_out, float* dv_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-tensor optimizer step with global-norm clip (DQN_agent.py:132-134; examples.py:67-68,139,204):
+ * flat float32 views of all parameters / gradients (one contiguous arena, n elements).
+ * clip_grad_norm_(max_norm) then RMSprop(centered) or Adam, torch semantics.  norm_scratch: 2048 bytes, zero on first
+ * use; after the call float32 norm_scratch[0] = total gradient norm (what clip_grad_norm_ returns).
+ * bf16_shadow (optional, uint16 [n]): refreshed copy of the updated parameters in bf16.
+ * ------------------------------------------------------------------------------------------- */
+int b2rl_clip_rmsprop(float* param, const float* grad, float* square_avg, float* grad_avg, int64_t n,
+                      float max_norm, float lr, float alpha, float eps, int32_t centered, float grad_scale,
+                      void* norm_scratch, uint16_t* bf16_shadow, void* stream);
+int b2rl_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float max_norm,
+                   float lr, float beta1, float beta2, float eps, int64_t* step_dev, float grad_scale,
+                   void* norm_scratch, uint16_t* bf16_shadow, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2RL_H */

@@ -1,0 +1,244 @@
+"""CPU-side tests (``-m "not gpu"``): the C-ABI library loads and exports every symbol include/b2rl.h declares
+(no compute calls -- there is no GPU here), the ctypes signature table matches the header, and the host logic
+(Config, schedules, normalizers, Task / envs, Storage, random_sample, A2C on the CPU device = BASELINE configs[0]).
+"""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import deeprl_b200 as rl
+from deeprl_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_decls():
+    hdr = open(os.path.join(ROOT, "include", "b2rl.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int|void|int64_t|const char\*)\s+(b2rl_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S):
+        args = [a.strip() for a in m.group(2).split(",") if a.strip() and a.strip() != "void"]
+        out[m.group(1)] = args
+    return out
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    decl = _header_decls()
+    assert len(decl) >= 20
+    syms = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], check=True, capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\b(b2rl_[a-z0-9_]+)\b", syms))
+    assert set(decl) <= exported, sorted(set(decl) - exported)
+    L = _lib.lib()                      # dlopen + resolve every entry of the signature table
+    assert L.b2rl_version() >= 100
+    assert L.b2rl_last_error() is not None
+
+
+def test_ctypes_signatures_match_header():
+    decl = _header_decls()
+    kinds = {"c_void_p": "p", "c_int": "i32", "c_long": "i64", "c_ulong": "u64", "c_float": "f32", "c_double": "f64"}
+    for name, argtypes in _lib.SIGNATURES.items():
+        assert name in decl, name
+        assert len(argtypes) == len(decl[name]), (name, len(argtypes), len(decl[name]))
+        for ct, c_arg in zip(argtypes, decl[name]):
+            k = kinds[ct.__name__]
+            if "*" in c_arg:
+                assert k == "p", (name, c_arg)
+            elif c_arg.startswith("int32_t"):
+                assert k == "i32", (name, c_arg)
+            elif c_arg.startswith("int64_t"):
+                assert k == "i64", (name, c_arg)
+            elif c_arg.startswith("uint64_t"):
+                assert k == "u64", (name, c_arg)
+            elif c_arg.startswith("float"):
+                assert k == "f32", (name, c_arg)
+            elif c_arg.startswith("double"):
+                assert k == "f64", (name, c_arg)
+            else:
+                raise AssertionError((name, c_arg))
+
+
+def test_device_components_refuse_cpu():
+    rl.select_device(-1)
+    with pytest.raises(_lib.B2RLError, match="no CPU fallback"):
+        rl.UniformReplay(16, 4)
+    with pytest.raises(_lib.B2RLError):
+        rl.PrioritizedReplay(16, 4)
+    with pytest.raises(_lib.B2RLError):
+        rl.SumTree(16)
+
+
+def test_schedules_and_normalizers():
+    s = rl.LinearSchedule(1.0, 0.1, 9)
+    vals = [s() for _ in range(12)]
+    assert vals[0] == 1.0 and abs(vals[9] - 0.1) < 1e-12 and vals[11] == 0.1          # advances on every call, clamps
+    up = rl.LinearSchedule(0.4, 1.0, 3)
+    assert [round(up(), 6) for _ in range(5)] == [0.4, 0.6, 0.8, 1.0, 1.0]
+    assert rl.ConstantSchedule(0.3)(5) == 0.3
+    assert rl.LinearSchedule(0.5)() == 0.5
+    x = np.array([[0, 128, 255]], np.uint8)
+    assert np.allclose(rl.ImageNormalizer()(x), x / 255.0)
+    assert list(rl.SignNormalizer()(np.array([-3.0, 0.0, 2.0]))) == [-1.0, 0.0, 1.0]
+    n = rl.MeanStdNormalizer()
+    rng = np.random.RandomState(0)
+    data = [rng.randn(5, 3) * 4 + 2 for _ in range(50)]
+    for d in data:
+        out = n(d)
+    assert np.abs(out).max() <= 10.0
+    allx = np.concatenate(data)
+    np.testing.assert_allclose(n.rms.mean[0], allx.mean(0), atol=1e-3)
+    np.testing.assert_allclose(n.rms.var[0], allx.var(0), rtol=1e-3)
+    n.set_read_only()
+    before = n.rms.mean.copy()
+    n(data[0] + 100)
+    assert np.array_equal(before, n.rms.mean)
+    st = n.state_dict()
+    m2 = rl.MeanStdNormalizer()
+    m2(data[0])
+    m2.load_state_dict(st)
+    assert np.array_equal(m2.rms.mean, n.rms.mean)
+
+
+def test_config_and_misc():
+    c = rl.Config()
+    assert (c.categorical_n_atoms, c.optimization_epochs, c.mini_batch_size, c.async_actor, c.n_step) == (51, 4, 64, True, 1)
+    assert isinstance(c.state_normalizer, rl.RescaleNormalizer) and c.gae_tau == 1.0 and c.double_q is False
+    c.merge(dict(game="X", foo=3))
+    assert c.foo == 3
+    t = rl.Task("CartPole-v0", seed=1)
+    c.eval_env = t
+    assert (c.state_dim, c.action_dim, c.task_name) == (4, 2, "CartPole-v0")
+    np.random.seed(0)
+    rows = list(rl.random_sample(np.arange(10), 4))
+    assert [len(r) for r in rows] == [4, 4, 2] and sorted(np.concatenate(rows)) == list(range(10))
+    kw = dict(game="Breakout", run=2, lr=0.1)
+    rl.generate_tag(kw)
+    assert kw["tag"] == "Breakout-lr_0.1-run-2"
+    np.random.seed(3)
+    q = np.array([[0.1, 0.9], [0.8, 0.2]])
+    assert list(rl.epsilon_greedy(0.0, q)) == [1, 0]
+    assert rl.epsilon_greedy(0.0, q[0]) == 1
+
+
+def test_task_and_envs():
+    t = rl.Task("SyntheticAtari-v0", num_envs=3, seed=5)
+    obs = t.reset()
+    assert len(obs) == 3 and isinstance(obs[0], rl.LazyFrames) and np.asarray(obs[0]).shape == (4, 84, 84)
+    assert np.asarray(obs[0]).dtype == np.uint8 and obs[0][-1].shape == (84, 84)
+    o, r, d, info = t.step(np.array([0, 1, 2]))
+    assert isinstance(o, tuple) and r.shape == (3,) and d.shape == (3,) and isinstance(info, tuple)
+    assert set(info[0]) >= {"episodic_return"} and (t.state_dim, t.action_dim) == (4 * 84 * 84, 4)
+    c = rl.Task("SyntheticCheetah-v0", num_envs=2, seed=1)
+    c.reset()
+    o, r, d, info = c.step(np.full((2, 6), 5.0))             # Box actions are clipped to [-1, 1] (envs.py:188)
+    assert (c.state_dim, c.action_dim) == (17, 6) and np.asarray(o).shape == (2, 17)
+    cp = rl.Task("CartPole-v0", seed=0)
+    cp.reset()
+    rets = []
+    for _ in range(300):
+        _, _, done, info = cp.step([1])
+        if info[0]["episodic_return"] is not None:
+            rets.append(info[0]["episodic_return"])
+    assert rets and all(5 <= x <= 200 for x in rets)        # always pushing right falls over quickly; auto-reset works
+    with pytest.raises(NotImplementedError):
+        rl.Task("CartPole-v0", single_process=False)
+
+
+def test_storage():
+    s = rl.Storage(3)
+    for i in range(3):
+        s.feed(dict(reward=torch.full((2, 1), float(i)), mask=torch.ones(2, 1)))
+    s.placeholder()
+    assert s.v == [None] * 3
+    e = s.extract(["reward", "mask"])
+    assert e.reward.shape == (6, 1) and e.reward[:, 0].tolist() == [0, 0, 1, 1, 2, 2]          # t-major rows
+    with pytest.raises(RuntimeError, match="Undefined key"):
+        s.feed(dict(nope=1))
+
+
+def test_a2c_feature_cartpole_8_workers_cpu():
+    """BASELINE configs[0]: a2c_feature CartPole-v0, 8 parallel workers, CPU only (examples.py:340-360 wiring)."""
+    rl.select_device(-1)
+    rl.random_seed(0)
+    c = rl.Config()
+    c.merge(dict(tag=None))
+    c.num_workers = 8
+    c.task_fn = lambda: rl.Task("CartPole-v0", num_envs=c.num_workers, seed=0)
+    c.eval_env = rl.Task("CartPole-v0", seed=0)
+    c.optimizer_fn = lambda p: torch.optim.RMSprop(p, 0.001)
+    c.network_fn = lambda: rl.CategoricalActorCriticNet(c.state_dim, c.action_dim, rl.FCBody(c.state_dim, gate=torch.tanh))
+    c.discount, c.use_gae, c.gae_tau, c.entropy_weight, c.rollout_length, c.gradient_clip = 0.99, True, 0.95, 0.01, 5, 0.5
+    c.max_steps, c.log_interval = 8 * 5 * 60, 0
+    ag = rl.A2CAgent(c)
+    rl.run_steps(ag)
+    assert ag.total_steps == c.max_steps and torch.isfinite(ag.last_loss)
+    assert len(ag.eval_step(c.eval_env.reset())) == 1
+
+
+def test_a2c_cpu_matches_oracle_trajectory(golden):
+    """The A2C statements of the product on the CPU device reproduce the reference's parameter trajectory when the
+    env interaction is replayed from the golden record (atol 2e-6)."""
+    rl.select_device(-1)
+    g = golden("onpolicy")
+    keys = [str(k) for k in g["a2c_keys"]]
+
+    class Replay:                                          # Task stand-in that replays the recorded env stream
+        def __init__(self):
+            self.k = 0
+            self.state_dim, self.action_dim, self.name = 4, 2, "replayed"
+
+        def reset(self):
+            return list(g["a2c_state0"])
+
+        def step(self, actions):
+            k = self.k
+            self.k += 1
+            assert np.array_equal(np.asarray(actions), g["a2c_actions"][k])
+            return list(g["a2c_next_states"][k]), g["a2c_rewards"][k], g["a2c_dones"][k], tuple({"episodic_return": None} for _ in range(8))
+
+        def close(self):
+            pass
+
+    c = rl.Config()
+    c.merge(dict(tag=None))
+    c.num_workers = 8
+    c.task_fn = Replay
+    c.optimizer_fn = lambda p: torch.optim.RMSprop(p, 0.001)
+    c.network_fn = lambda: rl.CategoricalActorCriticNet(4, 2, rl.FCBody(4, gate=torch.tanh))
+    c.discount, c.use_gae, c.gae_tau, c.entropy_weight, c.rollout_length, c.gradient_clip = 0.99, True, 0.95, 0.01, 5, 0.5
+    ag = rl.A2CAgent(c)
+    ag.network.load_state_dict({k: torch.from_numpy(g["a2c_init." + k]) for k in keys})
+    acts = iter(g["a2c_actions"])
+    fwd = ag.network.forward
+
+    def forced(obs, action=None):                          # the sampled actions are part of the record
+        if action is None and forced.live:
+            try:
+                action = torch.from_numpy(next(acts))
+            except StopIteration:
+                action = None
+        return fwd(obs, action)
+
+    forced.live = True
+    ag.network.forward = forced
+    for it in range(g["a2c_params"].shape[0]):
+        n_before = ag.task.k
+        # the bootstrap forward at the end of a rollout must not consume a recorded action
+        orig = ag.task.step
+        ag.step.__func__
+        forced.budget = 5
+        def forced(obs, action=None, _f=fwd):
+            if action is None and forced.budget > 0:
+                forced.budget -= 1
+                action = torch.from_numpy(g["a2c_actions"][ag.task.k])
+            return _f(obs, action)
+        forced.budget = 5
+        ag.network.forward = forced
+        ag.step()
+        flat = np.concatenate([p.detach().numpy().ravel() for p in ag.network.parameters()])
+        np.testing.assert_allclose(flat, g["a2c_params"][it], rtol=0, atol=2e-6)
