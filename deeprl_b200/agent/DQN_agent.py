@@ -18,6 +18,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..component import LazyFrames, PrioritizedTransition
+from ..network.fused import frame_scale
 from ..utils import Config, RescaleNormalizer, close_obj, epsilon_greedy, tensor, to_np
 from .BaseAgent import BaseActor, BaseAgent
 
@@ -199,12 +200,15 @@ class DQNAgent(BaseAgent):
     def _sample(self):
         config = self.config
         inner = getattr(self.replay, "replay", self.replay)
-        if _pre_normalized(config, self.replay):
-            dtype = Config.COMPUTE_DTYPE
-            cl = dtype == torch.bfloat16 and inner.history_length > 1 and len(inner.item_shape) == 2
-            t = inner.sample_normalized(out_dtype=dtype, scale=config.state_normalizer.coef, channels_last=cl)
+        self._batch_scale = 1.0
+        if _pre_normalized(config, self.replay) and len(inner.item_shape) == 2:
+            dtype, coef = Config.COMPUTE_DTYPE, config.state_normalizer.coef
             self._batch_is_normalized = True
-            return t
+            if dtype == torch.bfloat16 and inner.item_shape[0] % 4 == 0 and inner.item_shape[1] % 4 == 0:
+                # throughput mode: exact integer frames in space-to-depth layout, 1/255 folded into conv1
+                self._batch_scale = coef
+                return inner.sample_normalized(out_dtype=dtype, scale=None, layout="s2d")
+            return inner.sample_normalized(out_dtype=dtype, scale=coef, layout="nchw")     # parity mode: exact LUT
         self._batch_is_normalized = False
         return self.replay.sample()
 
@@ -225,10 +229,11 @@ class DQNAgent(BaseAgent):
             if config.noisy_linear:
                 self.target_network.reset_noise()
                 self.network.reset_noise()
-            if self._uses_reference_hooks():
-                self.last_loss = self._generic_update(transitions)
-            else:
-                self.last_loss = self._fused_update(transitions)
+            with frame_scale(self._batch_scale):
+                if self._uses_reference_hooks():
+                    self.last_loss = self._generic_update(transitions)
+                else:
+                    self.last_loss = self._fused_update(transitions)
 
         if self.total_steps / config.sgd_update_frequency % config.target_network_update_freq == 0:
             self.target_network.load_state_dict(self.network.state_dict())

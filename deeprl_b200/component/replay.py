@@ -198,16 +198,14 @@ class UniformReplay:
         return np.asarray(idx)
 
     # ------------------------------------------------------------------ sampling
-    def _buffers(self, B, out_dtype, channels_last, tag=0):
-        key = (B, out_dtype, channels_last, tag)
+    LAYOUTS = {"nchw": 0, "nhwc": 1, "s2d": 2, False: 0, True: 1}
+
+    def _buffers(self, B, out_dtype, layout, tag=0):
+        layout = self.LAYOUTS[layout]
+        key = (B, out_dtype, layout, tag)
         if key not in self._bufs:
             dev, hl = self.device, self.history_length
-            if out_dtype == torch.uint8:
-                shape = (B, hl, self.row_bytes)
-            elif channels_last:
-                shape = (B, self.row_bytes, hl)
-            else:
-                shape = (B, hl, self.row_bytes)
+            shape = (B, self.row_bytes, hl) if layout else (B, hl, self.row_bytes)     # same byte count for s2d
             self._bufs[key] = dict(
                 idx=torch.empty(B, dtype=torch.int64, device=dev),
                 state=torch.empty(shape, dtype=out_dtype, device=dev), next_state=torch.empty(shape, dtype=out_dtype, device=dev),
@@ -230,12 +228,23 @@ class UniformReplay:
         _lib.call("b2rl_replay_select_uniform", _lib.ptr(self.ring_state), _lib.ptr(candidates), int(n_cand), self.seed,
                   self.history_length, self.n_step, int(B), _lib.ptr(idx_out), _lib.ptr(self._status), _lib.stream())
 
-    def gather(self, idx, B, bufs, out_dtype=torch.uint8, lut=None, channels_last=False):
+    def gather(self, idx, B, bufs, out_dtype=torch.uint8, lut=None, layout="nchw"):
+        frame_w = self.item_shape[-1] if len(getattr(self, "item_shape", ())) >= 2 else 0
         _lib.call("b2rl_replay_gather", _lib.ptr(self.frames), _lib.ptr(self.action), _lib.ptr(self.reward),
                   _lib.ptr(self.mask), self.memory_size, self.row_bytes, _lib.ptr(idx), int(B), self.history_length,
-                  self.n_step, self.discount, _lib.ptr(lut), _lib.DTYPE_CODE[out_dtype], int(bool(channels_last)),
+                  self.n_step, self.discount, _lib.ptr(lut), _lib.DTYPE_CODE[out_dtype], self.LAYOUTS[layout], int(frame_w),
                   _lib.ptr(bufs["state"]), _lib.ptr(bufs["next_state"]), _lib.ptr(bufs["action"]), _lib.ptr(bufs["reward"]),
                   _lib.ptr(bufs["mask"]), _lib.stream())
+
+    def _image_view(self, x, B, layout):
+        """Logical [B, C, H, W] view of a gathered batch buffer."""
+        hw, hl = tuple(self.item_shape[-2:]), self.history_length
+        layout = self.LAYOUTS[layout]
+        if layout == 2:
+            return x.view(B, hw[0] // 4, hw[1] // 4, 16 * hl).permute(0, 3, 1, 2)       # [B, 16*hl, H/4, W/4], NHWC memory
+        if layout == 1:
+            return x.view((B,) + hw + (hl,)).permute(0, 3, 1, 2)                        # [B, hl, H, W], NHWC memory
+        return x.view((B, hl) + hw)
 
     def _typed(self, raw, B):
         """uint8 rows -> stored dtype and shape; the frame-stack axis disappears when history_length == 1."""
@@ -250,7 +259,7 @@ class UniformReplay:
         B = self.batch_size if batch_size is None else int(batch_size)
         if self._size == 0:
             raise ValueError("cannot sample from an empty replay")
-        bufs = self._buffers(B, torch.uint8, False, tag)
+        bufs = self._buffers(B, torch.uint8, "nchw", tag)
         if candidates is not None and not isinstance(candidates, torch.Tensor):
             candidates = torch.as_tensor(np.asarray(candidates, dtype=np.int64), device=self.device)
         self.select(B, bufs["idx"], candidates)
@@ -262,31 +271,31 @@ class UniformReplay:
         return Transition(self._typed(bufs["state"], B), bufs["action"], bufs["reward"], self._typed(bufs["next_state"], B),
                           bufs["mask"])
 
-    def sample_normalized(self, batch_size=None, out_dtype=torch.float32, scale=1.0 / 255, channels_last=False,
-                          candidates=None, tag=0):
-        """Fused gather -> normalize (``ImageNormalizer``) for uint8 frame rings: state / next_state come back
-        as ``out_dtype`` [B, history, H, W] (``channels_last`` -> torch channels_last memory format)."""
+    def sample_normalized(self, batch_size=None, out_dtype=torch.float32, scale=1.0 / 255, layout="nchw", candidates=None,
+                          tag=0, channels_last=None):
+        """Fused gather -> normalize (``ImageNormalizer``) for uint8 frame rings.  state / next_state come back as
+        ``out_dtype`` [B, history, H, W] (``layout="nhwc"``: same logical shape, channels_last memory) or, with
+        ``layout="s2d"``, as the space-to-depth(4) tensor [B, 16*history, H/4, W/4] (channels_last memory).
+        ``scale=None`` emits the exact integers 0..255 (the consumer folds 1/255 into its first layer, see
+        ``network.frame_scale``); otherwise ``float32(float64(v) * scale)`` rounded to ``out_dtype``."""
+        if channels_last is not None:
+            layout = "nhwc" if channels_last else "nchw"
         B = self.batch_size if batch_size is None else int(batch_size)
-        if self.item_dtype != np.uint8:
-            raise TypeError("sample_normalized is for uint8 frame rings")
-        bufs = self._buffers(B, out_dtype, channels_last, tag)
+        if self.item_dtype != np.uint8 or len(self.item_shape) < 2:
+            raise TypeError("sample_normalized is for uint8 image rings")
+        bufs = self._buffers(B, out_dtype, layout, tag)
+        if candidates is not None and not isinstance(candidates, torch.Tensor):
+            candidates = torch.as_tensor(np.asarray(candidates, dtype=np.int64), device=self.device)
         self.select(B, bufs["idx"], candidates)
-        self.gather(bufs["idx"], B, bufs, out_dtype, self.lut(scale), channels_last)
-        hw = self.item_shape[-2:] if len(self.item_shape) >= 2 else (self.row_bytes,)
-        hl = self.history_length
-
-        def view(x):
-            if channels_last:
-                return x.view((B,) + tuple(hw) + (hl,)).permute(0, 3, 1, 2)      # logical NCHW, NHWC in memory
-            return x.view((B, hl) + tuple(hw))
-
-        return Transition(view(bufs["state"]), bufs["action"], bufs["reward"], view(bufs["next_state"]), bufs["mask"])
+        self.gather(bufs["idx"], B, bufs, out_dtype, None if scale is None else self.lut(scale), layout)
+        return Transition(self._image_view(bufs["state"], B, layout), bufs["action"], bufs["reward"],
+                          self._image_view(bufs["next_state"], B, layout), bufs["mask"])
 
     def construct_transition(self, index):
         """replay.py:112-140 for ONE index (inspection / tests): device gather of a batch of one."""
         if not self.valid_index(index):
             return None
-        bufs = self._buffers(1, torch.uint8, False, tag=-1)
+        bufs = self._buffers(1, torch.uint8, "nchw", tag=-1)
         bufs["idx"][0] = int(index)
         self.gather(bufs["idx"], 1, bufs)
         t = Transition(self._typed(bufs["state"], 1)[0].clone(), bufs["action"][0].clone(), bufs["reward"][0].clone(),
@@ -344,7 +353,7 @@ class PrioritizedReplay(UniformReplay):
     def sample(self, batch_size=None, uniforms=None, fills=None, check=True, tag=0):
         """replay.py:164-191 -> ``PrioritizedTransition`` (sampling_prob float32 = tensor(p / total), idx = TREE index)."""
         B = self.batch_size if batch_size is None else int(batch_size)
-        bufs = self._buffers(B, torch.uint8, False, tag)
+        bufs = self._buffers(B, torch.uint8, "nchw", tag)
         self._select_per(B, bufs, uniforms, fills, check)
         self.gather(bufs["idx"], B, bufs)
         return PrioritizedTransition(self._typed(bufs["state"], B), bufs["action"], bufs["reward"],
@@ -359,17 +368,17 @@ class PrioritizedReplay(UniformReplay):
             raise IndexError("no valid transition among the stratified draws (random.choice on an empty list)")
         bufs["prob"].copy_(bufs["prob64"])              # tensor(sampling_prob): float64 -> float32, one rounding
 
-    def sample_normalized(self, batch_size=None, out_dtype=torch.float32, scale=1.0 / 255, channels_last=False,
-                          uniforms=None, fills=None, tag=0):
+    def sample_normalized(self, batch_size=None, out_dtype=torch.float32, scale=1.0 / 255, layout="nchw", uniforms=None,
+                          fills=None, tag=0, channels_last=None):
+        if channels_last is not None:
+            layout = "nhwc" if channels_last else "nchw"
         B = self.batch_size if batch_size is None else int(batch_size)
-        bufs = self._buffers(B, out_dtype, channels_last, tag)
+        bufs = self._buffers(B, out_dtype, layout, tag)
         self._select_per(B, bufs, uniforms, fills)
-        self.gather(bufs["idx"], B, bufs, out_dtype, self.lut(scale), channels_last)
-        hw, hl = self.item_shape[-2:], self.history_length
-        view = (lambda x: x.view((B,) + tuple(hw) + (hl,)).permute(0, 3, 1, 2)) if channels_last else \
-            (lambda x: x.view((B, hl) + tuple(hw)))
-        return PrioritizedTransition(view(bufs["state"]), bufs["action"], bufs["reward"], view(bufs["next_state"]),
-                                     bufs["mask"], bufs["prob"], bufs["tree_idx"])
+        self.gather(bufs["idx"], B, bufs, out_dtype, None if scale is None else self.lut(scale), layout)
+        return PrioritizedTransition(self._image_view(bufs["state"], B, layout), bufs["action"], bufs["reward"],
+                                     self._image_view(bufs["next_state"], B, layout), bufs["mask"], bufs["prob"],
+                                     bufs["tree_idx"])
 
     def update_priorities(self, info):
         """replay.py:193-196.  ``info``: iterable of (tree_idx, priority) pairs (the reference's zip of numpy

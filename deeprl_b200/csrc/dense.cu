@@ -1,0 +1,129 @@
+// dense.cu -- epilogues of the dense path (NatureConvBody / FCBody layers, network_bodies.py:27-33,70-73):
+//   forward   y = relu(conv_or_linear(x) + bias)          -> b2rl_bias_act_bf16 (in place on the bf16 GEMM output)
+//   backward  g = gy * (y > 0);  dbias = sum_rows g       -> b2rl_act_bwd_bias_grad_bf16 (one pass, deterministic)
+// Activations are bf16 [rows][C] (NHWC flattened: rows = batch x spatial), bias / dbias are fp32.
+// Both kernels are pure streaming passes (L2 / HBM bound): 16-byte vector loads, 8 channels per thread.  sm_100a only.
+#include "common.cuh"
+
+namespace b2rl {
+
+__device__ __forceinline__ void unpack8(const int4& v, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float2 t = __bfloat1622float2(h[k]);
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
+__device__ __forceinline__ int4 pack8(const float* f) {
+  int4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) bias_act_kernel(__nv_bfloat16* __restrict__ y, const float* __restrict__ bias,
+                                                       int64_t n8, int C8, int relu) {
+  // n8 = rows*C/8 vectors; vector e covers channels (e % C8)*8 .. +7
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n8; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(e % C8) * 8;
+    int4 v = reinterpret_cast<const int4*>(y)[e];
+    float f[8];
+    unpack8(v, f);
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + c0), b1 = *reinterpret_cast<const float4*>(bias + c0 + 4);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      f[k] += bb[k];
+      if (relu) f[k] = fmaxf(f[k], 0.0f);
+    }
+    reinterpret_cast<int4*>(y)[e] = pack8(f);
+  }
+}
+
+// each thread owns one 8-channel group and walks rows with stride (threads per block / C8) * gridDim
+__global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __restrict__ gy,
+                                                      const __nv_bfloat16* __restrict__ y, int64_t rows, int C8, int relu,
+                                                      __nv_bfloat16* __restrict__ gx, float* __restrict__ dbias,
+                                                      float* __restrict__ partial, int32_t* __restrict__ counter) {
+  extern __shared__ float sred[];          // [rows_per_block][C] partial sums
+  __shared__ bool is_last;
+  const int C = C8 * 8;
+  const int rpb = blockDim.x / C8;         // rows handled per block per iteration
+  const int lr = threadIdx.x / C8, cg = threadIdx.x % C8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (lr < rpb) {
+    for (int64_t r = (int64_t)blockIdx.x * rpb + lr; r < rows; r += (int64_t)gridDim.x * rpb) {
+      const int64_t e = r * C8 + cg;
+      int4 g4 = reinterpret_cast<const int4*>(gy)[e];
+      float g[8];
+      unpack8(g4, g);
+      if (relu) {
+        int4 y4 = reinterpret_cast<const int4*>(y)[e];
+        float yv[8];
+        unpack8(y4, yv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = yv[k] > 0.0f ? g[k] : 0.0f;
+        if (gx) reinterpret_cast<int4*>(gx)[e] = pack8(g);
+      } else if (gx && gx != gy) {
+        reinterpret_cast<int4*>(gx)[e] = g4;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += g[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sred[lr * C + cg * 8 + k] = acc[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.0f;
+    for (int q = 0; q < rpb; ++q) s += sred[q * C + c];
+    partial[(int64_t)blockIdx.x * C + c] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(counter, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float s = 0.0f;
+      for (int b = 0; b < (int)gridDim.x; ++b) s += __ldcg(partial + (int64_t)b * C + c);
+      dbias[c] = s;
+    }
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+
+}  // namespace b2rl
+
+using namespace b2rl;
+
+extern "C" int b2rl_bias_act_bf16(uint16_t* y, const float* bias, int64_t rows, int32_t C, int32_t relu, void* stream) {
+  B2RL_REQUIRE(y && bias, "null pointer");
+  B2RL_REQUIRE(rows > 0 && C > 0 && C % 8 == 0, "C must be a positive multiple of 8");
+  B2RL_REQUIRE(reinterpret_cast<uintptr_t>(y) % 16 == 0 && reinterpret_cast<uintptr_t>(bias) % 16 == 0, "16-byte alignment");
+  const int64_t n8 = rows * C / 8;
+  int blocks = (int)((n8 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  bias_act_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(y), bias, n8, C / 8, relu);
+  return check_launch("b2rl_bias_act_bf16");
+}
+
+extern "C" int b2rl_act_bwd_bias_grad_bf16(const uint16_t* gy, const uint16_t* y, int64_t rows, int32_t C, int32_t relu,
+                                           uint16_t* gx, float* dbias, float* partial, int32_t* counter, void* stream) {
+  B2RL_REQUIRE(gy && dbias && partial && counter && (y || !relu), "null pointer");
+  B2RL_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && C <= 2048, "C must be a multiple of 8, <= 2048");
+  const int C8 = C / 8;
+  const int rpb = 256 / C8 > 0 ? 256 / C8 : 1;
+  B2RL_REQUIRE(C8 <= 256, "C too large");
+  int64_t want = (rows + rpb - 1) / rpb;
+  int blocks = (int)(want < 296 ? want : 296);
+  size_t smem = (size_t)rpb * C * sizeof(float);
+  act_bwd_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(gy), reinterpret_cast<const __nv_bfloat16*>(y), rows, C8, relu,
+      reinterpret_cast<__nv_bfloat16*>(gx), dbias, partial, counter);
+  return check_launch("b2rl_act_bwd_bias_grad_bf16");
+}

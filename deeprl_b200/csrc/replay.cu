@@ -218,9 +218,42 @@ __global__ void __launch_bounds__(32) gather_raw_tma_kernel(const uint8_t* __res
   }
 }
 
-// converted stacks (lut: uint8 -> float): TMA bulk load, then vectorised convert + store.
-// CL = channels_last ([B][row_bytes][hl]), else [B][hl][row_bytes].
-template <typename T, bool CL>
+// converted stacks: TMA bulk load, then vectorised convert + store.
+// LAYOUT 0: [B][hl][row_bytes] (NCHW)   1: [B][row_bytes][hl] (NHWC)
+//        2: space-to-depth by 4: [B][H/4][W/4][hl*16], channel = f*16 + dy*4 + dx  (an 8x8/stride-4 convolution over
+//           the frames becomes a 2x2/stride-1 convolution over 16*hl channels: conv1 turns into a plain implicit GEMM)
+// lut != NULL: value = lut[v] rounded to T (exact ImageNormalizer semantics in float32);
+// lut == NULL: value = (T)v, the integer 0..255 exactly (the 1/255 scale is folded into the consumer's weights).
+template <typename T>
+__device__ __forceinline__ void cvt_word(uint32_t w, const T* __restrict__ slut, bool use_lut, T* out4) {
+  if (use_lut) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out4[k] = slut[(w >> (8 * k)) & 255];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out4[k] = Cvt<T>::f((float)((w >> (8 * k)) & 255));
+  }
+}
+template <>
+__device__ __forceinline__ void cvt_word<__nv_bfloat16>(uint32_t w, const __nv_bfloat16* __restrict__ slut, bool use_lut,
+                                                        __nv_bfloat16* out4) {
+  if (use_lut) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out4[k] = slut[(w >> (8 * k)) & 255];
+  } else {
+    // exact u8 -> bf16 without I2F: 0x4B0000vv is the float 2^23 + v; subtract 2^23; the top 16 bits are the bf16
+    const float m = 8388608.0f;
+    uint32_t f0 = __float_as_uint(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)) - m);
+    uint32_t f1 = __float_as_uint(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541)) - m);
+    uint32_t f2 = __float_as_uint(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)) - m);
+    uint32_t f3 = __float_as_uint(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543)) - m);
+    uint32_t* o = reinterpret_cast<uint32_t*>(out4);
+    o[0] = __byte_perm(f0, f1, 0x7632);
+    o[1] = __byte_perm(f2, f3, 0x7632);
+  }
+}
+
+template <typename T, int LAYOUT>
 __global__ void __launch_bounds__(256) gather_cvt_kernel(const uint8_t* __restrict__ frames,
                                                          const int32_t* __restrict__ action,
                                                          const double* __restrict__ reward,
@@ -228,7 +261,8 @@ __global__ void __launch_bounds__(256) gather_cvt_kernel(const uint8_t* __restri
                                                          const int64_t* __restrict__ idx, int hl, int n,
                                                          double discount, const float* __restrict__ lut,
                                                          T* __restrict__ state_out, T* __restrict__ next_out,
-                                                         int64_t* a_out, float* r_out, float* m_out, int use_tma) {
+                                                         int64_t* a_out, float* r_out, float* m_out, int use_tma,
+                                                         int frame_w) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ T slut[256];
@@ -236,6 +270,7 @@ __global__ void __launch_bounds__(256) gather_cvt_kernel(const uint8_t* __restri
   const int64_t i = idx[b];
   const int64_t span = (int64_t)(hl + n) * row_bytes, stack = (int64_t)hl * row_bytes;
   const uint8_t* src = frames + (i - hl + 1) * row_bytes;
+  const bool use_lut = lut != nullptr;
   if (use_tma) {
     if (threadIdx.x == 0) {
       mbar_init(&bar, 1);
@@ -245,7 +280,7 @@ __global__ void __launch_bounds__(256) gather_cvt_kernel(const uint8_t* __restri
   } else {
     for (int64_t k = threadIdx.x; k < span; k += blockDim.x) smem[k] = src[k];
   }
-  slut[threadIdx.x] = Cvt<T>::f(lut[threadIdx.x]);
+  if (use_lut) slut[threadIdx.x] = Cvt<T>::f(lut[threadIdx.x]);
   if (threadIdx.x == 32) gather_scalars(action, reward, mask, i, n, discount, a_out, r_out, m_out, b);
   __syncthreads();                       // barrier init + lut visible
   if (use_tma) mbar_wait(&bar, 0);       // every thread observes the completed phase
@@ -257,44 +292,58 @@ __global__ void __launch_bounds__(256) gather_cvt_kernel(const uint8_t* __restri
     if (!out) continue;
     out += (int64_t)b * stack;
     const uint8_t* s = smem + (which ? (int64_t)n * row_bytes : 0);
-    if (CL && hl == 4 && row_bytes % 4 == 0) {
-      // 4 pixels x 4 frames per thread: 4 LDS.32 -> 16 outputs
-      for (int64_t p4 = threadIdx.x; p4 < row_bytes / 4; p4 += blockDim.x) {
-        uint32_t f0 = *reinterpret_cast<const uint32_t*>(s + 0 * row_bytes + p4 * 4);
-        uint32_t f1 = *reinterpret_cast<const uint32_t*>(s + 1 * row_bytes + p4 * 4);
-        uint32_t f2 = *reinterpret_cast<const uint32_t*>(s + 2 * row_bytes + p4 * 4);
-        uint32_t f3 = *reinterpret_cast<const uint32_t*>(s + 3 * row_bytes + p4 * 4);
+    if (LAYOUT == 2) {
+      // unit = (position (Y,X), frame f): 4 words (rows 4Y..4Y+3, cols 4X..4X+3) -> 16 contiguous outputs
+      const int Wq = frame_w / 4, Hq = (int)(row_bytes / frame_w) / 4;
+      const int units = Hq * Wq * hl;
+      for (int u = threadIdx.x; u < units; u += blockDim.x) {
+        const int pos = u / hl, f = u - pos * hl;
+        const int Y = pos / Wq, X = pos - Y * Wq;
+        const uint8_t* base = s + (int64_t)f * row_bytes + (4 * Y) * frame_w + 4 * X;
         __align__(16) T v[16];
 #pragma unroll
-        for (int px = 0; px < 4; ++px) {
-          v[px * 4 + 0] = slut[(f0 >> (8 * px)) & 255];
-          v[px * 4 + 1] = slut[(f1 >> (8 * px)) & 255];
-          v[px * 4 + 2] = slut[(f2 >> (8 * px)) & 255];
-          v[px * 4 + 3] = slut[(f3 >> (8 * px)) & 255];
-        }
+        for (int dy = 0; dy < 4; ++dy)
+          cvt_word<T>(*reinterpret_cast<const uint32_t*>(base + dy * frame_w), slut, use_lut, v + 4 * dy);
+        int4* o = reinterpret_cast<int4*>(out + (int64_t)u * 16);
+#pragma unroll
+        for (int q = 0; q < 16 / VEC; ++q) o[q] = reinterpret_cast<const int4*>(v)[q];
+      }
+    } else if (LAYOUT == 1 && hl == 4 && row_bytes % 4 == 0) {
+      // 4 pixels x 4 frames per thread: 4 LDS.32 -> 16 outputs
+      for (int64_t p4 = threadIdx.x; p4 < row_bytes / 4; p4 += blockDim.x) {
+        __align__(16) T c[4][4];
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+          cvt_word<T>(*reinterpret_cast<const uint32_t*>(s + f * row_bytes + p4 * 4), slut, use_lut, c[f]);
+        __align__(16) T v[16];
+#pragma unroll
+        for (int px = 0; px < 4; ++px)
+#pragma unroll
+          for (int f = 0; f < 4; ++f) v[px * 4 + f] = c[f][px];
         int4* o = reinterpret_cast<int4*>(out + p4 * 16);
 #pragma unroll
         for (int q = 0; q < 16 / VEC; ++q) o[q] = reinterpret_cast<const int4*>(v)[q];
       }
-    } else if (CL) {
+    } else if (LAYOUT == 1) {
       for (int64_t e = threadIdx.x; e < stack; e += blockDim.x) {
         int64_t p = e / hl;
         int c = (int)(e - p * hl);
-        out[e] = slut[s[(int64_t)c * row_bytes + p]];
+        uint8_t v = s[(int64_t)c * row_bytes + p];
+        out[e] = use_lut ? slut[v] : Cvt<T>::f((float)v);
       }
     } else if (stack % 16 == 0) {
       for (int64_t e16 = threadIdx.x; e16 < stack / 16; e16 += blockDim.x) {
         int4 raw = *reinterpret_cast<const int4*>(s + e16 * 16);
-        const uint8_t* rb = reinterpret_cast<const uint8_t*>(&raw);
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(&raw);
         __align__(16) T v[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = slut[rb[k]];
+        for (int k = 0; k < 4; ++k) cvt_word<T>(rw[k], slut, use_lut, v + 4 * k);
         int4* o = reinterpret_cast<int4*>(out + e16 * 16);
 #pragma unroll
         for (int q = 0; q < 16 / VEC; ++q) o[q] = reinterpret_cast<const int4*>(v)[q];
       }
     } else {
-      for (int64_t e = threadIdx.x; e < stack; e += blockDim.x) out[e] = slut[s[e]];
+      for (int64_t e = threadIdx.x; e < stack; e += blockDim.x) out[e] = use_lut ? slut[s[e]] : Cvt<T>::f((float)s[e]);
     }
   }
 }
@@ -319,23 +368,31 @@ __global__ void __launch_bounds__(128) gather_raw_generic_kernel(const uint8_t* 
   }
 }
 
+template <typename T, int LAYOUT>
+static int launch_cvt1(dim3 grid, size_t smem, cudaStream_t st, const uint8_t* frames, const int32_t* action,
+                       const double* reward, const int32_t* mask, int64_t row_bytes, const int64_t* idx, int hl, int n,
+                       double discount, const float* lut, void* so, void* no, int64_t* a, float* r, float* m, int use_tma,
+                       int frame_w) {
+  auto k = gather_cvt_kernel<T, LAYOUT>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k<<<grid, 256, smem, st>>>(frames, action, reward, mask, row_bytes, idx, hl, n, discount, lut, (T*)so, (T*)no, a, r, m,
+                             use_tma, frame_w);
+  return check_launch("b2rl_replay_gather");
+}
+
 template <typename T>
-static int launch_cvt(bool cl, dim3 grid, size_t smem, cudaStream_t st, const uint8_t* frames, const int32_t* action,
+static int launch_cvt(int layout, dim3 grid, size_t smem, cudaStream_t st, const uint8_t* frames, const int32_t* action,
                       const double* reward, const int32_t* mask, int64_t row_bytes, const int64_t* idx, int hl, int n,
                       double discount, const float* lut, void* so, void* no, int64_t* a, float* r, float* m,
-                      int use_tma) {
-  if (cl) {
-    auto k = gather_cvt_kernel<T, true>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, 256, smem, st>>>(frames, action, reward, mask, row_bytes, idx, hl, n, discount, lut, (T*)so, (T*)no, a, r,
-                               m, use_tma);
-  } else {
-    auto k = gather_cvt_kernel<T, false>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, 256, smem, st>>>(frames, action, reward, mask, row_bytes, idx, hl, n, discount, lut, (T*)so, (T*)no, a, r,
-                               m, use_tma);
-  }
-  return check_launch("b2rl_replay_gather");
+                      int use_tma, int frame_w) {
+  if (layout == 2)
+    return launch_cvt1<T, 2>(grid, smem, st, frames, action, reward, mask, row_bytes, idx, hl, n, discount, lut, so, no,
+                             a, r, m, use_tma, frame_w);
+  if (layout == 1)
+    return launch_cvt1<T, 1>(grid, smem, st, frames, action, reward, mask, row_bytes, idx, hl, n, discount, lut, so, no,
+                             a, r, m, use_tma, frame_w);
+  return launch_cvt1<T, 0>(grid, smem, st, frames, action, reward, mask, row_bytes, idx, hl, n, discount, lut, so, no, a,
+                           r, m, use_tma, frame_w);
 }
 
 }  // namespace b2rl
@@ -370,13 +427,16 @@ extern "C" int b2rl_replay_select_uniform(int64_t* ring_state, const int64_t* ca
 extern "C" int b2rl_replay_gather(const uint8_t* frames, const int32_t* action, const double* reward,
                                   const int32_t* mask, int64_t capacity, int64_t row_bytes, const int64_t* idx,
                                   int32_t B, int32_t history, int32_t n_step, double discount, const float* lut,
-                                  int32_t out_dtype, int32_t channels_last, void* state_out, void* next_out,
+                                  int32_t out_dtype, int32_t layout, int32_t frame_w, void* state_out, void* next_out,
                                   int64_t* action_out, float* reward_out, float* mask_out, void* stream) {
   B2RL_REQUIRE(frames && action && reward && mask && idx, "null pointer");
   B2RL_REQUIRE(B > 0 && history >= 1 && n_step >= 1 && row_bytes > 0 && capacity > 0, "bad shape");
   B2RL_REQUIRE(out_dtype >= B2RL_U8 && out_dtype <= B2RL_F32, "bad out_dtype");
-  B2RL_REQUIRE((out_dtype == B2RL_U8) == (lut == nullptr), "lut is required for (and only for) converted output");
-  B2RL_REQUIRE(!(out_dtype == B2RL_U8 && channels_last), "channels_last needs a converted dtype");
+  B2RL_REQUIRE(!(out_dtype == B2RL_U8 && lut != nullptr), "a lut needs a converted (non-uint8) output dtype");
+  B2RL_REQUIRE(layout >= 0 && layout <= 2, "layout must be 0 (NCHW), 1 (NHWC) or 2 (space-to-depth 4)");
+  B2RL_REQUIRE(!(out_dtype == B2RL_U8 && layout != 0), "NHWC / space-to-depth need a converted dtype");
+  B2RL_REQUIRE(layout != 2 || (frame_w > 0 && frame_w % 4 == 0 && row_bytes % frame_w == 0 && (row_bytes / frame_w) % 4 == 0),
+               "space-to-depth needs frame_w and frame height multiples of 4");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t span = (size_t)(history + n_step) * row_bytes;
   B2RL_REQUIRE(span <= 200 * 1024, "history+n_step rows do not fit in shared memory");
@@ -399,14 +459,14 @@ extern "C" int b2rl_replay_gather(const uint8_t* frames, const int32_t* action, 
   const int use_tma = aligned ? 1 : 0;
   switch (out_dtype) {
     case B2RL_F16:
-      return launch_cvt<__half>(channels_last, B, smem, st, frames, action, reward, mask, row_bytes, idx, history,
-                                n_step, discount, lut, state_out, next_out, action_out, reward_out, mask_out, use_tma);
+      return launch_cvt<__half>(layout, B, smem, st, frames, action, reward, mask, row_bytes, idx, history, n_step,
+                                discount, lut, state_out, next_out, action_out, reward_out, mask_out, use_tma, frame_w);
     case B2RL_BF16:
-      return launch_cvt<__nv_bfloat16>(channels_last, B, smem, st, frames, action, reward, mask, row_bytes, idx,
-                                       history, n_step, discount, lut, state_out, next_out, action_out, reward_out,
-                                       mask_out, use_tma);
+      return launch_cvt<__nv_bfloat16>(layout, B, smem, st, frames, action, reward, mask, row_bytes, idx, history,
+                                       n_step, discount, lut, state_out, next_out, action_out, reward_out, mask_out,
+                                       use_tma, frame_w);
     default:
-      return launch_cvt<float>(channels_last, B, smem, st, frames, action, reward, mask, row_bytes, idx, history,
-                               n_step, discount, lut, state_out, next_out, action_out, reward_out, mask_out, use_tma);
+      return launch_cvt<float>(layout, B, smem, st, frames, action, reward, mask, row_bytes, idx, history, n_step,
+                               discount, lut, state_out, next_out, action_out, reward_out, mask_out, use_tma, frame_w);
   }
 }

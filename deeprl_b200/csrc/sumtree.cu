@@ -7,7 +7,7 @@
 // an internal node therefore depend on the ORDER of the additions it received.  A batch of B updates
 // is applied here as
 //   prep      (B threads)    first-occurrence + pending guard, change_i = p_i - leaf_i, leaf write
-//   propagate (one CTA per tree level, B threads)   thread i owns node(level, i) iff it is the first
+//   propagate (one CTA per tree DEPTH, B threads)   thread i owns node(depth, i) iff it is the first
 //             row of the batch touching that node; it folds the changes of all later rows touching
 //             the same node IN BATCH ORDER in a register (a chain of float64 adds), then stores.
 // Different nodes are independent, so this is exactly the reference's sequence of additions per node.
@@ -77,14 +77,21 @@ __global__ void __launch_bounds__(ST_MAX_B) sumtree_prep_kernel(double* __restri
 __global__ void __launch_bounds__(ST_MAX_B) sumtree_propagate_kernel(double* __restrict__ tree,
                                                                      const double* __restrict__ change,
                                                                      const int64_t* __restrict__ idx, int B) {
+  // One CTA per tree DEPTH d (root = depth 0): with a non-power-of-two capacity the leaves sit on two depths, so
+  // the ancestor of row i at depth d is k_i = depth(leaf_i) - d levels up.  Indexing CTAs by depth (not by k)
+  // guarantees that every node is owned by exactly one CTA.
   __shared__ int64_t node[ST_MAX_B];
   __shared__ double ch[ST_MAX_B];
-  const int k = blockIdx.x + 1;     // level distance from the leaf
+  const int d = blockIdx.x;
   const int i = threadIdx.x;
   int64_t mine = -1;
   if (i < B) {
     int64_t x = idx[i];
-    if (x >= 0 && ((x + 1) >> k) >= 1) mine = ancestor(x, k);
+    if (x >= 0) {
+      const int depth = 63 - __clzll((unsigned long long)(x + 1));   // bitlength(x+1) - 1
+      const int k = depth - d;
+      if (k >= 1) mine = ancestor(x, k);
+    }
     ch[i] = change[i];
   }
   node[i] = mine;
@@ -218,7 +225,7 @@ __global__ void sumtree_get_kernel(const double* __restrict__ tree, uint8_t* __r
 using namespace b2rl;
 
 static int tree_levels(int64_t cap) {
-  // number of ancestor levels of the deepest leaf: bitlength(2cap-1) - 1
+  // number of internal depths (0 .. depth(deepest leaf) - 1): bitlength(2cap-1) - 1
   int bl = 0;
   for (uint64_t x = (uint64_t)(2 * cap - 1); x; x >>= 1) ++bl;
   return bl - 1;

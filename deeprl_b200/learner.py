@@ -14,6 +14,7 @@ import torch.distributed as dist
 
 from . import _lib, ops
 from .component.replay import PrioritizedReplay
+from .network.fused import frame_scale
 
 
 class GraphedDQNLearner:
@@ -67,13 +68,19 @@ class GraphedDQNLearner:
                                add_leaf=True)
             else:
                 rp.feed_device(self.d_frames[j:j + 1], self.d_action[j:j + 1], self.d_reward[j:j + 1], self.d_mask[j:j + 1], 1)
-        cl = self.dtype == torch.bfloat16
-        t = rp.sample_normalized(out_dtype=self.dtype, scale=self.scale, channels_last=cl)
+        if self.dtype == torch.bfloat16:
+            # exact integer frames, space-to-depth layout; ImageNormalizer's scale is folded into conv1's weights
+            t = rp.sample_normalized(out_dtype=self.dtype, scale=None, layout="s2d")
+            fs = self.scale
+        else:
+            t = rp.sample_normalized(out_dtype=self.dtype, scale=self.scale, layout="nchw")
+            fs = 1.0
         per = dict(is_prob=t.sampling_prob, eps=self.eps, alpha=self.alpha, beta_dev=self.d_beta) if self.per else {}
-        with torch.no_grad():
-            nxt_t = self.tgt(t.next_state)
-            nxt_o = self.net(t.next_state) if self.double_q else None
-        out = self.net(t.state)
+        with frame_scale(fs):
+            with torch.no_grad():
+                nxt_t = self.tgt(t.next_state)
+                nxt_o = self.net(t.next_state) if self.double_q else None
+            out = self.net(t.state)
         if self.kind == "dqn":
             head = out["q"]
             r = ops.dqn_loss_fused(head.detach(), nxt_t["q"], nxt_o["q"] if nxt_o else None, t.action, t.reward, t.mask,

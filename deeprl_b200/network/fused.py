@@ -1,0 +1,127 @@
+"""Fused dense layers for the throughput mode (bf16 operands, fp32 accumulation, fp32 master weights).
+
+``y = relu(conv(x, W) + b)`` and ``y = relu(x W^T + b)`` (network_bodies.py:27-33,70-73) as autograd Functions:
+the contraction is a library call this round (cuDNN / cuBLAS implicit-GEMM on bf16 NHWC operands), the bias + ReLU
+epilogue and the ReLU-mask + bias-gradient reduction of the backward pass are ``csrc/dense.cu`` kernels
+(one streaming pass each instead of ~6 eager elementwise / reduce launches per layer).
+"""
+import contextlib
+import threading
+
+import torch
+
+from .. import _lib
+from ..ops import _Scratch
+
+_bf16 = torch.bfloat16
+_tls = threading.local()
+
+
+@contextlib.contextmanager
+def frame_scale(scale):
+    """Declare that image inputs inside the block are raw integers 0..255 scaled by ``scale`` (the fused replay
+    gather emits exact integers in bf16; NatureConvBody folds ``scale`` -- ImageNormalizer's 1/255 -- into conv1)."""
+    prev = getattr(_tls, "scale", 1.0)
+    _tls.scale = float(scale)
+    try:
+        yield
+    finally:
+        _tls.scale = prev
+
+
+def current_frame_scale():
+    return getattr(_tls, "scale", 1.0)
+
+
+def _rows_c(y):
+    """(rows, C) of a bf16 activation stored NHWC (4-d channels_last) or [rows, C] (2-d contiguous)."""
+    if y.dim() == 4:
+        assert y.is_contiguous(memory_format=torch.channels_last), "activations must be channels_last"
+        return y.shape[0] * y.shape[2] * y.shape[3], y.shape[1]
+    assert y.is_contiguous()
+    return y.shape[0], y.shape[1]
+
+
+def bias_act_(y, bias, relu=True):
+    rows, C = _rows_c(y)
+    _lib.call("b2rl_bias_act_bf16", _lib.ptr(y), _lib.ptr(bias), rows, C, int(relu), _lib.stream())
+    return y
+
+
+def act_bwd_bias_grad(gy, y, relu=True):
+    """-> (g = gy * (y > 0) in bf16, dbias fp32 [C])."""
+    rows, C = _rows_c(y)
+    if gy.dim() == 4 and not gy.is_contiguous(memory_format=torch.channels_last):
+        gy = gy.contiguous(memory_format=torch.channels_last)
+    elif gy.dim() == 2 and not gy.is_contiguous():
+        gy = gy.contiguous()
+    if gy.dtype != _bf16:
+        gy = gy.to(_bf16)
+    g = torch.empty_like(gy)
+    db = torch.empty(C, dtype=torch.float32, device=y.device)
+    partial = _Scratch.get(y.device, "act_bwd_partial", 296 * 2048, torch.float32)
+    counter = _Scratch.get(y.device, "act_bwd_counter", 1, torch.int32)
+    _lib.call("b2rl_act_bwd_bias_grad_bf16", _lib.ptr(gy), _lib.ptr(y), rows, C, int(relu), _lib.ptr(g), _lib.ptr(db),
+              _lib.ptr(partial), _lib.ptr(counter), _lib.stream())
+    return g, db
+
+
+class _ConvBiasReLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, need_input_grad):
+        w16 = weight.detach().to(_bf16).contiguous(memory_format=torch.channels_last)
+        y = torch.ops.aten.convolution(x, w16, None, [stride, stride], [0, 0], [1, 1], False, [0, 0], 1)
+        if not y.is_contiguous(memory_format=torch.channels_last):
+            y = y.contiguous(memory_format=torch.channels_last)
+        bias_act_(y, bias.detach(), True)
+        ctx.save_for_backward(x, w16, y)
+        ctx.stride, ctx.need_input_grad = stride, need_input_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w16, y = ctx.saved_tensors
+        g, db = act_bwd_bias_grad(gy, y, True)
+        s = ctx.stride
+        gx, gw, _ = torch.ops.aten.convolution_backward(g, x, w16, None, [s, s], [0, 0], [1, 1], False, [0, 0], 1,
+                                                        [ctx.need_input_grad, True, False])
+        return gx, gw.float(), db, None, None
+
+
+def conv_bias_relu(x, weight, bias, stride, need_input_grad=True):
+    """``relu(conv2d(x, weight, bias, stride))`` on bf16 channels_last ``x``; ``weight`` / ``bias`` are fp32 (master)."""
+    return _ConvBiasReLU.apply(x, weight, bias, stride, need_input_grad)
+
+
+class _LinearBiasReLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        w16 = weight.detach().to(_bf16)
+        y = torch.mm(x, w16.t())
+        bias_act_(y, bias.detach(), relu)
+        ctx.save_for_backward(x, w16, y)
+        ctx.relu = relu
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w16, y = ctx.saved_tensors
+        g, db = act_bwd_bias_grad(gy, y, ctx.relu)
+        gx = torch.mm(g, w16) if ctx.needs_input_grad[0] else None
+        gw = torch.mm(g.t(), x).float()
+        return gx, gw, db, None
+
+
+def linear_bias_relu(x, weight, bias, relu=True):
+    """``relu(x @ weight.T + bias)`` on bf16 ``x`` [rows, K]; fp32 master ``weight`` [N, K] and ``bias``."""
+    return _LinearBiasReLU.apply(x, weight, bias, relu)
+
+
+def space_to_depth_weight(weight, block=4):
+    """[Cout, Cin, k, k] with k = 2*block, stride = block  ->  [Cout, Cin*block*block, 2, 2]: the kernel that, applied
+    with stride 1 to the space-to-depth(block) input (channel = cin*block^2 + dy*block + dx), equals the original
+    stride-``block`` convolution."""
+    co, ci, kh, kw = weight.shape
+    assert kh == kw == 2 * block
+    w = weight.view(co, ci, 2, block, 2, block)          # (n, f, ky2, dy, kx2, dx)
+    return w.permute(0, 1, 3, 5, 2, 4).reshape(co, ci * block * block, 2, 2)

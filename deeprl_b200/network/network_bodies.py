@@ -12,6 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..utils import Config
+from . import fused
 from .network_utils import NoisyLinear, layer_init
 
 
@@ -38,12 +39,40 @@ class NatureConvBody(nn.Module):
             self.fc4.reset_noise()
 
     def forward(self, x):
+        """``x``: [B, C, 84, 84] images, or the space-to-depth(4) tensor [B, 16*C, 21, 21] the fused replay gather
+        emits (conv1 then runs as a 2x2 / stride-1 convolution over 16*C channels: same arithmetic, tensor-core
+        friendly).  bf16 CUDA inputs take the fused path (``network/fused.py``)."""
+        if x.is_cuda and x.dtype == torch.bfloat16 and Config.COMPUTE_DTYPE == torch.bfloat16 and not self.noisy_linear:
+            return self._forward_fused(x)
+        if x.dim() == 4 and x.shape[1] == 16 * self.conv1.in_channels and x.shape[-1] * 4 == 84:
+            x = F.pixel_shuffle(x.view(x.shape[0], self.conv1.in_channels, 16, x.shape[2], x.shape[3]).flatten(0, 1), 4) \
+                .view(x.shape[0], self.conv1.in_channels, 84, 84)
+        scale = fused.current_frame_scale()
         with _autocast():
-            y = F.relu(self.conv1(x))
+            y = F.relu(self.conv1(x * scale if scale != 1.0 else x))
             y = F.relu(self.conv2(y))
             y = F.relu(self.conv3(y))
             y = y.reshape(y.size(0), -1)          # NCHW flatten order whatever the memory format
             return F.relu(self.fc4(y))
+
+    def _forward_fused(self, x):
+        scale = fused.current_frame_scale()
+        w1 = self.conv1.weight
+        if x.shape[1] == 16 * self.conv1.in_channels:                    # space-to-depth input
+            w1, stride1 = fused.space_to_depth_weight(w1, 4), 1
+        else:
+            stride1 = 4
+        if scale != 1.0:
+            w1 = w1 * scale
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.contiguous(memory_format=torch.channels_last)
+        y = fused.conv_bias_relu(x, w1, self.conv1.bias, stride1, need_input_grad=False)
+        y = fused.conv_bias_relu(y, self.conv2.weight, self.conv2.bias, 2)
+        y = fused.conv_bias_relu(y, self.conv3.weight, self.conv3.bias, 1)
+        # fc4 over the NHWC-flattened features: permute the (C,H,W)-ordered weight columns instead of the activations
+        B, C, H, W = y.shape
+        w4 = self.fc4.weight.view(-1, C, H, W).permute(0, 2, 3, 1).reshape(self.fc4.weight.shape[0], -1)
+        return fused.linear_bias_relu(y.permute(0, 2, 3, 1).reshape(B, -1), w4, self.fc4.bias, True)
 
 
 class FCBody(nn.Module):

@@ -62,15 +62,18 @@ int b2rl_replay_select_uniform(int64_t* ring_state, const int64_t* candidates, i
                                void* stream);
 
 /* construct_transition for B indices (replay.py:112-140): frame-stack gather + n-step return.
- * state_out/next_out: [B][history][row_bytes] converted to out_dtype through `lut` (float32 [256]; NULL = raw
- * copy, only with B2RL_U8).  channels_last != 0 writes [B][row_bytes][history] (NHWC for 84x84 frames).
+ * out_dtype B2RL_U8: raw stacks [B][history][row_bytes] (lut must be NULL, layout 0).
+ * converted dtypes (F16/BF16/F32): value = lut[v] (float32 [256] table, e.g. float32(float64(v)/255) = the reference's
+ * ImageNormalizer + tensor() rounding) or, with lut == NULL, the integer v itself (exact; the consumer folds the scale
+ * into its weights).  layout 0 = [B][history][row_bytes] (NCHW), 1 = [B][row_bytes][history] (NHWC),
+ * 2 = space-to-depth by 4 over frames of width frame_w: [B][H/4][W/4][history*16], channel = f*16 + dy*4 + dx.
  * action_out int64 [B]; reward_out float32 [B] (float64 n-step sum rounded once, as tensor() does,
  * utils/torch_utils.py:23); mask_out float32 [B].  Any *_out may be NULL to skip it. */
 int b2rl_replay_gather(const uint8_t* frames, const int32_t* action, const double* reward, const int32_t* mask,
                        int64_t capacity, int64_t row_bytes, const int64_t* idx, int32_t B, int32_t history,
-                       int32_t n_step, double discount, const float* lut, int32_t out_dtype, int32_t channels_last,
-                       void* state_out, void* next_out, int64_t* action_out, float* reward_out, float* mask_out,
-                       void* stream);
+                       int32_t n_step, double discount, const float* lut, int32_t out_dtype, int32_t layout,
+                       int32_t frame_w, void* state_out, void* next_out, int64_t* action_out, float* reward_out,
+                       float* mask_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Sum tree in HBM -- SumTree (utils/sum_tree.py:6-67) + PrioritizedReplay (component/replay.py:152-196)
@@ -177,6 +180,16 @@ int b2rl_clip_rmsprop(float* param, const float* grad, float* square_avg, float*
 int b2rl_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float max_norm,
                    float lr, float beta1, float beta2, float eps, int64_t* step_dev, float grad_scale,
                    void* norm_scratch, uint16_t* bf16_shadow, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense-layer epilogues (network_bodies.py:27-33,70-73: y = relu(layer(x))), bf16 activations [rows][C] (NHWC
+ * flattened), fp32 bias.  Forward: y = act(y + bias) in place.  Backward: gx = gy * (y > 0) (gx may alias gy or be
+ * NULL) and dbias[c] = sum over rows of gx, deterministic.  partial: float32 [296*C] scratch; counter: int32 [1], zero
+ * on first use.
+ * ------------------------------------------------------------------------------------------- */
+int b2rl_bias_act_bf16(uint16_t* y, const float* bias, int64_t rows, int32_t C, int32_t relu, void* stream);
+int b2rl_act_bwd_bias_grad_bf16(const uint16_t* gy, const uint16_t* y, int64_t rows, int32_t C, int32_t relu,
+                                uint16_t* gx, float* dbias, float* partial, int32_t* counter, void* stream);
 
 #ifdef __cplusplus
 }

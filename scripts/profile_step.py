@@ -28,7 +28,7 @@ torch.cuda.synchronize()
 torch.cuda.nvtx.range_pop()
 # the raw uint8 gather variant too
 rp = learner.replay
-bufs = rp._buffers(bench.B, torch.uint8, False, tag=9)
+bufs = rp._buffers(bench.B, torch.uint8, "nchw", tag=9)
 rp.select(bench.B, bufs["idx"])
 rp.gather(bufs["idx"], bench.B, bufs)
 torch.cuda.synchronize()

@@ -96,7 +96,7 @@ def test_sumtree_million_leaves_vs_oracle(rl):
     ora = O(cap)
     ora.tree[:] = rp.tree.tree.cpu().numpy()
     ora.write = 123457
-    bufs = rp._buffers(B, torch.uint8, False)
+    bufs = rp._buffers(B, torch.uint8, "nchw")
     for it in range(6):
         u = rng.rand(B)
         rp._select_per(B, bufs, uniforms=u, fills=np.zeros(B, np.int64))
@@ -212,7 +212,7 @@ def test_prioritized_replay_matches_reference(rl, golden):
             assert np.array_equal(smp.reward.cpu().numpy(), g[pre + "s_reward"][rd].astype(np.float32))
             assert np.array_equal(smp.mask.cpu().numpy(), g[pre + "s_mask"][rd].astype(np.float32))
             assert np.array_equal(smp.sampling_prob.cpu().numpy(), g[pre + "s_sampling_prob"][rd].astype(np.float32))
-            assert np.array_equal(rp._buffers(B, torch.uint8, False)["prob64"].cpu().numpy(), g[pre + "s_sampling_prob"][rd])
+            assert np.array_equal(rp._buffers(B, torch.uint8, "nchw")["prob64"].cpu().numpy(), g[pre + "s_sampling_prob"][rd])
             idx = np.asarray(g[pre + "s_idx"][rd], np.float32).astype(np.int64)      # tensor(idx).long() round trip
             rp.update_priorities(zip(idx, g[pre + "prio"][rd]))
             base = feeds + rd * 2
@@ -240,7 +240,7 @@ def test_gather_full_size_properties(rl):
     rp.item_shape, rp.item_dtype = (84, 84), np.dtype(np.uint8)
     rp.load_synthetic(frames, act, rew, msk, pos=123457)
     t = rp.sample()
-    idx = rp._buffers(B, torch.uint8, False)["idx"]
+    idx = rp._buffers(B, torch.uint8, "nchw")["idx"]
     assert t.state.shape == (B, 4, 84, 84) and t.state.dtype == torch.uint8
     rows = idx[:, None] + torch.arange(-3, 1, device="cuda")[None]
     assert torch.equal(t.state.view(B, 4, 7056), frames[rows])
@@ -257,12 +257,23 @@ def test_gather_full_size_properties(rl):
             assert x.state.shape == (B, 4, 84, 84)
             assert cl == x.state.is_contiguous(memory_format=torch.channels_last) or not cl
             assert torch.equal(x.state, lut64[t.state.long()].to(dt)) and torch.equal(x.next_state, lut64[t.next_state.long()].to(dt))
+    # space-to-depth(4) layout with exact integer conversion: [B, 64, 21, 21], channel = f*16 + dy*4 + dx
+    x = rp.sample_normalized(out_dtype=torch.bfloat16, scale=None, layout="s2d", candidates=cand)
+    assert x.state.shape == (B, 64, 21, 21) and x.state.is_contiguous(memory_format=torch.channels_last)
+    ref = t.state.view(B, 4, 21, 4, 21, 4).permute(0, 1, 3, 5, 2, 4).reshape(B, 64, 21, 21).to(torch.bfloat16)
+    assert torch.equal(x.state, ref)
+    refn = t.next_state.view(B, 4, 21, 4, 21, 4).permute(0, 1, 3, 5, 2, 4).reshape(B, 64, 21, 21).to(torch.bfloat16)
+    assert torch.equal(x.next_state, refn)
+    xf = rp.sample_normalized(out_dtype=torch.float32, scale=1.0 / 255, layout="s2d", candidates=cand)
+    assert torch.equal(xf.state, lut64[t.state.long()].view(B, 4, 21, 4, 21, 4).permute(0, 1, 3, 5, 2, 4).reshape(B, 64, 21, 21))
+    xi = rp.sample_normalized(out_dtype=torch.float16, scale=None, layout="nhwc", candidates=cand)
+    assert torch.equal(xi.state, t.state.to(torch.float16))
     # n-step returns (n=3) against the float64 recurrence of replay.py:137-139
     rp3 = rl.UniformReplay(cap, B, 3, 0.9, hl, seed=2)
     rp3.item_shape, rp3.item_dtype = (84, 84), np.dtype(np.uint8)
     rp3.load_synthetic(frames, act, rew, msk, pos=123457)
     t3 = rp3.sample()
-    i3 = rp3._buffers(B, torch.uint8, False)["idx"]
+    i3 = rp3._buffers(B, torch.uint8, "nchw")["idx"]
     r, m = rew.cpu().numpy(), msk.cpu().numpy()
     exp_r, exp_m = [], []
     for i in i3.cpu().numpy():
@@ -480,6 +491,57 @@ def test_fused_clip_optimizer_vs_torch(rl, kind):
         np.testing.assert_allclose(mopt.total_norm.item(), norm.item(), rtol=1e-5)
         for p, q_ in zip(ref, mine):
             np.testing.assert_allclose(q_.detach().cpu().numpy(), p.detach().numpy(), rtol=2e-5, atol=2e-7)
+
+
+# ------------------------------------------------------------------------------------------ dense path (fused layers)
+def test_fused_layers_and_space_to_depth_conv1(rl):
+    """csrc/dense.cu epilogues + network/fused.py against plain torch: bias+ReLU forward, ReLU-mask + bias-grad backward,
+    and the space-to-depth formulation of conv1 (8x8 stride 4 over 4 frames == 2x2 stride 1 over 64 channels)."""
+    from deeprl_b200.network import fused
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for rows, C in ((204800, 32), (41472, 64), (512, 512), (100, 8), (7, 2048)):
+        y = torch.randn(rows, C, device="cuda", generator=gen).to(torch.bfloat16)
+        b = torch.randn(C, device="cuda", generator=gen)
+        ref = torch.relu(y.float() + b).to(torch.bfloat16)
+        got = fused.bias_act_(y.clone(), b, True)
+        assert torch.equal(got, ref)
+        gy = torch.randn(rows, C, device="cuda", generator=gen).to(torch.bfloat16)
+        g, db = fused.act_bwd_bias_grad(gy, ref, True)
+        gref = torch.where(ref > 0, gy, torch.zeros_like(gy))
+        assert torch.equal(g, gref)
+        torch.testing.assert_close(db, gref.float().sum(0), rtol=1e-4, atol=1e-3 * max(1.0, rows ** 0.5))
+    # space-to-depth conv1 == direct conv1 (fp32, exact same products; summation order differs)
+    w = torch.randn(32, 4, 8, 8, device="cuda", generator=gen) * 0.05
+    x = torch.randint(0, 256, (16, 4, 84, 84), device="cuda", generator=gen).float()
+    xs = x.view(16, 4, 21, 4, 21, 4).permute(0, 1, 3, 5, 2, 4).reshape(16, 64, 21, 21)
+    ref = torch.nn.functional.conv2d(x, w, stride=4)
+    got = torch.nn.functional.conv2d(xs, fused.space_to_depth_weight(w, 4), stride=1)
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-3)
+    # whole NatureConvBody: fused bf16 path (s2d integer frames, 1/255 folded) vs plain fp32 path on normalized frames
+    rl.Config.COMPUTE_DTYPE = torch.bfloat16
+    try:
+        torch.manual_seed(0)
+        net = rl.VanillaNet(6, rl.NatureConvBody(in_channels=4))
+        frames = torch.randint(0, 256, (32, 4, 84, 84), device="cuda", generator=gen)
+        xs16 = frames.view(32, 4, 21, 4, 21, 4).permute(0, 1, 3, 5, 2, 4).reshape(32, 64, 21, 21).to(torch.bfloat16) \
+            .contiguous(memory_format=torch.channels_last)
+        with rl.frame_scale(1.0 / 255):
+            q_fused = net(xs16)["q"]
+        gq = torch.randn(32, 6, device="cuda", generator=gen)
+        net.zero_grad()
+        q_fused.backward(gq)
+        g_fused = {k: p.grad.clone() for k, p in net.named_parameters()}
+        rl.Config.COMPUTE_DTYPE = torch.float32
+        net.zero_grad()
+        q_ref = net(frames.float() / 255)["q"]
+        q_ref.backward(gq)
+        scale = q_ref.abs().max().item()
+        assert (q_fused - q_ref).abs().max().item() < 0.03 * scale          # bf16 operands: ~1e-2 relative
+        for k, p in net.named_parameters():
+            rel = (g_fused[k] - p.grad).norm() / (p.grad.norm() + 1e-12)
+            assert rel < 0.05, (k, float(rel))
+    finally:
+        rl.Config.COMPUTE_DTYPE = torch.float32
 
 
 # ------------------------------------------------------------------------------------------ agents (product code path)
