@@ -1,0 +1,331 @@
+// gemm.cu -- tcgen05 / TMEM / TMA GEMM for the dense layers of the path (NatureConvBody convolutions as implicit
+// GEMMs over space-to-depth / im2col operands, fc4, heads; network_bodies.py:27-33, network_heads.py:18-21).
+//
+//   D[M,N] (+)= A[M,K] * B[N,K]^T        bf16 operands, fp32 accumulation in tensor memory
+//
+// Operand storage is described per operand:
+//   K-major  (major = 0): row-major [rows = M or N][K], K contiguous            (activations x weights: y = x W^T)
+//   MN-major (major = 1): row-major [K][rows = M or N], M/N contiguous          (weight gradients: dW = g^T x)
+// so no operand is ever transposed in memory.  One CTA computes one 128 x BN output tile for one K split:
+//   warp 0   TMA producer  (cp.async.bulk.tensor, 128B-swizzled 64-wide boxes, STAGES-deep mbarrier ring)
+//   warp 1   MMA issuer    (one elected thread: tcgen05.mma.cta_group::1.kind::f16, accumulator in TMEM)
+//   warp 2   TMEM allocator / deallocator
+//   warps 2-5 epilogue     (tcgen05.ld 32 lanes x 32 columns per warp -> bias / ReLU -> bf16 / fp32 / atomic fp32)
+// sm_100a only.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace b2rl {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;           // 64 bf16 = 128 bytes = one swizzle-128B atom row
+constexpr int GEMM_THREADS = 192;
+
+__device__ __forceinline__ uint32_t s2u(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s2u(bar)), "r"(count));
+}
+__device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s2u(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(s2u(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          s2u(smem_dst)),
+      "l"(map), "r"(s2u(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s2u(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128B swizzle, version 1 (Blackwell)
+//   K-major : 8-row groups 1024 B apart (SBO), LBO = 1
+//   MN-major: 64-element MN groups `mn_group_bytes` apart (LBO), 8-K-row groups 1024 B apart (SBO)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;       // version
+  d |= (uint64_t)2 << 61;       // SWIZZLE_128B
+  return d;
+}
+
+struct GemmParams {
+  int M, N, K;
+  int ldd;                 // row stride of D in elements
+  int k_tiles_per_split;   // K tiles (of 64) handled by one blockIdx.z
+  int a_mn, b_mn;          // operand majors (0 = K-major, 1 = MN-major)
+  int relu, out_mode;      // out_mode 0: bf16 store, 1: fp32 store, 2: fp32 atomicAdd (split-K)
+  const float* bias;       // [N] or null (added by split 0 only)
+  void* D;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                       const __grid_constant__ CUtensorMap tmB,
+                                                                       const GemmParams p) {
+  constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2, B_BYTES = BN * GEMM_BK * 2;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * BN;
+  const int kt_total = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int kt_begin = blockIdx.z * p.k_tiles_per_split;
+  const int kt_end = min(kt_total, kt_begin + p.k_tiles_per_split);
+  const int n_kt = kt_end - kt_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mb_init(&full[s], 1); mb_init(&empty[s], 1); }
+    mb_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (n_kt > 0) {
+    if (warp == 0 && lane == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      for (int i = 0; i < n_kt; ++i) {
+        const int s = i % STAGES, it = i / STAGES;
+        mb_wait(&empty[s], (it & 1) ^ 1);
+        mb_expect_tx(&full[s], A_BYTES + B_BYTES);
+        const int k0 = (kt_begin + i) * GEMM_BK;
+        uint8_t* a = sA + s * A_BYTES;
+        uint8_t* b = sB + s * B_BYTES;
+        if (!p.a_mn) {
+          tma_load_2d(a, &tmA, &full[s], k0, m0);                    // box [128 rows][64 k]
+        } else {
+          tma_load_2d(a, &tmA, &full[s], m0, k0);                    // 2 boxes [64 k][64 m]
+          tma_load_2d(a + 8192, &tmA, &full[s], m0 + 64, k0);
+        }
+        if (!p.b_mn) {
+          tma_load_2d(b, &tmB, &full[s], k0, n0);                    // box [BN rows][64 k]
+        } else {
+#pragma unroll
+          for (int g = 0; g < BN / 64; ++g) tma_load_2d(b + g * 8192, &tmB, &full[s], n0 + g * 64, k0);
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+      for (int i = 0; i < n_kt; ++i) {
+        const int s = i % STAGES, it = i / STAGES;
+        mb_wait(&full[s], it & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_addr = s2u(sA + s * A_BYTES), b_addr = s2u(sB + s * B_BYTES);
+#pragma unroll
+        for (int k = 0; k < GEMM_BK / 16; ++k) {
+          // K-major: 16 k-elements = 32 bytes along the swizzled row; MN-major: 16 k-rows = 2048 bytes
+          const uint64_t ad = p.a_mn ? make_desc(a_addr + k * 2048, 8192, 1024) : make_desc(a_addr + k * 32, 16, 1024);
+          const uint64_t bd = p.b_mn ? make_desc(b_addr + k * 2048, 8192, 1024) : make_desc(b_addr + k * 32, 16, 1024);
+          umma_f16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);                    // frees the smem stage when these MMAs retire
+      }
+      umma_commit(tmem_full);                      // accumulator complete
+    }
+  }
+  if (warp >= 2) {
+    // -------------------------------------------------------------------- epilogue (warp%4 selects the TMEM lane quarter)
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    if (n_kt > 0) {
+      mb_wait(tmem_full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+#pragma unroll
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      if (n_kt > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, r);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0;
+      }
+      if (row < p.M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + c + j;
+          float v = __uint_as_float(r[j]);
+          if (p.bias && blockIdx.z == 0 && n < p.N) v += p.bias[n];
+          if (p.relu) v = fmaxf(v, 0.0f);
+          r[j] = __float_as_uint(v);
+        }
+        const int64_t off = (int64_t)row * p.ldd + n0 + c;
+        if (p.out_mode == 0) {
+          __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + off;
+          if (n0 + c + 32 <= p.N && (off % 8 == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              int4 v;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+              for (int t = 0; t < 4; ++t)
+                h[t] = __floats2bfloat162_rn(__uint_as_float(r[j + 2 * t]), __uint_as_float(r[j + 2 * t + 1]));
+              *reinterpret_cast<int4*>(d + j) = v;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c + j < p.N) d[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
+          }
+        } else if (p.out_mode == 1) {
+          float* d = reinterpret_cast<float*>(p.D) + off;
+          if (n0 + c + 32 <= p.N && (off % 4 == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(d + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                              __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c + j < p.N) d[j] = __uint_as_float(r[j]);
+          }
+        } else {
+          float* d = reinterpret_cast<float*>(p.D) + off;
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c + j < p.N) atomicAdd(d + j, __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [outer][inner] matrix with row stride `ld` elements, box = [box_outer][64]
+static int make_map(CUtensorMap* m, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return B2RL_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return B2RL_ERR_CUDA; }
+  return B2RL_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int splits, cudaStream_t st) {
+  constexpr size_t smem = 1024 + (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + (2 * STAGES + 1) * 8 + 16;
+  auto k = gemm_tcgen05_kernel<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  dim3 grid((p.M + GEMM_BM - 1) / GEMM_BM, (p.N + BN - 1) / BN, splits);
+  k<<<grid, GEMM_THREADS, smem, st>>>(ta, tb, p);
+  return check_launch("b2rl_gemm_bf16");
+}
+
+}  // namespace b2rl
+
+using namespace b2rl;
+
+extern "C" int b2rl_gemm_bf16(const uint16_t* A, int32_t a_mn, int64_t lda, const uint16_t* B, int32_t b_mn, int64_t ldb,
+                              void* D, int64_t ldd, int32_t M, int32_t N, int32_t K, const float* bias, int32_t relu,
+                              int32_t out_mode, int32_t splits, int32_t block_n, void* stream) {
+  B2RL_REQUIRE(A && B && D, "null pointer");
+  B2RL_REQUIRE(M > 0 && N > 0 && K > 0, "bad shape");
+  B2RL_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "operand row strides must be multiples of 8 elements (16 bytes)");
+  B2RL_REQUIRE((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) % 16 == 0, "operands must be 16-byte aligned");
+  B2RL_REQUIRE(out_mode >= 0 && out_mode <= 2, "out_mode 0 (bf16) | 1 (fp32) | 2 (fp32 atomic add)");
+  B2RL_REQUIRE(block_n == 32 || block_n == 64 || block_n == 128, "block_n must be 32, 64 or 128");
+  B2RL_REQUIRE(!(b_mn && block_n < 64), "MN-major B needs block_n >= 64");
+  B2RL_REQUIRE(splits >= 1 && (splits == 1 || out_mode == 2), "split-K needs out_mode 2 (atomic fp32 accumulation)");
+  B2RL_REQUIRE(!(relu && splits > 1), "ReLU cannot be fused into a split-K accumulation");
+  CUtensorMap ta, tb;
+  int rc;
+  // K-major: matrix [rows][K] -> inner = K, outer = rows, box [BM or BN rows][64 k]
+  // MN-major: matrix [K][rows] -> inner = rows, outer = K, box [64 k][64 rows]
+  rc = a_mn ? make_map(&ta, A, M, K, lda, 64) : make_map(&ta, A, K, M, lda, GEMM_BM);
+  if (rc) return rc;
+  rc = b_mn ? make_map(&tb, B, N, K, ldb, 64) : make_map(&tb, B, K, N, ldb, block_n);
+  if (rc) return rc;
+  const int kt_total = (K + GEMM_BK - 1) / GEMM_BK;
+  if (splits > kt_total) splits = kt_total;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.ldd = (int)ldd;
+  p.k_tiles_per_split = (kt_total + splits - 1) / splits;
+  splits = (kt_total + p.k_tiles_per_split - 1) / p.k_tiles_per_split;
+  p.a_mn = a_mn; p.b_mn = b_mn; p.relu = relu; p.out_mode = out_mode; p.bias = bias; p.D = D;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (block_n == 32) return launch_gemm<32, 6>(ta, tb, p, splits, st);
+  if (block_n == 64) return launch_gemm<64, 6>(ta, tb, p, splits, st);
+  return launch_gemm<128, 5>(ta, tb, p, splits, st);
+}

@@ -209,18 +209,22 @@ class FlatOptimizer:
         self.params = [p for p in params]
         dev = self.params[0].device
         _lib.require_cuda(dev)
-        n = sum(p.numel() for p in self.params)
+        # every parameter starts on a 16-byte boundary of the arena (vector loads in the consumers); the padding
+        # elements have zero gradient for ever, so they do not change the global norm or anything else
+        offs, n = [], 0
+        for p in self.params:
+            offs.append(n)
+            n += (p.numel() + 3) // 4 * 4
         self.n = n
-        pad = (n + 3) // 4 * 4
+        pad = n
         self.flat = torch.zeros(pad, dtype=_f32, device=dev)
         self.grad = torch.zeros(pad, dtype=_f32, device=dev)
-        off = 0
-        for p in self.params:                         # re-point every parameter and its .grad into the arenas
+        self.offsets = offs
+        for p, off in zip(self.params, offs):         # re-point every parameter and its .grad into the arenas
             k = p.numel()
             self.flat[off:off + k].copy_(p.detach().reshape(-1))
             p.data = self.flat[off:off + k].view_as(p)
             p.grad = self.grad[off:off + k].view_as(p)
-            off += k
         self.kind, self.lr, self.alpha, self.eps, self.centered, self.betas = kind, lr, alpha, eps, centered, betas
         self.s1 = torch.zeros(pad, dtype=_f32, device=dev)      # square_avg / exp_avg
         self.s2 = torch.zeros(pad, dtype=_f32, device=dev)      # grad_avg   / exp_avg_sq
@@ -262,3 +266,34 @@ class FlatOptimizer:
     @property
     def total_norm(self):
         return self.scratch[0]
+
+
+# ------------------------------------------------------------------------------------------------- tcgen05 GEMM
+def gemm_bf16(a, b, a_major="k", b_major="k", bias=None, relu=False, out_dtype=torch.bfloat16, out=None, splits=1,
+              block_n=None, accumulate=False):
+    """``D[M,N] (+)= A B^T`` on the 5th-generation tensor cores (csrc/gemm.cu: TMA -> tcgen05.mma -> TMEM).
+
+    ``a_major="k"``: ``a`` is [M, K] row-major; ``"mn"``: ``a`` is [K, M] row-major (its transpose is what is
+    multiplied, without being materialised).  Same for ``b`` ([N, K] or [K, N]).  ``splits > 1`` or ``accumulate``
+    accumulate into a fp32 ``out`` with atomics (``out`` is zeroed first unless ``accumulate``)."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() == 2 and b.dim() == 2
+    a_mn, b_mn = a_major == "mn", b_major == "mn"
+    M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn else b.shape
+    assert K == Kb, "inner dimensions differ"
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    if block_n is None:
+        block_n = 128 if N >= 128 else (64 if (N > 32 or b_mn) else 32)
+    atomic = splits > 1 or accumulate
+    if atomic:
+        out_dtype = torch.float32
+    if out is None:
+        out = (torch.zeros if atomic else torch.empty)((M, N), dtype=out_dtype, device=a.device)
+    elif atomic and not accumulate:
+        out.zero_()
+    assert out.dtype == out_dtype and out.stride(1) == 1
+    mode = 2 if atomic else (0 if out_dtype == torch.bfloat16 else 1)
+    _lib.call("b2rl_gemm_bf16", _lib.ptr(a), int(a_mn), a.stride(0), _lib.ptr(b), int(b_mn), b.stride(0), _lib.ptr(out),
+              out.stride(0), int(M), int(N), int(K), _lib.ptr(bias), int(relu), mode, int(splits), int(block_n),
+              _lib.stream())
+    return out

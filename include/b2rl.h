@@ -191,6 +191,19 @@ int b2rl_bias_act_bf16(uint16_t* y, const float* bias, int64_t rows, int32_t C, 
 int b2rl_act_bwd_bias_grad_bf16(const uint16_t* gy, const uint16_t* y, int64_t rows, int32_t C, int32_t relu,
                                 uint16_t* gx, float* dbias, float* partial, int32_t* counter, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * tcgen05 GEMM for the dense contractions (network_bodies.py:27-33, network_heads.py:18-21):
+ *   D[M,N] (+)= A[M,K] * B[N,K]^T, bf16 operands, fp32 accumulation in tensor memory (TMEM), TMA-fed.
+ * a_mn / b_mn = 0: operand stored row-major [rows][K] (K-major); 1: stored row-major [K][rows] (MN-major) -- weight
+ * gradients dW = g^T x read both operands as stored, nothing is transposed in memory.  lda/ldb/ldd: row strides in
+ * elements (operands: multiples of 8).  out_mode 0: bf16 store, 1: fp32 store, 2: fp32 atomicAdd into D (required for
+ * splits > 1; D must be pre-zeroed or hold the value to accumulate into).  bias (fp32 [N]) and relu are fused into the
+ * epilogue.  block_n in {32, 64, 128} = output tile width (tile height is 128).
+ * ------------------------------------------------------------------------------------------- */
+int b2rl_gemm_bf16(const uint16_t* A, int32_t a_mn, int64_t lda, const uint16_t* B, int32_t b_mn, int64_t ldb, void* D,
+                   int64_t ldd, int32_t M, int32_t N, int32_t K, const float* bias, int32_t relu, int32_t out_mode,
+                   int32_t splits, int32_t block_n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
