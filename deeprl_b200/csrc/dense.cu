@@ -41,11 +41,33 @@ __global__ void __launch_bounds__(256) bias_act_kernel(__nv_bfloat16* __restrict
   }
 }
 
+// destination row of source row r for the layout changes between the layers of the grid-GEMM convolution stack
+//   map 0: identity
+//   map 1: compact V x V positions per image -> G x G grid rows            (fc4's input gradient -> conv3's output grid)
+//   map 2: space-to-depth(2) rows [b][Y][X] x 4 channel groups (py,px) -> G x G grid rows (2Y+py, 2X+px); the source is
+//          addressed as rows*4 "virtual rows" of C channels                (conv2's input gradient -> conv1's output grid)
+__device__ __forceinline__ int64_t map_row(int64_t r, int map, int G, int V) {
+  if (map == 0) return r;
+  if (map == 1) {
+    const int64_t b = r / (V * V);
+    const int rem = (int)(r - b * V * V);
+    return b * G * G + (rem / V) * G + rem % V;
+  }
+  const int h = V >> 1;                       // source grid is h x h, 4 groups per source row
+  const int64_t sr = r >> 2;
+  const int grp = (int)(r & 3);
+  const int64_t b = sr / (h * h);
+  const int rem = (int)(sr - b * h * h);
+  const int Y = rem / h, X = rem - Y * h;
+  return b * G * G + (2 * Y + (grp >> 1)) * G + 2 * X + (grp & 1);
+}
+
 // each thread owns one 8-channel group and walks rows with stride (threads per block / C8) * gridDim
 __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __restrict__ gy,
                                                       const __nv_bfloat16* __restrict__ y, int64_t rows, int C8, int relu,
                                                       __nv_bfloat16* __restrict__ gx, float* __restrict__ dbias,
-                                                      float* __restrict__ partial, int32_t* __restrict__ counter) {
+                                                      float* __restrict__ partial, int32_t* __restrict__ counter,
+                                                      int map, int G, int V) {
   extern __shared__ float sred[];          // [rows_per_block][C] partial sums
   __shared__ bool is_last;
   const int C = C8 * 8;
@@ -64,9 +86,9 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __res
         unpack8(y4, yv);
 #pragma unroll
         for (int k = 0; k < 8; ++k) g[k] = yv[k] > 0.0f ? g[k] : 0.0f;
-        if (gx) reinterpret_cast<int4*>(gx)[e] = pack8(g);
-      } else if (gx && gx != gy) {
-        reinterpret_cast<int4*>(gx)[e] = g4;
+        if (gx) reinterpret_cast<int4*>(gx)[map_row(r, map, G, V) * C8 + cg] = pack8(g);
+      } else if (gx && (gx != gy || map != 0)) {
+        reinterpret_cast<int4*>(gx)[map_row(r, map, G, V) * C8 + cg] = g4;
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] += g[k];
@@ -125,7 +147,10 @@ extern "C" int b2rl_bias_act_bf16(uint16_t* y, const float* bias, int64_t rows, 
 }
 
 extern "C" int b2rl_act_bwd_bias_grad_bf16(const uint16_t* gy, const uint16_t* y, int64_t rows, int32_t C, int32_t relu,
-                                           uint16_t* gx, float* dbias, float* partial, int32_t* counter, void* stream) {
+                                           uint16_t* gx, float* dbias, float* partial, int32_t* counter, int32_t row_map,
+                                           int32_t G, int32_t V, void* stream) {
+  B2RL_REQUIRE(row_map >= 0 && row_map <= 2 && (row_map == 0 || (G > 0 && V > 0 && V <= G)), "bad row map");
+  B2RL_REQUIRE(row_map == 0 || gx != gy, "a row-mapped gradient cannot be written in place");
   B2RL_REQUIRE(gy && dbias && partial && counter && (y || !relu), "null pointer");
   B2RL_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && C <= 2048, "C must be a multiple of 8, <= 2048");
   const int C8 = C / 8;
@@ -136,6 +161,6 @@ extern "C" int b2rl_act_bwd_bias_grad_bf16(const uint16_t* gy, const uint16_t* y
   size_t smem = (size_t)rpb * C * sizeof(float);
   act_bwd_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(gy), reinterpret_cast<const __nv_bfloat16*>(y), rows, C8, relu,
-      reinterpret_cast<__nv_bfloat16*>(gx), dbias, partial, counter);
+      reinterpret_cast<__nv_bfloat16*>(gx), dbias, partial, counter, row_map, G, V);
   return check_launch("b2rl_act_bwd_bias_grad_bf16");
 }

@@ -1,16 +1,26 @@
-// gemm.cu -- tcgen05 / TMEM / TMA GEMM for the dense layers of the path (NatureConvBody convolutions as implicit
-// GEMMs over space-to-depth / im2col operands, fc4, heads; network_bodies.py:27-33, network_heads.py:18-21).
+// gemm.cu -- persistent tcgen05 / TMEM / TMA GEMM for the dense layers of the path: NatureConvBody convolutions as
+// shifted-row implicit GEMMs, fc4, heads (network_bodies.py:27-33, network_heads.py:18-21), forward, dgrad and wgrad.
 //
 //   D[M,N] (+)= A[M,K] * B[N,K]^T        bf16 operands, fp32 accumulation in tensor memory
 //
 // Operand storage is described per operand:
 //   K-major  (major = 0): row-major [rows = M or N][K], K contiguous            (activations x weights: y = x W^T)
 //   MN-major (major = 1): row-major [K][rows = M or N], M/N contiguous          (weight gradients: dW = g^T x)
-// so no operand is ever transposed in memory.  One CTA computes one 128 x BN output tile for one K split:
-//   warp 0   TMA producer  (cp.async.bulk.tensor, 128B-swizzled 64-wide boxes, STAGES-deep mbarrier ring)
-//   warp 1   MMA issuer    (one elected thread: tcgen05.mma.cta_group::1.kind::f16, accumulator in TMEM)
-//   warp 2   TMEM allocator / deallocator
-//   warps 2-5 epilogue     (tcgen05.ld 32 lanes x 32 columns per warp -> bias / ReLU -> bf16 / fp32 / atomic fp32)
+// so no operand is ever transposed in memory.
+//
+// Convolutions without im2col ("tap addressing").  Activations live as [batch * G * G][C] matrices over a G x G grid
+// per image.  A k x k / stride-1 convolution over that grid is  y[r] = sum_taps x[r + dy*G + dx] W_tap^T : the A operand
+// of k-tile `kt` is the SAME matrix read at a row offset that depends on the tap the k-tile belongs to (rows that run
+// off the grid produce garbage output rows, which the epilogue drops or the next layer never reads).  Stride-s
+// convolutions are first turned into stride-1 ones by a space-to-depth(s) layout of their input, which the PRODUCING
+// kernel writes directly (the replay gather for conv1, conv1's epilogue for conv2).  dgrad is the same with negative
+// shifts; wgrad reads both operands MN-major with the tap shift applied to the B operand per output column block.
+//
+// One persistent CTA per SM loops over output tiles (128 x BN):
+//   warp 0    TMA producer   cp.async.bulk.tensor into a STAGES-deep 128B-swizzled smem ring (mbarrier full/empty)
+//   warp 1    MMA issuer     one thread: tcgen05.mma.cta_group::1.kind::f16, accumulators double-buffered in TMEM
+//   warps 2-5 epilogue       tcgen05.ld (32 lanes x 32 columns per warp) -> bias / ReLU -> bf16 | fp32 | atomic fp32,
+//                            overlapped with the next tile's MMAs; warp 2 also owns TMEM alloc / dealloc
 // sm_100a only.
 #include <cuda.h>
 #include "common.cuh"
@@ -28,6 +38,9 @@ __device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s2u(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(bar)) : "memory");
 }
 __device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -74,8 +87,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128B swizzle, version 1 (Blackwell)
-//   K-major : 8-row groups 1024 B apart (SBO), LBO = 1
-//   MN-major: 64-element MN groups `mn_group_bytes` apart (LBO), 8-K-row groups 1024 B apart (SBO)
+//   K-major : 8-row groups 1024 B apart (SBO), LBO = 1 (x16 B)
+//   MN-major: 64-element MN groups `lbo` bytes apart, 8-K-row groups 1024 B apart (SBO)
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
@@ -91,36 +104,49 @@ struct GemmParams {
   int ldd;                 // row stride of D in elements
   int k_tiles_per_split;   // K tiles (of 64) handled by one blockIdx.z
   int a_mn, b_mn;          // operand majors (0 = K-major, 1 = MN-major)
-  int relu, out_mode;      // out_mode 0: bf16 store, 1: fp32 store, 2: fp32 atomicAdd (split-K)
+  int relu, out_mode;      // out_mode 0: bf16 store, 1: fp32 store, 2: fp32 atomicAdd (split-K / accumulate)
   const float* bias;       // [N] or null (added by split 0 only)
   void* D;
+  // tap addressing (0 = plain GEMM)
+  int a_tap_tiles;         // K-major A: k-tiles per tap (= channels / 64); the A matrix is [rows][a_tap_tiles*64]
+  int b_tap_tiles;         // MN-major B (wgrad): output column tiles per tap (= channels / BN); B is [rows][b_tap_tiles*BN]
+  int taps_x, grid_w, shift_sign;   // row shift of tap t = sign * ((t / taps_x) * grid_w + t % taps_x)
+  // output row mapping (rows of the GEMM are positions of a G x G grid per image)
+  int out_map;             // 0: identity; 1: G-grid -> space-to-depth(2) rows, valid V x V; 2: G-grid -> compact V x V
+  int G, V;
 };
+
+__device__ __forceinline__ int tap_shift(const GemmParams& p, int tap) {
+  return p.shift_sign * ((tap / p.taps_x) * p.grid_w + tap % p.taps_x);
+}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                        const __grid_constant__ CUtensorMap tmB,
                                                                        const GemmParams p) {
   constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2, B_BYTES = BN * GEMM_BK * 2;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;          // two accumulator stages
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
   uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * BN;
+  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (p.N + BN - 1) / BN;
+  const int tiles = m_tiles * n_tiles;
   const int kt_total = (p.K + GEMM_BK - 1) / GEMM_BK;
   const int kt_begin = blockIdx.z * p.k_tiles_per_split;
   const int kt_end = min(kt_total, kt_begin + p.k_tiles_per_split);
-  const int n_kt = kt_end - kt_begin;
+  const int n_kt = max(kt_end - kt_begin, 0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mb_init(&full[s], 1); mb_init(&empty[s], 1); }
-    mb_init(tmem_full, 1);
+    for (int s = 0; s < 2; ++s) { mb_init(&tmem_full[s], 1); mb_init(&tmem_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -134,36 +160,59 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (n_kt > 0) {
-    if (warp == 0 && lane == 0) {
-      // ------------------------------------------------------------------ TMA producer
-      for (int i = 0; i < n_kt; ++i) {
-        const int s = i % STAGES, it = i / STAGES;
-        mb_wait(&empty[s], (it & 1) ^ 1);
+  if (warp == 0 && lane == 0 && n_kt > 0) {
+    // ---------------------------------------------------------------------- TMA producer
+    uint32_t it = 0;                                         // global k-iteration counter across tiles
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      const int m0 = mt * GEMM_BM, n0 = nt * BN;
+      int b_shift = 0, b_col = n0;
+      if (p.b_tap_tiles > 0) {                               // wgrad: the tap is selected by the output column block
+        const int tap = nt / p.b_tap_tiles;
+        b_shift = tap_shift(p, tap);
+        b_col = (nt - tap * p.b_tap_tiles) * BN;
+      }
+      for (int i = 0; i < n_kt; ++i, ++it) {
+        const int s = it % STAGES;
+        mb_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
         mb_expect_tx(&full[s], A_BYTES + B_BYTES);
-        const int k0 = (kt_begin + i) * GEMM_BK;
+        const int g = kt_begin + i;
         uint8_t* a = sA + s * A_BYTES;
         uint8_t* b = sB + s * B_BYTES;
         if (!p.a_mn) {
-          tma_load_2d(a, &tmA, &full[s], k0, m0);                    // box [128 rows][64 k]
+          int ak = g * GEMM_BK, arow = m0;
+          if (p.a_tap_tiles > 0) {
+            const int tap = g / p.a_tap_tiles;
+            ak = (g - tap * p.a_tap_tiles) * GEMM_BK;
+            arow = m0 + tap_shift(p, tap);
+          }
+          tma_load_2d(a, &tmA, &full[s], ak, arow);                       // box [128 rows][64 k]
         } else {
-          tma_load_2d(a, &tmA, &full[s], m0, k0);                    // 2 boxes [64 k][64 m]
-          tma_load_2d(a + 8192, &tmA, &full[s], m0 + 64, k0);
+          tma_load_2d(a, &tmA, &full[s], m0, g * GEMM_BK);                // 2 boxes [64 k][64 m]
+          tma_load_2d(a + 8192, &tmA, &full[s], m0 + 64, g * GEMM_BK);
         }
         if (!p.b_mn) {
-          tma_load_2d(b, &tmB, &full[s], k0, n0);                    // box [BN rows][64 k]
+          tma_load_2d(b, &tmB, &full[s], g * GEMM_BK, n0);                // box [BN rows][64 k]
         } else {
 #pragma unroll
-          for (int g = 0; g < BN / 64; ++g) tma_load_2d(b + g * 8192, &tmB, &full[s], n0 + g * 64, k0);
+          for (int q = 0; q < (BN + 63) / 64; ++q)
+            tma_load_2d(b + q * 8192, &tmB, &full[s], b_col + q * 64, g * GEMM_BK + b_shift);
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ------------------------------------------------------------------ MMA issuer
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
-      for (int i = 0; i < n_kt; ++i) {
-        const int s = i % STAGES, it = i / STAGES;
-        mb_wait(&full[s], it & 1);
+    }
+  } else if (warp == 1 && lane == 0 && n_kt > 0) {
+    // ---------------------------------------------------------------------- MMA issuer
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t as = tcount & 1;
+      mb_wait(&tmem_empty[as], ((tcount >> 1) & 1) ^ 1);     // epilogue drained this accumulator stage
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc = tmem_base + as * BN;
+      for (int i = 0; i < n_kt; ++i, ++it) {
+        const int s = it % STAGES;
+        mb_wait(&full[s], (it / STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_addr = s2u(sA + s * A_BYTES), b_addr = s2u(sB + s * B_BYTES);
 #pragma unroll
@@ -171,71 +220,98 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           // K-major: 16 k-elements = 32 bytes along the swizzled row; MN-major: 16 k-rows = 2048 bytes
           const uint64_t ad = p.a_mn ? make_desc(a_addr + k * 2048, 8192, 1024) : make_desc(a_addr + k * 32, 16, 1024);
           const uint64_t bd = p.b_mn ? make_desc(b_addr + k * 2048, 8192, 1024) : make_desc(b_addr + k * 32, 16, 1024);
-          umma_f16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          umma_f16(acc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty[s]);                    // frees the smem stage when these MMAs retire
       }
-      umma_commit(tmem_full);                      // accumulator complete
+      umma_commit(&tmem_full[as]);                 // accumulator of this tile complete
     }
-  }
-  if (warp >= 2) {
-    // -------------------------------------------------------------------- epilogue (warp%4 selects the TMEM lane quarter)
+  } else if (warp >= 2) {
+    // ---------------------------------------------------------------------- epilogue (warp%4 selects the TMEM lane quarter)
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
-    if (n_kt > 0) {
-      mb_wait(tmem_full, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
-#pragma unroll
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t r[32];
-      if (n_kt > 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, r);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0;
-      }
-      if (row < p.M) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + c + j;
-          float v = __uint_as_float(r[j]);
-          if (p.bias && blockIdx.z == 0 && n < p.N) v += p.bias[n];
-          if (p.relu) v = fmaxf(v, 0.0f);
-          r[j] = __float_as_uint(v);
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tcount) {
+      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      const int m0 = mt * GEMM_BM, n0 = nt * BN;
+      const uint32_t as = tcount & 1;
+      const int row = m0 + q * 32 + lane;
+      // destination row / validity
+      bool valid = row < p.M;
+      int64_t drow = row;
+      int dcol0 = 0;
+      if (p.out_map != 0 && valid) {
+        const int gg = p.G * p.G;
+        const int b = row / gg, rem = row - b * gg;
+        const int oy = rem / p.G, ox = rem - oy * p.G;
+        valid = oy < p.V && ox < p.V;
+        if (p.out_map == 1) {
+          const int h = p.V >> 1;
+          drow = (int64_t)b * h * h + (oy >> 1) * h + (ox >> 1);
+          dcol0 = (((oy & 1) << 1) | (ox & 1)) * p.N;
+        } else {
+          drow = (int64_t)b * p.V * p.V + oy * p.V + ox;
         }
-        const int64_t off = (int64_t)row * p.ldd + n0 + c;
-        if (p.out_mode == 0) {
-          __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + off;
-          if (n0 + c + 32 <= p.N && (off % 8 == 0)) {
+      }
+      if (n_kt > 0) {
+        mb_wait(&tmem_full[as], (tcount >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              int4 v;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        if (n_kt > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c, r);
+        } else {
 #pragma unroll
-              for (int t = 0; t < 4; ++t)
-                h[t] = __floats2bfloat162_rn(__uint_as_float(r[j + 2 * t]), __uint_as_float(r[j + 2 * t + 1]));
-              *reinterpret_cast<int4*>(d + j) = v;
+          for (int j = 0; j < 32; ++j) r[j] = 0;
+        }
+        if (c + 32 >= BN && n_kt > 0) {
+          // all TMEM reads of this warp for this tile are done: hand the accumulator stage back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          if (lane == 0) mb_arrive(&tmem_empty[as]);
+        }
+        if (valid && n0 + c < p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c + j;
+            float v = __uint_as_float(r[j]);
+            if (p.bias && blockIdx.z == 0 && n < p.N) v += __ldg(p.bias + n);
+            if (p.relu) v = fmaxf(v, 0.0f);
+            r[j] = __float_as_uint(v);
+          }
+          const int64_t off = drow * p.ldd + dcol0 + n0 + c;
+          if (p.out_mode == 0) {
+            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + off;
+            if (n0 + c + 32 <= p.N && (off % 8 == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                int4 v;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                  h[t] = __floats2bfloat162_rn(__uint_as_float(r[j + 2 * t]), __uint_as_float(r[j + 2 * t + 1]));
+                *reinterpret_cast<int4*>(d + j) = v;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (n0 + c + j < p.N) d[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
+            }
+          } else if (p.out_mode == 1) {
+            float* d = reinterpret_cast<float*>(p.D) + off;
+            if (n0 + c + 32 <= p.N && (off % 4 == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(d + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (n0 + c + j < p.N) d[j] = __uint_as_float(r[j]);
             }
           } else {
+            float* d = reinterpret_cast<float*>(p.D) + off;
             for (int j = 0; j < 32; ++j)
-              if (n0 + c + j < p.N) d[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
+              if (n0 + c + j < p.N) atomicAdd(d + j, __uint_as_float(r[j]));
           }
-        } else if (p.out_mode == 1) {
-          float* d = reinterpret_cast<float*>(p.D) + off;
-          if (n0 + c + 32 <= p.N && (off % 4 == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(d + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                              __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (n0 + c + j < p.N) d[j] = __uint_as_float(r[j]);
-          }
-        } else {
-          float* d = reinterpret_cast<float*>(p.D) + off;
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c + j < p.N) atomicAdd(d + j, __uint_as_float(r[j]));
         }
       }
     }
@@ -279,27 +355,59 @@ static int make_map(CUtensorMap* m, const void* ptr, int64_t inner, int64_t oute
   return B2RL_OK;
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int BN, int STAGES>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int splits, cudaStream_t st) {
-  constexpr size_t smem = 1024 + (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + (2 * STAGES + 1) * 8 + 16;
+  constexpr size_t smem = 1024 + (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + (2 * STAGES + 4) * 8 + 16;
   auto k = gemm_tcgen05_kernel<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
-  dim3 grid((p.M + GEMM_BM - 1) / GEMM_BM, (p.N + BN - 1) / BN, splits);
+  const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN);
+  int ctas = sm_count() / splits;
+  if (ctas < 1) ctas = 1;
+  if (ctas > tiles) ctas = tiles;
+  dim3 grid(ctas, 1, splits);
   k<<<grid, GEMM_THREADS, smem, st>>>(ta, tb, p);
   return check_launch("b2rl_gemm_bf16");
+}
+
+static int gemm_dispatch(const uint16_t* A, int a_mn, int64_t lda, int64_t a_rows, int64_t a_cols, const uint16_t* B,
+                         int b_mn, int64_t ldb, int64_t b_rows, int64_t b_cols, GemmParams p, int splits, int block_n,
+                         cudaStream_t st) {
+  CUtensorMap ta, tb;
+  int rc;
+  // the tensor map describes the matrix AS STORED: [a_rows][a_cols]; box = [128|64 rows][64 cols]
+  rc = make_map(&ta, A, a_cols, a_rows, lda, a_mn ? 64 : GEMM_BM);
+  if (rc) return rc;
+  rc = make_map(&tb, B, b_cols, b_rows, ldb, b_mn ? 64 : block_n);
+  if (rc) return rc;
+  const int kt_total = (p.K + GEMM_BK - 1) / GEMM_BK;
+  if (splits > kt_total) splits = kt_total;
+  p.k_tiles_per_split = (kt_total + splits - 1) / splits;
+  splits = (kt_total + p.k_tiles_per_split - 1) / p.k_tiles_per_split;
+  if (block_n == 32) return launch_gemm<32, 6>(ta, tb, p, splits, st);
+  if (block_n == 64) return launch_gemm<64, 6>(ta, tb, p, splits, st);
+  return launch_gemm<128, 5>(ta, tb, p, splits, st);
 }
 
 }  // namespace b2rl
 
 using namespace b2rl;
 
-extern "C" int b2rl_gemm_bf16(const uint16_t* A, int32_t a_mn, int64_t lda, const uint16_t* B, int32_t b_mn, int64_t ldb,
-                              void* D, int64_t ldd, int32_t M, int32_t N, int32_t K, const float* bias, int32_t relu,
-                              int32_t out_mode, int32_t splits, int32_t block_n, void* stream) {
+static int check_common(const void* A, const void* B, const void* D, int64_t lda, int64_t ldb, int M, int N, int K,
+                        int out_mode, int splits, int block_n, int b_mn, int relu) {
   B2RL_REQUIRE(A && B && D, "null pointer");
   B2RL_REQUIRE(M > 0 && N > 0 && K > 0, "bad shape");
   B2RL_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "operand row strides must be multiples of 8 elements (16 bytes)");
@@ -308,24 +416,53 @@ extern "C" int b2rl_gemm_bf16(const uint16_t* A, int32_t a_mn, int64_t lda, cons
   B2RL_REQUIRE(block_n == 32 || block_n == 64 || block_n == 128, "block_n must be 32, 64 or 128");
   B2RL_REQUIRE(!(b_mn && block_n < 64), "MN-major B needs block_n >= 64");
   B2RL_REQUIRE(splits >= 1 && (splits == 1 || out_mode == 2), "split-K needs out_mode 2 (atomic fp32 accumulation)");
-  B2RL_REQUIRE(!(relu && splits > 1), "ReLU cannot be fused into a split-K accumulation");
-  CUtensorMap ta, tb;
-  int rc;
-  // K-major: matrix [rows][K] -> inner = K, outer = rows, box [BM or BN rows][64 k]
-  // MN-major: matrix [K][rows] -> inner = rows, outer = K, box [64 k][64 rows]
-  rc = a_mn ? make_map(&ta, A, M, K, lda, 64) : make_map(&ta, A, K, M, lda, GEMM_BM);
+  B2RL_REQUIRE(!(relu && out_mode == 2), "ReLU cannot be fused into an atomic accumulation");
+  return B2RL_OK;
+}
+
+extern "C" int b2rl_gemm_bf16(const uint16_t* A, int32_t a_mn, int64_t lda, const uint16_t* B, int32_t b_mn, int64_t ldb,
+                              void* D, int64_t ldd, int32_t M, int32_t N, int32_t K, const float* bias, int32_t relu,
+                              int32_t out_mode, int32_t splits, int32_t block_n, void* stream) {
+  int rc = check_common(A, B, D, lda, ldb, M, N, K, out_mode, splits, block_n, b_mn, relu);
   if (rc) return rc;
-  rc = b_mn ? make_map(&tb, B, N, K, ldb, 64) : make_map(&tb, B, K, N, ldb, block_n);
-  if (rc) return rc;
-  const int kt_total = (K + GEMM_BK - 1) / GEMM_BK;
-  if (splits > kt_total) splits = kt_total;
-  GemmParams p;
+  GemmParams p = {};
   p.M = M; p.N = N; p.K = K; p.ldd = (int)ldd;
-  p.k_tiles_per_split = (kt_total + splits - 1) / splits;
-  splits = (kt_total + p.k_tiles_per_split - 1) / p.k_tiles_per_split;
   p.a_mn = a_mn; p.b_mn = b_mn; p.relu = relu; p.out_mode = out_mode; p.bias = bias; p.D = D;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (block_n == 32) return launch_gemm<32, 6>(ta, tb, p, splits, st);
-  if (block_n == 64) return launch_gemm<64, 6>(ta, tb, p, splits, st);
-  return launch_gemm<128, 5>(ta, tb, p, splits, st);
+  p.taps_x = 1; p.shift_sign = 1;
+  // K-major: stored [rows][K]; MN-major: stored [K][rows]
+  return gemm_dispatch(A, a_mn, lda, a_mn ? K : M, a_mn ? M : K, B, b_mn, ldb, b_mn ? K : N, b_mn ? N : K, p, splits,
+                       block_n, (cudaStream_t)stream);
+}
+
+// Convolution over a G x G grid as a shifted-row GEMM (see the header of this file).
+//   mode 0 (forward / dgrad):  D[r, :] = sum_taps  X[r + shift(tap), :] * W[:, tap*C .. tap*C+C]^T
+//        X: [rows][C] bf16 (C multiple of 64), W: [N][taps*C] bf16 K-major, shift(tap) = sign*((tap/taps_x)*grid_w + tap%taps_x)
+//   mode 1 (wgrad):            D[n, tap*C + c] (+)= sum_r G[r, n] * X[r + shift(tap), c]
+//        G: [rows][N_out] bf16, X: [rows][C] bf16 (C multiple of block_n), D: fp32 [N_out][taps*C], atomic accumulation
+extern "C" int b2rl_conv_gemm_bf16(int32_t mode, const uint16_t* X, int64_t rows, int32_t C, const uint16_t* W_or_G,
+                                   int32_t n_out, int32_t taps, int32_t taps_x, int32_t grid_w, int32_t shift_sign,
+                                   void* D, int64_t ldd, const float* bias, int32_t relu, int32_t out_mode,
+                                   int32_t out_map, int32_t G, int32_t V, int32_t splits, int32_t block_n, void* stream) {
+  B2RL_REQUIRE(mode == 0 || mode == 1, "mode 0 (forward/dgrad) or 1 (wgrad)");
+  B2RL_REQUIRE(rows > 0 && C > 0 && taps > 0 && taps_x > 0 && n_out > 0, "bad shape");
+  B2RL_REQUIRE(out_map >= 0 && out_map <= 2, "bad out_map");
+  GemmParams p = {};
+  p.relu = relu; p.out_mode = out_mode; p.bias = bias; p.D = D; p.ldd = (int)ldd;
+  p.taps_x = taps_x; p.grid_w = grid_w; p.shift_sign = shift_sign;
+  p.out_map = out_map; p.G = G; p.V = V;
+  if (mode == 0) {
+    B2RL_REQUIRE(C % 64 == 0, "forward/dgrad needs channels in multiples of 64");
+    const int K = taps * C;
+    int rc = check_common(X, W_or_G, D, C, K, (int)rows, n_out, K, out_mode, splits, block_n, 0, relu);
+    if (rc) return rc;
+    p.M = (int)rows; p.N = n_out; p.K = K; p.a_mn = 0; p.b_mn = 0; p.a_tap_tiles = C / 64;
+    return gemm_dispatch(X, 0, C, rows, C, W_or_G, 0, K, n_out, K, p, splits, block_n, (cudaStream_t)stream);
+  }
+  B2RL_REQUIRE(C % block_n == 0, "wgrad needs channels in multiples of block_n");
+  B2RL_REQUIRE(n_out % 8 == 0, "wgrad needs n_out in multiples of 8");
+  int rc = check_common(W_or_G, X, D, n_out, C, n_out, taps * C, (int)rows, out_mode, splits, block_n, 1, relu);
+  if (rc) return rc;
+  B2RL_REQUIRE(out_mode == 2, "wgrad accumulates with out_mode 2");
+  p.M = n_out; p.N = taps * C; p.K = (int)rows; p.a_mn = 1; p.b_mn = 1; p.b_tap_tiles = C / block_n;
+  return gemm_dispatch(W_or_G, 1, n_out, rows, n_out, X, 1, C, rows, C, p, splits, block_n, (cudaStream_t)stream);
 }

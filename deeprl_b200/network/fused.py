@@ -48,8 +48,18 @@ def bias_act_(y, bias, relu=True):
     return y
 
 
-def act_bwd_bias_grad(gy, y, relu=True):
-    """-> (g = gy * (y > 0) in bf16, dbias fp32 [C])."""
+def act_bwd_bias_grad(gy, y, relu=True, row_map=0, G=0, V=0, out_rows=None):
+    """-> (g = gy * (y > 0) in bf16, dbias fp32 [C]).  ``row_map`` re-lays ``g`` out on a G x G grid (csrc/dense.cu)."""
+    if row_map:
+        rows, C = (gy.shape[0] * 4, gy.shape[1] // 4) if row_map == 2 else gy.shape
+        assert gy.is_contiguous() and y.is_contiguous() and gy.dtype == _bf16
+        g = torch.zeros((out_rows, C), dtype=_bf16, device=gy.device)
+        db = torch.empty(C, dtype=torch.float32, device=gy.device)
+        partial = _Scratch.get(y.device, "act_bwd_partial", 296 * 2048, torch.float32)
+        counter = _Scratch.get(y.device, "act_bwd_counter", 1, torch.int32)
+        _lib.call("b2rl_act_bwd_bias_grad_bf16", _lib.ptr(gy), _lib.ptr(y), rows, C, int(relu), _lib.ptr(g), _lib.ptr(db),
+                  _lib.ptr(partial), _lib.ptr(counter), int(row_map), int(G), int(V), _lib.stream())
+        return g, db
     rows, C = _rows_c(y)
     if gy.dim() == 4 and not gy.is_contiguous(memory_format=torch.channels_last):
         gy = gy.contiguous(memory_format=torch.channels_last)
@@ -62,7 +72,7 @@ def act_bwd_bias_grad(gy, y, relu=True):
     partial = _Scratch.get(y.device, "act_bwd_partial", 296 * 2048, torch.float32)
     counter = _Scratch.get(y.device, "act_bwd_counter", 1, torch.int32)
     _lib.call("b2rl_act_bwd_bias_grad_bf16", _lib.ptr(gy), _lib.ptr(y), rows, C, int(relu), _lib.ptr(g), _lib.ptr(db),
-              _lib.ptr(partial), _lib.ptr(counter), _lib.stream())
+              _lib.ptr(partial), _lib.ptr(counter), 0, 0, 0, _lib.stream())
     return g, db
 
 

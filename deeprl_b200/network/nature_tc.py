@@ -1,0 +1,121 @@
+"""NatureConvBody forward + backward entirely on the tcgen05 GEMM of ``csrc/gemm.cu`` (no cuDNN / cuBLAS).
+
+Reference layer stack: ``network_bodies.py:10-33`` -- conv(4->32,k8,s4), conv(32->64,k4,s2), conv(64->64,k3,s1), fc(3136->512),
+ReLU after each.  Every layer is a GEMM over activations stored as [batch * G * G][C] grid matrices:
+
+    x0  [B*21*21][ 64]   frames, space-to-depth(4): written by the replay gather           (conv1 = 2x2 taps, K = 256)
+    x1  [B*10*10][128]   relu(conv1), space-to-depth(2): written by conv1's GEMM epilogue   (conv2 = 2x2 taps, K = 512)
+    y2  [B*10*10][ 64]   relu(conv2) on the 10-grid (row/col 9 are never read)               (conv3 = 3x3 taps, K = 576)
+    y3  [B* 7* 7][ 64]   relu(conv3), compacted by conv3's epilogue == fc4's input in (h, w, c) order
+    y4  [B][512]         relu(fc4)
+
+Backward: ReLU mask + bias gradient + re-layout in one pass (``csrc/dense.cu``), then dgrad = the same shifted-row GEMM
+with negative shifts and wgrad = MN-major GEMMs with split-K.  Weights are re-laid out from the reference's parameter
+layout ([Cout, Cin, kh, kw], (c, h, w)-ordered fc4 columns) to the tap-major bf16 layouts once per forward, and the
+weight gradients are mapped back, so ``state_dict``s and optimizers see the reference layout only.
+"""
+import torch
+
+from .. import _lib
+from ..ops import gemm_bf16
+from .fused import act_bwd_bias_grad
+
+_bf16 = torch.bfloat16
+
+
+def conv_gemm(mode, X, W_or_G, n_out, taps, taps_x, grid_w, sign, out, bias=None, relu=False, out_map=0, G=0, V=0, splits=1,
+              block_n=64):
+    rows, C = X.shape
+    out_mode = 2 if mode == 1 else (0 if out.dtype == _bf16 else 1)
+    _lib.call("b2rl_conv_gemm_bf16", int(mode), _lib.ptr(X), int(rows), int(C), _lib.ptr(W_or_G), int(n_out), int(taps),
+              int(taps_x), int(grid_w), int(sign), _lib.ptr(out), out.stride(0), _lib.ptr(bias), int(relu), out_mode,
+              int(out_map), int(G), int(V), int(splits), int(block_n), _lib.stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------- weight layouts
+def pack_weights(w1, w2, w3, w4, scale):
+    """Reference layouts -> tap-major bf16 GEMM operands (forward ``f`` and dgrad ``d`` orientations)."""
+    n1, c1 = w1.shape[0], w1.shape[1]
+    w1f = (w1.view(n1, c1, 2, 4, 2, 4).permute(0, 2, 4, 1, 3, 5) * scale).reshape(n1, 4 * c1 * 16).to(_bf16)
+    v2 = w2.view(64, 32, 2, 2, 2, 2)                                           # (n, c, ty, py, tx, px)
+    w2f = v2.permute(0, 2, 4, 3, 5, 1).reshape(64, 512).to(_bf16)              # [n][(ty,tx),(py,px,c)]
+    w2d = v2.permute(3, 5, 1, 2, 4, 0).reshape(128, 256).to(_bf16)             # [(py,px,c)][(ty,tx),n]
+    w3f = w3.permute(0, 2, 3, 1).reshape(64, 576).to(_bf16)                    # [n][(ky,kx),c]
+    w3d = w3.permute(1, 2, 3, 0).reshape(64, 576).to(_bf16)                    # [c][(ky,kx),n]
+    w4p = w4.view(-1, 64, 7, 7).permute(0, 2, 3, 1).reshape(w4.shape[0], 3136).to(_bf16)   # columns in (h, w, c) order
+    return w1f, w2f, w2d, w3f, w3d, w4p
+
+
+def unpack_grads(g1f, g2f, g3f, g4p, scale, c1):
+    """fp32 gradients in GEMM layout -> the reference's parameter layouts."""
+    n1 = g1f.shape[0]
+    g1 = (g1f.view(n1, 2, 2, c1, 4, 4).permute(0, 3, 1, 4, 2, 5) * scale).reshape(n1, c1, 8, 8)
+    g2 = g2f.view(64, 2, 2, 2, 2, 32).permute(0, 5, 1, 3, 2, 4).reshape(64, 32, 4, 4)
+    g3 = g3f.view(64, 3, 3, 64).permute(0, 3, 1, 2).contiguous()
+    g4 = g4p.view(-1, 7, 7, 64).permute(0, 3, 1, 2).reshape(g4p.shape[0], 3136)
+    return g1, g2, g3, g4
+
+
+def forward_only(x0, packed, b1, b2, b3, b4):
+    """x0: [B, 64, 21, 21] channels_last bf16 (space-to-depth frames).  Returns (y4, saved activations)."""
+    w1f, w2f, _, w3f, _, w4p = packed
+    B = x0.shape[0]
+    dev = x0.device
+    x0m = x0.permute(0, 2, 3, 1).reshape(B * 441, 64)                         # free view of the NHWC memory
+    x1 = torch.empty((B * 100, 128), dtype=_bf16, device=dev)
+    conv_gemm(0, x0m, w1f, 32, 4, 2, 21, 1, x1, bias=b1, relu=True, out_map=1, G=21, V=20, block_n=32)
+    y2 = torch.empty((B * 100, 64), dtype=_bf16, device=dev)
+    conv_gemm(0, x1, w2f, 64, 4, 2, 10, 1, y2, bias=b2, relu=True, block_n=64)
+    y3 = torch.empty((B * 49, 64), dtype=_bf16, device=dev)
+    conv_gemm(0, y2, w3f, 64, 9, 3, 10, 1, y3, bias=b3, relu=True, out_map=2, G=10, V=7, block_n=64)
+    y4 = gemm_bf16(y3.view(B, 3136), w4p, bias=b4, relu=True, block_n=64)
+    return y4, (x0m, x1, y2, y3)
+
+
+class _NatureBody(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x0, w1, b1, w2, b2, w3, b3, w4, b4, scale):
+        packed = pack_weights(w1.detach(), w2.detach(), w3.detach(), w4.detach(), scale)
+        y4, (x0m, x1, y2, y3) = forward_only(x0, packed, b1.detach(), b2.detach(), b3.detach(), b4.detach())
+        ctx.save_for_backward(x0m, x1, y2, y3, y4, packed[2], packed[4], packed[5])
+        ctx.scale, ctx.c1 = scale, w1.shape[1]
+        return y4
+
+    @staticmethod
+    def backward(ctx, gy4):
+        x0m, x1, y2, y3, y4, w2d, w3d, w4p = ctx.saved_tensors
+        B = y4.shape[0]
+        dev = y4.device
+        f32 = torch.float32
+        # ---- fc4
+        g4, db4 = act_bwd_bias_grad(gy4, y4, True)                                        # [B, 512]
+        y3c = y3.view(B, 3136)
+        gw4p = gemm_bf16(g4, y3c, a_major="mn", b_major="mn", out_dtype=f32, block_n=128)  # [512, 3136]
+        gy3c = gemm_bf16(g4, w4p, a_major="k", b_major="mn", block_n=128)                  # [B, 3136] bf16
+        # ---- conv3: mask + bias grad, re-laid out from the compact 7x7 rows to the 10-grid
+        g3, db3 = act_bwd_bias_grad(gy3c.view(B * 49, 64), y3, True, row_map=1, G=10, V=7, out_rows=B * 100)
+        gw3f = torch.zeros((64, 576), dtype=f32, device=dev)
+        conv_gemm(1, y2, g3, 64, 9, 3, 10, 1, gw3f, splits=16, block_n=64)
+        gy2 = torch.empty((B * 100, 64), dtype=_bf16, device=dev)
+        conv_gemm(0, g3, w3d, 64, 9, 3, 10, -1, gy2, block_n=64)
+        # ---- conv2
+        g2, db2 = act_bwd_bias_grad(gy2, y2, True)                                        # rows 9 / cols 9 of gy2 are exact zeros
+        gw2f = torch.zeros((64, 512), dtype=f32, device=dev)
+        conv_gemm(1, x1, g2, 64, 4, 2, 10, 1, gw2f, splits=16, block_n=128)
+        gy1 = torch.empty((B * 100, 128), dtype=_bf16, device=dev)
+        conv_gemm(0, g2, w2d, 128, 4, 2, 10, -1, gy1, block_n=128)
+        # ---- conv1: mask + bias grad, re-laid out from space-to-depth(2) rows to the 21-grid of conv1's output positions
+        g1, db1 = act_bwd_bias_grad(gy1, x1, True, row_map=2, G=21, V=20, out_rows=B * 441)
+        gw1f = torch.zeros((32, x0m.shape[1] * 4), dtype=f32, device=dev)
+        conv_gemm(1, x0m, g1, 32, 4, 2, 21, 1, gw1f, splits=32, block_n=64)
+        g1w, g2w, g3w, g4w = unpack_grads(gw1f, gw2f, gw3f, gw4p, ctx.scale, ctx.c1)
+        return None, g1w, db1, g2w, db2, g3w, db3, g4w, db4, None
+
+
+def nature_body(x0, conv1, conv2, conv3, fc4, scale):
+    """``relu(fc4(flatten(relu(conv3(relu(conv2(relu(conv1(x * scale)))))))))`` for space-to-depth bf16 frames ``x0``."""
+    if not x0.is_contiguous(memory_format=torch.channels_last):
+        x0 = x0.contiguous(memory_format=torch.channels_last)
+    return _NatureBody.apply(x0, conv1.weight, conv1.bias, conv2.weight, conv2.bias, conv3.weight, conv3.bias, fc4.weight,
+                             fc4.bias, float(scale))

@@ -57,6 +57,10 @@ class NatureConvBody(nn.Module):
 
     def _forward_fused(self, x):
         scale = fused.current_frame_scale()
+        if (Config.DENSE_BACKEND == "tcgen05" and x.shape[1] == 16 * self.conv1.in_channels and x.shape[1] % 64 == 0
+                and tuple(x.shape[2:]) == (21, 21)):
+            from . import nature_tc                          # whole body on the tcgen05 GEMM (csrc/gemm.cu)
+            return nature_tc.nature_body(x, self.conv1, self.conv2, self.conv3, self.fc4, scale)
         w1 = self.conv1.weight
         if x.shape[1] == 16 * self.conv1.in_channels:                    # space-to-depth input
             w1, stride1 = fused.space_to_depth_weight(w1, 4), 1

@@ -28,6 +28,7 @@ _DEFAULTS = dict(
 class Config:
     DEVICE = torch.device("cpu")
     COMPUTE_DTYPE = torch.float32      # torch.bfloat16 = throughput mode of the dense contractions (not in the reference)
+    DENSE_BACKEND = "tcgen05"          # bf16 mode: "tcgen05" = csrc/gemm.cu for the whole NatureConvBody, "library" = cuDNN/cuBLAS
     NOISY_LAYER_STD = 0.1
     DEFAULT_REPLAY = "replay"
     PRIORITIZED_REPLAY = "prioritized_replay"

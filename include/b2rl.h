@@ -188,8 +188,12 @@ int b2rl_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_a
  * on first use.
  * ------------------------------------------------------------------------------------------- */
 int b2rl_bias_act_bf16(uint16_t* y, const float* bias, int64_t rows, int32_t C, int32_t relu, void* stream);
+/* row_map re-lays the gradient out for the next GEMM of the grid-convolution stack (csrc/gemm.cu): 0 identity;
+ * 1: compact V x V rows per image -> G x G grid rows; 2: space-to-depth(2) rows (rows/4 x 4 groups of C channels) ->
+ * G x G grid rows.  With a map, gx must be a pre-zeroed buffer of [batch*G*G][C] (padding rows stay zero). */
 int b2rl_act_bwd_bias_grad_bf16(const uint16_t* gy, const uint16_t* y, int64_t rows, int32_t C, int32_t relu,
-                                uint16_t* gx, float* dbias, float* partial, int32_t* counter, void* stream);
+                                uint16_t* gx, float* dbias, float* partial, int32_t* counter, int32_t row_map, int32_t G,
+                                int32_t V, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * tcgen05 GEMM for the dense contractions (network_bodies.py:27-33, network_heads.py:18-21):
@@ -203,6 +207,18 @@ int b2rl_act_bwd_bias_grad_bf16(const uint16_t* gy, const uint16_t* y, int64_t r
 int b2rl_gemm_bf16(const uint16_t* A, int32_t a_mn, int64_t lda, const uint16_t* B, int32_t b_mn, int64_t ldb, void* D,
                    int64_t ldd, int32_t M, int32_t N, int32_t K, const float* bias, int32_t relu, int32_t out_mode,
                    int32_t splits, int32_t block_n, void* stream);
+
+/* Convolution over a G x G position grid as a shifted-row GEMM, no im2col (csrc/gemm.cu header).
+ * mode 0 (forward / dgrad): D[r,:] = sum_taps X[r + shift(tap), :] * W[:, tap*C .. tap*C + C]^T, X bf16 [rows][C] (C % 64
+ *   == 0), W bf16 [n_out][taps*C]; shift(tap) = shift_sign * ((tap / taps_x) * grid_w + tap % taps_x); rows off the grid
+ *   read zeros.  out_map 1 writes the valid V x V positions of the G grid in space-to-depth(2) layout
+ *   ([batch*(V/2)^2][4*n_out], ldd = 4*n_out), out_map 2 compacts them to [batch*V*V][n_out].
+ * mode 1 (wgrad): D[n, tap*C + c] += sum_r Gr[r, n] * X[r + shift(tap), c], Gr bf16 [rows][n_out] passed as W_or_G,
+ *   D fp32 [n_out][taps*C] (out_mode 2, atomic accumulation over `splits` K slices). */
+int b2rl_conv_gemm_bf16(int32_t mode, const uint16_t* X, int64_t rows, int32_t C, const uint16_t* W_or_G, int32_t n_out,
+                        int32_t taps, int32_t taps_x, int32_t grid_w, int32_t shift_sign, void* D, int64_t ldd,
+                        const float* bias, int32_t relu, int32_t out_mode, int32_t out_map, int32_t G, int32_t V,
+                        int32_t splits, int32_t block_n, void* stream);
 
 #ifdef __cplusplus
 }

