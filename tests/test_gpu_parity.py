@@ -605,7 +605,7 @@ def test_conv_grid_gemm_vs_torch(rl):
     w1r = tc.unpack_grads(deq(w1f), deq(w2f), deq(w3f), deq(w4p), 1.0, 4)       # bf16-rounded weights back in NCHW layouts
     r1 = torch.relu(F.conv2d(frames.float(), w1r[0], b1, stride=4))            # (scale already folded into w1f)
     x1_ref = r1.view(B, 32, 10, 2, 10, 2).permute(0, 2, 4, 3, 5, 1).reshape(B * 100, 128)
-    torch.testing.assert_close(x1.float(), x1_ref, rtol=1e-2, atol=2e-2)
+    torch.testing.assert_close(x1.float(), x1_ref, rtol=1e-2, atol=5e-2)
     x1n = x1.float().view(B, 10, 10, 2, 2, 32).permute(0, 5, 1, 3, 2, 4).reshape(B, 32, 20, 20)       # NCHW view of OUR x1
     r2 = torch.relu(F.conv2d(x1n, w1r[1], b2, stride=2))                      # [B,64,9,9]
     y2v = y2.float().view(B, 10, 10, 64)[:, :9, :9].permute(0, 3, 1, 2)
