@@ -41,6 +41,22 @@ __global__ void __launch_bounds__(256) bias_act_kernel(__nv_bfloat16* __restrict
   }
 }
 
+// split-K GEMM results (fp32) -> bf16 activations with bias + ReLU
+__global__ void __launch_bounds__(256) bias_act_f32_kernel(const float* __restrict__ x, const float* __restrict__ bias,
+                                                           __nv_bfloat16* __restrict__ y, int64_t n8, int C8, int relu) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n8; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(e % C8) * 8;
+    const float4 a = reinterpret_cast<const float4*>(x)[2 * e], b = reinterpret_cast<const float4*>(x)[2 * e + 1];
+    float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      f[k] += __ldg(bias + c0 + k);
+      if (relu) f[k] = fmaxf(f[k], 0.0f);
+    }
+    reinterpret_cast<int4*>(y)[e] = pack8(f);
+  }
+}
+
 // destination row of source row r for the layout changes between the layers of the grid-GEMM convolution stack
 //   map 0: identity
 //   map 1: compact V x V positions per image -> G x G grid rows            (fc4's input gradient -> conv3's output grid)
@@ -157,10 +173,24 @@ extern "C" int b2rl_act_bwd_bias_grad_bf16(const uint16_t* gy, const uint16_t* y
   const int rpb = 256 / C8 > 0 ? 256 / C8 : 1;
   B2RL_REQUIRE(C8 <= 256, "C too large");
   int64_t want = (rows + rpb - 1) / rpb;
+  int64_t by_work = rows * C / 16384 + 1;              // ~16K elements per block: few partials for small layers
+  if (want > by_work) want = by_work;
   int blocks = (int)(want < 148 ? want : 148);
   size_t smem = (size_t)rpb * C * sizeof(float);
   act_bwd_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(gy), reinterpret_cast<const __nv_bfloat16*>(y), rows, C8, relu,
       reinterpret_cast<__nv_bfloat16*>(gx), dbias, partial, counter, row_map, G, V);
   return check_launch("b2rl_act_bwd_bias_grad_bf16");
+}
+
+extern "C" int b2rl_bias_act_f32_to_bf16(const float* x, const float* bias, uint16_t* y, int64_t rows, int32_t C,
+                                         int32_t relu, void* stream) {
+  B2RL_REQUIRE(x && bias && y, "null pointer");
+  B2RL_REQUIRE(rows > 0 && C > 0 && C % 8 == 0, "C must be a positive multiple of 8");
+  B2RL_REQUIRE(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0, "16-byte alignment");
+  const int64_t n8 = rows * C / 8;
+  int blocks = (int)((n8 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  bias_act_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, bias, reinterpret_cast<__nv_bfloat16*>(y), n8, C / 8, relu);
+  return check_launch("b2rl_bias_act_f32_to_bf16");
 }

@@ -76,6 +76,7 @@ class GraphedDQNLearner:
             t = rp.sample_normalized(out_dtype=self.dtype, scale=self.scale, layout="nchw")
             fs = 1.0
         per = dict(is_prob=t.sampling_prob, eps=self.eps, alpha=self.alpha, beta_dev=self.d_beta) if self.per else {}
+        self._repack(self.net, fs)                       # online weights changed in the previous optimizer step
         with frame_scale(fs):
             with torch.no_grad():
                 nxt_t = self.tgt(t.next_state)
@@ -101,6 +102,18 @@ class GraphedDQNLearner:
         head.backward(grad)
         self.loss.copy_(r["loss"])
 
+    def _repack(self, net, fs):
+        """tcgen05 backend: the learner owns the packed bf16 operands of both networks -- the online body is re-packed
+        once per update (one launch), the target body only when it is synchronised."""
+        body = getattr(net, "body", None)
+        if body is not None and hasattr(body, "repack") and self.dtype == torch.bfloat16:
+            body.auto_repack = False
+            body.repack(fs)
+
+    def sync_target(self):
+        self.tgt.load_state_dict(self.net.state_dict())        # DQN_agent.py:136-138
+        self._repack(self.tgt, self.scale if self.dtype == torch.bfloat16 else 1.0)
+
     def _opt(self):
         self.opt.step(max_norm=self.clip, grad_scale=1.0 / self.world)
 
@@ -108,6 +121,7 @@ class GraphedDQNLearner:
     def capture(self, warmup=3, with_h2d=False):
         """Warm up eagerly on a side stream (cuDNN autotune, lazy allocations), then capture."""
         self.with_h2d = with_h2d
+        self._repack(self.tgt, self.scale if self.dtype == torch.bfloat16 else 1.0)
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -148,7 +162,7 @@ class GraphedDQNLearner:
             self.g_opt.replay()
         self.updates += 1
         if self.sync_every and self.updates % self.sync_every == 0:
-            self.tgt.load_state_dict(self.net.state_dict())        # DQN_agent.py:136-138
+            self.sync_target()
         return self.loss
 
     def update_from_host(self, frames, action, reward, mask, beta=None):

@@ -11,8 +11,9 @@ ReLU after each.  Every layer is a GEMM over activations stored as [batch * G * 
 
 Backward: ReLU mask + bias gradient + re-layout in one pass (``csrc/dense.cu``), then dgrad = the same shifted-row GEMM
 with negative shifts and wgrad = MN-major GEMMs with split-K.  Weights are re-laid out from the reference's parameter
-layout ([Cout, Cin, kh, kw], (c, h, w)-ordered fc4 columns) to the tap-major bf16 layouts once per forward, and the
-weight gradients are mapped back, so ``state_dict``s and optimizers see the reference layout only.
+layout ([Cout, Cin, kh, kw], (c, h, w)-ordered fc4 columns) to the tap-major bf16 layouts by ONE kernel
+(``csrc/pack.cu``) and the weight gradients are mapped back and accumulated into ``.grad`` by ONE kernel, so
+``state_dict``s and optimizers see the reference layout only.
 """
 import torch
 
@@ -21,6 +22,7 @@ from ..ops import gemm_bf16
 from .fused import act_bwd_bias_grad
 
 _bf16 = torch.bfloat16
+_f32 = torch.float32
 
 
 def conv_gemm(mode, X, W_or_G, n_out, taps, taps_x, grid_w, sign, out, bias=None, relu=False, out_map=0, G=0, V=0, splits=1,
@@ -34,21 +36,37 @@ def conv_gemm(mode, X, W_or_G, n_out, taps, taps_x, grid_w, sign, out, bias=None
 
 
 # ------------------------------------------------------------------------------------------------- weight layouts
+class PackedWeights:
+    """Persistent bf16 GEMM operands of one NatureConvBody (fixed addresses: CUDA-graph friendly)."""
+
+    def __init__(self, c1, n4, device):
+        e = lambda *s: torch.empty(s, dtype=_bf16, device=device)
+        self.c1, self.n4 = c1, n4
+        self.w1f, self.w2f, self.w2d = e(32, 64 * c1), e(64, 512), e(128, 256)
+        self.w3f, self.w3d, self.w4p = e(64, 576), e(64, 576), e(n4, 3136)
+        self.scale = None
+
+    def pack(self, w1, w2, w3, w4, scale):
+        _lib.call("b2rl_nature_pack_weights", _lib.ptr(w1), _lib.ptr(w2), _lib.ptr(w3), _lib.ptr(w4), self.c1, self.n4,
+                  float(scale), _lib.ptr(self.w1f), _lib.ptr(self.w2f), _lib.ptr(self.w2d), _lib.ptr(self.w3f),
+                  _lib.ptr(self.w3d), _lib.ptr(self.w4p), _lib.stream())
+        self.scale = float(scale)
+        return self
+
+    def tensors(self):
+        return self.w1f, self.w2f, self.w2d, self.w3f, self.w3d, self.w4p
+
+
 def pack_weights(w1, w2, w3, w4, scale):
     """Reference layouts -> tap-major bf16 GEMM operands (forward ``f`` and dgrad ``d`` orientations)."""
-    n1, c1 = w1.shape[0], w1.shape[1]
-    w1f = (w1.view(n1, c1, 2, 4, 2, 4).permute(0, 2, 4, 1, 3, 5) * scale).reshape(n1, 4 * c1 * 16).to(_bf16)
-    v2 = w2.view(64, 32, 2, 2, 2, 2)                                           # (n, c, ty, py, tx, px)
-    w2f = v2.permute(0, 2, 4, 3, 5, 1).reshape(64, 512).to(_bf16)              # [n][(ty,tx),(py,px,c)]
-    w2d = v2.permute(3, 5, 1, 2, 4, 0).reshape(128, 256).to(_bf16)             # [(py,px,c)][(ty,tx),n]
-    w3f = w3.permute(0, 2, 3, 1).reshape(64, 576).to(_bf16)                    # [n][(ky,kx),c]
-    w3d = w3.permute(1, 2, 3, 0).reshape(64, 576).to(_bf16)                    # [c][(ky,kx),n]
-    w4p = w4.view(-1, 64, 7, 7).permute(0, 2, 3, 1).reshape(w4.shape[0], 3136).to(_bf16)   # columns in (h, w, c) order
-    return w1f, w2f, w2d, w3f, w3d, w4p
+    ok = all(t.is_contiguous() and t.dtype == _f32 for t in (w1, w2, w3, w4))
+    assert ok and tuple(w2.shape) == (64, 32, 4, 4) and tuple(w3.shape) == (64, 64, 3, 3) and w4.shape[1] == 3136
+    return PackedWeights(w1.shape[1], w4.shape[0], w1.device).pack(w1, w2, w3, w4, scale).tensors()
 
 
 def unpack_grads(g1f, g2f, g3f, g4p, scale, c1):
-    """fp32 gradients in GEMM layout -> the reference's parameter layouts."""
+    """fp32 gradients in GEMM layout -> the reference's parameter layouts (torch expressions; tests and the generic
+    autograd path -- the training step accumulates with ``b2rl_nature_unpack_grads`` instead)."""
     n1 = g1f.shape[0]
     g1 = (g1f.view(n1, 2, 2, c1, 4, 4).permute(0, 3, 1, 4, 2, 5) * scale).reshape(n1, c1, 8, 8)
     g2 = g2f.view(64, 2, 2, 2, 2, 32).permute(0, 5, 1, 3, 2, 4).reshape(64, 32, 4, 4)
@@ -62,24 +80,32 @@ def forward_only(x0, packed, b1, b2, b3, b4):
     w1f, w2f, _, w3f, _, w4p = packed
     B = x0.shape[0]
     dev = x0.device
-    x0m = x0.permute(0, 2, 3, 1).reshape(B * 441, 64)                         # free view of the NHWC memory
+    x0m = x0.permute(0, 2, 3, 1).reshape(B * 441, x0.shape[1])                # free view of the NHWC memory
     x1 = torch.empty((B * 100, 128), dtype=_bf16, device=dev)
     conv_gemm(0, x0m, w1f, 32, 4, 2, 21, 1, x1, bias=b1, relu=True, out_map=1, G=21, V=20, block_n=32)
     y2 = torch.empty((B * 100, 64), dtype=_bf16, device=dev)
     conv_gemm(0, x1, w2f, 64, 4, 2, 10, 1, y2, bias=b2, relu=True, block_n=64)
     y3 = torch.empty((B * 49, 64), dtype=_bf16, device=dev)
     conv_gemm(0, y2, w3f, 64, 9, 3, 10, 1, y3, bias=b3, relu=True, out_map=2, G=10, V=7, block_n=64)
-    y4 = gemm_bf16(y3.view(B, 3136), w4p, bias=b4, relu=True, block_n=64)
+    n4 = w4p.shape[0]
+    if B <= 1024:
+        # few output tiles, long K (3136): split K over CTAs, finish (bias + ReLU + bf16) in a streaming pass
+        acc = gemm_bf16(y3.view(B, 3136), w4p, out_dtype=_f32, splits=4, block_n=64)
+        y4 = torch.empty((B, n4), dtype=_bf16, device=dev)
+        _lib.call("b2rl_bias_act_f32_to_bf16", _lib.ptr(acc), _lib.ptr(b4), _lib.ptr(y4), B, n4, 1, _lib.stream())
+    else:
+        y4 = gemm_bf16(y3.view(B, 3136), w4p, bias=b4, relu=True, block_n=64)
     return y4, (x0m, x1, y2, y3)
 
 
 class _NatureBody(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x0, w1, b1, w2, b2, w3, b3, w4, b4, scale):
-        packed = pack_weights(w1.detach(), w2.detach(), w3.detach(), w4.detach(), scale)
-        y4, (x0m, x1, y2, y3) = forward_only(x0, packed, b1.detach(), b2.detach(), b3.detach(), b4.detach())
-        ctx.save_for_backward(x0m, x1, y2, y3, y4, packed[2], packed[4], packed[5])
+    def forward(ctx, x0, w1, b1, w2, b2, w3, b3, w4, b4, scale, packed):
+        pk = packed.tensors()
+        y4, (x0m, x1, y2, y3) = forward_only(x0, pk, b1.detach(), b2.detach(), b3.detach(), b4.detach())
+        ctx.save_for_backward(x0m, x1, y2, y3, y4, pk[2], pk[4], pk[5])
         ctx.scale, ctx.c1 = scale, w1.shape[1]
+        ctx.params = (w1, b1, w2, b2, w3, b3, w4, b4)
         return y4
 
     @staticmethod
@@ -87,35 +113,61 @@ class _NatureBody(torch.autograd.Function):
         x0m, x1, y2, y3, y4, w2d, w3d, w4p = ctx.saved_tensors
         B = y4.shape[0]
         dev = y4.device
-        f32 = torch.float32
         # ---- fc4
         g4, db4 = act_bwd_bias_grad(gy4, y4, True)                                        # [B, 512]
         y3c = y3.view(B, 3136)
-        gw4p = gemm_bf16(g4, y3c, a_major="mn", b_major="mn", out_dtype=f32, block_n=128)  # [512, 3136]
+        gw4p = gemm_bf16(g4, y3c, a_major="mn", b_major="mn", out_dtype=_f32, block_n=128)  # [512, 3136]
         gy3c = gemm_bf16(g4, w4p, a_major="k", b_major="mn", block_n=128)                  # [B, 3136] bf16
         # ---- conv3: mask + bias grad, re-laid out from the compact 7x7 rows to the 10-grid
         g3, db3 = act_bwd_bias_grad(gy3c.view(B * 49, 64), y3, True, row_map=1, G=10, V=7, out_rows=B * 100)
-        gw3f = torch.zeros((64, 576), dtype=f32, device=dev)
+        gw3f = torch.zeros((64, 576), dtype=_f32, device=dev)
         conv_gemm(1, y2, g3, 64, 9, 3, 10, 1, gw3f, splits=16, block_n=64)
         gy2 = torch.empty((B * 100, 64), dtype=_bf16, device=dev)
         conv_gemm(0, g3, w3d, 64, 9, 3, 10, -1, gy2, block_n=64)
         # ---- conv2
         g2, db2 = act_bwd_bias_grad(gy2, y2, True)                                        # rows 9 / cols 9 of gy2 are exact zeros
-        gw2f = torch.zeros((64, 512), dtype=f32, device=dev)
+        gw2f = torch.zeros((64, 512), dtype=_f32, device=dev)
         conv_gemm(1, x1, g2, 64, 4, 2, 10, 1, gw2f, splits=16, block_n=128)
         gy1 = torch.empty((B * 100, 128), dtype=_bf16, device=dev)
         conv_gemm(0, g2, w2d, 128, 4, 2, 10, -1, gy1, block_n=128)
         # ---- conv1: mask + bias grad, re-laid out from space-to-depth(2) rows to the 21-grid of conv1's output positions
         g1, db1 = act_bwd_bias_grad(gy1, x1, True, row_map=2, G=21, V=20, out_rows=B * 441)
-        gw1f = torch.zeros((32, x0m.shape[1] * 4), dtype=f32, device=dev)
+        gw1f = torch.zeros((32, x0m.shape[1] * 4), dtype=_f32, device=dev)
         conv_gemm(1, x0m, g1, 32, 4, 2, 21, 1, gw1f, splits=32, block_n=64)
+        params = ctx.params
+        if all(p.grad is not None and p.grad.dtype == _f32 and p.grad.is_contiguous() for p in params):
+            # accumulate straight into the .grad arena (reference layouts), one launch
+            w1, b1, w2, b2, w3, b3, w4, b4 = params
+            _lib.call("b2rl_nature_unpack_grads", _lib.ptr(gw1f), _lib.ptr(gw2f), _lib.ptr(gw3f), _lib.ptr(gw4p), _lib.ptr(db1),
+                      _lib.ptr(db2), _lib.ptr(db3), _lib.ptr(db4), ctx.c1, w4.shape[0], float(ctx.scale), _lib.ptr(w1.grad),
+                      _lib.ptr(w2.grad), _lib.ptr(w3.grad), _lib.ptr(w4.grad), _lib.ptr(b1.grad), _lib.ptr(b2.grad),
+                      _lib.ptr(b3.grad), _lib.ptr(b4.grad), _lib.stream())
+            return (None,) * 11
         g1w, g2w, g3w, g4w = unpack_grads(gw1f, gw2f, gw3f, gw4p, ctx.scale, ctx.c1)
-        return None, g1w, db1, g2w, db2, g3w, db3, g4w, db4, None
+        return None, g1w, db1, g2w, db2, g3w, db3, g4w, db4, None, None
 
 
-def nature_body(x0, conv1, conv2, conv3, fc4, scale):
-    """``relu(fc4(flatten(relu(conv3(relu(conv2(relu(conv1(x * scale)))))))))`` for space-to-depth bf16 frames ``x0``."""
+def nature_body(body, x0, scale):
+    """``relu(fc4(flatten(relu(conv3(relu(conv2(relu(conv1(x * scale)))))))))`` for space-to-depth bf16 frames ``x0``.
+    ``body`` is the NatureConvBody; its packed bf16 operands are refreshed here unless the owner manages them
+    (``body.auto_repack = False`` + ``body.repack(scale)`` after every parameter change)."""
     if not x0.is_contiguous(memory_format=torch.channels_last):
         x0 = x0.contiguous(memory_format=torch.channels_last)
-    return _NatureBody.apply(x0, conv1.weight, conv1.bias, conv2.weight, conv2.bias, conv3.weight, conv3.bias, fc4.weight,
-                             fc4.bias, float(scale))
+    pk = getattr(body, "_packed", None)
+    if pk is None:
+        pk = body._packed = PackedWeights(body.conv1.in_channels, body.fc4.out_features, x0.device)
+    if getattr(body, "auto_repack", True) or pk.scale != float(scale):
+        repack(body, scale)
+    c1, c2, c3, f4 = body.conv1, body.conv2, body.conv3, body.fc4
+    return _NatureBody.apply(x0, c1.weight, c1.bias, c2.weight, c2.bias, c3.weight, c3.bias, f4.weight, f4.bias,
+                             float(scale), pk)
+
+
+def repack(body, scale):
+    pk = getattr(body, "_packed", None)
+    if pk is None:
+        pk = body._packed = PackedWeights(body.conv1.in_channels, body.fc4.out_features, body.conv1.weight.device)
+    w = [m.weight.detach() for m in (body.conv1, body.conv2, body.conv3, body.fc4)]
+    w = [t if t.is_contiguous() else t.contiguous() for t in w]
+    pk.pack(w[0], w[1], w[2], w[3], scale)
+    return pk

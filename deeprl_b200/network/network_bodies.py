@@ -38,6 +38,14 @@ class NatureConvBody(nn.Module):
         if self.noisy_linear:
             self.fc4.reset_noise()
 
+    auto_repack = True        # tcgen05 backend: refresh the packed bf16 operands at every forward (safe default)
+
+    def repack(self, scale=None):
+        """Refresh the packed bf16 GEMM operands from the fp32 parameters (owners that set ``auto_repack = False``
+        call this after every parameter change: optimizer step, load_state_dict)."""
+        from . import nature_tc
+        return nature_tc.repack(self, fused.current_frame_scale() if scale is None else scale)
+
     def forward(self, x):
         """``x``: [B, C, 84, 84] images, or the space-to-depth(4) tensor [B, 16*C, 21, 21] the fused replay gather
         emits (conv1 then runs as a 2x2 / stride-1 convolution over 16*C channels: same arithmetic, tensor-core
@@ -60,7 +68,7 @@ class NatureConvBody(nn.Module):
         if (Config.DENSE_BACKEND == "tcgen05" and x.shape[1] == 16 * self.conv1.in_channels and x.shape[1] % 64 == 0
                 and tuple(x.shape[2:]) == (21, 21)):
             from . import nature_tc                          # whole body on the tcgen05 GEMM (csrc/gemm.cu)
-            return nature_tc.nature_body(x, self.conv1, self.conv2, self.conv3, self.fc4, scale)
+            return nature_tc.nature_body(self, x, scale)
         w1 = self.conv1.weight
         if x.shape[1] == 16 * self.conv1.in_channels:                    # space-to-depth input
             w1, stride1 = fused.space_to_depth_weight(w1, 4), 1

@@ -188,6 +188,9 @@ int b2rl_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_a
  * on first use.
  * ------------------------------------------------------------------------------------------- */
 int b2rl_bias_act_bf16(uint16_t* y, const float* bias, int64_t rows, int32_t C, int32_t relu, void* stream);
+/* same epilogue for a split-K GEMM result: y(bf16) = act(x(fp32) + bias) */
+int b2rl_bias_act_f32_to_bf16(const float* x, const float* bias, uint16_t* y, int64_t rows, int32_t C, int32_t relu,
+                              void* stream);
 /* row_map re-lays the gradient out for the next GEMM of the grid-convolution stack (csrc/gemm.cu): 0 identity;
  * 1: compact V x V rows per image -> G x G grid rows; 2: space-to-depth(2) rows (rows/4 x 4 groups of C channels) ->
  * G x G grid rows.  With a map, gx must be a pre-zeroed buffer of [batch*G*G][C] (padding rows stay zero). */
@@ -219,6 +222,19 @@ int b2rl_conv_gemm_bf16(int32_t mode, const uint16_t* X, int64_t rows, int32_t C
                         int32_t taps, int32_t taps_x, int32_t grid_w, int32_t shift_sign, void* D, int64_t ldd,
                         const float* bias, int32_t relu, int32_t out_mode, int32_t out_map, int32_t G, int32_t V,
                         int32_t splits, int32_t block_n, void* stream);
+
+/* NatureConvBody weights (network_bodies.py:13-20) between the reference's parameter layouts and the tap-major bf16
+ * operands of the grid-GEMM stack: w1 [32,c1,8,8] -> w1f [32][4 taps][16*c1] (times `scale` = ImageNormalizer's 1/255);
+ * w2 [64,32,4,4] -> w2f [64][4][128], w2d [128][4][64]; w3 [64,64,3,3] -> w3f [64][9][64], w3d [64][9][64];
+ * w4 [n4, 64*7*7 in (c,h,w) order] -> w4p [n4][(h,w,c)].  unpack maps fp32 gradients in the GEMM layouts back and ADDS
+ * them (and the four bias gradients) into the reference-layout .grad buffers. */
+int b2rl_nature_pack_weights(const float* w1, const float* w2, const float* w3, const float* w4, int32_t c1, int32_t n4,
+                             float scale, uint16_t* w1f, uint16_t* w2f, uint16_t* w2d, uint16_t* w3f, uint16_t* w3d,
+                             uint16_t* w4p, void* stream);
+int b2rl_nature_unpack_grads(const float* g1f, const float* g2f, const float* g3f, const float* g4p, const float* db1,
+                             const float* db2, const float* db3, const float* db4, int32_t c1, int32_t n4, float scale,
+                             float* gw1, float* gw2, float* gw3, float* gw4, float* gb1, float* gb2, float* gb3,
+                             float* gb4, void* stream);
 
 #ifdef __cplusplus
 }

@@ -669,6 +669,17 @@ def test_conv_grid_gemm_vs_torch(rl):
                 q = net(xs16)["q"]
             q.backward(gq)
             outs[backend] = (q.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters()})
+        # the training step's path: gradients accumulated straight into the .grad arena by b2rl_nature_unpack_grads
+        rl.Config.DENSE_BACKEND = "tcgen05"
+        opt = rl.ops.FlatOptimizer.from_torch(torch.optim.RMSprop(net.parameters(), lr=1e-4))
+        opt.zero_grad()
+        net.body.auto_repack = False
+        net.body.repack(1.0 / 255)
+        with rl.frame_scale(1.0 / 255):
+            net(xs16)["q"].backward(gq)
+        net.body.auto_repack = True
+        for k, p in net.named_parameters():
+            torch.testing.assert_close(p.grad, outs["tcgen05"][1][k], rtol=1e-3, atol=1e-5 * float(outs["tcgen05"][1][k].abs().max() + 1))
         qa, qb = outs["tcgen05"][0], outs["library"][0]
         assert (qa - qb).abs().max() < 0.02 * qb.abs().max()
         for k in outs["library"][1]:
