@@ -120,6 +120,14 @@ def call(name, *args):
         raise B2RLError("%s failed (%d): %s" % (name, rc, L.b2rl_last_error().decode()))
 
 
+def set_conv_slab(on):
+    """Forward / dgrad convolution GEMMs: slab kernel (default) or per-tap operand loads (csrc/gemm.cu)."""
+    L = lib()
+    L.b2rl_set_conv_slab.restype = None
+    L.b2rl_set_conv_slab.argtypes = [ctypes.c_int32]
+    L.b2rl_set_conv_slab(int(bool(on)))
+
+
 def launch_count():
     return int(lib().b2rl_launch_count())
 

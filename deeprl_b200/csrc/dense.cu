@@ -173,9 +173,9 @@ extern "C" int b2rl_act_bwd_bias_grad_bf16(const uint16_t* gy, const uint16_t* y
   const int rpb = 256 / C8 > 0 ? 256 / C8 : 1;
   B2RL_REQUIRE(C8 <= 256, "C too large");
   int64_t want = (rows + rpb - 1) / rpb;
-  int64_t by_work = rows * C / 16384 + 1;              // ~16K elements per block: few partials for small layers
+  int64_t by_work = rows * C / 4096 + 1;               // >= 4K elements per block: few partials for small layers
   if (want > by_work) want = by_work;
-  int blocks = (int)(want < 148 ? want : 148);
+  int blocks = (int)(want < 592 ? want : 592);         // 4 CTAs per SM keep enough 16-byte loads in flight
   size_t smem = (size_t)rpb * C * sizeof(float);
   act_bwd_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(gy), reinterpret_cast<const __nv_bfloat16*>(y), rows, C8, relu,

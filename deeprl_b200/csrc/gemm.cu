@@ -89,8 +89,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128B swizzle, version 1 (Blackwell)
 //   K-major : 8-row groups 1024 B apart (SBO), LBO = 1 (x16 B)
 //   MN-major: 64-element MN groups `lbo` bytes apart, 8-K-row groups 1024 B apart (SBO)
+// base_offset (bits 49-51) = (start address >> 7) & 7 when the start is not aligned to the 1024-byte swizzle pattern
+// (a window that begins s rows into a swizzled slab); 0 for pattern-aligned tiles.
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
+  d |= (uint64_t)(((smem_addr >> 7) & 7)) << 49;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
@@ -118,6 +121,93 @@ struct GemmParams {
 
 __device__ __forceinline__ int tap_shift(const GemmParams& p, int tap) {
   return p.shift_sign * ((tap / p.taps_x) * p.grid_w + tap % p.taps_x);
+}
+
+// Epilogue of one 128 x BN tile for one warp (TMEM lane quarter q): wait for the accumulator stage, read it 32 columns
+// at a time, hand the stage back to the MMA warp, apply bias / ReLU and store through the output row map.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n0, int q, int lane, uint32_t tmem_base,
+                                              uint32_t as, uint32_t parity, bool has_acc, uint64_t* tmem_full,
+                                              uint64_t* tmem_empty) {
+  const int row = m0 + q * 32 + lane;
+  bool valid = row < p.M;
+  int64_t drow = row;
+  int dcol0 = 0;
+  if (p.out_map != 0 && valid) {
+    const int gg = p.G * p.G;
+    const int b = row / gg, rem = row - b * gg;
+    const int oy = rem / p.G, ox = rem - oy * p.G;
+    valid = oy < p.V && ox < p.V;
+    if (p.out_map == 1) {
+      const int h = p.V >> 1;
+      drow = (int64_t)b * h * h + (oy >> 1) * h + (ox >> 1);
+      dcol0 = (((oy & 1) << 1) | (ox & 1)) * p.N;
+    } else {
+      drow = (int64_t)b * p.V * p.V + oy * p.V + ox;
+    }
+  }
+  if (has_acc) {
+    mb_wait(&tmem_full[as], parity);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+#pragma unroll
+  for (int c = 0; c < BN; c += 32) {
+    uint32_t r[32];
+    if (has_acc) {
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c, r);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = 0;
+    }
+    if (c + 32 >= BN && has_acc) {
+      // all TMEM reads of this warp for this tile are done: hand the accumulator stage back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (lane == 0) mb_arrive(&tmem_empty[as]);
+    }
+    if (valid && n0 + c < p.N) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int n = n0 + c + j;
+        float v = __uint_as_float(r[j]);
+        if (p.bias && blockIdx.z == 0 && n < p.N) v += __ldg(p.bias + n);
+        if (p.relu) v = fmaxf(v, 0.0f);
+        r[j] = __float_as_uint(v);
+      }
+      const int64_t off = drow * p.ldd + dcol0 + n0 + c;
+      if (p.out_mode == 0) {
+        __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + off;
+        if (n0 + c + 32 <= p.N && (off % 8 == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            int4 v;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              h[t] = __floats2bfloat162_rn(__uint_as_float(r[j + 2 * t]), __uint_as_float(r[j + 2 * t + 1]));
+            *reinterpret_cast<int4*>(d + j) = v;
+          }
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c + j < p.N) d[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
+        }
+      } else if (p.out_mode == 1) {
+        float* d = reinterpret_cast<float*>(p.D) + off;
+        if (n0 + c + 32 <= p.N && (off % 4 == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(d + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c + j < p.N) d[j] = __uint_as_float(r[j]);
+        }
+      } else {
+        float* d = reinterpret_cast<float*>(p.D) + off;
+        for (int j = 0; j < 32; ++j)
+          if (n0 + c + j < p.N) atomicAdd(d + j, __uint_as_float(r[j]));
+      }
+    }
+  }
 }
 
 template <int BN, int STAGES>
@@ -233,88 +323,121 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tcount) {
       const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
       const int m0 = mt * GEMM_BM, n0 = nt * BN;
-      const uint32_t as = tcount & 1;
-      const int row = m0 + q * 32 + lane;
-      // destination row / validity
-      bool valid = row < p.M;
-      int64_t drow = row;
-      int dcol0 = 0;
-      if (p.out_map != 0 && valid) {
-        const int gg = p.G * p.G;
-        const int b = row / gg, rem = row - b * gg;
-        const int oy = rem / p.G, ox = rem - oy * p.G;
-        valid = oy < p.V && ox < p.V;
-        if (p.out_map == 1) {
-          const int h = p.V >> 1;
-          drow = (int64_t)b * h * h + (oy >> 1) * h + (ox >> 1);
-          dcol0 = (((oy & 1) << 1) | (ox & 1)) * p.N;
-        } else {
-          drow = (int64_t)b * p.V * p.V + oy * p.V + ox;
-        }
-      }
-      if (n_kt > 0) {
-        mb_wait(&tmem_full[as], (tcount >> 1) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      }
-#pragma unroll
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        if (n_kt > 0) {
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c, r);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0;
-        }
-        if (c + 32 >= BN && n_kt > 0) {
-          // all TMEM reads of this warp for this tile are done: hand the accumulator stage back to the MMA warp
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          if (lane == 0) mb_arrive(&tmem_empty[as]);
-        }
-        if (valid && n0 + c < p.N) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c + j;
-            float v = __uint_as_float(r[j]);
-            if (p.bias && blockIdx.z == 0 && n < p.N) v += __ldg(p.bias + n);
-            if (p.relu) v = fmaxf(v, 0.0f);
-            r[j] = __float_as_uint(v);
-          }
-          const int64_t off = drow * p.ldd + dcol0 + n0 + c;
-          if (p.out_mode == 0) {
-            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + off;
-            if (n0 + c + 32 <= p.N && (off % 8 == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                int4 v;
-                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                  h[t] = __floats2bfloat162_rn(__uint_as_float(r[j + 2 * t]), __uint_as_float(r[j + 2 * t + 1]));
-                *reinterpret_cast<int4*>(d + j) = v;
-              }
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (n0 + c + j < p.N) d[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
-            }
-          } else if (p.out_mode == 1) {
-            float* d = reinterpret_cast<float*>(p.D) + off;
-            if (n0 + c + 32 <= p.N && (off % 4 == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(d + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (n0 + c + j < p.N) d[j] = __uint_as_float(r[j]);
-            }
-          } else {
-            float* d = reinterpret_cast<float*>(p.D) + off;
-            for (int j = 0; j < 32; ++j)
-              if (n0 + c + j < p.N) atomicAdd(d + j, __uint_as_float(r[j]));
-          }
-        }
-      }
+      epilogue_tile<BN>(p, m0, n0, q, lane, tmem_base, tcount & 1, (tcount >> 1) & 1, n_kt > 0, tmem_full, tmem_empty);
     }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Slab variant of the forward / dgrad convolution GEMM: the taps of a tile read overlapping row windows of the same
+// activation matrix, so the CTA loads ONE slab of 128 + max_shift rows per tile and issues every tap's MMAs on windows
+// that start `shift` rows (x 128 bytes) into that swizzled slab (descriptor base_offset = address bits 7-9 of the
+// window start); the weights (all taps) are loaded once per CTA and stay resident.  Activation traffic drops by the
+// number of taps (4x conv1/conv2, 9x conv3) and the weight traffic per tile to zero.
+// ---------------------------------------------------------------------------------------------------------------
+struct SlabParams {
+  GemmParams g;            // M, N, ldd, relu, out_mode, bias, D, taps_x, grid_w, shift_sign, out_map, G, V
+  int taps, col_blocks;    // taps, channels / 64
+  int slab_rows;           // multiple of 8, >= 128 + max_shift
+  int min_shift;           // row offset of the slab start relative to m0 (0 for forward, -max_shift for dgrad)
+  int stages;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                            const __grid_constant__ CUtensorMap tmB,
+                                                                            const SlabParams sp) {
+  const GemmParams& p = sp.g;
+  constexpr uint32_t W_TILE = BN * 128;                               // one 64-wide k-tile of the weights
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  constexpr int MAX_STAGES = 6;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int k_tiles = sp.taps * sp.col_blocks;
+  const uint32_t slab_block = (uint32_t)sp.slab_rows * 128;          // one 64-channel column block of a slab
+  const uint32_t slab_bytes = slab_block * sp.col_blocks;
+  uint8_t* sW = smem;
+  uint8_t* sS = smem + (size_t)k_tiles * W_TILE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sS + (size_t)sp.stages * slab_bytes);
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* tmem_full = empty + MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* w_full = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MAX_STAGES; ++s) { mb_init(&full[s], 1); mb_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mb_init(&tmem_full[s], 1); mb_init(&tmem_empty[s], 4); }
+    mb_init(w_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ---------------------------------------------------------------------- TMA producer
+    mb_expect_tx(w_full, (uint32_t)k_tiles * W_TILE);
+    for (int kt = 0; kt < k_tiles; ++kt) tma_load_2d(sW + (size_t)kt * W_TILE, &tmB, w_full, kt * GEMM_BK, 0);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const int s = it % sp.stages;
+      mb_wait(&empty[s], ((it / sp.stages) & 1) ^ 1);
+      mb_expect_tx(&full[s], slab_bytes);
+      for (int cb = 0; cb < sp.col_blocks; ++cb)
+        tma_load_2d(sS + (size_t)s * slab_bytes + (size_t)cb * slab_block, &tmA, &full[s], cb * GEMM_BK,
+                    tile * GEMM_BM + sp.min_shift);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------------------------------------------------------------- MMA issuer
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+    mb_wait(w_full, 0);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const uint32_t as = it & 1;
+      const int s = it % sp.stages;
+      mb_wait(&tmem_empty[as], ((it >> 1) & 1) ^ 1);
+      mb_wait(&full[s], (it / sp.stages) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc = tmem_base + as * BN;
+      const uint32_t slab = s2u(sS + (size_t)s * slab_bytes);
+      uint32_t first = 0;
+      for (int tap = 0; tap < sp.taps; ++tap) {
+        const uint32_t win = (uint32_t)(tap_shift(p, tap) - sp.min_shift) * 128;     // window start inside the slab
+        for (int cb = 0; cb < sp.col_blocks; ++cb) {
+          const uint32_t a_addr = slab + (uint32_t)cb * slab_block + win;
+          const uint32_t b_addr = s2u(sW + (size_t)(tap * sp.col_blocks + cb) * W_TILE);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            umma_f16(acc, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 32, 16, 1024), idesc, first);
+            first = 1;
+          }
+        }
+      }
+      umma_commit(&empty[s]);
+      umma_commit(&tmem_full[as]);
+    }
+  } else if (warp >= 2) {
+    const int q = warp & 3;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it)
+      epilogue_tile<BN>(p, tile * GEMM_BM, 0, q, lane, tmem_base, it & 1, (it >> 1) & 1, true, tmem_full, tmem_empty);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -402,9 +525,35 @@ static int gemm_dispatch(const uint16_t* A, int a_mn, int64_t lda, int64_t a_row
   return launch_gemm<128, 5>(ta, tb, p, splits, st);
 }
 
+template <int BN>
+static int launch_slab(const CUtensorMap& ta, const CUtensorMap& tb, SlabParams sp, cudaStream_t st) {
+  const size_t w_bytes = (size_t)sp.taps * sp.col_blocks * BN * 128;
+  const size_t slab_bytes = (size_t)sp.slab_rows * 128 * sp.col_blocks;
+  const size_t budget = 200 * 1024;
+  if (w_bytes + 2 * slab_bytes > budget) return 1;                   // does not fit: caller falls back to tap addressing
+  int stages = (int)((budget - w_bytes) / slab_bytes);
+  if (stages > 6) stages = 6;
+  sp.stages = stages;
+  const size_t smem = 1024 + w_bytes + stages * slab_bytes + (2 * 6 + 5) * 8 + 16;
+  auto k = conv_slab_tcgen05_kernel<BN>;
+  static size_t attr = 0;
+  if (attr < smem) {
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  const int tiles = (sp.g.M + GEMM_BM - 1) / GEMM_BM;
+  int ctas = sm_count();
+  if (ctas > tiles) ctas = tiles;
+  k<<<ctas, GEMM_THREADS, smem, st>>>(ta, tb, sp);
+  return check_launch("b2rl_conv_gemm_bf16(slab)");
+}
+
 }  // namespace b2rl
 
 using namespace b2rl;
+
+static int g_use_slab = 1;
+extern "C" void b2rl_set_conv_slab(int32_t on) { g_use_slab = on; }
 
 static int check_common(const void* A, const void* B, const void* D, int64_t lda, int64_t ldb, int M, int N, int K,
                         int out_mode, int splits, int block_n, int b_mn, int relu) {
@@ -456,6 +605,24 @@ extern "C" int b2rl_conv_gemm_bf16(int32_t mode, const uint16_t* X, int64_t rows
     int rc = check_common(X, W_or_G, D, C, K, (int)rows, n_out, K, out_mode, splits, block_n, 0, relu);
     if (rc) return rc;
     p.M = (int)rows; p.N = n_out; p.K = K; p.a_mn = 0; p.b_mn = 0; p.a_tap_tiles = C / 64;
+    if (g_use_slab && splits == 1 && n_out <= block_n && out_mode != 2) {
+      const int max_shift = ((taps - 1) / taps_x) * grid_w + (taps - 1) % taps_x;
+      SlabParams sp = {};
+      sp.g = p; sp.taps = taps; sp.col_blocks = C / 64;
+      sp.slab_rows = (GEMM_BM + max_shift + 7) / 8 * 8;
+      sp.min_shift = shift_sign > 0 ? 0 : -max_shift;
+      if (sp.slab_rows <= 256) {
+        CUtensorMap ta, tb;
+        rc = make_map(&ta, X, C, rows, C, sp.slab_rows);            // box [slab_rows][64]
+        if (rc) return rc;
+        rc = make_map(&tb, W_or_G, K, n_out, K, block_n);           // box [block_n][64]
+        if (rc) return rc;
+        int r2 = block_n == 32 ? launch_slab<32>(ta, tb, sp, (cudaStream_t)stream)
+                 : block_n == 64 ? launch_slab<64>(ta, tb, sp, (cudaStream_t)stream)
+                                 : launch_slab<128>(ta, tb, sp, (cudaStream_t)stream);
+        if (r2 <= 0) return r2;                                      // launched (0) or failed (<0); 1 = does not fit
+      }
+    }
     return gemm_dispatch(X, 0, C, rows, C, W_or_G, 0, K, n_out, K, p, splits, block_n, (cudaStream_t)stream);
   }
   B2RL_REQUIRE(C % block_n == 0, "wgrad needs channels in multiples of block_n");

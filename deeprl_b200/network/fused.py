@@ -55,7 +55,7 @@ def act_bwd_bias_grad(gy, y, relu=True, row_map=0, G=0, V=0, out_rows=None):
         assert gy.is_contiguous() and y.is_contiguous() and gy.dtype == _bf16
         g = torch.zeros((out_rows, C), dtype=_bf16, device=gy.device)
         db = torch.empty(C, dtype=torch.float32, device=gy.device)
-        partial = _Scratch.get(y.device, "act_bwd_partial", 296 * 2048, torch.float32)
+        partial = _Scratch.get(y.device, "act_bwd_partial", 592 * 2048, torch.float32)
         counter = _Scratch.get(y.device, "act_bwd_counter", 1, torch.int32)
         _lib.call("b2rl_act_bwd_bias_grad_bf16", _lib.ptr(gy), _lib.ptr(y), rows, C, int(relu), _lib.ptr(g), _lib.ptr(db),
                   _lib.ptr(partial), _lib.ptr(counter), int(row_map), int(G), int(V), _lib.stream())
@@ -69,7 +69,7 @@ def act_bwd_bias_grad(gy, y, relu=True, row_map=0, G=0, V=0, out_rows=None):
         gy = gy.to(_bf16)
     g = torch.empty_like(gy)
     db = torch.empty(C, dtype=torch.float32, device=y.device)
-    partial = _Scratch.get(y.device, "act_bwd_partial", 296 * 2048, torch.float32)
+    partial = _Scratch.get(y.device, "act_bwd_partial", 592 * 2048, torch.float32)
     counter = _Scratch.get(y.device, "act_bwd_counter", 1, torch.int32)
     _lib.call("b2rl_act_bwd_bias_grad_bf16", _lib.ptr(gy), _lib.ptr(y), rows, C, int(relu), _lib.ptr(g), _lib.ptr(db),
               _lib.ptr(partial), _lib.ptr(counter), 0, 0, 0, _lib.stream())

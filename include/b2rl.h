@@ -184,7 +184,7 @@ int b2rl_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_a
 /* ---------------------------------------------------------------------------------------------
  * Dense-layer epilogues (network_bodies.py:27-33,70-73: y = relu(layer(x))), bf16 activations [rows][C] (NHWC
  * flattened), fp32 bias.  Forward: y = act(y + bias) in place.  Backward: gx = gy * (y > 0) (gx may alias gy or be
- * NULL) and dbias[c] = sum over rows of gx, deterministic.  partial: float32 [296*C] scratch; counter: int32 [1], zero
+ * NULL) and dbias[c] = sum over rows of gx, deterministic.  partial: float32 [592*C] scratch; counter: int32 [1], zero
  * on first use.
  * ------------------------------------------------------------------------------------------- */
 int b2rl_bias_act_bf16(uint16_t* y, const float* bias, int64_t rows, int32_t C, int32_t relu, void* stream);
@@ -218,6 +218,8 @@ int b2rl_gemm_bf16(const uint16_t* A, int32_t a_mn, int64_t lda, const uint16_t*
  *   ([batch*(V/2)^2][4*n_out], ldd = 4*n_out), out_map 2 compacts them to [batch*V*V][n_out].
  * mode 1 (wgrad): D[n, tap*C + c] += sum_r Gr[r, n] * X[r + shift(tap), c], Gr bf16 [rows][n_out] passed as W_or_G,
  *   D fp32 [n_out][taps*C] (out_mode 2, atomic accumulation over `splits` K slices). */
+/* forward / dgrad calls use the slab kernel (one activation slab per tile, resident weights) unless switched off */
+void b2rl_set_conv_slab(int32_t on);
 int b2rl_conv_gemm_bf16(int32_t mode, const uint16_t* X, int64_t rows, int32_t C, const uint16_t* W_or_G, int32_t n_out,
                         int32_t taps, int32_t taps_x, int32_t grid_w, int32_t shift_sign, void* D, int64_t ldd,
                         const float* bias, int32_t relu, int32_t out_mode, int32_t out_map, int32_t G, int32_t V,

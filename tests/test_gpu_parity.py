@@ -582,7 +582,16 @@ def test_tcgen05_gemm_vs_torch(rl):
     torch.testing.assert_close(got, g.float() @ w.float(), rtol=1e-4, atol=1e-3 * 512 ** 0.5)
 
 
-def test_conv_grid_gemm_vs_torch(rl):
+@pytest.mark.parametrize("slab", [True, False])
+def test_conv_grid_gemm_vs_torch(rl, slab):
+    rl._lib.set_conv_slab(slab)
+    try:
+        _conv_grid_gemm_vs_torch(rl)
+    finally:
+        rl._lib.set_conv_slab(True)
+
+
+def _conv_grid_gemm_vs_torch(rl):
     """Shifted-row tcgen05 GEMMs of network/nature_tc.py against torch convolutions in fp32 on the same bf16 operands:
     each layer's forward (with the space-to-depth / compaction epilogues), dgrad and wgrad, then the whole body."""
     import torch.nn.functional as F
