@@ -121,11 +121,11 @@ def call(name, *args):
 
 
 def set_conv_slab(on):
-    """Forward / dgrad convolution GEMMs: slab kernel (default) or per-tap operand loads (csrc/gemm.cu)."""
+    """Forward / dgrad convolution GEMMs: 2 = slab kernel (default), 0 = per-tap operand loads (csrc/gemm.cu)."""
     L = lib()
     L.b2rl_set_conv_slab.restype = None
     L.b2rl_set_conv_slab.argtypes = [ctypes.c_int32]
-    L.b2rl_set_conv_slab(int(bool(on)))
+    L.b2rl_set_conv_slab(int(on))
 
 
 def launch_count():

@@ -91,9 +91,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 //   MN-major: 64-element MN groups `lbo` bytes apart, 8-K-row groups 1024 B apart (SBO)
 // base_offset (bits 49-51) = (start address >> 7) & 7 when the start is not aligned to the 1024-byte swizzle pattern
 // (a window that begins s rows into a swizzled slab); 0 for pattern-aligned tiles.
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t base_offset = 0) {
   uint64_t d = 0;
-  d |= (uint64_t)(((smem_addr >> 7) & 7)) << 49;
+  d |= (uint64_t)(base_offset & 7) << 49;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
@@ -337,8 +338,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 // ---------------------------------------------------------------------------------------------------------------
 // Slab variant of the forward / dgrad convolution GEMM: the taps of a tile read overlapping row windows of the same
 // activation matrix, so the CTA loads ONE slab of 128 + max_shift rows per tile and issues every tap's MMAs on windows
-// that start `shift` rows (x 128 bytes) into that swizzled slab (descriptor base_offset = address bits 7-9 of the
-// window start); the weights (all taps) are loaded once per CTA and stay resident.  Activation traffic drops by the
+// that start `shift` rows (x 128 bytes) into that swizzled slab.  The 128-byte swizzle is a pure function of the shared
+// memory ADDRESS (bits 4-6 ^= bits 7-9), for TMA writes and UMMA reads alike, so a window may start at any row of a
+// 1024-byte-aligned slab with descriptor base_offset = 0 (measured on B200: base_offset = (start >> 7) & 7 gives wrong
+// results, 0 gives the right ones).  The weights (all taps) are loaded once per CTA and stay resident.  Activation traffic drops by the
 // number of taps (4x conv1/conv2, 9x conv3) and the weight traffic per tile to zero.
 // ---------------------------------------------------------------------------------------------------------------
 struct SlabParams {
@@ -347,6 +350,7 @@ struct SlabParams {
   int slab_rows;           // multiple of 8, >= 128 + max_shift
   int min_shift;           // row offset of the slab start relative to m0 (0 for forward, -max_shift for dgrad)
   int stages;
+  int base_offset_mode;    // 1: descriptor base_offset = (window start >> 7) & 7; 2: base_offset = 0 (address-based swizzle)
 };
 
 template <int BN>
@@ -425,7 +429,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
           const uint32_t b_addr = s2u(sW + (size_t)(tap * sp.col_blocks + cb) * W_TILE);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
-            umma_f16(acc, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 32, 16, 1024), idesc, first);
+            const uint32_t bo = sp.base_offset_mode == 1 ? ((a_addr >> 7) & 7) : 0;
+            umma_f16(acc, make_desc(a_addr + k * 32, 16, 1024, bo), make_desc(b_addr + k * 32, 16, 1024), idesc, first);
             first = 1;
           }
         }
@@ -552,7 +557,7 @@ static int launch_slab(const CUtensorMap& ta, const CUtensorMap& tb, SlabParams 
 
 using namespace b2rl;
 
-static int g_use_slab = 1;
+static int g_use_slab = 2;   // 2: shifted windows with base_offset 0 -- the 128B swizzle is a pure function of the smem address (verified on B200)
 extern "C" void b2rl_set_conv_slab(int32_t on) { g_use_slab = on; }
 
 static int check_common(const void* A, const void* B, const void* D, int64_t lda, int64_t ldb, int M, int N, int K,
@@ -611,6 +616,7 @@ extern "C" int b2rl_conv_gemm_bf16(int32_t mode, const uint16_t* X, int64_t rows
       sp.g = p; sp.taps = taps; sp.col_blocks = C / 64;
       sp.slab_rows = (GEMM_BM + max_shift + 7) / 8 * 8;
       sp.min_shift = shift_sign > 0 ? 0 : -max_shift;
+      sp.base_offset_mode = g_use_slab;
       if (sp.slab_rows <= 256) {
         CUtensorMap ta, tb;
         rc = make_map(&ta, X, C, rows, C, sp.slab_rows);            // box [slab_rows][64]

@@ -582,13 +582,13 @@ def test_tcgen05_gemm_vs_torch(rl):
     torch.testing.assert_close(got, g.float() @ w.float(), rtol=1e-4, atol=1e-3 * 512 ** 0.5)
 
 
-@pytest.mark.parametrize("slab", [True, False])
+@pytest.mark.parametrize("slab", [0, 2])
 def test_conv_grid_gemm_vs_torch(rl, slab):
     rl._lib.set_conv_slab(slab)
     try:
         _conv_grid_gemm_vs_torch(rl)
     finally:
-        rl._lib.set_conv_slab(True)
+        rl._lib.set_conv_slab(2)
 
 
 def _conv_grid_gemm_vs_torch(rl):
