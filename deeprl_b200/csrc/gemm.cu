@@ -74,6 +74,26 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// descriptor halves: the single MMA-issuing thread must stay lean (every instruction it executes is on the critical
+// path of the tensor pipe), so the 64-bit descriptors are kept as a constant high word and a low word that only
+// receives 32-bit adds.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16);
+}
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);      // SBO = 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ void umma_f16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "mov.b64 da, {%1, %5};\n"
+      "mov.b64 db, {%2, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -295,6 +315,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     // ---------------------------------------------------------------------- MMA issuer
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+    const uint32_t a_lo0 = desc_lo(s2u(sA), p.a_mn ? 8192 : 16), b_lo0 = desc_lo(s2u(sB), p.b_mn ? 8192 : 16);
+    const uint32_t a_step = p.a_mn ? 128 : 2, b_step = p.b_mn ? 128 : 2;
     uint32_t it = 0, tcount = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tcount) {
       const uint32_t as = tcount & 1;
@@ -305,13 +327,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         const int s = it % STAGES;
         mb_wait(&full[s], (it / STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_addr = s2u(sA + s * A_BYTES), b_addr = s2u(sB + s * B_BYTES);
+        // K-major: 16 k-elements = 32 bytes along the swizzled row; MN-major: 16 k-rows = 2048 bytes (in 16-byte units: 2 / 128)
+        uint32_t a_lo = a_lo0 + (uint32_t)s * (A_BYTES >> 4), b_lo = b_lo0 + (uint32_t)s * (B_BYTES >> 4);
 #pragma unroll
         for (int k = 0; k < GEMM_BK / 16; ++k) {
-          // K-major: 16 k-elements = 32 bytes along the swizzled row; MN-major: 16 k-rows = 2048 bytes
-          const uint64_t ad = p.a_mn ? make_desc(a_addr + k * 2048, 8192, 1024) : make_desc(a_addr + k * 32, 16, 1024);
-          const uint64_t bd = p.b_mn ? make_desc(b_addr + k * 2048, 8192, 1024) : make_desc(b_addr + k * 32, 16, 1024);
-          umma_f16(acc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          umma_f16_lh(acc, a_lo, b_lo, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          a_lo += a_step;
+          b_lo += b_step;
         }
         umma_commit(&empty[s]);                    // frees the smem stage when these MMAs retire
       }
@@ -412,6 +434,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
     // ---------------------------------------------------------------------- MMA issuer
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
     mb_wait(w_full, 0);
+    const uint32_t slab_lo0 = desc_lo(s2u(sS), 16), w_lo0 = desc_lo(s2u(sW), 16);
+    const int taps_y = sp.taps / p.taps_x;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const uint32_t as = it & 1;
@@ -420,18 +444,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
       mb_wait(&full[s], (it / sp.stages) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t acc = tmem_base + as * BN;
-      const uint32_t slab = s2u(sS + (size_t)s * slab_bytes);
-      uint32_t first = 0;
-      for (int tap = 0; tap < sp.taps; ++tap) {
-        const uint32_t win = (uint32_t)(tap_shift(p, tap) - sp.min_shift) * 128;     // window start inside the slab
-        for (int cb = 0; cb < sp.col_blocks; ++cb) {
-          const uint32_t a_addr = slab + (uint32_t)cb * slab_block + win;
-          const uint32_t b_addr = s2u(sW + (size_t)(tap * sp.col_blocks + cb) * W_TILE);
+      const uint32_t slab_lo = slab_lo0 + (uint32_t)s * (slab_bytes >> 4);
+      uint32_t first = 0, b_lo = w_lo0;
+      // taps in (dy, dx) order; the window of tap (dy, dx) starts sign*(dy*grid_w + dx) - min_shift rows into the slab
+      int row_dy = -sp.min_shift;                                   // rows, for dx = 0
+      for (int dy = 0; dy < taps_y; ++dy, row_dy += p.shift_sign * p.grid_w) {
+        int row = row_dy;
+        for (int dx = 0; dx < p.taps_x; ++dx, row += p.shift_sign) {
+          uint32_t a_cb = slab_lo + (uint32_t)row * 8;              // 128 bytes per row = 8 x 16 B
+          for (int cb = 0; cb < sp.col_blocks; ++cb, a_cb += slab_block >> 4) {
+            uint32_t a_lo = a_cb;
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            const uint32_t bo = sp.base_offset_mode == 1 ? ((a_addr >> 7) & 7) : 0;
-            umma_f16(acc, make_desc(a_addr + k * 32, 16, 1024, bo), make_desc(b_addr + k * 32, 16, 1024), idesc, first);
-            first = 1;
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              umma_f16_lh(acc, a_lo, b_lo, idesc, first);
+              first = 1;
+              a_lo += 2;
+              b_lo += 2;
+            }
+            b_lo += (W_TILE >> 4) - 8;                              // next 64-wide k-tile of the resident weights
           }
         }
       }
