@@ -1,6 +1,6 @@
 // dense.cu -- epilogues of the dense path (NatureConvBody / FCBody layers, network_bodies.py:27-33,70-73):
 //   forward   y = relu(conv_or_linear(x) + bias)          -> b2rl_bias_act_bf16 (in place on the bf16 GEMM output)
-//   backward  g = gy * (y > 0);  dbias = sum_rows g       -> b2rl_act_bwd_bias_grad_bf16 (one pass, deterministic)
+//   backward  g = gy * (y > 0);  dbias = sum_rows g       -> b2rl_act_bwd_bias_grad_bf16 (one pass, block partials + atomics)
 // Activations are bf16 [rows][C] (NHWC flattened: rows = batch x spatial), bias / dbias are fp32.
 // Both kernels are pure streaming passes (L2 / HBM bound): 16-byte vector loads, 8 channels per thread.  sm_100a only.
 #include "common.cuh"
@@ -82,10 +82,8 @@ __device__ __forceinline__ int64_t map_row(int64_t r, int map, int G, int V) {
 __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __restrict__ gy,
                                                       const __nv_bfloat16* __restrict__ y, int64_t rows, int C8, int relu,
                                                       __nv_bfloat16* __restrict__ gx, float* __restrict__ dbias,
-                                                      float* __restrict__ partial, int32_t* __restrict__ counter,
                                                       int map, int G, int V) {
   extern __shared__ float sred[];          // [rows_per_block][C] partial sums
-  __shared__ bool is_last;
   const int C = C8 * 8;
   const int rpb = blockDim.x / C8;         // rows handled per block per iteration
   const int lr = threadIdx.x / C8, cg = threadIdx.x % C8;
@@ -113,37 +111,13 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __res
     for (int k = 0; k < 8; ++k) sred[lr * C + cg * 8 + k] = acc[k];
   }
   __syncthreads();
+  // block partial -> dbias with fp32 atomics (dbias is zeroed by the caller; the summation order over blocks is not
+  // fixed, which perturbs the last bits of a bias gradient -- the deterministic single-block reduction it replaces was
+  // latency-bound at 15-25 us per layer)
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.0f;
     for (int q = 0; q < rpb; ++q) s += sred[q * C + c];
-    partial[(int64_t)blockIdx.x * C + c] = s;
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(counter, 1) == (int)gridDim.x - 1;
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    // 8 consecutive lanes share a channel: lane j sums blocks j, j+8, ... (4 independent loads in flight), then a
-    // fixed-order shuffle tree -> deterministic
-    const int sub = threadIdx.x & 7, nb = (int)gridDim.x;
-    for (int c = threadIdx.x >> 3; c < C; c += blockDim.x >> 3) {
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      int b = sub;
-      for (; b + 24 < nb; b += 32) {
-        s0 += __ldcg(partial + (int64_t)b * C + c);
-        s1 += __ldcg(partial + (int64_t)(b + 8) * C + c);
-        s2 += __ldcg(partial + (int64_t)(b + 16) * C + c);
-        s3 += __ldcg(partial + (int64_t)(b + 24) * C + c);
-      }
-      for (; b < nb; b += 8) s0 += __ldcg(partial + (int64_t)b * C + c);
-      float s = (s0 + s1) + (s2 + s3);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      if (sub == 0) dbias[c] = s;
-    }
-    if (threadIdx.x == 0) *counter = 0;
+    atomicAdd(dbias + c, s);
   }
 }
 
@@ -167,7 +141,9 @@ extern "C" int b2rl_act_bwd_bias_grad_bf16(const uint16_t* gy, const uint16_t* y
                                            int32_t G, int32_t V, void* stream) {
   B2RL_REQUIRE(row_map >= 0 && row_map <= 2 && (row_map == 0 || (G > 0 && V > 0 && V <= G)), "bad row map");
   B2RL_REQUIRE(row_map == 0 || gx != gy, "a row-mapped gradient cannot be written in place");
-  B2RL_REQUIRE(gy && dbias && partial && counter && (y || !relu), "null pointer");
+  B2RL_REQUIRE(gy && dbias && (y || !relu), "null pointer");
+  (void)partial; (void)counter;
+  cudaMemsetAsync(dbias, 0, sizeof(float) * C, (cudaStream_t)stream);
   B2RL_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && C <= 2048, "C must be a multiple of 8, <= 2048");
   const int C8 = C / 8;
   const int rpb = 256 / C8 > 0 ? 256 / C8 : 1;
@@ -179,7 +155,7 @@ extern "C" int b2rl_act_bwd_bias_grad_bf16(const uint16_t* gy, const uint16_t* y
   size_t smem = (size_t)rpb * C * sizeof(float);
   act_bwd_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(gy), reinterpret_cast<const __nv_bfloat16*>(y), rows, C8, relu,
-      reinterpret_cast<__nv_bfloat16*>(gx), dbias, partial, counter, row_map, G, V);
+      reinterpret_cast<__nv_bfloat16*>(gx), dbias, row_map, G, V);
   return check_launch("b2rl_act_bwd_bias_grad_bf16");
 }
 

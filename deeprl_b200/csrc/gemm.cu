@@ -481,6 +481,116 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Slab variant of the convolution weight gradient:  D[n, tap*C + c] += sum_r G[r, n] * X[r + shift(tap), c].
+// Both operands are read as stored (MN-major, K = rows).  A CTA owns a contiguous range of 64-row k-tiles; per k-tile it
+// loads the gradient rows ONCE and ONE slab of 64 + max_shift activation rows, and issues every tap's MMAs on windows of
+// that slab (a K-row shift is a 128-byte step in the MN-major swizzled layout, address-based swizzle as above) into one
+// TMEM accumulator per tap (taps x C fp32 columns, <= 512).  At the end the accumulators are added to D with fp32
+// atomics (split-K across CTAs).
+// ---------------------------------------------------------------------------------------------------------------
+struct WgradParams {
+  int rows, n_out, C, col_blocks;
+  int tap0, ntaps, taps_x, grid_w;
+  int slab_rows, stages, k_tiles_per_cta, a_boxes;
+  float* D;
+  int ldd;
+};
+
+template <int TMEM_COLS>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmG,
+                                                                             const __grid_constant__ CUtensorMap tmX,
+                                                                             const WgradParams w) {
+  constexpr int MAX_STAGES = 6;
+  constexpr uint32_t A_BYTES = 2 * 8192;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t slab_block = (uint32_t)w.slab_rows * 128, slab_bytes = slab_block * w.col_blocks;
+  const uint32_t stage_bytes = A_BYTES + slab_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)w.stages * stage_bytes);
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* tmem_full = empty + MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kt_total = (w.rows + GEMM_BK - 1) / GEMM_BK;
+  const int kt_begin = blockIdx.x * w.k_tiles_per_cta;
+  const int n_kt = max(min(kt_total, kt_begin + w.k_tiles_per_cta) - kt_begin, 0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MAX_STAGES; ++s) { mb_init(&full[s], 1); mb_init(&empty[s], 1); }
+    mb_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < n_kt; ++i) {
+      const int s = i % w.stages;
+      mb_wait(&empty[s], ((i / w.stages) & 1) ^ 1);
+      mb_expect_tx(&full[s], (uint32_t)w.a_boxes * 8192 + slab_bytes);
+      uint8_t* st = smem + (size_t)s * stage_bytes;
+      const int k0 = (kt_begin + i) * GEMM_BK;
+      for (int g = 0; g < w.a_boxes; ++g) tma_load_2d(st + g * 8192, &tmG, &full[s], g * 64, k0);       // [64 k][64 n]
+      for (int cb = 0; cb < w.col_blocks; ++cb)
+        tma_load_2d(st + A_BYTES + (size_t)cb * slab_block, &tmX, &full[s], cb * GEMM_BK, k0);           // [slab_rows][64 c]
+    }
+  } else if (warp == 1 && lane == 0 && n_kt > 0) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(w.C >> 3) << 17) |
+                           ((uint32_t)(GEMM_BM >> 4) << 24);
+    const uint32_t a_lo0 = desc_lo(s2u(smem), 8192), b_lo0 = desc_lo(s2u(smem + A_BYTES), slab_block);
+    const int tap_end = w.tap0 + w.ntaps;
+    for (int i = 0; i < n_kt; ++i) {
+      const int s = i % w.stages;
+      mb_wait(&full[s], (i / w.stages) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_st = a_lo0 + (uint32_t)s * (stage_bytes >> 4), b_st = b_lo0 + (uint32_t)s * (stage_bytes >> 4);
+      uint32_t acc = tmem_base;
+      for (int tap = w.tap0; tap < tap_end; ++tap, acc += w.C) {
+        const int shift = (tap / w.taps_x) * w.grid_w + tap % w.taps_x;
+        uint32_t a_lo = a_st, b_lo = b_st + (uint32_t)shift * 8;       // 128 bytes per k-row
+#pragma unroll
+        for (int k = 0; k < GEMM_BK / 16; ++k) {
+          umma_f16_lh(acc, a_lo, b_lo, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          a_lo += 128;                                                  // 16 k-rows = 2048 bytes
+          b_lo += 128;
+        }
+      }
+      umma_commit(&empty[s]);
+    }
+    umma_commit(tmem_full);
+  } else if (warp >= 2 && n_kt > 0) {
+    const int q = warp & 3;
+    const int n = q * 32 + lane;
+    mb_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int cols = w.ntaps * w.C;
+    for (int c = 0; c < cols; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, r);
+      if (n < w.n_out) {
+        float* d = w.D + (int64_t)n * w.ldd + (int64_t)w.tap0 * w.C + c;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(d + j, __uint_as_float(r[j]));
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -583,6 +693,29 @@ static int launch_slab(const CUtensorMap& ta, const CUtensorMap& tb, SlabParams 
   return check_launch("b2rl_conv_gemm_bf16(slab)");
 }
 
+template <int TMEM_COLS>
+static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, WgradParams w, cudaStream_t st) {
+  const size_t slab_bytes = (size_t)w.slab_rows * 128 * w.col_blocks, stage = 16384 + slab_bytes;
+  int stages = (int)((200 * 1024) / stage);
+  if (stages > 6) stages = 6;
+  if (stages < 2) return 1;
+  w.stages = stages;
+  const size_t smem = 1024 + stages * stage + (2 * 6 + 2) * 8 + 16;
+  auto k = conv_wgrad_tcgen05_kernel<TMEM_COLS>;
+  static size_t attr = 0;
+  if (attr < smem) {
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  const int kt_total = (w.rows + GEMM_BK - 1) / GEMM_BK;
+  int ctas = sm_count();
+  if (ctas > kt_total) ctas = kt_total;
+  w.k_tiles_per_cta = (kt_total + ctas - 1) / ctas;
+  ctas = (kt_total + w.k_tiles_per_cta - 1) / w.k_tiles_per_cta;
+  k<<<ctas, GEMM_THREADS, smem, st>>>(tg, tx, w);
+  return check_launch("b2rl_conv_gemm_bf16(wgrad slab)");
+}
+
 }  // namespace b2rl
 
 using namespace b2rl;
@@ -666,6 +799,31 @@ extern "C" int b2rl_conv_gemm_bf16(int32_t mode, const uint16_t* X, int64_t rows
   int rc = check_common(W_or_G, X, D, n_out, C, n_out, taps * C, (int)rows, out_mode, splits, block_n, 1, relu);
   if (rc) return rc;
   B2RL_REQUIRE(out_mode == 2, "wgrad accumulates with out_mode 2");
+  if (g_use_slab && C % 64 == 0 && C <= 128 && n_out <= 128 && shift_sign > 0) {
+    const int max_shift = ((taps - 1) / taps_x) * grid_w + (taps - 1) % taps_x;
+    WgradParams w = {};
+    w.rows = (int)rows; w.n_out = n_out; w.C = C; w.col_blocks = C / 64; w.taps_x = taps_x; w.grid_w = grid_w;
+    w.slab_rows = (GEMM_BK + max_shift + 7) / 8 * 8;
+    w.a_boxes = n_out > 64 ? 2 : 1;
+    w.D = reinterpret_cast<float*>(D); w.ldd = (int)ldd;
+    CUtensorMap tg, tx;
+    rc = make_map(&tg, W_or_G, n_out, rows, n_out, 64);             // gradient rows: box [64 k][64 n]
+    if (rc) return rc;
+    rc = make_map(&tx, X, C, rows, C, w.slab_rows);                 // activation slab: box [slab_rows][64 c]
+    if (rc) return rc;
+    const int per_launch = 512 / C;                                 // taps whose accumulators fit in TMEM together
+    int r2 = 0;
+    for (int t0 = 0; t0 < taps && r2 == 0; t0 += per_launch) {
+      w.tap0 = t0;
+      w.ntaps = taps - t0 < per_launch ? taps - t0 : per_launch;
+      const int cols = w.ntaps * C;
+      r2 = cols <= 64 ? launch_wgrad<64>(tg, tx, w, (cudaStream_t)stream)
+           : cols <= 128 ? launch_wgrad<128>(tg, tx, w, (cudaStream_t)stream)
+           : cols <= 256 ? launch_wgrad<256>(tg, tx, w, (cudaStream_t)stream)
+                         : launch_wgrad<512>(tg, tx, w, (cudaStream_t)stream);
+    }
+    if (r2 <= 0) return r2;
+  }
   p.M = n_out; p.N = taps * C; p.K = (int)rows; p.a_mn = 1; p.b_mn = 1; p.b_tap_tiles = C / block_n;
   return gemm_dispatch(W_or_G, 1, n_out, rows, n_out, X, 1, C, rows, C, p, splits, block_n, (cudaStream_t)stream);
 }

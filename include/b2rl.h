@@ -184,8 +184,8 @@ int b2rl_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_a
 /* ---------------------------------------------------------------------------------------------
  * Dense-layer epilogues (network_bodies.py:27-33,70-73: y = relu(layer(x))), bf16 activations [rows][C] (NHWC
  * flattened), fp32 bias.  Forward: y = act(y + bias) in place.  Backward: gx = gy * (y > 0) (gx may alias gy or be
- * NULL) and dbias[c] = sum over rows of gx, deterministic.  partial: float32 [592*C] scratch; counter: int32 [1], zero
- * on first use.
+ * NULL) and dbias[c] = sum over rows of gx (block partials + fp32 atomics; dbias is zeroed by the call).  partial /
+ * counter: unused (kept for ABI stability), may be NULL.
  * ------------------------------------------------------------------------------------------- */
 int b2rl_bias_act_bf16(uint16_t* y, const float* bias, int64_t rows, int32_t C, int32_t relu, void* stream);
 /* same epilogue for a split-K GEMM result: y(bf16) = act(x(fp32) + bias) */
