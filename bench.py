@@ -121,8 +121,9 @@ def build_learner(rl, workload, device, rank, world):
         kind = "qr"
     net, tgt = mk(), mk()
     tgt.load_state_dict(net.state_dict())
-    net = net.to(memory_format=torch.channels_last)
-    tgt = tgt.to(memory_format=torch.channels_last)
+    if rl.Config.DENSE_BACKEND != "tcgen05":               # cuDNN prefers channels_last weights; the tcgen05 path packs its own
+        net = net.to(memory_format=torch.channels_last)
+        tgt = tgt.to(memory_format=torch.channels_last)
     opt = rl.ops.FlatOptimizer.from_torch(topt(net.parameters()))
     replay_cls = rl.PrioritizedReplay if workload == "per" else rl.UniformReplay
     rp = synthetic_ring(rl, replay_cls, device, seed=rank)
@@ -269,7 +270,9 @@ def run_b2rl(args):
                     batch=B, replay_capacity=CAP, replay_bytes=CAP * FRAME, actions=ACTIONS, feeds_per_update=4,
                     l2_policy="inputs larger than L2: 7.06 GB ring, fresh random indices every step",
                     parallelism="dp%d (rank-local replay shard, NCCL all-reduce of 6.7 MB fp32 gradients per step)" % world,
-                    dense="cuDNN/cuBLAS bf16 (fp32 accumulate, fp32 master weights)", cuda_graph=True),
+                    dense=("tcgen05 GEMM kernels (csrc/gemm.cu): bf16 operands, fp32 accumulation in TMEM, fp32 master weights"
+                           if rl.Config.DENSE_BACKEND == "tcgen05" else "cuDNN/cuBLAS bf16 (fp32 accumulate, fp32 master weights)"),
+                    cuda_graph=True),
         e2e=dict(value=round(e2e, 1), unit="updates/s", h2d_bytes_per_step=learner.h2d_bytes, d2h_bytes_per_step=4,
                  ms_per_step=round(e2e_ms / K, 4)),
         gpu_launches=int(launches_per_update * K), gpu_launches_per_step=int(launches_per_update),
