@@ -224,8 +224,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
         }
       } else {
         float* d = reinterpret_cast<float*>(p.D) + off;
-        for (int j = 0; j < 32; ++j)
-          if (n0 + c + j < p.N) atomicAdd(d + j, __uint_as_float(r[j]));
+        if (n0 + c + 32 <= p.N && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            atomicAdd(reinterpret_cast<float4*>(d + j), make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                    __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c + j < p.N) atomicAdd(d + j, __uint_as_float(r[j]));
+        }
       }
     }
   }
@@ -579,8 +586,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, r);
       if (n < w.n_out) {
         float* d = w.D + (int64_t)n * w.ldd + (int64_t)w.tap0 * w.C + c;
+        if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(d + j, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; j += 4)       // 16-byte vector reductions (red.global.add.v4.f32)
+            atomicAdd(reinterpret_cast<float4*>(d + j), make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                    __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(d + j, __uint_as_float(r[j]));
+        }
       }
     }
   }
@@ -708,8 +722,11 @@ static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, WgradParam
     attr = smem;
   }
   const int kt_total = (w.rows + GEMM_BK - 1) / GEMM_BK;
-  int ctas = sm_count();
-  if (ctas > kt_total) ctas = kt_total;
+  // split-K over CTAs: every CTA ends with n_out x cols atomic reductions into the same small D, so keep the CTA count
+  // moderate (>= 16 k-tiles each, at most 64 CTAs); a CTA streams ~100 GB/s through its 6-stage TMA ring
+  int ctas = kt_total / 16;
+  if (ctas > 64) ctas = 64;
+  if (ctas < 1) ctas = 1;
   w.k_tiles_per_cta = (kt_total + ctas - 1) / ctas;
   ctas = (kt_total + w.k_tiles_per_cta - 1) / w.k_tiles_per_cta;
   k<<<ctas, GEMM_THREADS, smem, st>>>(tg, tx, w);
