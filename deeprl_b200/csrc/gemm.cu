@@ -146,7 +146,10 @@ __device__ __forceinline__ int tap_shift(const GemmParams& p, int tap) {
 
 // Epilogue of one 128 x BN tile for one warp (TMEM lane quarter q): wait for the accumulator stage, read it 32 columns
 // at a time, hand the stage back to the MMA warp, apply bias / ReLU and store through the output row map.
-template <int BN>
+// The accumulator of a tile is kept as ACC partial sums (the MMA issuer rotates over them): back-to-back tcgen05.mma
+// into the SAME TMEM accumulator are latency-serialised (~180 cycles each on B200 for N <= 128), independent ones
+// pipeline, so small-N tiles need several accumulation chains in flight.  The epilogue adds the partials.
+template <int BN, int ACC>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n0, int q, int lane, uint32_t tmem_base,
                                               uint32_t as, uint32_t parity, bool has_acc, uint64_t* tmem_full,
                                               uint64_t* tmem_empty) {
@@ -175,7 +178,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
   for (int c = 0; c < BN; c += 32) {
     uint32_t r[32];
     if (has_acc) {
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c, r);
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + as * (ACC * BN) + c;
+      tmem_ld32(t0, r);
+#pragma unroll
+      for (int a = 1; a < ACC; ++a) {
+        uint32_t r2[32];
+        tmem_ld32(t0 + a * BN, r2);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) r[j] = 0;
@@ -243,7 +254,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                                                                        const __grid_constant__ CUtensorMap tmB,
                                                                        const GemmParams p) {
   constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2, B_BYTES = BN * GEMM_BK * 2;
-  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;          // two accumulator stages
+  constexpr int ACC = BN <= 64 ? 4 : 2;                               // partial accumulators per tile (see epilogue_tile)
+  constexpr uint32_t TMEM_COLS = 2 * ACC * BN;                        // two accumulator stages: 256 / 512 / 512 columns
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -329,7 +341,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       const uint32_t as = tcount & 1;
       mb_wait(&tmem_empty[as], ((tcount >> 1) & 1) ^ 1);     // epilogue drained this accumulator stage
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t acc = tmem_base + as * BN;
+      const uint32_t acc = tmem_base + as * (ACC * BN);
       for (int i = 0; i < n_kt; ++i, ++it) {
         const int s = it % STAGES;
         mb_wait(&full[s], (it / STAGES) & 1);
@@ -338,7 +350,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         uint32_t a_lo = a_lo0 + (uint32_t)s * (A_BYTES >> 4), b_lo = b_lo0 + (uint32_t)s * (B_BYTES >> 4);
 #pragma unroll
         for (int k = 0; k < GEMM_BK / 16; ++k) {
-          umma_f16_lh(acc, a_lo, b_lo, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          // k16 step k of every k-tile goes to partial accumulator k % ACC: ACC independent accumulation chains
+          umma_f16_lh(acc + (k % ACC) * BN, a_lo, b_lo, idesc, (i > 0 || k >= ACC) ? 1u : 0u);
           a_lo += a_step;
           b_lo += b_step;
         }
@@ -353,7 +366,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tcount) {
       const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
       const int m0 = mt * GEMM_BM, n0 = nt * BN;
-      epilogue_tile<BN>(p, m0, n0, q, lane, tmem_base, tcount & 1, (tcount >> 1) & 1, n_kt > 0, tmem_full, tmem_empty);
+      epilogue_tile<BN, ACC>(p, m0, n0, q, lane, tmem_base, tcount & 1, (tcount >> 1) & 1, n_kt > 0, tmem_full, tmem_empty);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -388,7 +401,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
                                                                             const SlabParams sp) {
   const GemmParams& p = sp.g;
   constexpr uint32_t W_TILE = BN * 128;                               // one 64-wide k-tile of the weights
-  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  constexpr int ACC = BN <= 64 ? 4 : 2;
+  constexpr uint32_t TMEM_COLS = 2 * ACC * BN;
   constexpr int MAX_STAGES = 6;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -450,9 +464,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
       mb_wait(&tmem_empty[as], ((it >> 1) & 1) ^ 1);
       mb_wait(&full[s], (it / sp.stages) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t acc = tmem_base + as * BN;
+      const uint32_t acc = tmem_base + as * (ACC * BN);
       const uint32_t slab_lo = slab_lo0 + (uint32_t)s * (slab_bytes >> 4);
-      uint32_t first = 0, b_lo = w_lo0;
+      uint32_t nmma = 0, b_lo = w_lo0;                                // nmma: MMAs issued for this tile (rotates the partials)
       // taps in (dy, dx) order; the window of tap (dy, dx) starts sign*(dy*grid_w + dx) - min_shift rows into the slab
       int row_dy = -sp.min_shift;                                   // rows, for dx = 0
       for (int dy = 0; dy < taps_y; ++dy, row_dy += p.shift_sign * p.grid_w) {
@@ -463,11 +477,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
             uint32_t a_lo = a_cb;
 #pragma unroll
             for (int k = 0; k < GEMM_BK / 16; ++k) {
-              umma_f16_lh(acc, a_lo, b_lo, idesc, first);
-              first = 1;
+              umma_f16_lh(acc + (k % ACC) * BN, a_lo, b_lo, idesc, (nmma > 0 || k >= ACC) ? 1u : 0u);
               a_lo += 2;
               b_lo += 2;
             }
+            nmma = 1;
             b_lo += (W_TILE >> 4) - 8;                              // next 64-wide k-tile of the resident weights
           }
         }
@@ -479,7 +493,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
     const int q = warp & 3;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it)
-      epilogue_tile<BN>(p, tile * GEMM_BM, 0, q, lane, tmem_base, it & 1, (it >> 1) & 1, true, tmem_full, tmem_empty);
+      epilogue_tile<BN, ACC>(p, tile * GEMM_BM, 0, q, lane, tmem_base, it & 1, (it >> 1) & 1, true, tmem_full, tmem_empty);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -561,15 +575,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
       mb_wait(&full[s], (i / w.stages) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_st = a_lo0 + (uint32_t)s * (stage_bytes >> 4), b_st = b_lo0 + (uint32_t)s * (stage_bytes >> 4);
-      uint32_t acc = tmem_base;
-      for (int tap = w.tap0; tap < tap_end; ++tap, acc += w.C) {
-        const int shift = (tap / w.taps_x) * w.grid_w + tap % w.taps_x;
-        uint32_t a_lo = a_st, b_lo = b_st + (uint32_t)shift * 8;       // 128 bytes per k-row
+      // k16 steps outer, taps inner: consecutive MMAs go to different accumulators (independent chains)
 #pragma unroll
-        for (int k = 0; k < GEMM_BK / 16; ++k) {
-          umma_f16_lh(acc, a_lo, b_lo, idesc, (i > 0 || k > 0) ? 1u : 0u);
-          a_lo += 128;                                                  // 16 k-rows = 2048 bytes
-          b_lo += 128;
+      for (int k = 0; k < GEMM_BK / 16; ++k) {
+        uint32_t acc = tmem_base;
+        int dy = w.tap0 / w.taps_x, dx = w.tap0 % w.taps_x;
+        for (int tap = w.tap0; tap < tap_end; ++tap, acc += w.C) {
+          const int shift = dy * w.grid_w + dx;
+          umma_f16_lh(acc, a_st + k * 128, b_st + (uint32_t)shift * 8 + k * 128, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          if (++dx == w.taps_x) { dx = 0; ++dy; }
         }
       }
       umma_commit(&empty[s]);
@@ -722,10 +736,10 @@ static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, WgradParam
     attr = smem;
   }
   const int kt_total = (w.rows + GEMM_BK - 1) / GEMM_BK;
-  // split-K over CTAs: every CTA ends with n_out x cols atomic reductions into the same small D, so keep the CTA count
-  // moderate (>= 16 k-tiles each, at most 64 CTAs); a CTA streams ~100 GB/s through its 6-stage TMA ring
-  int ctas = kt_total / 16;
-  if (ctas > 64) ctas = 64;
+  // split-K over all SMs (the MMAs are shared-memory-read bound per SM, so the work must be spread); every CTA ends with
+  // n_out x cols / 4 vector reductions (red.global.add.v4.f32) into the same small D
+  int ctas = kt_total / 4;
+  if (ctas > sm_count()) ctas = sm_count();
   if (ctas < 1) ctas = 1;
   w.k_tiles_per_cta = (kt_total + ctas - 1) / ctas;
   ctas = (kt_total + w.k_tiles_per_cta - 1) / w.k_tiles_per_cta;
