@@ -146,9 +146,10 @@ __device__ __forceinline__ int tap_shift(const GemmParams& p, int tap) {
 
 // Epilogue of one 128 x BN tile for one warp (TMEM lane quarter q): wait for the accumulator stage, read it 32 columns
 // at a time, hand the stage back to the MMA warp, apply bias / ReLU and store through the output row map.
-// The accumulator of a tile is kept as ACC partial sums (the MMA issuer rotates over them): back-to-back tcgen05.mma
-// into the SAME TMEM accumulator are latency-serialised (~180 cycles each on B200 for N <= 128), independent ones
-// pipeline, so small-N tiles need several accumulation chains in flight.  The epilogue adds the partials.
+// The accumulator of a tile may be kept as ACC partial sums (the MMA issuer rotates over them, the epilogue adds them).
+// scripts/microbench/umma_rate.cu measured on B200: one issuing thread sustains one tcgen05.mma (M=128, K=16) every
+// max(53, N/2) cycles whatever the operand majors and whether consecutive MMAs hit the same accumulator or not, so
+// ACC = 1 is used; small-N tiles are bound by that 53-cycle issue floor, not by accumulator dependencies.
 template <int BN, int ACC>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n0, int q, int lane, uint32_t tmem_base,
                                               uint32_t as, uint32_t parity, bool has_acc, uint64_t* tmem_full,
@@ -254,8 +255,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                                                                        const __grid_constant__ CUtensorMap tmB,
                                                                        const GemmParams p) {
   constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2, B_BYTES = BN * GEMM_BK * 2;
-  constexpr int ACC = BN <= 64 ? 4 : 2;                               // partial accumulators per tile (see epilogue_tile)
-  constexpr uint32_t TMEM_COLS = 2 * ACC * BN;                        // two accumulator stages: 256 / 512 / 512 columns
+  constexpr int ACC = 1;     // partial accumulators per tile: measured, independent chains do not raise the MMA rate
+  constexpr uint32_t TMEM_COLS = 2 * ACC * BN < 32 ? 32 : 2 * ACC * BN;   // two accumulator stages
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -401,8 +402,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
                                                                             const SlabParams sp) {
   const GemmParams& p = sp.g;
   constexpr uint32_t W_TILE = BN * 128;                               // one 64-wide k-tile of the weights
-  constexpr int ACC = BN <= 64 ? 4 : 2;
-  constexpr uint32_t TMEM_COLS = 2 * ACC * BN;
+  constexpr int ACC = 1;
+  constexpr uint32_t TMEM_COLS = 2 * ACC * BN < 32 ? 32 : 2 * ACC * BN;
   constexpr int MAX_STAGES = 6;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

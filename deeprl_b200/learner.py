@@ -62,12 +62,14 @@ class GraphedDQNLearner:
 
     def _main(self):
         rp = self.replay
-        for j in range(self.feeds):                      # DQN_agent.py:104-112: one feed() per env transition
+        # DQN_agent.py:104-112 calls feed() once per env transition; `feeds` single-item calls are exactly one multi-item
+        # call with each item in its own slot (reference_feed_quirk off) plus `feeds` tree.add(max_priority) -- one launch
+        if self.feeds:
+            quirk, rp.quirk = rp.quirk, False
+            rp.feed_device(self.d_frames, self.d_action, self.d_reward, self.d_mask, self.feeds)
+            rp.quirk = quirk
             if self.per:
-                rp.feed_device(self.d_frames[j:j + 1], self.d_action[j:j + 1], self.d_reward[j:j + 1], self.d_mask[j:j + 1], 1,
-                               add_leaf=True)
-            else:
-                rp.feed_device(self.d_frames[j:j + 1], self.d_action[j:j + 1], self.d_reward[j:j + 1], self.d_mask[j:j + 1], 1)
+                rp.tree.add_n(self.feeds, rp.max_priority_dev)
         if self.dtype == torch.bfloat16:
             # exact integer frames, space-to-depth layout; ImageNormalizer's scale is folded into conv1's weights
             t = rp.sample_normalized(out_dtype=self.dtype, scale=None, layout="s2d")
