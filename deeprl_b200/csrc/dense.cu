@@ -57,25 +57,21 @@ __global__ void __launch_bounds__(256) bias_act_f32_kernel(const float* __restri
   }
 }
 
-// destination row of source row r for the layout changes between the layers of the grid-GEMM convolution stack
+// Layout changes between the layers of the grid-GEMM convolution stack.  With a map the kernel walks the DESTINATION rows
+// (a G x G grid per image) and returns the source row that feeds each, or -1 for a padding row (written as zeros):
 //   map 0: identity
-//   map 1: compact V x V positions per image -> G x G grid rows            (fc4's input gradient -> conv3's output grid)
-//   map 2: space-to-depth(2) rows [b][Y][X] x 4 channel groups (py,px) -> G x G grid rows (2Y+py, 2X+px); the source is
-//          addressed as rows*4 "virtual rows" of C channels                (conv2's input gradient -> conv1's output grid)
-__device__ __forceinline__ int64_t map_row(int64_t r, int map, int G, int V) {
+//   map 1: G x G grid rows <- compact V x V positions per image             (fc4's input gradient -> conv3's output grid)
+//   map 2: G x G grid rows (oy, ox) <- space-to-depth(2) rows [b][oy/2][ox/2], channel group (oy%2, ox%2); the source is
+//          addressed as rows*4 "virtual rows" of C channels                 (conv2's input gradient -> conv1's output grid)
+__device__ __forceinline__ int64_t src_row(int64_t r, int map, int G, int V) {
   if (map == 0) return r;
-  if (map == 1) {
-    const int64_t b = r / (V * V);
-    const int rem = (int)(r - b * V * V);
-    return b * G * G + (rem / V) * G + rem % V;
-  }
-  const int h = V >> 1;                       // source grid is h x h, 4 groups per source row
-  const int64_t sr = r >> 2;
-  const int grp = (int)(r & 3);
-  const int64_t b = sr / (h * h);
-  const int rem = (int)(sr - b * h * h);
-  const int Y = rem / h, X = rem - Y * h;
-  return b * G * G + (2 * Y + (grp >> 1)) * G + 2 * X + (grp & 1);
+  const int64_t b = r / (G * G);
+  const int rem = (int)(r - b * G * G);
+  const int oy = rem / G, ox = rem - oy * G;
+  if (oy >= V || ox >= V) return -1;
+  if (map == 1) return b * V * V + oy * V + ox;
+  const int h = V >> 1;
+  return ((b * h * h + (oy >> 1) * h + (ox >> 1)) << 2) | (((oy & 1) << 1) | (ox & 1));
 }
 
 // each thread owns one 8-channel group and walks rows with stride (threads per block / C8) * gridDim
@@ -90,7 +86,12 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __res
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (lr < rpb) {
     for (int64_t r = (int64_t)blockIdx.x * rpb + lr; r < rows; r += (int64_t)gridDim.x * rpb) {
-      const int64_t e = r * C8 + cg;
+      const int64_t sr = src_row(r, map, G, V);
+      if (sr < 0) {                                        // padding row of the destination grid
+        reinterpret_cast<int4*>(gx)[r * C8 + cg] = make_int4(0, 0, 0, 0);
+        continue;
+      }
+      const int64_t e = sr * C8 + cg;
       int4 g4 = reinterpret_cast<const int4*>(gy)[e];
       float g[8];
       unpack8(g4, g);
@@ -100,9 +101,9 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __res
         unpack8(y4, yv);
 #pragma unroll
         for (int k = 0; k < 8; ++k) g[k] = yv[k] > 0.0f ? g[k] : 0.0f;
-        if (gx) reinterpret_cast<int4*>(gx)[map_row(r, map, G, V) * C8 + cg] = pack8(g);
+        if (gx) reinterpret_cast<int4*>(gx)[r * C8 + cg] = pack8(g);
       } else if (gx && (gx != gy || map != 0)) {
-        reinterpret_cast<int4*>(gx)[map_row(r, map, G, V) * C8 + cg] = g4;
+        reinterpret_cast<int4*>(gx)[r * C8 + cg] = g4;
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] += g[k];

@@ -1,0 +1,138 @@
+// head.cu -- value heads with a handful of outputs (VanillaNet / DuelingNet, network_heads.py:11-37) on CUDA cores:
+// the contraction is [B x 512] x [512 x A] with A = number of actions (4..18): far too narrow for a tensor-core tile,
+// and in eager form it costs ~12 launches per update (weight / bias casts, GEMM, float cast, dueling combine, and their
+// backward counterparts).  Forward: q = phi W_a^T + b_a, or the dueling combine q = v + adv - mean(adv) with
+// v = phi W_v^T + b_v.  Backward: dphi = geff W, dW += geff^T phi, db += sum geff, where geff is dq mapped through the
+// dueling combine.  phi is the bf16 feature vector of the fused body; weights and gradients are fp32 (master).
+// sm_100a only.
+#include "common.cuh"
+
+namespace b2rl {
+
+constexpr int HEAD_MAX_OUT = 32;       // A (+1 for the dueling value row)
+
+// one warp per batch row
+__global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __restrict__ phi, const float* __restrict__ Wa,
+                                                       const float* __restrict__ ba, const float* __restrict__ Wv,
+                                                       const float* __restrict__ bv, int B, int K, int A,
+                                                       float* __restrict__ q) {
+  const int lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const __nv_bfloat16* x = phi + (int64_t)b * K;
+  const int n_out = A + (Wv ? 1 : 0);
+  float out[HEAD_MAX_OUT + 1];
+#pragma unroll 1
+  for (int n = 0; n < n_out; ++n) {
+    const float* w = (n < A) ? Wa + (int64_t)n * K : Wv;
+    float s = 0.0f;
+    for (int k = lane * 2; k < K; k += 64) {
+      const float2 xv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + k));
+      const float2 wv = *reinterpret_cast<const float2*>(w + k);
+      s = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, s));
+    }
+    s = warp_reduce(s, OpAdd());
+    out[n] = s + ((n < A) ? ba[n] : bv[0]);
+  }
+  if (lane == 0) {
+    if (Wv) {                                     // network_heads.py:34-36: q = value + (adv - adv.mean(1))
+      float mean = 0.0f;
+      for (int a = 0; a < A; ++a) mean += out[a];
+      mean /= (float)A;
+      for (int a = 0; a < A; ++a) q[(int64_t)b * A + a] = out[A] + (out[a] - mean);
+    } else {
+      for (int a = 0; a < A; ++a) q[(int64_t)b * A + a] = out[a];
+    }
+  }
+}
+
+// grid (K/64, ceil(B/64)); block 256 = 64 columns x 4 row groups of 16 rows
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ gq, const __nv_bfloat16* __restrict__ phi,
+                                                       const float* __restrict__ Wa, const float* __restrict__ Wv, int B,
+                                                       int K, int A, __nv_bfloat16* __restrict__ gphi,
+                                                       float* __restrict__ gWa, float* __restrict__ gba,
+                                                       float* __restrict__ gWv, float* __restrict__ gbv) {
+  __shared__ float geff[64][HEAD_MAX_OUT + 1];       // [row][a], last used column = value gradient (dueling)
+  __shared__ float red[4][64][HEAD_MAX_OUT + 1];
+  const int k = blockIdx.x * 64 + (threadIdx.x & 63), rg = threadIdx.x >> 6;
+  const int r0 = blockIdx.y * 64;
+  const int n_out = A + (Wv ? 1 : 0);
+  for (int e = threadIdx.x; e < 64 * n_out; e += blockDim.x) {
+    const int r = e / n_out, n = e - r * n_out;
+    float g = 0.0f;
+    if (r0 + r < B) {
+      const float* gr = gq + (int64_t)(r0 + r) * A;
+      if (!Wv) g = gr[n];
+      else {
+        float sum = 0.0f;
+        for (int a = 0; a < A; ++a) sum += gr[a];
+        g = (n < A) ? gr[n] - sum / (float)A : sum;   // d/d adv_n and d/d value of q = v + adv - mean(adv)
+      }
+    }
+    geff[r][n] = g;
+  }
+  __syncthreads();
+  float w[HEAD_MAX_OUT + 1], acc[HEAD_MAX_OUT + 1];
+#pragma unroll
+  for (int n = 0; n < HEAD_MAX_OUT + 1; ++n) {
+    acc[n] = 0.0f;
+    w[n] = (n < n_out && k < K) ? ((n < A) ? Wa[(int64_t)n * K + k] : Wv[k]) : 0.0f;
+  }
+  if (k < K) {
+    for (int rr = 0; rr < 16; ++rr) {
+      const int r = rg * 16 + rr;
+      if (r0 + r >= B) break;
+      const float x = __bfloat162float(phi[(int64_t)(r0 + r) * K + k]);
+      float g = 0.0f;
+#pragma unroll
+      for (int n = 0; n < HEAD_MAX_OUT + 1; ++n) {
+        if (n < n_out) {
+          const float ge = geff[r][n];
+          g = fmaf(ge, w[n], g);
+          acc[n] = fmaf(ge, x, acc[n]);
+        }
+      }
+      gphi[(int64_t)(r0 + r) * K + k] = __float2bfloat16_rn(g);
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < HEAD_MAX_OUT + 1; ++n)
+    if (n < n_out) red[rg][threadIdx.x & 63][n] = acc[n];
+  __syncthreads();
+  for (int e = threadIdx.x; e < 64 * n_out; e += blockDim.x) {
+    const int c = e % 64, n = e / 64;
+    const int kk = blockIdx.x * 64 + c;
+    if (kk < K) {
+      const float s = red[0][c][n] + red[1][c][n] + red[2][c][n] + red[3][c][n];
+      atomicAdd((n < A) ? gWa + (int64_t)n * K + kk : gWv + kk, s);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < n_out) {      // bias gradients: sum of geff over this block's rows
+    float s = 0.0f;
+    for (int r = 0; r < 64; ++r) s += geff[r][threadIdx.x];
+    atomicAdd((threadIdx.x < A) ? gba + threadIdx.x : gbv, s);
+  }
+}
+
+}  // namespace b2rl
+
+using namespace b2rl;
+
+extern "C" int b2rl_head_fwd(const uint16_t* phi, const float* Wa, const float* ba, const float* Wv, const float* bv,
+                             int32_t B, int32_t K, int32_t A, float* q, void* stream) {
+  B2RL_REQUIRE(phi && Wa && ba && q && ((Wv == nullptr) == (bv == nullptr)), "null pointer");
+  B2RL_REQUIRE(B > 0 && K > 0 && K % 2 == 0 && A > 0 && A < HEAD_MAX_OUT, "need K even and 0 < A < 32");
+  head_fwd_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(phi), Wa, ba, Wv, bv,
+                                                                 B, K, A, q);
+  return check_launch("b2rl_head_fwd");
+}
+
+extern "C" int b2rl_head_bwd(const float* gq, const uint16_t* phi, const float* Wa, const float* Wv, int32_t B, int32_t K,
+                             int32_t A, uint16_t* gphi, float* gWa, float* gba, float* gWv, float* gbv, void* stream) {
+  B2RL_REQUIRE(gq && phi && Wa && gphi && gWa && gba && ((Wv == nullptr) == (gWv == nullptr)) && ((Wv == nullptr) == (gbv == nullptr)),
+               "null pointer");
+  B2RL_REQUIRE(B > 0 && K > 0 && A > 0 && A < HEAD_MAX_OUT, "need 0 < A < 32");
+  dim3 grid((K + 63) / 64, (B + 63) / 64);
+  head_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gq, reinterpret_cast<const __nv_bfloat16*>(phi), Wa, Wv, B, K, A,
+                                                          reinterpret_cast<__nv_bfloat16*>(gphi), gWa, gba, gWv, gbv);
+  return check_launch("b2rl_head_bwd");
+}

@@ -49,6 +49,7 @@ class GraphedDQNLearner:
         self.h_loss = torch.zeros(1, dtype=torch.float32, pin_memory=True)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.g_main = self.g_opt = None
+        self._side = None
         self.updates = 0
         self.with_h2d = False
 
@@ -79,11 +80,19 @@ class GraphedDQNLearner:
             fs = 1.0
         per = dict(is_prob=t.sampling_prob, eps=self.eps, alpha=self.alpha, beta_dev=self.d_beta) if self.per else {}
         self._repack(self.net, fs)                       # online weights changed in the previous optimizer step
+        # the target forward on s' and the online forward on s are independent: fork them onto two streams (two parallel
+        # branches of the captured graph) so that the prologue / tail of one chain overlaps the other
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side), frame_scale(fs), torch.no_grad():
+            nxt_t = self.tgt(t.next_state)
         with frame_scale(fs):
             with torch.no_grad():
-                nxt_t = self.tgt(t.next_state)
                 nxt_o = self.net(t.next_state) if self.double_q else None
             out = self.net(t.state)
+        cur.wait_stream(self._side)
         if self.kind == "dqn":
             head = out["q"]
             r = ops.dqn_loss_fused(head.detach(), nxt_t["q"], nxt_o["q"] if nxt_o else None, t.action, t.reward, t.mask,

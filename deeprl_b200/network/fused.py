@@ -51,9 +51,10 @@ def bias_act_(y, bias, relu=True):
 def act_bwd_bias_grad(gy, y, relu=True, row_map=0, G=0, V=0, out_rows=None):
     """-> (g = gy * (y > 0) in bf16, dbias fp32 [C]).  ``row_map`` re-lays ``g`` out on a G x G grid (csrc/dense.cu)."""
     if row_map:
-        rows, C = (gy.shape[0] * 4, gy.shape[1] // 4) if row_map == 2 else gy.shape
+        C = gy.shape[1] // 4 if row_map == 2 else gy.shape[1]
+        rows = out_rows                                  # the kernel walks destination rows and zero-fills padding rows
         assert gy.is_contiguous() and y.is_contiguous() and gy.dtype == _bf16
-        g = torch.zeros((out_rows, C), dtype=_bf16, device=gy.device)
+        g = torch.empty((out_rows, C), dtype=_bf16, device=gy.device)
         db = torch.empty(C, dtype=torch.float32, device=gy.device)
         partial = _Scratch.get(y.device, "act_bwd_partial", 592 * 2048, torch.float32)
         counter = _Scratch.get(y.device, "act_bwd_counter", 1, torch.int32)
@@ -135,3 +136,52 @@ def space_to_depth_weight(weight, block=4):
     assert kh == kw == 2 * block
     w = weight.view(co, ci, 2, block, 2, block)          # (n, f, ky2, dy, kx2, dx)
     return w.permute(0, 1, 3, 5, 2, 4).reshape(co, ci * block * block, 2, 2)
+
+
+class _NarrowHead(torch.autograd.Function):
+    """VanillaNet / DuelingNet head on bf16 features (csrc/head.cu): 2 launches per update instead of ~12."""
+
+    @staticmethod
+    def forward(ctx, phi, wa, ba, wv, bv):
+        B, K = phi.shape
+        A = wa.shape[0]
+        q = torch.empty((B, A), dtype=torch.float32, device=phi.device)
+        _lib.call("b2rl_head_fwd", _lib.ptr(phi), _lib.ptr(wa.detach()), _lib.ptr(ba.detach()),
+                  _lib.ptr(None if wv is None else wv.detach()), _lib.ptr(None if bv is None else bv.detach()), B, K, A,
+                  _lib.ptr(q), _lib.stream())
+        ctx.save_for_backward(phi)
+        ctx.params = (wa, ba, wv, bv)
+        return q
+
+    @staticmethod
+    def backward(ctx, gq):
+        (phi,) = ctx.saved_tensors
+        wa, ba, wv, bv = ctx.params
+        B, K = phi.shape
+        A = wa.shape[0]
+        gq = gq.contiguous().float()
+        gphi = torch.empty_like(phi)
+        params = [p for p in (wa, ba, wv, bv) if p is not None]
+        inplace = all(p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous() for p in params)
+        if inplace:
+            gwa, gba = wa.grad, ba.grad
+            gwv, gbv = (wv.grad, bv.grad) if wv is not None else (None, None)
+        else:
+            z = lambda p: None if p is None else torch.zeros_like(p, dtype=torch.float32)
+            gwa, gba, gwv, gbv = z(wa), z(ba), z(wv), z(bv)
+        _lib.call("b2rl_head_bwd", _lib.ptr(gq), _lib.ptr(phi), _lib.ptr(wa.detach()), _lib.ptr(None if wv is None else wv.detach()),
+                  B, K, A, _lib.ptr(gphi), _lib.ptr(gwa), _lib.ptr(gba), _lib.ptr(gwv), _lib.ptr(gbv), _lib.stream())
+        if inplace:
+            return gphi, None, None, None, None
+        return gphi, gwa, gba, gwv, gbv
+
+
+def narrow_head(phi, fc_action, fc_value=None):
+    """``q = fc_action(phi)`` or the dueling combine ``v + adv - mean(adv)`` (network_heads.py:18-21, 32-37)."""
+    return _NarrowHead.apply(phi.contiguous(), fc_action.weight, fc_action.bias,
+                             None if fc_value is None else fc_value.weight, None if fc_value is None else fc_value.bias)
+
+
+def narrow_head_ok(phi, fc_action):
+    return (phi.is_cuda and phi.dtype == _bf16 and phi.dim() == 2 and phi.shape[1] % 2 == 0
+            and isinstance(fc_action, torch.nn.Linear) and fc_action.out_features < 32)

@@ -113,6 +113,11 @@ class _NatureBody(torch.autograd.Function):
         x0m, x1, y2, y3, y4, w2d, w3d, w4p = ctx.saved_tensors
         B = y4.shape[0]
         dev = y4.device
+        c0 = x0m.shape[1]
+        gw_all = torch.zeros(32 * 4 * c0 + 64 * 512 + 64 * 576, dtype=_f32, device=dev)   # one memset for the three split-K targets
+        gw1f = gw_all[:32 * 4 * c0].view(32, 4 * c0)
+        gw2f = gw_all[32 * 4 * c0:32 * 4 * c0 + 64 * 512].view(64, 512)
+        gw3f = gw_all[32 * 4 * c0 + 64 * 512:].view(64, 576)
         # ---- fc4
         g4, db4 = act_bwd_bias_grad(gy4, y4, True)                                        # [B, 512]
         y3c = y3.view(B, 3136)
@@ -120,19 +125,16 @@ class _NatureBody(torch.autograd.Function):
         gy3c = gemm_bf16(g4, w4p, a_major="k", b_major="mn", block_n=128)                  # [B, 3136] bf16
         # ---- conv3: mask + bias grad, re-laid out from the compact 7x7 rows to the 10-grid
         g3, db3 = act_bwd_bias_grad(gy3c.view(B * 49, 64), y3, True, row_map=1, G=10, V=7, out_rows=B * 100)
-        gw3f = torch.zeros((64, 576), dtype=_f32, device=dev)
         conv_gemm(1, y2, g3, 64, 9, 3, 10, 1, gw3f, splits=16, block_n=64)
         gy2 = torch.empty((B * 100, 64), dtype=_bf16, device=dev)
         conv_gemm(0, g3, w3d, 64, 9, 3, 10, -1, gy2, block_n=64)
         # ---- conv2
         g2, db2 = act_bwd_bias_grad(gy2, y2, True)                                        # rows 9 / cols 9 of gy2 are exact zeros
-        gw2f = torch.zeros((64, 512), dtype=_f32, device=dev)
         conv_gemm(1, x1, g2, 64, 4, 2, 10, 1, gw2f, splits=16, block_n=128)
         gy1 = torch.empty((B * 100, 128), dtype=_bf16, device=dev)
         conv_gemm(0, g2, w2d, 128, 4, 2, 10, -1, gy1, block_n=128)
         # ---- conv1: mask + bias grad, re-laid out from space-to-depth(2) rows to the 21-grid of conv1's output positions
         g1, db1 = act_bwd_bias_grad(gy1, x1, True, row_map=2, G=21, V=20, out_rows=B * 441)
-        gw1f = torch.zeros((32, x0m.shape[1] * 4), dtype=_f32, device=dev)
         conv_gemm(1, x0m, g1, 32, 4, 2, 21, 1, gw1f, splits=32, block_n=64)
         params = ctx.params
         if all(p.grad is not None and p.grad.dtype == _f32 and p.grad.is_contiguous() for p in params):

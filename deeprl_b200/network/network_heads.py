@@ -9,6 +9,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..utils import Config, tensor
+from . import fused
 from .network_bodies import DummyBody, _autocast
 from .network_utils import BaseNet, NoisyLinear, layer_init
 
@@ -29,6 +30,8 @@ class VanillaNet(nn.Module, BaseNet):
 
     def forward(self, x):
         phi = _phi(self.body, x)
+        if fused.narrow_head_ok(phi, self.fc_head):
+            return dict(q=fused.narrow_head(phi, self.fc_head))
         with _autocast():
             q = self.fc_head(phi)
         return dict(q=q.float())
@@ -44,6 +47,8 @@ class DuelingNet(nn.Module, BaseNet):
 
     def forward(self, x, to_numpy=False):
         phi = _phi(self.body, x)
+        if fused.narrow_head_ok(phi, self.fc_advantage):
+            return dict(q=fused.narrow_head(phi, self.fc_advantage, self.fc_value))
         with _autocast():
             value = self.fc_value(phi).float()
             adv = self.fc_advantage(phi).float()

@@ -192,8 +192,9 @@ int b2rl_bias_act_bf16(uint16_t* y, const float* bias, int64_t rows, int32_t C, 
 int b2rl_bias_act_f32_to_bf16(const float* x, const float* bias, uint16_t* y, int64_t rows, int32_t C, int32_t relu,
                               void* stream);
 /* row_map re-lays the gradient out for the next GEMM of the grid-convolution stack (csrc/gemm.cu): 0 identity;
- * 1: compact V x V rows per image -> G x G grid rows; 2: space-to-depth(2) rows (rows/4 x 4 groups of C channels) ->
- * G x G grid rows.  With a map, gx must be a pre-zeroed buffer of [batch*G*G][C] (padding rows stay zero). */
+ * 1: compact V x V rows per image -> G x G grid rows; 2: space-to-depth(2) rows (4 groups of C channels per row) ->
+ * G x G grid rows.  With a map, `rows` counts the DESTINATION rows (batch*G*G) and gx is [rows][C]; padding rows of the
+ * grid are written as zeros. */
 int b2rl_act_bwd_bias_grad_bf16(const uint16_t* gy, const uint16_t* y, int64_t rows, int32_t C, int32_t relu,
                                 uint16_t* gx, float* dbias, float* partial, int32_t* counter, int32_t row_map, int32_t G,
                                 int32_t V, void* stream);
@@ -237,6 +238,15 @@ int b2rl_nature_unpack_grads(const float* g1f, const float* g2f, const float* g3
                              const float* db2, const float* db3, const float* db4, int32_t c1, int32_t n4, float scale,
                              float* gw1, float* gw2, float* gw3, float* gw4, float* gb1, float* gb2, float* gb3,
                              float* gb4, void* stream);
+
+/* Narrow value heads (VanillaNet / DuelingNet, network_heads.py:11-37) on the bf16 features phi [B][K] of the fused body:
+ * forward q [B][A] (fp32) = phi Wa^T + ba, or with Wv/bv != NULL the dueling combine q = v + adv - mean(adv);
+ * backward from gq [B][A]: gphi [B][K] (bf16), and gWa [A][K], gba [A], gWv [K], gbv [1] ACCUMULATED (atomics) into the
+ * given fp32 buffers.  0 < A < 32. */
+int b2rl_head_fwd(const uint16_t* phi, const float* Wa, const float* ba, const float* Wv, const float* bv, int32_t B,
+                  int32_t K, int32_t A, float* q, void* stream);
+int b2rl_head_bwd(const float* gq, const uint16_t* phi, const float* Wa, const float* Wv, int32_t B, int32_t K, int32_t A,
+                  uint16_t* gphi, float* gWa, float* gba, float* gWv, float* gbv, void* stream);
 
 #ifdef __cplusplus
 }

@@ -699,6 +699,34 @@ def _conv_grid_gemm_vs_torch(rl):
         rl.Config.DENSE_BACKEND = "tcgen05"
 
 
+def test_narrow_head_kernels_vs_torch(rl):
+    """csrc/head.cu (VanillaNet / DuelingNet heads on bf16 features) against the torch expressions of network_heads.py."""
+    from deeprl_b200.network import fused
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for (B, K, A) in ((512, 512, 4), (512, 512, 18), (37, 64, 6), (1, 512, 2)):
+        phi = torch.randn(B, K, device="cuda", generator=gen).to(torch.bfloat16)
+        fa, fv = torch.nn.Linear(K, A).cuda(), torch.nn.Linear(K, 1).cuda()
+        gq = torch.randn(B, A, device="cuda", generator=gen)
+        for dueling in (False, True):
+            x = phi.float().requires_grad_(True)
+            adv = fa(x)
+            q_ref = (fv(x).expand_as(adv) + (adv - adv.mean(1, keepdim=True))) if dueling else adv
+            for m in (fa, fv):
+                m.zero_grad()
+            q_ref.backward(gq)
+            ref = [p.grad.clone() for p in (list(fa.parameters()) + (list(fv.parameters()) if dueling else []))]
+            for m in (fa, fv):
+                m.zero_grad()
+            xp = phi.clone().requires_grad_(True)
+            q = fused.narrow_head(xp, fa, fv if dueling else None)
+            torch.testing.assert_close(q, q_ref.detach(), rtol=1e-5, atol=1e-5)
+            q.backward(gq)
+            got = [p.grad for p in (list(fa.parameters()) + (list(fv.parameters()) if dueling else []))]
+            for a, b in zip(got, ref):
+                torch.testing.assert_close(a.reshape(b.shape), b, rtol=1e-4, atol=1e-4)
+            torch.testing.assert_close(xp.grad.float(), x.grad, rtol=1e-2, atol=1e-3)       # bf16 output
+
+
 # ------------------------------------------------------------------------------------------ agents (product code path)
 class _Batch:
     pass
