@@ -35,17 +35,22 @@ class GraphedDQNLearner:
         self.B = B
         n = max(self.feeds, 1)
         rb = replay.row_bytes
-        # pinned host staging for the env transitions of one update + device mirrors (one packed copy each)
-        self.h_frames = torch.zeros((n, rb), dtype=torch.uint8, pin_memory=True)
-        self.h_action = torch.zeros(n, dtype=torch.int32, pin_memory=True)
-        self.h_reward = torch.zeros(n, dtype=torch.float64, pin_memory=True)
-        self.h_mask = torch.ones(n, dtype=torch.int32, pin_memory=True)
-        self.d_frames = torch.zeros((n, rb), dtype=torch.uint8, device=dev)
-        self.d_action = torch.zeros(n, dtype=torch.int32, device=dev)
-        self.d_reward = torch.zeros(n, dtype=torch.float64, device=dev)
-        self.d_mask = torch.ones(n, dtype=torch.int32, device=dev)
-        self.h_beta = torch.full((1,), 0.4, dtype=torch.float32, pin_memory=True)
-        self.d_beta = torch.full((1,), 0.4, dtype=torch.float32, device=dev)
+        # ONE packed pinned staging buffer for the env transitions of an update (+ PER beta) and ONE device mirror:
+        # [frames n*rb | reward n*8 | action n*4 | mask n*4 | beta 4] -> a single host->device copy node in the graph
+        o_r = (n * rb + 7) // 8 * 8
+        o_a, o_m, o_b = o_r + 8 * n, o_r + 12 * n, o_r + 16 * n
+        total = (o_b + 4 + 15) // 16 * 16
+        self.h_pack = torch.zeros(total, dtype=torch.uint8, pin_memory=True)
+        self.d_pack = torch.zeros(total, dtype=torch.uint8, device=dev)
+
+        def views(buf):
+            return (buf[:n * rb].view(n, rb), buf[o_a:o_a + 4 * n].view(torch.int32), buf[o_r:o_r + 8 * n].view(torch.float64),
+                    buf[o_m:o_m + 4 * n].view(torch.int32), buf[o_b:o_b + 4].view(torch.float32))
+
+        self.h_frames, self.h_action, self.h_reward, self.h_mask, self.h_beta = views(self.h_pack)
+        self.d_frames, self.d_action, self.d_reward, self.d_mask, self.d_beta = views(self.d_pack)
+        self.h_mask.fill_(1), self.h_beta.fill_(0.4)
+        self.d_pack.copy_(self.h_pack)
         self.h_loss = torch.zeros(1, dtype=torch.float32, pin_memory=True)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.g_main = self.g_opt = None
@@ -55,11 +60,7 @@ class GraphedDQNLearner:
 
     # ------------------------------------------------------------------ the update, as eager code
     def _h2d(self):
-        self.d_frames.copy_(self.h_frames, non_blocking=True)
-        self.d_action.copy_(self.h_action, non_blocking=True)
-        self.d_reward.copy_(self.h_reward, non_blocking=True)
-        self.d_mask.copy_(self.h_mask, non_blocking=True)
-        self.d_beta.copy_(self.h_beta, non_blocking=True)
+        self.d_pack.copy_(self.h_pack, non_blocking=True)
 
     def _main(self):
         rp = self.replay
@@ -193,4 +194,4 @@ class GraphedDQNLearner:
 
     @property
     def h2d_bytes(self):
-        return sum(t.numel() * t.element_size() for t in (self.h_frames, self.h_action, self.h_reward, self.h_mask, self.h_beta))
+        return self.h_pack.numel()
