@@ -518,6 +518,7 @@ struct WgradParams {
   int slab_rows, stages, k_tiles_per_cta, a_boxes;
   float* D;
   int ldd;
+  int64_t partial_stride;   // 0: atomically accumulate into D; > 0: CTA i stores its partial sums at D + i*partial_stride
 };
 
 template <int TMEM_COLS>
@@ -600,8 +601,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, r);
       if (n < w.n_out) {
-        float* d = w.D + (int64_t)n * w.ldd + (int64_t)w.tap0 * w.C + c;
-        if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+        float* d = w.D + (int64_t)blockIdx.x * w.partial_stride + (int64_t)n * w.ldd + (int64_t)w.tap0 * w.C + c;
+        if (w.partial_stride > 0) {
+          // split-K partials are stored plainly (coalesced 16-byte stores) and summed by the consumer
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(d + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        } else if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)       // 16-byte vector reductions (red.global.add.v4.f32)
             atomicAdd(reinterpret_cast<float4*>(d + j), make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
@@ -723,7 +730,7 @@ static int launch_slab(const CUtensorMap& ta, const CUtensorMap& tb, SlabParams 
 }
 
 template <int TMEM_COLS>
-static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, WgradParams w, cudaStream_t st) {
+static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, WgradParams w, cudaStream_t st, int* n_ctas = nullptr) {
   const size_t slab_bytes = (size_t)w.slab_rows * 128 * w.col_blocks, stage = 16384 + slab_bytes;
   int stages = (int)((200 * 1024) / stage);
   if (stages > 6) stages = 6;
@@ -744,6 +751,7 @@ static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, WgradParam
   if (ctas < 1) ctas = 1;
   w.k_tiles_per_cta = (kt_total + ctas - 1) / ctas;
   ctas = (kt_total + w.k_tiles_per_cta - 1) / w.k_tiles_per_cta;
+  if (n_ctas) *n_ctas = ctas;
   k<<<ctas, GEMM_THREADS, smem, st>>>(tg, tx, w);
   return check_launch("b2rl_conv_gemm_bf16(wgrad slab)");
 }
@@ -752,6 +760,10 @@ static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, WgradParam
 
 using namespace b2rl;
 
+static int g_wgrad_partials = 0;          // set by b2rl_conv_wgrad_partials for the duration of one call
+static float* g_partial_buf = nullptr;
+static int64_t g_partial_stride = 0;
+static int g_partial_count = 0;
 static int g_use_slab = 2;   // 2: shifted windows with base_offset 0 -- the 128B swizzle is a pure function of the smem address (verified on B200)
 extern "C" void b2rl_set_conv_slab(int32_t on) { g_use_slab = on; }
 
@@ -838,6 +850,7 @@ extern "C" int b2rl_conv_gemm_bf16(int32_t mode, const uint16_t* X, int64_t rows
     w.slab_rows = (GEMM_BK + max_shift + 7) / 8 * 8;
     w.a_boxes = n_out > 64 ? 2 : 1;
     w.D = reinterpret_cast<float*>(D); w.ldd = (int)ldd;
+    if (g_wgrad_partials) { w.D = g_partial_buf; w.partial_stride = g_partial_stride; }
     CUtensorMap tg, tx;
     rc = make_map(&tg, W_or_G, n_out, rows, n_out, 64);             // gradient rows: box [64 k][64 n]
     if (rc) return rc;
@@ -849,13 +862,29 @@ extern "C" int b2rl_conv_gemm_bf16(int32_t mode, const uint16_t* X, int64_t rows
       w.tap0 = t0;
       w.ntaps = taps - t0 < per_launch ? taps - t0 : per_launch;
       const int cols = w.ntaps * C;
-      r2 = cols <= 64 ? launch_wgrad<64>(tg, tx, w, (cudaStream_t)stream)
-           : cols <= 128 ? launch_wgrad<128>(tg, tx, w, (cudaStream_t)stream)
-           : cols <= 256 ? launch_wgrad<256>(tg, tx, w, (cudaStream_t)stream)
-                         : launch_wgrad<512>(tg, tx, w, (cudaStream_t)stream);
+      r2 = cols <= 64 ? launch_wgrad<64>(tg, tx, w, (cudaStream_t)stream, &g_partial_count)
+           : cols <= 128 ? launch_wgrad<128>(tg, tx, w, (cudaStream_t)stream, &g_partial_count)
+           : cols <= 256 ? launch_wgrad<256>(tg, tx, w, (cudaStream_t)stream, &g_partial_count)
+                         : launch_wgrad<512>(tg, tx, w, (cudaStream_t)stream, &g_partial_count);
     }
     if (r2 <= 0) return r2;
   }
   p.M = n_out; p.N = taps * C; p.K = (int)rows; p.a_mn = 1; p.b_mn = 1; p.b_tap_tiles = C / block_n;
   return gemm_dispatch(W_or_G, 1, n_out, rows, n_out, X, 1, C, rows, C, p, splits, block_n, (cudaStream_t)stream);
+}
+
+// Weight gradient as split-K PARTIALS: partial i (one per CTA, n_partials_host of them, at most 148) is stored at
+// partials + i * n_out * taps * C; the consumer (b2rl_nature_unpack_grads) sums them.  Replaces ~1M fp32 atomics per
+// layer by coalesced stores.
+extern "C" int b2rl_conv_wgrad_partials(const uint16_t* X, int64_t rows, int32_t C, const uint16_t* G, int32_t n_out,
+                                        int32_t taps, int32_t taps_x, int32_t grid_w, float* partials,
+                                        int32_t* n_partials_host, void* stream) {
+  B2RL_REQUIRE(partials && n_partials_host, "null pointer");
+  B2RL_REQUIRE(g_use_slab && C % 64 == 0 && C <= 128 && n_out <= 128, "partials need the slab wgrad kernel");
+  g_wgrad_partials = 1; g_partial_buf = partials; g_partial_stride = (int64_t)n_out * taps * C; g_partial_count = 0;
+  int rc = b2rl_conv_gemm_bf16(1, X, rows, C, G, n_out, taps, taps_x, grid_w, 1, partials, (int64_t)taps * C, nullptr, 0, 2,
+                               0, 0, 0, 1, C == 128 ? 128 : 64, stream);
+  g_wgrad_partials = 0;
+  *n_partials_host = g_partial_count;
+  return rc;
 }

@@ -72,7 +72,21 @@ struct UnpackArgs {
   float* gb1; float* gb2; float* gb3; float* gb4;
   int c1, n4;
   float scale;
+  int p1, p2, p3;      // number of split-K partials of g1f / g2f / g3f (1 = already reduced)
 };
+
+__device__ __forceinline__ float sum_partials(const float* g, int64_t idx, int parts, int64_t stride) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int p = 0;
+  for (; p + 3 < parts; p += 4) {                    // 4 independent loads in flight
+    s0 += g[idx + (int64_t)p * stride];
+    s1 += g[idx + (int64_t)(p + 1) * stride];
+    s2 += g[idx + (int64_t)(p + 2) * stride];
+    s3 += g[idx + (int64_t)(p + 3) * stride];
+  }
+  for (; p < parts; ++p) s0 += g[idx + (int64_t)p * stride];
+  return (s0 + s1) + (s2 + s3);
+}
 
 __global__ void __launch_bounds__(256) unpack_grads_kernel(UnpackArgs a) {
   const int64_t s1 = 32LL * a.c1 * 64, s2 = 64 * 512, s3 = 64 * 576, s4 = (int64_t)a.n4 * 3136;
@@ -83,20 +97,20 @@ __global__ void __launch_bounds__(256) unpack_grads_kernel(UnpackArgs a) {
     if (i < s1) {       // gw1[n][f][ky][kx]
       const int kx = (int)(i % 8), ky = (int)((i / 8) % 8), f = (int)((i / 64) % a.c1), n = (int)(i / (64 * a.c1));
       const int tap = (ky / 4) * 2 + kx / 4, c = f * 16 + (ky % 4) * 4 + kx % 4;
-      a.gw1[i] += a.g1f[(int64_t)n * 64 * a.c1 + tap * 16 * a.c1 + c] * a.scale;
+      a.gw1[i] += sum_partials(a.g1f, (int64_t)n * 64 * a.c1 + tap * 16 * a.c1 + c, a.p1, s1) * a.scale;
       continue;
     }
     i -= s1;
     if (i < s2) {       // gw2[n][c][ky][kx]
       const int kx = (int)(i % 4), ky = (int)((i / 4) % 4), c = (int)((i / 16) % 32), n = (int)(i / 512);
       const int tap = (ky / 2) * 2 + kx / 2, r = ((ky % 2) * 2 + kx % 2) * 32 + c;
-      a.gw2[i] += a.g2f[n * 512 + tap * 128 + r];
+      a.gw2[i] += sum_partials(a.g2f, n * 512 + tap * 128 + r, a.p2, s2);
       continue;
     }
     i -= s2;
     if (i < s3) {       // gw3[n][c][ky][kx]
       const int tap = (int)(i % 9), c = (int)((i / 9) % 64), n = (int)(i / 576);
-      a.gw3[i] += a.g3f[n * 576 + tap * 64 + c];
+      a.gw3[i] += sum_partials(a.g3f, n * 576 + tap * 64 + c, a.p3, s3);
       continue;
     }
     i -= s3;
@@ -139,13 +153,15 @@ extern "C" int b2rl_nature_pack_weights(const float* w1, const float* w2, const 
 extern "C" int b2rl_nature_unpack_grads(const float* g1f, const float* g2f, const float* g3f, const float* g4p,
                                         const float* db1, const float* db2, const float* db3, const float* db4,
                                         int32_t c1, int32_t n4, float scale, float* gw1, float* gw2, float* gw3,
-                                        float* gw4, float* gb1, float* gb2, float* gb3, float* gb4, void* stream) {
+                                        float* gw4, float* gb1, float* gb2, float* gb3, float* gb4, int32_t p1,
+                                        int32_t p2, int32_t p3, void* stream) {
   B2RL_REQUIRE(g1f && g2f && g3f && g4p && db1 && db2 && db3 && db4 && gw1 && gw2 && gw3 && gw4 && gb1 && gb2 && gb3 && gb4,
                "null pointer");
   UnpackArgs a;
   a.g1f = g1f; a.g2f = g2f; a.g3f = g3f; a.g4p = g4p; a.db1 = db1; a.db2 = db2; a.db3 = db3; a.db4 = db4;
   a.gw1 = gw1; a.gw2 = gw2; a.gw3 = gw3; a.gw4 = gw4; a.gb1 = gb1; a.gb2 = gb2; a.gb3 = gb3; a.gb4 = gb4;
   a.c1 = c1; a.n4 = n4; a.scale = scale;
+  a.p1 = p1 < 1 ? 1 : p1; a.p2 = p2 < 1 ? 1 : p2; a.p3 = p3 < 1 ? 1 : p3;
   unpack_grads_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(a);
   return check_launch("b2rl_nature_unpack_grads");
 }

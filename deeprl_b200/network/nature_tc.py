@@ -25,6 +25,17 @@ _bf16 = torch.bfloat16
 _f32 = torch.float32
 
 
+def wgrad_partials(X, G_rows, n_out, taps, taps_x, grid_w):
+    """Split-K partial weight gradients (one per CTA, no atomics): returns (partials [P_max, n_out, taps*C] fp32, P)."""
+    import ctypes
+    rows, C = X.shape
+    buf = torch.empty((148, n_out, taps * C), dtype=_f32, device=X.device)
+    n = ctypes.c_int32(0)
+    _lib.call("b2rl_conv_wgrad_partials", _lib.ptr(X), int(rows), int(C), _lib.ptr(G_rows), int(n_out), int(taps), int(taps_x),
+              int(grid_w), _lib.ptr(buf), ctypes.byref(n), _lib.stream())
+    return buf, int(n.value)
+
+
 def conv_gemm(mode, X, W_or_G, n_out, taps, taps_x, grid_w, sign, out, bias=None, relu=False, out_map=0, G=0, V=0, splits=1,
               block_n=64):
     rows, C = X.shape
@@ -113,11 +124,6 @@ class _NatureBody(torch.autograd.Function):
         x0m, x1, y2, y3, y4, w2d, w3d, w4p = ctx.saved_tensors
         B = y4.shape[0]
         dev = y4.device
-        c0 = x0m.shape[1]
-        gw_all = torch.zeros(32 * 4 * c0 + 64 * 512 + 64 * 576, dtype=_f32, device=dev)   # one memset for the three split-K targets
-        gw1f = gw_all[:32 * 4 * c0].view(32, 4 * c0)
-        gw2f = gw_all[32 * 4 * c0:32 * 4 * c0 + 64 * 512].view(64, 512)
-        gw3f = gw_all[32 * 4 * c0 + 64 * 512:].view(64, 576)
         # ---- fc4
         g4, db4 = act_bwd_bias_grad(gy4, y4, True)                                        # [B, 512]
         y3c = y3.view(B, 3136)
@@ -125,26 +131,28 @@ class _NatureBody(torch.autograd.Function):
         gy3c = gemm_bf16(g4, w4p, a_major="k", b_major="mn", block_n=128)                  # [B, 3136] bf16
         # ---- conv3: mask + bias grad, re-laid out from the compact 7x7 rows to the 10-grid
         g3, db3 = act_bwd_bias_grad(gy3c.view(B * 49, 64), y3, True, row_map=1, G=10, V=7, out_rows=B * 100)
-        conv_gemm(1, y2, g3, 64, 9, 3, 10, 1, gw3f, splits=16, block_n=64)
+        gw3p, p3 = wgrad_partials(y2, g3, 64, 9, 3, 10)
         gy2 = torch.empty((B * 100, 64), dtype=_bf16, device=dev)
         conv_gemm(0, g3, w3d, 64, 9, 3, 10, -1, gy2, block_n=64)
         # ---- conv2
         g2, db2 = act_bwd_bias_grad(gy2, y2, True)                                        # rows 9 / cols 9 of gy2 are exact zeros
-        conv_gemm(1, x1, g2, 64, 4, 2, 10, 1, gw2f, splits=16, block_n=128)
+        gw2p, p2 = wgrad_partials(x1, g2, 64, 4, 2, 10)
         gy1 = torch.empty((B * 100, 128), dtype=_bf16, device=dev)
         conv_gemm(0, g2, w2d, 128, 4, 2, 10, -1, gy1, block_n=128)
         # ---- conv1: mask + bias grad, re-laid out from space-to-depth(2) rows to the 21-grid of conv1's output positions
         g1, db1 = act_bwd_bias_grad(gy1, x1, True, row_map=2, G=21, V=20, out_rows=B * 441)
-        conv_gemm(1, x0m, g1, 32, 4, 2, 21, 1, gw1f, splits=32, block_n=64)
+        gw1p, p1 = wgrad_partials(x0m, g1, 32, 4, 2, 21)
         params = ctx.params
         if all(p.grad is not None and p.grad.dtype == _f32 and p.grad.is_contiguous() for p in params):
             # accumulate straight into the .grad arena (reference layouts), one launch
             w1, b1, w2, b2, w3, b3, w4, b4 = params
-            _lib.call("b2rl_nature_unpack_grads", _lib.ptr(gw1f), _lib.ptr(gw2f), _lib.ptr(gw3f), _lib.ptr(gw4p), _lib.ptr(db1),
+            # (the kernel also sums the split-K partials of the three convolution weight gradients)
+            _lib.call("b2rl_nature_unpack_grads", _lib.ptr(gw1p), _lib.ptr(gw2p), _lib.ptr(gw3p), _lib.ptr(gw4p), _lib.ptr(db1),
                       _lib.ptr(db2), _lib.ptr(db3), _lib.ptr(db4), ctx.c1, w4.shape[0], float(ctx.scale), _lib.ptr(w1.grad),
                       _lib.ptr(w2.grad), _lib.ptr(w3.grad), _lib.ptr(w4.grad), _lib.ptr(b1.grad), _lib.ptr(b2.grad),
-                      _lib.ptr(b3.grad), _lib.ptr(b4.grad), _lib.stream())
+                      _lib.ptr(b3.grad), _lib.ptr(b4.grad), p1, p2, p3, _lib.stream())
             return (None,) * 11
+        gw1f, gw2f, gw3f = gw1p[:p1].sum(0), gw2p[:p2].sum(0), gw3p[:p3].sum(0)
         g1w, g2w, g3w, g4w = unpack_grads(gw1f, gw2f, gw3f, gw4p, ctx.scale, ctx.c1)
         return None, g1w, db1, g2w, db2, g3w, db3, g4w, db4, None, None
 

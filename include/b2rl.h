@@ -237,7 +237,8 @@ int b2rl_nature_pack_weights(const float* w1, const float* w2, const float* w3, 
 int b2rl_nature_unpack_grads(const float* g1f, const float* g2f, const float* g3f, const float* g4p, const float* db1,
                              const float* db2, const float* db3, const float* db4, int32_t c1, int32_t n4, float scale,
                              float* gw1, float* gw2, float* gw3, float* gw4, float* gb1, float* gb2, float* gb3,
-                             float* gb4, void* stream);
+                             float* gb4, int32_t p1, int32_t p2, int32_t p3 /* split-K partial counts of g1f/g2f/g3f, stored
+                             n_out*K floats apart (b2rl_conv_wgrad_partials); 1 = plain */, void* stream);
 
 /* Narrow value heads (VanillaNet / DuelingNet, network_heads.py:11-37) on the bf16 features phi [B][K] of the fused body:
  * forward q [B][A] (fp32) = phi Wa^T + ba, or with Wv/bv != NULL the dueling combine q = v + adv - mean(adv);
@@ -247,6 +248,11 @@ int b2rl_head_fwd(const uint16_t* phi, const float* Wa, const float* ba, const f
                   int32_t K, int32_t A, float* q, void* stream);
 int b2rl_head_bwd(const float* gq, const uint16_t* phi, const float* Wa, const float* Wv, int32_t B, int32_t K, int32_t A,
                   uint16_t* gphi, float* gWa, float* gba, float* gWv, float* gbv, void* stream);
+
+/* Convolution weight gradient as split-K partials (no atomics): partial i of *n_partials_host (<= 148, written on the
+ * HOST, deterministic for given shapes) is stored at partials + i * n_out*taps*C floats. */
+int b2rl_conv_wgrad_partials(const uint16_t* X, int64_t rows, int32_t C, const uint16_t* G, int32_t n_out, int32_t taps,
+                             int32_t taps_x, int32_t grid_w, float* partials, int32_t* n_partials_host, void* stream);
 
 #ifdef __cplusplus
 }
