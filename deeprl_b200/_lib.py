@@ -129,6 +129,15 @@ def set_conv_slab(on):
     L.b2rl_set_conv_slab.restype = None
     L.b2rl_set_conv_slab.argtypes = [ctypes.c_int32]
     L.b2rl_set_conv_slab(int(on))
+    global CONV_SLAB
+    CONV_SLAB = int(on)
+
+
+CONV_SLAB = 2
+
+
+def _unused():
+    pass
 
 
 def launch_count():

@@ -29,6 +29,10 @@ def wgrad_partials(X, G_rows, n_out, taps, taps_x, grid_w):
     """Split-K partial weight gradients (one per CTA, no atomics): returns (partials [P_max, n_out, taps*C] fp32, P)."""
     import ctypes
     rows, C = X.shape
+    if not _lib.CONV_SLAB:                       # tap-addressing mode (tests): atomic accumulation into one "partial"
+        out = torch.zeros((1, n_out, taps * C), dtype=_f32, device=X.device)
+        conv_gemm(1, X, G_rows, n_out, taps, taps_x, grid_w, 1, out[0], splits=16, block_n=128 if C == 128 else 64)
+        return out, 1
     buf = torch.empty((148, n_out, taps * C), dtype=_f32, device=X.device)
     n = ctypes.c_int32(0)
     _lib.call("b2rl_conv_wgrad_partials", _lib.ptr(X), int(rows), int(C), _lib.ptr(G_rows), int(n_out), int(taps), int(taps_x),
