@@ -75,58 +75,50 @@ struct UnpackArgs {
   int p1, p2, p3;      // number of split-K partials of g1f / g2f / g3f (1 = already reduced)
 };
 
-// sum over split-K partials with 8 cooperating lanes per output element (lane `sub` takes partials sub, sub+8, ...)
-__device__ __forceinline__ float sum_partials8(const float* g, int64_t idx, int parts, int64_t stride, int sub) {
-  float s0 = 0.f, s1 = 0.f;
-  int p = sub;
-  for (; p + 8 < parts; p += 16) {
-    s0 += g[idx + (int64_t)p * stride];
-    s1 += g[idx + (int64_t)(p + 8) * stride];
+// sum over split-K partials; consecutive threads read consecutive elements of the same partial (coalesced), 16
+// independent loads in flight per thread hide the L2 latency
+__device__ __forceinline__ float sum_partials(const float* __restrict__ g, int64_t idx, int parts, int64_t stride) {
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
+  int p = 0;
+  for (; p + 15 < parts; p += 16) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] += __ldg(g + idx + (int64_t)(p + j) * stride);
   }
-  if (p < parts) s0 += g[idx + (int64_t)p * stride];
-  float s = s0 + s1;
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
-  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  for (; p < parts; ++p) acc[0] += __ldg(g + idx + (int64_t)p * stride);
+  float s = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s += acc[j];
   return s;
 }
 
 __global__ void __launch_bounds__(256) unpack_grads_kernel(UnpackArgs a) {
-  // work items: 8 lanes per convolution-weight element (they sum the split-K partials), 1 per fc4 / bias element
   const int64_t s1 = 32LL * a.c1 * 64, s2 = 64 * 512, s3 = 64 * 576, s4 = (int64_t)a.n4 * 3136;
   const int64_t sb = 32 + 64 + 64 + a.n4;
-  const int64_t conv8 = (s1 + s2 + s3) * 8;
-  const int64_t total = conv8 + s4 + sb;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (total + 31) / 32 * 32;
-       e += (int64_t)gridDim.x * blockDim.x) {
-    if (e < conv8) {                                 // whole warps take this branch together (conv8 is a multiple of 32)
-      const int sub = (int)(e & 7);
-      int64_t i = e >> 3;                            // i indexes the REFERENCE-layout destination
-      if (i < s1) {       // gw1[n][f][ky][kx]
-        const int kx = (int)(i % 8), ky = (int)((i / 8) % 8), f = (int)((i / 64) % a.c1), n = (int)(i / (64 * a.c1));
-        const int tap = (ky / 4) * 2 + kx / 4, c = f * 16 + (ky % 4) * 4 + kx % 4;
-        const float v = sum_partials8(a.g1f, (int64_t)n * 64 * a.c1 + tap * 16 * a.c1 + c, a.p1, s1, sub);
-        if (sub == 0) a.gw1[i] += v * a.scale;
-        continue;
-      }
-      i -= s1;
-      if (i < s2) {       // gw2[n][c][ky][kx]
-        const int kx = (int)(i % 4), ky = (int)((i / 4) % 4), c = (int)((i / 16) % 32), n = (int)(i / 512);
-        const int tap = (ky / 2) * 2 + kx / 2, r = ((ky % 2) * 2 + kx % 2) * 32 + c;
-        const float v = sum_partials8(a.g2f, n * 512 + tap * 128 + r, a.p2, s2, sub);
-        if (sub == 0) a.gw2[i] += v;
-        continue;
-      }
-      i -= s2;
-      {                   // gw3[n][c][ky][kx]
-        const int tap = (int)(i % 9), c = (int)((i / 9) % 64), n = (int)(i / 576);
-        const float v = sum_partials8(a.g3f, n * 576 + tap * 64 + c, a.p3, s3, sub);
-        if (sub == 0) a.gw3[i] += v;
-      }
+  const int64_t total = s1 + s2 + s3 + s4 + sb;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i = e;      // i indexes the REFERENCE-layout destination (coalesced writes)
+    if (i < s1) {       // gw1[n][f][ky][kx]
+      const int kx = (int)(i % 8), ky = (int)((i / 8) % 8), f = (int)((i / 64) % a.c1), n = (int)(i / (64 * a.c1));
+      const int tap = (ky / 4) * 2 + kx / 4, c = f * 16 + (ky % 4) * 4 + kx % 4;
+      a.gw1[i] += sum_partials(a.g1f, (int64_t)n * 64 * a.c1 + tap * 16 * a.c1 + c, a.p1, s1) * a.scale;
       continue;
     }
-    if (e >= total) continue;
-    int64_t i = e - conv8;
+    i -= s1;
+    if (i < s2) {       // gw2[n][c][ky][kx]
+      const int kx = (int)(i % 4), ky = (int)((i / 4) % 4), c = (int)((i / 16) % 32), n = (int)(i / 512);
+      const int tap = (ky / 2) * 2 + kx / 2, r = ((ky % 2) * 2 + kx % 2) * 32 + c;
+      a.gw2[i] += sum_partials(a.g2f, n * 512 + tap * 128 + r, a.p2, s2);
+      continue;
+    }
+    i -= s2;
+    if (i < s3) {       // gw3[n][c][ky][kx]
+      const int tap = (int)(i % 9), c = (int)((i / 9) % 64), n = (int)(i / 576);
+      a.gw3[i] += sum_partials(a.g3f, n * 576 + tap * 64 + c, a.p3, s3);
+      continue;
+    }
+    i -= s3;
     if (i < s4) {       // gw4[n][c*49 + hw]
       const int64_t n = i / 3136;
       const int k = (int)(i % 3136), c = k / 49, hw = k % 49;

@@ -292,37 +292,42 @@ __global__ void __launch_bounds__(256) gather_cvt_kernel(const uint8_t* __restri
     if (!out) continue;
     out += (int64_t)b * stack;
     const uint8_t* s = smem + (which ? (int64_t)n * row_bytes : 0);
+    // Every fast path below gives one thread exactly one 16-byte store per iteration, consecutive lanes writing
+    // consecutive 16-byte pieces: a warp store fills whole 32-byte sectors (two stores of a 32-byte-per-thread unit would
+    // each fill half of 32 sectors and double the L1->L2 write traffic).
+    constexpr int SUBS = 16 / VEC;         // 16-byte pieces per 16-element unit (bf16/fp16: 2, fp32: 4)
     if (LAYOUT == 2) {
-      // unit = (position (Y,X), frame f): 4 words (rows 4Y..4Y+3, cols 4X..4X+3) -> 16 contiguous outputs
+      // unit = (position (Y,X), frame f): rows 4Y..4Y+3, cols 4X..4X+3 -> 16 contiguous outputs; piece = ROWS rows of it
+      constexpr int ROWS = 4 / SUBS;
       const int Wq = frame_w / 4, Hq = (int)(row_bytes / frame_w) / 4;
-      const int units = Hq * Wq * hl;
-      for (int u = threadIdx.x; u < units; u += blockDim.x) {
+      const int pieces = Hq * Wq * hl * SUBS;
+      for (int h = threadIdx.x; h < pieces; h += blockDim.x) {
+        const int u = h / SUBS, sub = h - u * SUBS;
         const int pos = u / hl, f = u - pos * hl;
         const int Y = pos / Wq, X = pos - Y * Wq;
-        const uint8_t* base = s + (int64_t)f * row_bytes + (4 * Y) * frame_w + 4 * X;
-        __align__(16) T v[16];
+        const uint8_t* base = s + (int64_t)f * row_bytes + (4 * Y + sub * ROWS) * frame_w + 4 * X;
+        __align__(16) T v[VEC];
 #pragma unroll
-        for (int dy = 0; dy < 4; ++dy)
+        for (int dy = 0; dy < ROWS; ++dy)
           cvt_word<T>(*reinterpret_cast<const uint32_t*>(base + dy * frame_w), slut, use_lut, v + 4 * dy);
-        int4* o = reinterpret_cast<int4*>(out + (int64_t)u * 16);
-#pragma unroll
-        for (int q = 0; q < 16 / VEC; ++q) o[q] = reinterpret_cast<const int4*>(v)[q];
+        *reinterpret_cast<int4*>(out + (int64_t)h * VEC) = *reinterpret_cast<const int4*>(v);
       }
     } else if (LAYOUT == 1 && hl == 4 && row_bytes % 4 == 0) {
-      // 4 pixels x 4 frames per thread: 4 LDS.32 -> 16 outputs
-      for (int64_t p4 = threadIdx.x; p4 < row_bytes / 4; p4 += blockDim.x) {
+      // piece = PX pixels x 4 frames: one LDS.32 per frame (the word holding the pixels), shifted to the piece
+      constexpr int PX = VEC / 4;
+      const int pieces = (int)(row_bytes / 4) * SUBS;
+      for (int h = threadIdx.x; h < pieces; h += blockDim.x) {
+        const int p4 = h / SUBS, sub = h - p4 * SUBS;
         __align__(16) T c[4][4];
 #pragma unroll
         for (int f = 0; f < 4; ++f)
-          cvt_word<T>(*reinterpret_cast<const uint32_t*>(s + f * row_bytes + p4 * 4), slut, use_lut, c[f]);
-        __align__(16) T v[16];
+          cvt_word<T>(*reinterpret_cast<const uint32_t*>(s + f * row_bytes + p4 * 4) >> (8 * PX * sub), slut, use_lut, c[f]);
+        __align__(16) T v[VEC];
 #pragma unroll
-        for (int px = 0; px < 4; ++px)
+        for (int px = 0; px < PX; ++px)
 #pragma unroll
           for (int f = 0; f < 4; ++f) v[px * 4 + f] = c[f][px];
-        int4* o = reinterpret_cast<int4*>(out + p4 * 16);
-#pragma unroll
-        for (int q = 0; q < 16 / VEC; ++q) o[q] = reinterpret_cast<const int4*>(v)[q];
+        *reinterpret_cast<int4*>(out + (int64_t)h * VEC) = *reinterpret_cast<const int4*>(v);
       }
     } else if (LAYOUT == 1) {
       for (int64_t e = threadIdx.x; e < stack; e += blockDim.x) {
@@ -331,16 +336,14 @@ __global__ void __launch_bounds__(256) gather_cvt_kernel(const uint8_t* __restri
         uint8_t v = s[(int64_t)c * row_bytes + p];
         out[e] = use_lut ? slut[v] : Cvt<T>::f((float)v);
       }
-    } else if (stack % 16 == 0) {
-      for (int64_t e16 = threadIdx.x; e16 < stack / 16; e16 += blockDim.x) {
-        int4 raw = *reinterpret_cast<const int4*>(s + e16 * 16);
-        const uint32_t* rw = reinterpret_cast<const uint32_t*>(&raw);
-        __align__(16) T v[16];
+    } else if (row_bytes % 16 == 0) {
+      // NCHW: VEC input bytes -> one 16-byte store
+      for (int64_t e = threadIdx.x; e < stack / VEC; e += blockDim.x) {
+        __align__(16) T v[VEC];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) cvt_word<T>(rw[k], slut, use_lut, v + 4 * k);
-        int4* o = reinterpret_cast<int4*>(out + e16 * 16);
-#pragma unroll
-        for (int q = 0; q < 16 / VEC; ++q) o[q] = reinterpret_cast<const int4*>(v)[q];
+        for (int k = 0; k < VEC / 4; ++k)
+          cvt_word<T>(*reinterpret_cast<const uint32_t*>(s + e * VEC + 4 * k), slut, use_lut, v + 4 * k);
+        *reinterpret_cast<int4*>(out + e * VEC) = *reinterpret_cast<const int4*>(v);
       }
     } else {
       for (int64_t e = threadIdx.x; e < stack; e += blockDim.x) out[e] = use_lut ? slut[s[e]] : Cvt<T>::f((float)s[e]);
