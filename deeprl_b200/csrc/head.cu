@@ -45,18 +45,20 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __re
   }
 }
 
-// grid (K/64, ceil(B/64)); block 256 = 64 columns x 4 row groups of 16 rows
+// grid (K/64, ceil(B/HB_ROWS)); block 256 = 64 columns x 4 row groups of HB_ROWS/4 rows (many small CTAs: the kernel is
+// latency-bound, 16 rows per CTA puts 256 CTAs in flight at B = 512)
+constexpr int HB_ROWS = 16;
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ gq, const __nv_bfloat16* __restrict__ phi,
                                                        const float* __restrict__ Wa, const float* __restrict__ Wv, int B,
                                                        int K, int A, __nv_bfloat16* __restrict__ gphi,
                                                        float* __restrict__ gWa, float* __restrict__ gba,
                                                        float* __restrict__ gWv, float* __restrict__ gbv) {
-  __shared__ float geff[64][HEAD_MAX_OUT + 1];       // [row][a], last used column = value gradient (dueling)
+  __shared__ float geff[HB_ROWS][HEAD_MAX_OUT + 1];       // [row][a], last used column = value gradient (dueling)
   __shared__ float red[4][64][HEAD_MAX_OUT + 1];
   const int k = blockIdx.x * 64 + (threadIdx.x & 63), rg = threadIdx.x >> 6;
-  const int r0 = blockIdx.y * 64;
+  const int r0 = blockIdx.y * HB_ROWS;
   const int n_out = A + (Wv ? 1 : 0);
-  for (int e = threadIdx.x; e < 64 * n_out; e += blockDim.x) {
+  for (int e = threadIdx.x; e < HB_ROWS * n_out; e += blockDim.x) {
     const int r = e / n_out, n = e - r * n_out;
     float g = 0.0f;
     if (r0 + r < B) {
@@ -78,10 +80,17 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     w[n] = (n < n_out && k < K) ? ((n < A) ? Wa[(int64_t)n * K + k] : Wv[k]) : 0.0f;
   }
   if (k < K) {
-    for (int rr = 0; rr < 16; ++rr) {
-      const int r = rg * 16 + rr;
+    float xs[HB_ROWS / 4];
+#pragma unroll
+    for (int rr = 0; rr < HB_ROWS / 4; ++rr) {         // all loads in flight before the FMAs
+      const int r = r0 + rg * (HB_ROWS / 4) + rr;
+      xs[rr] = r < B ? __bfloat162float(phi[(int64_t)r * K + k]) : 0.0f;
+    }
+#pragma unroll
+    for (int rr = 0; rr < HB_ROWS / 4; ++rr) {
+      const int r = rg * (HB_ROWS / 4) + rr;
       if (r0 + r >= B) break;
-      const float x = __bfloat162float(phi[(int64_t)(r0 + r) * K + k]);
+      const float x = xs[rr];
       float g = 0.0f;
 #pragma unroll
       for (int n = 0; n < HEAD_MAX_OUT + 1; ++n) {
@@ -108,7 +117,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
   }
   if (blockIdx.x == 0 && threadIdx.x < n_out) {      // bias gradients: sum of geff over this block's rows
     float s = 0.0f;
-    for (int r = 0; r < 64; ++r) s += geff[r][threadIdx.x];
+    for (int r = 0; r < HB_ROWS; ++r) s += geff[r][threadIdx.x];
     atomicAdd((threadIdx.x < A) ? gba + threadIdx.x : gbv, s);
   }
 }
@@ -131,7 +140,7 @@ extern "C" int b2rl_head_bwd(const float* gq, const uint16_t* phi, const float* 
   B2RL_REQUIRE(gq && phi && Wa && gphi && gWa && gba && ((Wv == nullptr) == (gWv == nullptr)) && ((Wv == nullptr) == (gbv == nullptr)),
                "null pointer");
   B2RL_REQUIRE(B > 0 && K > 0 && A > 0 && A < HEAD_MAX_OUT, "need 0 < A < 32");
-  dim3 grid((K + 63) / 64, (B + 63) / 64);
+  dim3 grid((K + 63) / 64, (B + HB_ROWS - 1) / HB_ROWS);
   head_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gq, reinterpret_cast<const __nv_bfloat16*>(phi), Wa, Wv, B, K, A,
                                                           reinterpret_cast<__nv_bfloat16*>(gphi), gWa, gba, gWv, gbv);
   return check_launch("b2rl_head_bwd");

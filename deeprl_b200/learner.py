@@ -14,6 +14,7 @@ import torch.distributed as dist
 
 from . import _lib, ops
 from .component.replay import PrioritizedReplay
+from .network import nature_tc
 from .network.fused import frame_scale
 
 
@@ -64,6 +65,17 @@ class GraphedDQNLearner:
 
     def _main(self):
         rp = self.replay
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+            self._packed_ev = torch.cuda.Event()
+        side = self._side
+        fs = self.scale if self.dtype == torch.bfloat16 else 1.0
+        # online weights changed in the previous optimizer step: re-pack them on the side branch, next to feed + sample
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self._repack(self.net, fs)
+            self._packed_ev.record(side)
         # DQN_agent.py:104-112 calls feed() once per env transition; `feeds` single-item calls are exactly one multi-item
         # call with each item in its own slot (reference_feed_quirk off) plus `feeds` tree.add(max_priority) -- one launch
         if self.feeds:
@@ -75,25 +87,20 @@ class GraphedDQNLearner:
         if self.dtype == torch.bfloat16:
             # exact integer frames, space-to-depth layout; ImageNormalizer's scale is folded into conv1's weights
             t = rp.sample_normalized(out_dtype=self.dtype, scale=None, layout="s2d")
-            fs = self.scale
         else:
             t = rp.sample_normalized(out_dtype=self.dtype, scale=self.scale, layout="nchw")
-            fs = 1.0
         per = dict(is_prob=t.sampling_prob, eps=self.eps, alpha=self.alpha, beta_dev=self.d_beta) if self.per else {}
-        self._repack(self.net, fs)                       # online weights changed in the previous optimizer step
         # the target forward on s' and the online forward on s are independent: fork them onto two streams (two parallel
         # branches of the captured graph) so that the prologue / tail of one chain overlaps the other
-        cur = torch.cuda.current_stream()
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=self.dev)
-        self._side.wait_stream(cur)
-        with torch.cuda.stream(self._side), frame_scale(fs), torch.no_grad():
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), frame_scale(fs), torch.no_grad():
             nxt_t = self.tgt(t.next_state)
+        cur.wait_event(self._packed_ev)
         with frame_scale(fs):
             with torch.no_grad():
                 nxt_o = self.net(t.next_state) if self.double_q else None
             out = self.net(t.state)
-        cur.wait_stream(self._side)
+        cur.wait_stream(side)
         if self.kind == "dqn":
             head = out["q"]
             r = ops.dqn_loss_fused(head.detach(), nxt_t["q"], nxt_o["q"] if nxt_o else None, t.action, t.reward, t.mask,
@@ -111,7 +118,8 @@ class GraphedDQNLearner:
         if self.per:
             rp.update_priorities((t.idx, r["priority"]))
         self.opt.zero_grad()
-        head.backward(grad)
+        with nature_tc.wgrad_stream(side):           # weight-gradient GEMMs on the side branch, next to the dgrad chain
+            head.backward(grad)
         self.loss.copy_(r["loss"])
 
     def _repack(self, net, fs):

@@ -15,6 +15,9 @@ layout ([Cout, Cin, kh, kw], (c, h, w)-ordered fc4 columns) to the tap-major bf1
 (``csrc/pack.cu``) and the weight gradients are mapped back and accumulated into ``.grad`` by ONE kernel, so
 ``state_dict``s and optimizers see the reference layout only.
 """
+import contextlib
+import ctypes
+
 import torch
 
 from .. import _lib
@@ -25,9 +28,39 @@ _bf16 = torch.bfloat16
 _f32 = torch.float32
 
 
-def wgrad_partials(X, G_rows, n_out, taps, taps_x, grid_w):
+_WGRAD = {"stream": None}
+
+
+@contextlib.contextmanager
+def wgrad_stream(stream):
+    """Inside this context the backward pass launches its weight-gradient GEMMs on ``stream`` (a second branch of the
+    captured graph): they only feed the final gradient unpack, so they overlap the dgrad / ReLU-mask chain, which is
+    latency-bound with one CTA per SM.  Buffers are allocated on the current stream and the branch is joined before
+    ``backward`` returns, so no allocator bookkeeping is needed."""
+    old, _WGRAD["stream"] = _WGRAD["stream"], stream
+    try:
+        yield
+    finally:
+        _WGRAD["stream"] = old
+
+
+def _fork():
+    """Stream handle for the next weight-gradient launch (ordered after everything queued on the current stream)."""
+    side = _WGRAD["stream"]
+    if side is None:
+        return None
+    side.wait_stream(torch.cuda.current_stream())
+    return side.cuda_stream
+
+
+def _join():
+    side = _WGRAD["stream"]
+    if side is not None:
+        torch.cuda.current_stream().wait_stream(side)
+
+
+def wgrad_partials(X, G_rows, n_out, taps, taps_x, grid_w, stream=None):
     """Split-K partial weight gradients (one per CTA, no atomics): returns (partials [P_max, n_out, taps*C] fp32, P)."""
-    import ctypes
     rows, C = X.shape
     if not _lib.CONV_SLAB:                       # tap-addressing mode (tests): atomic accumulation into one "partial"
         out = torch.zeros((1, n_out, taps * C), dtype=_f32, device=X.device)
@@ -36,7 +69,7 @@ def wgrad_partials(X, G_rows, n_out, taps, taps_x, grid_w):
     buf = torch.empty((148, n_out, taps * C), dtype=_f32, device=X.device)
     n = ctypes.c_int32(0)
     _lib.call("b2rl_conv_wgrad_partials", _lib.ptr(X), int(rows), int(C), _lib.ptr(G_rows), int(n_out), int(taps), int(taps_x),
-              int(grid_w), _lib.ptr(buf), ctypes.byref(n), _lib.stream())
+              int(grid_w), _lib.ptr(buf), ctypes.byref(n), stream if stream is not None else _lib.stream())
     return buf, int(n.value)
 
 
@@ -131,21 +164,22 @@ class _NatureBody(torch.autograd.Function):
         # ---- fc4
         g4, db4 = act_bwd_bias_grad(gy4, y4, True)                                        # [B, 512]
         y3c = y3.view(B, 3136)
-        gw4p = gemm_bf16(g4, y3c, a_major="mn", b_major="mn", out_dtype=_f32, block_n=128)  # [512, 3136]
+        gw4p = gemm_bf16(g4, y3c, a_major="mn", b_major="mn", out_dtype=_f32, block_n=128, stream=_fork())  # [512, 3136]
         gy3c = gemm_bf16(g4, w4p, a_major="k", b_major="mn", block_n=128)                  # [B, 3136] bf16
         # ---- conv3: mask + bias grad, re-laid out from the compact 7x7 rows to the 10-grid
         g3, db3 = act_bwd_bias_grad(gy3c.view(B * 49, 64), y3, True, row_map=1, G=10, V=7, out_rows=B * 100)
-        gw3p, p3 = wgrad_partials(y2, g3, 64, 9, 3, 10)
+        gw3p, p3 = wgrad_partials(y2, g3, 64, 9, 3, 10, stream=_fork())
         gy2 = torch.empty((B * 100, 64), dtype=_bf16, device=dev)
         conv_gemm(0, g3, w3d, 64, 9, 3, 10, -1, gy2, block_n=64)
         # ---- conv2
         g2, db2 = act_bwd_bias_grad(gy2, y2, True)                                        # rows 9 / cols 9 of gy2 are exact zeros
-        gw2p, p2 = wgrad_partials(x1, g2, 64, 4, 2, 10)
+        gw2p, p2 = wgrad_partials(x1, g2, 64, 4, 2, 10, stream=_fork())
         gy1 = torch.empty((B * 100, 128), dtype=_bf16, device=dev)
         conv_gemm(0, g2, w2d, 128, 4, 2, 10, -1, gy1, block_n=128)
         # ---- conv1: mask + bias grad, re-laid out from space-to-depth(2) rows to the 21-grid of conv1's output positions
         g1, db1 = act_bwd_bias_grad(gy1, x1, True, row_map=2, G=21, V=20, out_rows=B * 441)
-        gw1p, p1 = wgrad_partials(x0m, g1, 32, 4, 2, 21)
+        gw1p, p1 = wgrad_partials(x0m, g1, 32, 4, 2, 21, stream=_fork())
+        _join()
         params = ctx.params
         if all(p.grad is not None and p.grad.dtype == _f32 and p.grad.is_contiguous() for p in params):
             # accumulate straight into the .grad arena (reference layouts), one launch

@@ -270,7 +270,7 @@ class FlatOptimizer:
 
 # ------------------------------------------------------------------------------------------------- tcgen05 GEMM
 def gemm_bf16(a, b, a_major="k", b_major="k", bias=None, relu=False, out_dtype=torch.bfloat16, out=None, splits=1,
-              block_n=None, accumulate=False):
+              block_n=None, accumulate=False, stream=None):
     """``D[M,N] (+)= A B^T`` on the 5th-generation tensor cores (csrc/gemm.cu: TMA -> tcgen05.mma -> TMEM).
 
     ``a_major="k"``: ``a`` is [M, K] row-major; ``"mn"``: ``a`` is [K, M] row-major (its transpose is what is
@@ -295,5 +295,5 @@ def gemm_bf16(a, b, a_major="k", b_major="k", bias=None, relu=False, out_dtype=t
     mode = 2 if atomic else (0 if out_dtype == torch.bfloat16 else 1)
     _lib.call("b2rl_gemm_bf16", _lib.ptr(a), int(a_mn), a.stride(0), _lib.ptr(b), int(b_mn), b.stride(0), _lib.ptr(out),
               out.stride(0), int(M), int(N), int(K), _lib.ptr(bias), int(relu), mode, int(splits), int(block_n),
-              _lib.stream())
+              stream if stream is not None else _lib.stream())
     return out
