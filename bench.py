@@ -81,8 +81,10 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- product arm
-def synthetic_ring(rl, replay_cls, device, seed, capacity=CAP):
+def synthetic_ring(rl, replay_cls, device, seed, capacity=None):
     """SURVEY 8d synthetic inputs, generated on the device in chunks."""
+    capacity = CAP if capacity is None else capacity
+    pos = 123_457 if capacity > 200_000 else capacity // 3
     g = torch.Generator(device=device).manual_seed(seed)
     frames = torch.empty((capacity, FRAME), dtype=torch.uint8, device=device)
     step = 50_000
@@ -97,13 +99,13 @@ def synthetic_ring(rl, replay_cls, device, seed, capacity=CAP):
     rp.item_shape, rp.item_dtype = (84, 84), np.dtype(np.uint8)
     if replay_cls.__name__ == "PrioritizedReplay":
         pr = (torch.randn(capacity, device=device, generator=g).abs() + 0.01).sqrt()
-        rp.load_synthetic(frames, action, reward, mask, pos=123_457, priorities=pr)
+        rp.load_synthetic(frames, action, reward, mask, pos=pos, priorities=pr)
     else:
-        rp.load_synthetic(frames, action, reward, mask, pos=123_457)
+        rp.load_synthetic(frames, action, reward, mask, pos=pos)
     return rp
 
 
-def build_learner(rl, workload, device, rank, world):
+def build_learner(rl, workload, device, rank, world, prefetch=True):
     from deeprl_b200.learner import GraphedDQNLearner
     torch.manual_seed(0)                                   # identical initial parameters on every rank
     body = lambda: rl.NatureConvBody(in_channels=HIST)
@@ -129,7 +131,7 @@ def build_learner(rl, workload, device, rank, world):
     rp = synthetic_ring(rl, replay_cls, device, seed=rank)
     return GraphedDQNLearner(net, tgt, opt, rp, kind=kind, double_q=(workload == "per"), gradient_clip=5.0,
                              feeds_per_update=4, compute_dtype=torch.bfloat16, world_size=world,
-                             target_sync_every=0)
+                             target_sync_every=0, prefetch=prefetch)
 
 
 def time_gather_kernel(rl, rp, iters=64, reps=5):
@@ -182,7 +184,7 @@ def run_b2rl(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    learner = build_learner(rl, args.workload, dev, rank, world)
+    learner = build_learner(rl, args.workload, dev, rank, world, prefetch=(args.replay == "async"))
     if world > 1:                                          # parameters identical on every rank
         dist.broadcast(learner.opt.flat, 0)
         learner.tgt.load_state_dict(learner.net.state_dict())
@@ -238,6 +240,26 @@ def run_b2rl(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms)
 
+    # ---- the other replay mode (async_replay on / off), resident inputs, same networks / optimizer / ring
+    from deeprl_b200.learner import GraphedDQNLearner
+    other = GraphedDQNLearner(learner.net, learner.tgt, learner.opt, learner.replay, kind=learner.kind, double_q=learner.double_q,
+                              gradient_clip=learner.clip, feeds_per_update=learner.feeds, compute_dtype=learner.dtype,
+                              world_size=world, target_sync_every=0, prefetch=not learner.prefetch)
+    other.capture(warmup=2, with_h2d=False)
+    for _ in range(W):
+        other.update()
+    barrier()
+    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    o0.record()
+    for _ in range(K):
+        other.update()
+    o1.record()
+    barrier()
+    other_ms = torch.tensor([o0.elapsed_time(o1)], device=dev)
+    if world > 1:
+        dist.all_reduce(other_ms, op=dist.ReduceOp.MAX)
+    other_ms = float(other_ms)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -272,10 +294,15 @@ def run_b2rl(args):
                     parallelism="dp%d (rank-local replay shard, NCCL all-reduce of 6.7 MB fp32 gradients per step)" % world,
                     dense=("tcgen05 GEMM kernels (csrc/gemm.cu): bf16 operands, fp32 accumulation in TMEM, fp32 master weights"
                            if rl.Config.DENSE_BACKEND == "tcgen05" else "cuDNN/cuBLAS bf16 (fp32 accumulate, fp32 master weights)"),
+                    replay=("async_replay=True (examples.py:16,60 default; ReplayWrapper replay.py:214-262): batch k+1 is fed + sampled "
+                            "on a parallel graph branch while update k trains on the batch sampled during update k-1"
+                            if learner.prefetch else "async_replay=False: feed -> sample -> update in sequence (examples.py:646)"),
                     cuda_graph=True),
         e2e=dict(value=round(e2e, 1), unit="updates/s", h2d_bytes_per_step=learner.h2d_bytes, d2h_bytes_per_step=4,
                  ms_per_step=round(e2e_ms / K, 4)),
         gpu_launches=int(launches_per_update * K), gpu_launches_per_step=int(launches_per_update),
+        other_replay_mode=dict(replay="async_replay=False" if learner.prefetch else "async_replay=True",
+                               value=round(world * K / (other_ms * 1e-3), 1), ms_per_step=round(other_ms / K, 4)),
         clocks=clocks.summary(), roofline=roof, cpu_baseline=cpu, loss=loss_value, last_e2e_loss=last,
         tensor_frac_of_sustained=(round(flops * value / world / (pk.get("bf16_tflops_sustained", 1447.2) * 1e12), 4) if flops else None),
     )
@@ -386,5 +413,8 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b2rl", choices=["b2rl", "reference"])
     ap.add_argument("--workload", default="dqn", choices=["dqn", "per", "c51", "qr"])
+    ap.add_argument("--replay", default="async", choices=["async", "sync"],
+                    help="async_replay of the reference's launchers (examples.py:16 default True; :646 runs False); the other "
+                         "mode is timed as well and reported under other_replay_mode")
     a = ap.parse_args()
     run_reference(a) if a.impl == "reference" else run_b2rl(a)

@@ -11,8 +11,10 @@ namespace b2rl {
 
 constexpr int HEAD_MAX_OUT = 32;       // A (+1 for the dueling value row)
 
-// one warp per batch row
-__global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __restrict__ phi, const float* __restrict__ Wa,
+// one warp per batch row; the row of phi is read once (16-byte loads, 8 features per lane per 256-feature chunk) and
+// every output accumulates against it, so all weight loads of a chunk are independent and in flight together
+template <int NB>
+__global__ void __launch_bounds__(128) head_fwd_kernel(const __nv_bfloat16* __restrict__ phi, const float* __restrict__ Wa,
                                                        const float* __restrict__ ba, const float* __restrict__ Wv,
                                                        const float* __restrict__ bv, int B, int K, int A,
                                                        float* __restrict__ q) {
@@ -20,27 +22,53 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __re
   if (b >= B) return;
   const __nv_bfloat16* x = phi + (int64_t)b * K;
   const int n_out = A + (Wv ? 1 : 0);
-  float out[HEAD_MAX_OUT + 1];
-#pragma unroll 1
-  for (int n = 0; n < n_out; ++n) {
-    const float* w = (n < A) ? Wa + (int64_t)n * K : Wv;
-    float s = 0.0f;
-    for (int k = lane * 2; k < K; k += 64) {
-      const float2 xv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + k));
-      const float2 wv = *reinterpret_cast<const float2*>(w + k);
-      s = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, s));
+  float acc[NB];
+#pragma unroll
+  for (int n = 0; n < NB; ++n) acc[n] = 0.0f;
+  for (int k0 = lane * 8; k0 < K; k0 += 256) {
+    const int4 xr = *reinterpret_cast<const int4*>(x + k0);
+    const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&xr);
+    float xf[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(xp[j]);
+      xf[2 * j] = f.x, xf[2 * j + 1] = f.y;
     }
-    s = warp_reduce(s, OpAdd());
-    out[n] = s + ((n < A) ? ba[n] : bv[0]);
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+      if (n < n_out) {
+        const float* w = ((n < A) ? Wa + (int64_t)n * K : Wv) + k0;
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w)), w1 = __ldg(reinterpret_cast<const float4*>(w) + 1);
+        float s = acc[n];
+        s = fmaf(xf[0], w0.x, s), s = fmaf(xf[1], w0.y, s), s = fmaf(xf[2], w0.z, s), s = fmaf(xf[3], w0.w, s);
+        s = fmaf(xf[4], w1.x, s), s = fmaf(xf[5], w1.y, s), s = fmaf(xf[6], w1.z, s), s = fmaf(xf[7], w1.w, s);
+        acc[n] = s;
+      }
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < NB; ++n) {
+    if (n < n_out) {
+      const float s = warp_reduce(acc[n], OpAdd());
+      acc[n] = s + ((n < A) ? ba[n] : bv[0]);
+    }
   }
   if (lane == 0) {
     if (Wv) {                                     // network_heads.py:34-36: q = value + (adv - adv.mean(1))
-      float mean = 0.0f;
-      for (int a = 0; a < A; ++a) mean += out[a];
+      float mean = 0.0f, value = 0.0f;
+#pragma unroll
+      for (int n = 0; n < NB; ++n) {
+        if (n < A) mean += acc[n];
+        if (n == A) value = acc[n];
+      }
       mean /= (float)A;
-      for (int a = 0; a < A; ++a) q[(int64_t)b * A + a] = out[A] + (out[a] - mean);
+#pragma unroll
+      for (int n = 0; n < NB; ++n)
+        if (n < A) q[(int64_t)b * A + n] = value + (acc[n] - mean);
     } else {
-      for (int a = 0; a < A; ++a) q[(int64_t)b * A + a] = out[a];
+#pragma unroll
+      for (int n = 0; n < NB; ++n)
+        if (n < A) q[(int64_t)b * A + n] = acc[n];
     }
   }
 }
@@ -129,9 +157,16 @@ using namespace b2rl;
 extern "C" int b2rl_head_fwd(const uint16_t* phi, const float* Wa, const float* ba, const float* Wv, const float* bv,
                              int32_t B, int32_t K, int32_t A, float* q, void* stream) {
   B2RL_REQUIRE(phi && Wa && ba && q && ((Wv == nullptr) == (bv == nullptr)), "null pointer");
-  B2RL_REQUIRE(B > 0 && K > 0 && K % 2 == 0 && A > 0 && A < HEAD_MAX_OUT, "need K even and 0 < A < 32");
-  head_fwd_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(phi), Wa, ba, Wv, bv,
-                                                                 B, K, A, q);
+  B2RL_REQUIRE(B > 0 && K > 0 && K % 8 == 0 && A > 0 && A < HEAD_MAX_OUT, "need K % 8 == 0 and 0 < A < 32");
+  B2RL_REQUIRE(reinterpret_cast<uintptr_t>(phi) % 16 == 0 && (reinterpret_cast<uintptr_t>(Wa) | reinterpret_cast<uintptr_t>(Wv)) % 16 == 0,
+               "phi and the weights must be 16-byte aligned");
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(phi);
+  const int n_out = A + (Wv ? 1 : 0);
+  const dim3 grid((B + 3) / 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_out <= 8) head_fwd_kernel<8><<<grid, 128, 0, st>>>(x, Wa, ba, Wv, bv, B, K, A, q);
+  else if (n_out <= 19) head_fwd_kernel<19><<<grid, 128, 0, st>>>(x, Wa, ba, Wv, bv, B, K, A, q);
+  else head_fwd_kernel<HEAD_MAX_OUT><<<grid, 128, 0, st>>>(x, Wa, ba, Wv, bv, B, K, A, q);
   return check_launch("b2rl_head_fwd");
 }
 

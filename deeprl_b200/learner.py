@@ -21,7 +21,8 @@ from .network.fused import frame_scale
 class GraphedDQNLearner:
     def __init__(self, network, target_network, optimizer, replay, kind="dqn", discount=0.99, n_step=1, double_q=False,
                  gradient_clip=5.0, feeds_per_update=4, compute_dtype=torch.bfloat16, state_scale=1.0 / 255,
-                 replay_eps=0.01, replay_alpha=0.5, categorical=(-10.0, 10.0), world_size=1, target_sync_every=10000):
+                 replay_eps=0.01, replay_alpha=0.5, categorical=(-10.0, 10.0), world_size=1, target_sync_every=10000,
+                 prefetch=False):
         self.net, self.tgt, self.opt, self.replay = network, target_network, optimizer, replay
         self.kind, self.gamma_n, self.double_q = kind, discount ** n_step, double_q
         self.clip, self.feeds = gradient_clip, feeds_per_update
@@ -56,6 +57,13 @@ class GraphedDQNLearner:
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.g_main = self.g_opt = None
         self._side = None
+        # prefetch = the graph form of ReplayWrapper(async_=True) (replay.py:214-262: the worker hands out the batch it
+        # sampled right after the previous request and immediately samples the next one into the other cache): update k
+        # trains on the batch sampled during update k-1 while a third branch of the graph feeds + samples batch k+1
+        # into the other buffer set.  Two graphs (one per buffer parity) are captured and replayed alternately.
+        self.prefetch = bool(prefetch)
+        self._batch = [None, None]
+        self._parity = 0
         self.updates = 0
         self.with_h2d = False
 
@@ -63,19 +71,9 @@ class GraphedDQNLearner:
     def _h2d(self):
         self.d_pack.copy_(self.h_pack, non_blocking=True)
 
-    def _main(self):
+    def _sample(self, tag=0):
+        """feeds of this update + one sampled batch into buffer set ``tag`` (on the current stream)."""
         rp = self.replay
-        cur = torch.cuda.current_stream()
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=self.dev)
-            self._packed_ev = torch.cuda.Event()
-        side = self._side
-        fs = self.scale if self.dtype == torch.bfloat16 else 1.0
-        # online weights changed in the previous optimizer step: re-pack them on the side branch, next to feed + sample
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            self._repack(self.net, fs)
-            self._packed_ev.record(side)
         # DQN_agent.py:104-112 calls feed() once per env transition; `feeds` single-item calls are exactly one multi-item
         # call with each item in its own slot (reference_feed_quirk off) plus `feeds` tree.add(max_priority) -- one launch
         if self.feeds:
@@ -86,9 +84,38 @@ class GraphedDQNLearner:
                 rp.tree.add_n(self.feeds, rp.max_priority_dev)
         if self.dtype == torch.bfloat16:
             # exact integer frames, space-to-depth layout; ImageNormalizer's scale is folded into conv1's weights
-            t = rp.sample_normalized(out_dtype=self.dtype, scale=None, layout="s2d")
+            return rp.sample_normalized(out_dtype=self.dtype, scale=None, layout="s2d", tag=tag)
+        return rp.sample_normalized(out_dtype=self.dtype, scale=self.scale, layout="nchw", tag=tag)
+
+    def _main(self, parity=None):
+        rp = self.replay
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+            self._pre = torch.cuda.Stream(device=self.dev)
+            self._packed_ev, self._sampled_ev = torch.cuda.Event(), torch.cuda.Event()
+        side, pre = self._side, self._pre
+        fs = self.scale if self.dtype == torch.bfloat16 else 1.0
+        # online weights changed in the previous optimizer step: re-pack them on the side branch, next to feed + sample
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self._repack(self.net, fs)
+            self._packed_ev.record(side)
+        if self.prefetch:
+            eager = parity is None
+            if eager:
+                parity = self._parity
+            if self._batch[parity] is None:                              # very first update: nothing prefetched yet
+                self._batch[parity] = self._sample(parity)
+            t = self._batch[parity]
+            pre.wait_stream(cur)                                         # after the host->device copy of this update's feeds
+            with torch.cuda.stream(pre):
+                self._batch[1 - parity] = self._sample(1 - parity)
+                self._sampled_ev.record(pre)
+            if eager:
+                self._parity = 1 - parity
         else:
-            t = rp.sample_normalized(out_dtype=self.dtype, scale=self.scale, layout="nchw")
+            t = self._sample(0)
         per = dict(is_prob=t.sampling_prob, eps=self.eps, alpha=self.alpha, beta_dev=self.d_beta) if self.per else {}
         # the target forward on s' and the online forward on s are independent: fork them onto two streams (two parallel
         # branches of the captured graph) so that the prologue / tail of one chain overlaps the other
@@ -116,11 +143,15 @@ class GraphedDQNLearner:
             r = ops.qr_loss_fused(head.detach(), nxt_t["quantile"], t.action, t.reward, t.mask, self.gamma_n)
             grad = r["dquant"]
         if self.per:
+            if self.prefetch:                            # the sum tree is read by the prefetch branch: update after it
+                cur.wait_event(self._sampled_ev)
             rp.update_priorities((t.idx, r["priority"]))
         self.opt.zero_grad()
         with nature_tc.wgrad_stream(side):           # weight-gradient GEMMs on the side branch, next to the dgrad chain
             head.backward(grad)
         self.loss.copy_(r["loss"])
+        if self.prefetch:
+            cur.wait_stream(pre)
 
     def _repack(self, net, fs):
         """tcgen05 backend: the learner owns the packed bf16 operands of both networks -- the online body is re-packed
@@ -153,13 +184,16 @@ class GraphedDQNLearner:
                 self._opt()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        self.g_main = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_main):
-            if with_h2d:
-                self._h2d()
-            self._main()
-            if self.world == 1:                          # single GPU: the whole update is ONE graph
-                self._opt()
+        self.g_main = []
+        for parity in ((0, 1) if self.prefetch else (None,)):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self.g_main[0].pool() if self.g_main else None):
+                if with_h2d:
+                    self._h2d()
+                self._main(parity)
+                if self.world == 1:                      # single GPU: the whole update is ONE graph
+                    self._opt()
+            self.g_main.append(g)
         if self.world > 1:                               # multi GPU: [sample..backward] | NCCL all-reduce | [clip+opt]
             self.g_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g_opt):
@@ -176,7 +210,11 @@ class GraphedDQNLearner:
 
     def update(self):
         """One gradient update (graph replay).  Returns the device loss tensor (no sync)."""
-        self.g_main.replay()
+        if self.prefetch:
+            self.g_main[self._parity].replay()
+            self._parity = 1 - self._parity
+        else:
+            self.g_main[0].replay()
         if self.world > 1:
             self._allreduce()
             self.g_opt.replay()

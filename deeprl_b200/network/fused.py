@@ -182,6 +182,7 @@ def narrow_head(phi, fc_action, fc_value=None):
                              None if fc_value is None else fc_value.weight, None if fc_value is None else fc_value.bias)
 
 
-def narrow_head_ok(phi, fc_action):
-    return (phi.is_cuda and phi.dtype == _bf16 and phi.dim() == 2 and phi.shape[1] % 2 == 0
+def narrow_head_ok(phi, fc_action, fc_value=None):
+    aligned = all(m is None or m.weight.data_ptr() % 16 == 0 for m in (fc_action, fc_value))
+    return (phi.is_cuda and phi.dtype == _bf16 and phi.dim() == 2 and phi.shape[1] % 8 == 0 and aligned
             and isinstance(fc_action, torch.nn.Linear) and fc_action.out_features < 32)

@@ -47,7 +47,7 @@ class DuelingNet(nn.Module, BaseNet):
 
     def forward(self, x, to_numpy=False):
         phi = _phi(self.body, x)
-        if fused.narrow_head_ok(phi, self.fc_advantage):
+        if fused.narrow_head_ok(phi, self.fc_advantage, self.fc_value):
             return dict(q=fused.narrow_head(phi, self.fc_advantage, self.fc_value))
         with _autocast():
             value = self.fc_value(phi).float()
