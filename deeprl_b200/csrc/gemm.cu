@@ -147,13 +147,28 @@ __device__ __forceinline__ int tap_shift(const GemmParams& p, int tap) {
 // Epilogue of one 128 x BN tile for one warp (TMEM lane quarter q): wait for the accumulator stage, read it 32 columns
 // at a time, hand the stage back to the MMA warp, apply bias / ReLU and store through the output row map.
 // The accumulator of a tile may be kept as ACC partial sums (the MMA issuer rotates over them, the epilogue adds them).
+// Optional in-kernel timeline (scripts/microbench/slab_trace.py builds a private copy of the library with -DB2RL_TRACE):
+// clock64 stamps per CTA / role / tile, never compiled into the shipped library.
+#ifdef B2RL_TRACE
+__device__ unsigned long long* g_trace_buf = nullptr;
+#define B2RL_TRACE_AT(role, it, slot)                                                                            \
+  do {                                                                                                           \
+    if (g_trace_buf && (it) < 16)                                                                                \
+      g_trace_buf[((((size_t)blockIdx.x * 4 + (role)) * 16 + (it)) * 4) + (slot)] = (unsigned long long)clock64(); \
+  } while (0)
+#else
+#define B2RL_TRACE_AT(role, it, slot)
+#endif
+
 // scripts/microbench/umma_rate.cu measured on B200: one issuing thread sustains one tcgen05.mma (M=128, K=16) every
 // max(53, N/2) cycles whatever the operand majors and whether consecutive MMAs hit the same accumulator or not, so
 // ACC = 1 is used; small-N tiles are bound by that 53-cycle issue floor, not by accumulator dependencies.
 template <int BN, int ACC>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n0, int q, int lane, uint32_t tmem_base,
                                               uint32_t as, uint32_t parity, bool has_acc, uint64_t* tmem_full,
-                                              uint64_t* tmem_empty) {
+                                              uint64_t* tmem_empty, uint32_t trace_it = 1u << 30) {
+  const bool tr = q == 0 && lane == 0;
+  if (tr) B2RL_TRACE_AT(2, trace_it, 0);
   const int row = m0 + q * 32 + lane;
   bool valid = row < p.M;
   int64_t drow = row;
@@ -175,6 +190,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
     mb_wait(&tmem_full[as], parity);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
+  if (tr) B2RL_TRACE_AT(2, trace_it, 1);
 #pragma unroll
   for (int c = 0; c < BN; c += 32) {
     uint32_t r[32];
@@ -196,6 +212,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
       // all TMEM reads of this warp for this tile are done: hand the accumulator stage back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       if (lane == 0) mb_arrive(&tmem_empty[as]);
+      if (tr) B2RL_TRACE_AT(2, trace_it, 2);
     }
     if (valid && n0 + c < p.N) {
 #pragma unroll
@@ -248,6 +265,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
       }
     }
   }
+  if (tr) B2RL_TRACE_AT(2, trace_it, 3);
 }
 
 template <int BN, int STAGES>
@@ -401,6 +419,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
                                                                             const __grid_constant__ CUtensorMap tmB,
                                                                             const SlabParams sp) {
   const GemmParams& p = sp.g;
+  if (threadIdx.x == 0) B2RL_TRACE_AT(3, 0, 0);
   constexpr uint32_t W_TILE = BN * 128;                               // one 64-wide k-tile of the weights
   constexpr int ACC = 1;
   constexpr uint32_t TMEM_COLS = 2 * ACC * BN < 32 ? 32 : 2 * ACC * BN;
@@ -441,12 +460,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
 
   if (warp == 0 && lane == 0) {
     // ---------------------------------------------------------------------- TMA producer
+    B2RL_TRACE_AT(3, 0, 1);
     mb_expect_tx(w_full, (uint32_t)k_tiles * W_TILE);
     for (int kt = 0; kt < k_tiles; ++kt) tma_load_2d(sW + (size_t)kt * W_TILE, &tmB, w_full, kt * GEMM_BK, 0);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const int s = it % sp.stages;
+      B2RL_TRACE_AT(0, it, 0);
       mb_wait(&empty[s], ((it / sp.stages) & 1) ^ 1);
+      B2RL_TRACE_AT(0, it, 1);
       mb_expect_tx(&full[s], slab_bytes);
       for (int cb = 0; cb < sp.col_blocks; ++cb)
         tma_load_2d(sS + (size_t)s * slab_bytes + (size_t)cb * slab_block, &tmA, &full[s], cb * GEMM_BK,
@@ -456,14 +478,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
     // ---------------------------------------------------------------------- MMA issuer
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
     mb_wait(w_full, 0);
+    B2RL_TRACE_AT(3, 0, 2);
     const uint32_t slab_lo0 = desc_lo(s2u(sS), 16), w_lo0 = desc_lo(s2u(sW), 16);
     const int taps_y = sp.taps / p.taps_x;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const uint32_t as = it & 1;
       const int s = it % sp.stages;
+      B2RL_TRACE_AT(1, it, 0);
       mb_wait(&tmem_empty[as], ((it >> 1) & 1) ^ 1);
+      B2RL_TRACE_AT(1, it, 1);
       mb_wait(&full[s], (it / sp.stages) & 1);
+      B2RL_TRACE_AT(1, it, 2);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t acc = tmem_base + as * (ACC * BN);
       const uint32_t slab_lo = slab_lo0 + (uint32_t)s * (slab_bytes >> 4);
@@ -489,15 +515,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
       }
       umma_commit(&empty[s]);
       umma_commit(&tmem_full[as]);
+      B2RL_TRACE_AT(1, it, 3);
     }
   } else if (warp >= 2) {
     const int q = warp & 3;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it)
-      epilogue_tile<BN, ACC>(p, tile * GEMM_BM, 0, q, lane, tmem_base, it & 1, (it >> 1) & 1, true, tmem_full, tmem_empty);
+      epilogue_tile<BN, ACC>(p, tile * GEMM_BM, 0, q, lane, tmem_base, it & 1, (it >> 1) & 1, true, tmem_full, tmem_empty, it);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (threadIdx.x == 0) B2RL_TRACE_AT(3, 0, 3);
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
@@ -757,6 +785,12 @@ static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, WgradParam
 }
 
 }  // namespace b2rl
+
+#ifdef B2RL_TRACE
+extern "C" int b2rl_debug_set_trace(unsigned long long* buf) {
+  return cudaMemcpyToSymbol(b2rl::g_trace_buf, &buf, sizeof(buf)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 using namespace b2rl;
 
