@@ -29,7 +29,7 @@ namespace b2rl {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;           // 64 bf16 = 128 bytes = one swizzle-128B atom row
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5 / 6-9: epilogue of even / odd tiles
 
 __device__ __forceinline__ uint32_t s2u(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -60,6 +60,20 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
           s2u(smem_dst)),
       "l"(map), "r"(s2u(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// One elected lane of a fully active warp.  Code guarded by this predicate (instead of `lane == 0`) lets the compiler issue
+// the uniform-datapath instructions (UTCHMMA, UTMALDG, UTCBAR) directly; behind a plain lane test it wraps every one
+// of them in an ELECT / BRA.U.ANY loop, which costs ~50 extra cycles per MMA on the issuing thread.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s2u(bar)) : "memory");
@@ -215,13 +229,26 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
       if (tr) B2RL_TRACE_AT(2, trace_it, 2);
     }
     if (valid && n0 + c < p.N) {
+      if (p.bias && blockIdx.z == 0) {
+        const float* bp = p.bias + n0 + c;
+        if (n0 + c + 32 <= p.N && (reinterpret_cast<uintptr_t>(bp) & 15) == 0) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = n0 + c + j;
-        float v = __uint_as_float(r[j]);
-        if (p.bias && blockIdx.z == 0 && n < p.N) v += __ldg(p.bias + n);
-        if (p.relu) v = fmaxf(v, 0.0f);
-        r[j] = __float_as_uint(v);
+          for (int j = 0; j < 32; j += 4) {                             // 8 broadcast 16-byte loads instead of 32 scalar ones
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + j));
+            r[j] = __float_as_uint(__uint_as_float(r[j]) + b4.x);
+            r[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + b4.y);
+            r[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + b4.z);
+            r[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + b4.w);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c + j < p.N) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(bp + j));
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]), 0.0f));
       }
       const int64_t off = drow * p.ldd + dcol0 + n0 + c;
       if (p.out_mode == 0) {
@@ -285,7 +312,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
   const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (p.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;
   const int kt_total = (p.K + GEMM_BK - 1) / GEMM_BK;
@@ -309,7 +336,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0 && n_kt > 0) {
+  if (warp == 0 && n_kt > 0 && elect_one()) {
     // ---------------------------------------------------------------------- TMA producer
     uint32_t it = 0;                                         // global k-iteration counter across tiles
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -349,7 +376,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && n_kt > 0) {
+  } else if (warp == 1 && n_kt > 0 && elect_one()) {
     // ---------------------------------------------------------------------- MMA issuer
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
@@ -380,9 +407,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     }
   } else if (warp >= 2) {
     // ---------------------------------------------------------------------- epilogue (warp%4 selects the TMEM lane quarter)
+    // two groups of four warps, one per accumulator stage: the epilogue of tile t overlaps that of tile t+1
     const int q = warp & 3;
+    const uint32_t grp = (uint32_t)(warp - 2) >> 2;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tcount) {
+      if ((tcount & 1) != grp) continue;
       const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
       const int m0 = mt * GEMM_BM, n0 = nt * BN;
       epilogue_tile<BN, ACC>(p, m0, n0, q, lane, tmem_base, tcount & 1, (tcount >> 1) & 1, n_kt > 0, tmem_full, tmem_empty);
@@ -438,7 +468,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
   uint64_t* w_full = tmem_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
   const int tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
 
   if (threadIdx.x == 0) {
@@ -458,7 +488,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     // ---------------------------------------------------------------------- TMA producer
     B2RL_TRACE_AT(3, 0, 1);
     mb_expect_tx(w_full, (uint32_t)k_tiles * W_TILE);
@@ -474,7 +504,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
         tma_load_2d(sS + (size_t)s * slab_bytes + (size_t)cb * slab_block, &tmA, &full[s], cb * GEMM_BK,
                     tile * GEMM_BM + sp.min_shift);
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one()) {
     // ---------------------------------------------------------------------- MMA issuer
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
     mb_wait(w_full, 0);
@@ -519,9 +549,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
     }
   } else if (warp >= 2) {
     const int q = warp & 3;
+    const uint32_t grp = (uint32_t)(warp - 2) >> 2;                    // accumulator stage this warp group drains
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it)
-      epilogue_tile<BN, ACC>(p, tile * GEMM_BM, 0, q, lane, tmem_base, it & 1, (it >> 1) & 1, true, tmem_full, tmem_empty, it);
+      if ((it & 1) == grp)
+        epilogue_tile<BN, ACC>(p, tile * GEMM_BM, 0, q, lane, tmem_base, it & 1, (it >> 1) & 1, true, tmem_full, tmem_empty, it);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -563,7 +595,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
   uint64_t* empty = full + MAX_STAGES;
   uint64_t* tmem_full = empty + MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
   const int kt_total = (w.rows + GEMM_BK - 1) / GEMM_BK;
   const int kt_begin = blockIdx.x * w.k_tiles_per_cta;
   const int n_kt = max(min(kt_total, kt_begin + w.k_tiles_per_cta) - kt_begin, 0);
@@ -584,7 +616,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     for (int i = 0; i < n_kt; ++i) {
       const int s = i % w.stages;
       mb_wait(&empty[s], ((i / w.stages) & 1) ^ 1);
@@ -595,7 +627,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
       for (int cb = 0; cb < w.col_blocks; ++cb)
         tma_load_2d(st + A_BYTES + (size_t)cb * slab_block, &tmX, &full[s], cb * GEMM_BK, k0);           // [slab_rows][64 c]
     }
-  } else if (warp == 1 && lane == 0 && n_kt > 0) {
+  } else if (warp == 1 && n_kt > 0 && elect_one()) {
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(w.C >> 3) << 17) |
                            ((uint32_t)(GEMM_BM >> 4) << 24);
     const uint32_t a_lo0 = desc_lo(s2u(smem), 8192), b_lo0 = desc_lo(s2u(smem + A_BYTES), slab_block);
@@ -625,7 +657,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
     mb_wait(tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int cols = w.ntaps * w.C;
-    for (int c = 0; c < cols; c += 32) {
+    for (int c = ((warp - 2) >> 2) * 32; c < cols; c += 64) {         // the two warp groups take alternate 32-column chunks
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, r);
       if (n < w.n_out) {

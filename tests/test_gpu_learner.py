@@ -2,7 +2,8 @@
 async-replay prefetch branch (the graph form of ReplayWrapper(async_=True), reference replay.py:214-262).
 
 Tolerance: the captured graph replays exactly the kernels of the eager update; the only run-to-run freedom is the order
-of fp32 atomic adds (bias gradients, narrow-head weight gradients), so losses agree to 2e-3 relative over a few updates."""
+of fp32 atomic adds (split-K fc4 accumulation, bias gradients, narrow-head weight gradients).  Whole trajectories are NOT
+comparable (an argmax or a prioritized draw can flip on one ulp), so the comparison is one update from copied state."""
 import os
 import sys
 
@@ -31,51 +32,79 @@ def make(env, workload, prefetch):
     return bench.build_learner(rl, workload, torch.device("cuda", 0), 0, 1, prefetch=prefetch)
 
 
-def eager_losses(learner, n):
-    out = []
-    for _ in range(n):
-        learner._main(), learner._opt()
-        out.append(float(learner.loss))
-    return out
+def copy_state(dst, src):
+    """Make learner ``dst`` an exact twin of ``src``: parameters, optimizer state, target network, ring, sum tree,
+    cursors and the batch buffers of the prefetch branch."""
+    do, so = dst.opt, src.opt
+    for a, b in ((do.flat, so.flat), (do.s1, so.s1), (do.s2, so.s2), (do.step_dev, so.step_dev), (do.scratch, so.scratch)):
+        a.copy_(b)
+    dst.tgt.load_state_dict(src.tgt.state_dict())
+    dst._repack(dst.tgt, dst.scale)
+    dr, sr = dst.replay, src.replay
+    for name in ("frames", "action", "reward", "mask", "ring_state"):
+        getattr(dr, name).copy_(getattr(sr, name))
+    dr.pos, dr._size = sr.pos, sr._size
+    if dst.per:
+        dr.tree.tree.copy_(sr.tree.tree), dr.tree.pending.copy_(sr.tree.pending)
+        dr.max_priority_dev.copy_(sr.max_priority_dev)
+        dr.tree.n_entries = sr.tree.n_entries
+    for key, bufs in sr._bufs.items():
+        if key in dr._bufs:
+            for k, v in bufs.items():
+                dr._bufs[key][k].copy_(v)
+    dst._parity = src._parity
+    dst.d_pack.copy_(src.d_pack)
+    torch.cuda.synchronize()
 
 
-def graph_losses(learner, n):
-    out = []
-    for _ in range(n):
-        learner.update()
-        out.append(float(learner.loss))
-    return out
+def params(learner):
+    return learner.opt.flat.detach().clone()
 
 
 @pytest.mark.parametrize("workload", ["dqn", "per", "c51", "qr"])
-def test_graph_replay_equals_eager_updates(env, workload):
-    a, b = make(env, workload, False), make(env, workload, False)
-    ref = eager_losses(a, 8)                               # 3 warm-up + 5 compared
+@pytest.mark.parametrize("prefetch", [False, True])
+def test_graph_replay_equals_eager_update(env, workload, prefetch):
+    """One update from IDENTICAL state, once as eager launches and once as a graph replay.  The loss depends on the
+    forward pass only and must agree to fp32 rounding; the updated parameters differ by the order of fp32 atomic adds in
+    the bias / head gradients (|dp| <= lr * O(1e-6 relative gradient noise))."""
+    a, b = make(env, workload, prefetch), make(env, workload, prefetch)
+    for _ in range(3):
+        a._main(), a._opt()                                # creates a's buffers (overwritten below)
     b.capture(warmup=3)
-    got = graph_losses(b, 5)
-    assert all(np.isfinite(ref)) and all(np.isfinite(got))
-    np.testing.assert_allclose(got, ref[3:], rtol=2e-3)
-    # the ring cursor advanced by feeds_per_update per update in both
-    sa, sb = a.replay.ring_state.cpu().tolist(), b.replay.ring_state.cpu().tolist()
-    assert sa[:3] == sb[:3]
+    copy_state(a, b)
+    a._main(), a._opt()
+    b.update()
+    torch.cuda.synchronize()
+    la, lb = float(a.loss), float(b.loss)
+    assert np.isfinite(la) and la > 0
+    np.testing.assert_allclose(lb, la, rtol=1e-4)
+    np.testing.assert_allclose(params(b).cpu().numpy(), params(a).cpu().numpy(), rtol=0, atol=2e-6)
+    assert a.replay.ring_state.cpu().tolist()[:4] == b.replay.ring_state.cpu().tolist()[:4]
+    if a.per:                                              # same leaves updated, priorities equal to forward-pass noise
+        np.testing.assert_allclose(a.replay.tree.tree.cpu().numpy(), b.replay.tree.tree.cpu().numpy(), rtol=1e-3)
+    # and a second update, now from (almost) identical state: same batch, loss within bf16-activation noise
+    a._main(), a._opt()
+    b.update()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(float(b.loss), float(a.loss), rtol=5e-2)
 
 
 @pytest.mark.parametrize("workload", ["dqn", "per"])
 def test_prefetch_trains_on_the_previous_sample(env, workload):
-    """async replay: update k uses the batch sampled during update k-1.  The very first update samples its own batch
-    (nothing was prefetched), so it must equal the synchronous learner's first update; every later one must equal an eager
-    replay of the same schedule."""
-    sync, pre, pre2 = make(env, workload, False), make(env, workload, True), make(env, workload, True)
-    l_sync = eager_losses(sync, 1)
-    l_pre = eager_losses(pre, 8)
-    np.testing.assert_allclose(l_pre[0], l_sync[0], rtol=2e-3)
-    # 8 prefetch updates fed 9 x feeds rows (the first one also primed its own batch); the sync learner fed 1 x feeds
-    assert pre.replay.ring_state.cpu().tolist()[0] == sync.replay.ring_state.cpu().tolist()[0] + 7 * pre.feeds + pre.feeds
-    pre2.capture(warmup=3)
-    got = graph_losses(pre2, 5)
-    np.testing.assert_allclose(got, l_pre[3:], rtol=2e-3)
-    # the batch buffers alternate: the two parities are different tensors
-    assert pre2._batch[0].state.data_ptr() != pre2._batch[1].state.data_ptr()
+    """async replay: update k uses the batch sampled during update k-1; the very first update samples its own batch
+    (nothing was prefetched), so it equals the synchronous learner's first update."""
+    sync, pre = make(env, workload, False), make(env, workload, True)
+    sync._main(), sync._opt()
+    pre._main(), pre._opt()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(float(pre.loss), float(sync.loss), rtol=1e-5)
+    # the prefetch learner has fed twice (its own batch + the prefetched one) and holds the next batch in the other set
+    assert int(pre.replay.ring_state[0]) == int(sync.replay.ring_state[0]) + pre.feeds
+    assert pre._batch[0].state.data_ptr() != pre._batch[1].state.data_ptr()
+    ready = pre._batch[pre._parity].state.clone()          # sampled during update 1
+    pre._main(), pre._opt()                                # trains on it and refills the OTHER buffer set
+    torch.cuda.synchronize()
+    assert torch.equal(pre._batch[1 - pre._parity].state, ready)
 
 
 def test_update_from_host_feeds_the_ring(env):
