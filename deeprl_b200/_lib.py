@@ -136,6 +136,14 @@ def set_conv_slab(on):
 CONV_SLAB = 2
 
 
+def set_pdl(on):
+    """Programmatic dependent launch of the per-update kernels (csrc/common.cuh); on by default."""
+    L = lib()
+    L.b2rl_set_pdl.restype = None
+    L.b2rl_set_pdl.argtypes = [ctypes.c_int32]
+    L.b2rl_set_pdl(int(on))
+
+
 def _unused():
     pass
 

@@ -22,6 +22,37 @@ inline int check_launch(const char* what) {
   return B2RL_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Kernels on the per-update chain are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs are scheduled, and run their prologue
+// (barrier init, TMEM allocation, tensor-map prefetch), while the previous kernel is still executing; they then block in
+// pdl_wait() until the previous kernel has completed and its memory is visible.  Contract for every kernel launched
+// through launch_pdl(): (1) pdl_wait() is executed on EVERY path before the first global-memory access of any kind and
+// before any early return; (2) pdl_trigger() comes after pdl_wait(), so that the kernel after this one can only start once
+// the kernel before this one has completed (no kernel ever overlaps its grand-predecessor).
+// Without the launch attribute both instructions are no-ops.  b2rl_set_pdl(0) / B2RL_PDL=0 turns the attribute off.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define B2RL_REQUIRE(cond, msg)                     \
   do {                                              \
     if (!(cond)) {                                  \

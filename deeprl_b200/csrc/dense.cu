@@ -26,6 +26,7 @@ __device__ __forceinline__ int4 pack8(const float* f) {
 
 __global__ void __launch_bounds__(256) bias_act_kernel(__nv_bfloat16* __restrict__ y, const float* __restrict__ bias,
                                                        int64_t n8, int C8, int relu) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
   // n8 = rows*C/8 vectors; vector e covers channels (e % C8)*8 .. +7
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n8; e += (int64_t)gridDim.x * blockDim.x) {
     const int c0 = (int)(e % C8) * 8;
@@ -44,6 +45,7 @@ __global__ void __launch_bounds__(256) bias_act_kernel(__nv_bfloat16* __restrict
 // split-K GEMM results (fp32) -> bf16 activations with bias + ReLU
 __global__ void __launch_bounds__(256) bias_act_f32_kernel(const float* __restrict__ x, const float* __restrict__ bias,
                                                            __nv_bfloat16* __restrict__ y, int64_t n8, int C8, int relu) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n8; e += (int64_t)gridDim.x * blockDim.x) {
     const int c0 = (int)(e % C8) * 8;
     const float4 a = reinterpret_cast<const float4*>(x)[2 * e], b = reinterpret_cast<const float4*>(x)[2 * e + 1];
@@ -79,6 +81,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __res
                                                       const __nv_bfloat16* __restrict__ y, int64_t rows, int C8, int relu,
                                                       __nv_bfloat16* __restrict__ gx, float* __restrict__ dbias,
                                                       int map, int G, int V) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
   extern __shared__ float sred[];          // [rows_per_block][C] partial sums
   const int C = C8 * 8;
   const int rpb = blockDim.x / C8;         // rows handled per block per iteration
@@ -133,7 +136,7 @@ extern "C" int b2rl_bias_act_bf16(uint16_t* y, const float* bias, int64_t rows, 
   const int64_t n8 = rows * C / 8;
   int blocks = (int)((n8 + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  bias_act_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(y), bias, n8, C / 8, relu);
+  launch_pdl(bias_act_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<__nv_bfloat16*>(y), bias, n8, C / 8, relu);
   return check_launch("b2rl_bias_act_bf16");
 }
 
@@ -154,7 +157,7 @@ extern "C" int b2rl_act_bwd_bias_grad_bf16(const uint16_t* gy, const uint16_t* y
   if (want > by_work) want = by_work;
   int blocks = (int)(want < 592 ? want : 592);         // 4 CTAs per SM keep enough 16-byte loads in flight
   size_t smem = (size_t)rpb * C * sizeof(float);
-  act_bwd_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(
+  launch_pdl(act_bwd_kernel, dim3(blocks), dim3(256), smem, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(gy), reinterpret_cast<const __nv_bfloat16*>(y), rows, C8, relu,
       reinterpret_cast<__nv_bfloat16*>(gx), dbias, row_map, G, V);
   return check_launch("b2rl_act_bwd_bias_grad_bf16");
@@ -168,6 +171,6 @@ extern "C" int b2rl_bias_act_f32_to_bf16(const float* x, const float* bias, uint
   const int64_t n8 = rows * C / 8;
   int blocks = (int)((n8 + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  bias_act_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, bias, reinterpret_cast<__nv_bfloat16*>(y), n8, C / 8, relu);
+  launch_pdl(bias_act_f32_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, bias, reinterpret_cast<__nv_bfloat16*>(y), n8, C / 8, relu);
   return check_launch("b2rl_bias_act_f32_to_bf16");
 }

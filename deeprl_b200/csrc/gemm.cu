@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // everything above (barriers, tensor-map prefetch, TMEM allocation) overlaps the previous kernel's tail
 
   if (warp == 0 && n_kt > 0 && elect_one()) {
     // ---------------------------------------------------------------------- TMA producer
@@ -487,6 +488,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // everything above (barriers, tensor-map prefetch, TMEM allocation) overlaps the previous kernel's tail
 
   if (warp == 0 && elect_one()) {
     // ---------------------------------------------------------------------- TMA producer
@@ -615,6 +617,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // everything above (barriers, tensor-map prefetch, TMEM allocation) overlaps the previous kernel's tail
 
   if (warp == 0 && elect_one()) {
     for (int i = 0; i < n_kt; ++i) {
@@ -743,7 +746,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   if (ctas < 1) ctas = 1;
   if (ctas > tiles) ctas = tiles;
   dim3 grid(ctas, 1, splits);
-  k<<<grid, GEMM_THREADS, smem, st>>>(ta, tb, p);
+  launch_pdl(k, dim3(grid), dim3(GEMM_THREADS), smem, st, ta, tb, p);
   return check_launch("b2rl_gemm_bf16");
 }
 
@@ -785,7 +788,7 @@ static int launch_slab(const CUtensorMap& ta, const CUtensorMap& tb, SlabParams 
   const int tiles = (sp.g.M + GEMM_BM - 1) / GEMM_BM;
   int ctas = sm_count();
   if (ctas > tiles) ctas = tiles;
-  k<<<ctas, GEMM_THREADS, smem, st>>>(ta, tb, sp);
+  launch_pdl(k, dim3(ctas), dim3(GEMM_THREADS), smem, st, ta, tb, sp);
   return check_launch("b2rl_conv_gemm_bf16(slab)");
 }
 
@@ -812,7 +815,7 @@ static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, WgradParam
   w.k_tiles_per_cta = (kt_total + ctas - 1) / ctas;
   ctas = (kt_total + w.k_tiles_per_cta - 1) / w.k_tiles_per_cta;
   if (n_ctas) *n_ctas = ctas;
-  k<<<ctas, GEMM_THREADS, smem, st>>>(tg, tx, w);
+  launch_pdl(k, dim3(ctas), dim3(GEMM_THREADS), smem, st, tg, tx, w);
   return check_launch("b2rl_conv_gemm_bf16(wgrad slab)");
 }
 

@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(128) head_fwd_kernel(const __nv_bfloat16* __re
                                                        const float* __restrict__ ba, const float* __restrict__ Wv,
                                                        const float* __restrict__ bv, int B, int K, int A,
                                                        float* __restrict__ q) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
   const int lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   const __nv_bfloat16* x = phi + (int64_t)b * K;
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
                                                        int K, int A, __nv_bfloat16* __restrict__ gphi,
                                                        float* __restrict__ gWa, float* __restrict__ gba,
                                                        float* __restrict__ gWv, float* __restrict__ gbv) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
   __shared__ float geff[HB_ROWS][HEAD_MAX_OUT + 1];       // [row][a], last used column = value gradient (dueling)
   __shared__ float red[4][64][HEAD_MAX_OUT + 1];
   const int k = blockIdx.x * 64 + (threadIdx.x & 63), rg = threadIdx.x >> 6;
@@ -164,9 +166,9 @@ extern "C" int b2rl_head_fwd(const uint16_t* phi, const float* Wa, const float* 
   const int n_out = A + (Wv ? 1 : 0);
   const dim3 grid((B + 3) / 4);
   cudaStream_t st = (cudaStream_t)stream;
-  if (n_out <= 8) head_fwd_kernel<8><<<grid, 128, 0, st>>>(x, Wa, ba, Wv, bv, B, K, A, q);
-  else if (n_out <= 19) head_fwd_kernel<19><<<grid, 128, 0, st>>>(x, Wa, ba, Wv, bv, B, K, A, q);
-  else head_fwd_kernel<HEAD_MAX_OUT><<<grid, 128, 0, st>>>(x, Wa, ba, Wv, bv, B, K, A, q);
+  if (n_out <= 8) launch_pdl(head_fwd_kernel<8>, dim3(grid), dim3(128), 0, st, x, Wa, ba, Wv, bv, B, K, A, q);
+  else if (n_out <= 19) launch_pdl(head_fwd_kernel<19>, dim3(grid), dim3(128), 0, st, x, Wa, ba, Wv, bv, B, K, A, q);
+  else launch_pdl(head_fwd_kernel<HEAD_MAX_OUT>, dim3(grid), dim3(128), 0, st, x, Wa, ba, Wv, bv, B, K, A, q);
   return check_launch("b2rl_head_fwd");
 }
 
@@ -176,7 +178,7 @@ extern "C" int b2rl_head_bwd(const float* gq, const uint16_t* phi, const float* 
                "null pointer");
   B2RL_REQUIRE(B > 0 && K > 0 && A > 0 && A < HEAD_MAX_OUT, "need 0 < A < 32");
   dim3 grid((K + 63) / 64, (B + HB_ROWS - 1) / HB_ROWS);
-  head_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gq, reinterpret_cast<const __nv_bfloat16*>(phi), Wa, Wv, B, K, A,
+  launch_pdl(head_bwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, gq, reinterpret_cast<const __nv_bfloat16*>(phi), Wa, Wv, B, K, A,
                                                           reinterpret_cast<__nv_bfloat16*>(gphi), gWa, gba, gWv, gbv);
   return check_launch("b2rl_head_bwd");
 }

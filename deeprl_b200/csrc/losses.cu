@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(1024) dqn_loss_kernel(const float* __restrict_
                                                         float alpha, float* __restrict__ delta_out,
                                                         float* __restrict__ prio_out, float* __restrict__ loss_out,
                                                         float* __restrict__ dq_out, const float* __restrict__ beta_dev) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
   __shared__ float red[32];
   if (beta_dev) beta = *beta_dev;
   float wmax = 1.0f;
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(64) c51_loss_kernel(const float* __restrict__ 
                                                       float* __restrict__ prio_out, float* __restrict__ loss_out,
                                                       float* __restrict__ dlogp_out, float* __restrict__ tp_out,
                                                       int32_t* __restrict__ counter, const float* __restrict__ beta_dev) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
   extern __shared__ float sm[];
   if (beta_dev) beta = *beta_dev;
   float* z = sm;            // [N] atoms
@@ -194,6 +196,7 @@ __global__ void __launch_bounds__(256) qr_loss_kernel(const float* __restrict__ 
                                                       float* __restrict__ loss_out, float* __restrict__ dq_out,
                                                       float* __restrict__ partial, int32_t* __restrict__ counter,
                                                       const float* __restrict__ gw) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
   extern __shared__ float sm[];
   float* T = sm;           // [N] target quantiles  r + gamma^n * m * theta'(s', a*)
   float* th = sm + N;      // [N] theta(s, a)
@@ -288,7 +291,7 @@ extern "C" int b2rl_dqn_loss(const float* q, const float* q_next_target, const f
   B2RL_REQUIRE(q && q_next_target && action && reward && mask, "null pointer");
   B2RL_REQUIRE(B > 0 && A > 0, "bad shape");
   int threads = B >= 1024 ? 1024 : ((B + 31) / 32) * 32;
-  dqn_loss_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(q, q_next_target, q_next_online, action, reward, mask,
+  launch_pdl(dqn_loss_kernel, dim3(1), dim3(threads), 0, (cudaStream_t)stream, q, q_next_target, q_next_online, action, reward, mask,
                                                            gamma_n, B, A, is_prob, beta, eps, alpha, delta_out,
                                                            priority_out, loss_out, dq_out, beta_dev);
   return check_launch("b2rl_dqn_loss");
@@ -304,7 +307,7 @@ extern "C" int b2rl_c51_loss(const float* log_prob, const float* prob_next_targe
   const double start = (double)v_min, step = ((double)v_max - (double)v_min) / (double)(N - 1);
   const float delta_atom = (float)(((double)v_max - (double)v_min) / (double)(N - 1));   // CategoricalDQN_agent.py:46
   size_t smem = (size_t)(3 * N + A) * sizeof(float);
-  c51_loss_kernel<<<B, 64, smem, (cudaStream_t)stream>>>(log_prob, prob_next_target, prob_next_online, action, reward,
+  launch_pdl(c51_loss_kernel, dim3(B), dim3(64), smem, (cudaStream_t)stream, log_prob, prob_next_target, prob_next_online, action, reward,
                                                          mask, gamma_n, v_min, v_max, start, step, delta_atom, B, A, N,
                                                          is_prob, beta, eps, alpha, kl_out, priority_out, loss_out,
                                                          dlogp_out, target_prob_out, counter, beta_dev);
@@ -319,7 +322,7 @@ extern "C" int b2rl_qr_loss(const float* quantile, const float* quantile_next, c
   B2RL_REQUIRE((partial && counter) || dquant_out, "nothing to compute");
   B2RL_REQUIRE(B > 0 && A > 0 && N > 0 && N <= 4096 && A <= 4096, "bad shape");
   size_t smem = (size_t)(3 * N + A) * sizeof(float);
-  qr_loss_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(quantile, quantile_next, action, reward, mask, gamma_n, kappa,
+  launch_pdl(qr_loss_kernel, dim3(B), dim3(256), smem, (cudaStream_t)stream, quantile, quantile_next, action, reward, mask, gamma_n, kappa,
                                                          B, A, N, vec_out, loss_out, dquant_out, partial, counter,
                                                          grad_weight);
   return check_launch("b2rl_qr_loss");

@@ -14,6 +14,7 @@ struct NormScratch { float sumsq; float coef; int32_t counter; int32_t pad; };
 __global__ void __launch_bounds__(512) sumsq_kernel(const float* __restrict__ g, int64_t n, float grad_scale,
                                                     float max_norm, float* __restrict__ partial,
                                                     NormScratch* __restrict__ sc) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
   __shared__ float red[32];
   __shared__ bool is_last;
   float s = 0.0f;
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(float* __restrict__ p, con
                                                       float lr, float alpha, float eps, int centered,
                                                       const NormScratch* __restrict__ sc,
                                                       __nv_bfloat16* __restrict__ shadow) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
   const float coef = sc->coef;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gr = g[i] * coef;
@@ -79,6 +81,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float b1, float b2, float eps, const int64_t* __restrict__ step_dev,
                                                    const NormScratch* __restrict__ sc,
                                                    __nv_bfloat16* __restrict__ shadow) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
   const float coef = sc->coef;
   const float t = (float)(*step_dev);
   const float bc1 = 1.0f - powf(b1, t), bc2 = 1.0f - powf(b2, t);
@@ -96,7 +99,10 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
-__global__ void bump_step_kernel(int64_t* step) { *step += 1; }
+__global__ void bump_step_kernel(int64_t* step) {
+  pdl_sync();
+  *step += 1;
+}
 
 }  // namespace b2rl
 
@@ -110,7 +116,7 @@ static int norm_pass(const float* grad, int64_t n, float grad_scale, float max_n
   int blocks = (int)((n + 512 * 4 - 1) / (512 * 4));
   if (blocks > 296) blocks = 296;
   if (blocks < 1) blocks = 1;
-  sumsq_kernel<<<blocks, 512, 0, st>>>(grad, n, grad_scale, max_norm, partial, sc);
+  launch_pdl(sumsq_kernel, dim3(blocks), dim3(512), 0, st, grad, n, grad_scale, max_norm, partial, sc);
   return check_launch("clip/sumsq");
 }
 
@@ -124,7 +130,7 @@ extern "C" int b2rl_clip_rmsprop(float* param, const float* grad, float* square_
   if (rc) return rc;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  rmsprop_kernel<<<blocks, 256, 0, st>>>(param, grad, square_avg, grad_avg, n, lr, alpha, eps, centered,
+  launch_pdl(rmsprop_kernel, dim3(blocks), dim3(256), 0, st, param, grad, square_avg, grad_avg, n, lr, alpha, eps, centered,
                                          reinterpret_cast<NormScratch*>(norm_scratch),
                                          reinterpret_cast<__nv_bfloat16*>(bf16_shadow));
   return check_launch("b2rl_clip_rmsprop");
@@ -138,12 +144,12 @@ extern "C" int b2rl_clip_adam(float* param, const float* grad, float* exp_avg, f
   cudaStream_t st = (cudaStream_t)stream;
   int rc = norm_pass(grad, n, grad_scale, max_norm, norm_scratch, st);
   if (rc) return rc;
-  bump_step_kernel<<<1, 1, 0, st>>>(step_dev);
+  launch_pdl(bump_step_kernel, dim3(1), dim3(1), 0, st, step_dev);
   rc = check_launch("adam/step");
   if (rc) return rc;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  adam_kernel<<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step_dev,
+  launch_pdl(adam_kernel, dim3(blocks), dim3(256), 0, st, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step_dev,
                                       reinterpret_cast<NormScratch*>(norm_scratch),
                                       reinterpret_cast<__nv_bfloat16*>(bf16_shadow));
   return check_launch("b2rl_clip_adam");

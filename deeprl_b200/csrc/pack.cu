@@ -17,6 +17,7 @@ struct PackArgs {
 
 // segment sizes: w1f 32*64*c1 | w2f 64*512 | w2d 128*256 | w3f 64*576 | w3d 64*576 | w4p n4*3136
 __global__ void __launch_bounds__(256) pack_weights_kernel(PackArgs a) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
   const int64_t s1 = 32LL * 64 * a.c1, s2 = 64 * 512, s3 = 128 * 256, s4 = 64 * 576, s5 = 64 * 576,
                 s6 = (int64_t)a.n4 * 3136;
   const int64_t total = s1 + s2 + s3 + s4 + s5 + s6;
@@ -94,6 +95,7 @@ __device__ __forceinline__ float sum_partials(const float* __restrict__ g, int64
 }
 
 __global__ void __launch_bounds__(256) unpack_grads_kernel(UnpackArgs a) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
   const int64_t s1 = 32LL * a.c1 * 64, s2 = 64 * 512, s3 = 64 * 576, s4 = (int64_t)a.n4 * 3136;
   const int64_t sb = 32 + 64 + 64 + a.n4;
   const int64_t total = s1 + s2 + s3 + s4 + sb;
@@ -151,7 +153,7 @@ extern "C" int b2rl_nature_pack_weights(const float* w1, const float* w2, const 
   a.w2d = reinterpret_cast<__nv_bfloat16*>(w2d); a.w3f = reinterpret_cast<__nv_bfloat16*>(w3f);
   a.w3d = reinterpret_cast<__nv_bfloat16*>(w3d); a.w4p = reinterpret_cast<__nv_bfloat16*>(w4p);
   a.c1 = c1; a.n4 = n4; a.scale = scale;
-  pack_weights_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(a);
+  launch_pdl(pack_weights_kernel, dim3(148 * 8), dim3(256), 0, (cudaStream_t)stream, a);
   return check_launch("b2rl_nature_pack_weights");
 }
 
@@ -167,6 +169,6 @@ extern "C" int b2rl_nature_unpack_grads(const float* g1f, const float* g2f, cons
   a.gw1 = gw1; a.gw2 = gw2; a.gw3 = gw3; a.gw4 = gw4; a.gb1 = gb1; a.gb2 = gb2; a.gb3 = gb3; a.gb4 = gb4;
   a.c1 = c1; a.n4 = n4; a.scale = scale;
   a.p1 = p1 < 1 ? 1 : p1; a.p2 = p2 < 1 ? 1 : p2; a.p3 = p3 < 1 ? 1 : p3;
-  unpack_grads_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(a);
+  launch_pdl(unpack_grads_kernel, dim3(148 * 8), dim3(256), 0, (cudaStream_t)stream, a);
   return check_launch("b2rl_nature_unpack_grads");
 }

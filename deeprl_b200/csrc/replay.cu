@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(512) feed_kernel(uint8_t* __restrict__ frames,
                                                    const uint8_t* __restrict__ nf, const int32_t* __restrict__ na,
                                                    const double* __restrict__ nr, const int32_t* __restrict__ nm,
                                                    int n, int quirk) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
   __shared__ int64_t slot[1024];
   __shared__ int64_t fin[2];
   if (threadIdx.x == 0) {
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_uniform_kernel(int64_t* __
                                                                      uint64_t seed, int hl, int n, int B,
                                                                      int64_t* __restrict__ idx_out,
                                                                      int32_t* __restrict__ status) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
   __shared__ int warp_tot[32];
   __shared__ int last_used;
   const int64_t pos = ring_state[0], size = ring_state[1];
@@ -198,6 +200,7 @@ __global__ void __launch_bounds__(32) gather_raw_tma_kernel(const uint8_t* __res
                                                             double discount, uint8_t* __restrict__ state_out,
                                                             uint8_t* __restrict__ next_out, int64_t* a_out,
                                                             float* r_out, float* m_out) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   const int b = blockIdx.x;
@@ -263,6 +266,7 @@ __global__ void __launch_bounds__(256) gather_cvt_kernel(const uint8_t* __restri
                                                          T* __restrict__ state_out, T* __restrict__ next_out,
                                                          int64_t* a_out, float* r_out, float* m_out, int use_tma,
                                                          int frame_w) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ T slut[256];
@@ -360,6 +364,7 @@ __global__ void __launch_bounds__(128) gather_raw_generic_kernel(const uint8_t* 
                                                                  double discount, uint8_t* __restrict__ state_out,
                                                                  uint8_t* __restrict__ next_out, int64_t* a_out,
                                                                  float* r_out, float* m_out) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
   const int b = blockIdx.x;
   const int64_t i = idx[b];
   const int64_t stack = (int64_t)hl * row_bytes;
@@ -378,7 +383,7 @@ static int launch_cvt1(dim3 grid, size_t smem, cudaStream_t st, const uint8_t* f
                        int frame_w) {
   auto k = gather_cvt_kernel<T, LAYOUT>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k<<<grid, 256, smem, st>>>(frames, action, reward, mask, row_bytes, idx, hl, n, discount, lut, (T*)so, (T*)no, a, r, m,
+  launch_pdl(k, dim3(grid), dim3(256), smem, st, frames, action, reward, mask, row_bytes, idx, hl, n, discount, lut, (T*)so, (T*)no, a, r, m,
                              use_tma, frame_w);
   return check_launch("b2rl_replay_gather");
 }
@@ -411,7 +416,7 @@ extern "C" int b2rl_replay_feed(uint8_t* frames, int32_t* action, double* reward
   B2RL_REQUIRE(n >= 0 && n <= 1024, "n must be in [0, 1024]");
   B2RL_REQUIRE(row_bytes > 0, "row_bytes must be positive");
   if (n == 0) return B2RL_OK;
-  feed_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(frames, action, reward, mask, ring_state, row_bytes, new_frames,
+  launch_pdl(feed_kernel, dim3(1), dim3(512), 0, (cudaStream_t)stream, frames, action, reward, mask, ring_state, row_bytes, new_frames,
                                                    new_action, new_reward, new_mask, n, reference_quirk);
   return check_launch("b2rl_replay_feed");
 }
@@ -422,7 +427,7 @@ extern "C" int b2rl_replay_select_uniform(int64_t* ring_state, const int64_t* ca
   B2RL_REQUIRE(ring_state && idx_out && status_out, "null pointer");
   B2RL_REQUIRE(B > 0 && n_cand >= B && n_cand <= SEL_THREADS * SEL_PER_THREAD, "need B <= n_cand <= 8192");
   B2RL_REQUIRE(history >= 1 && n_step >= 1, "history and n_step must be >= 1");
-  select_uniform_kernel<<<1, SEL_THREADS, 0, (cudaStream_t)stream>>>(ring_state, candidates, n_cand, seed, history,
+  launch_pdl(select_uniform_kernel, dim3(1), dim3(SEL_THREADS), 0, (cudaStream_t)stream, ring_state, candidates, n_cand, seed, history,
                                                                       n_step, B, idx_out, status_out);
   return check_launch("b2rl_replay_select_uniform");
 }
@@ -448,11 +453,11 @@ extern "C" int b2rl_replay_gather(const uint8_t* frames, const int32_t* action, 
     const bool out_aligned = (reinterpret_cast<uintptr_t>(state_out) | reinterpret_cast<uintptr_t>(next_out)) % 16 == 0;
     if (aligned && out_aligned) {
       cudaFuncSetAttribute(gather_raw_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)span);
-      gather_raw_tma_kernel<<<B, 32, span, st>>>(frames, action, reward, mask, row_bytes, idx, history, n_step,
+      launch_pdl(gather_raw_tma_kernel, dim3(B), dim3(32), span, st, frames, action, reward, mask, row_bytes, idx, history, n_step,
                                                  discount, (uint8_t*)state_out, (uint8_t*)next_out, action_out,
                                                  reward_out, mask_out);
     } else {
-      gather_raw_generic_kernel<<<B, 128, 0, st>>>(frames, action, reward, mask, row_bytes, idx, history, n_step,
+      launch_pdl(gather_raw_generic_kernel, dim3(B), dim3(128), 0, st, frames, action, reward, mask, row_bytes, idx, history, n_step,
                                                    discount, (uint8_t*)state_out, (uint8_t*)next_out, action_out,
                                                    reward_out, mask_out);
     }

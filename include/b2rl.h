@@ -37,6 +37,9 @@ const char* b2rl_last_error(void);
 /* number of kernels this library has launched since load / since the last reset (bench.py "gpu_launches") */
 int64_t b2rl_launch_count(void);
 void b2rl_reset_launch_count(void);
+/* Programmatic dependent launch of the per-update kernels (each kernel's prologue overlaps the tail of the one before it;
+ * csrc/common.cuh).  On by default; 0 launches every kernel with plain stream order (also: environment B2RL_PDL=0). */
+void b2rl_set_pdl(int32_t on);
 
 /* ---------------------------------------------------------------------------------------------
  * Replay ring -- UniformReplay.feed / valid_index / construct_transition / sample
