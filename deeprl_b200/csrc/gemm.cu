@@ -631,25 +631,52 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
         tma_load_2d(st + A_BYTES + (size_t)cb * slab_block, &tmX, &full[s], cb * GEMM_BK, k0);           // [slab_rows][64 c]
     }
   } else if (warp == 1 && n_kt > 0 && elect_one()) {
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(w.C >> 3) << 17) |
-                           ((uint32_t)(GEMM_BM >> 4) << 24);
-    const uint32_t a_lo0 = desc_lo(s2u(smem), 8192), b_lo0 = desc_lo(s2u(smem + A_BYTES), slab_block);
+    const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(GEMM_BM >> 4) << 24);
+    // With one 64-channel column block per tap (C == 64) the taps of one grid row (dx = 0..taps_x-1) are ONE MMA: their
+    // windows start 1 row = 128 bytes apart in the slab, which is exactly an MN-major B operand of N = run*64 columns
+    // whose 64-element groups are LBO = 128 bytes apart (the 128-byte swizzle is a function of the address, so overlapping
+    // groups read the right bytes), and their accumulators are adjacent TMEM columns.  The tensor pipe takes
+    // max(53, N/2) cycles per MMA, so a run of 3 taps costs 96 cycles instead of 3 x 53.
+    const bool merge = w.C == 64;
+    const uint32_t a_lo0 = desc_lo(s2u(smem), 8192), b_lo0 = desc_lo(s2u(smem + A_BYTES), merge ? 128u : slab_block);
     const int tap_end = w.tap0 + w.ntaps;
+    // the (window offset, accumulator column, instruction descriptor) of every MMA of a k16 step, computed once
+    constexpr int MAX_RUNS = 16;
+    uint32_t r_off[MAX_RUNS], r_acc[MAX_RUNS], r_idesc[MAX_RUNS];
+    int n_runs = 0;
+    {
+      int tap = w.tap0;
+      uint32_t acc = 0;
+#pragma unroll
+      for (int j = 0; j < MAX_RUNS; ++j) {
+        r_off[j] = r_acc[j] = r_idesc[j] = 0;
+        if (tap < tap_end) {
+          const int dy = tap / w.taps_x, dx = tap - dy * w.taps_x;
+          int run = 1;
+          if (merge) {
+            run = w.taps_x - dx;
+            if (run > tap_end - tap) run = tap_end - tap;
+          }
+          r_off[j] = (uint32_t)(dy * w.grid_w + dx) * 8;
+          r_acc[j] = acc;
+          r_idesc[j] = idesc0 | ((uint32_t)((run * w.C) >> 3) << 17);
+          acc += run * w.C;
+          tap += run;
+          n_runs = j + 1;
+        }
+      }
+    }
     for (int i = 0; i < n_kt; ++i) {
       const int s = i % w.stages;
       mb_wait(&full[s], (i / w.stages) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_st = a_lo0 + (uint32_t)s * (stage_bytes >> 4), b_st = b_lo0 + (uint32_t)s * (stage_bytes >> 4);
-      // k16 steps outer, taps inner: consecutive MMAs go to different accumulators (independent chains)
 #pragma unroll
       for (int k = 0; k < GEMM_BK / 16; ++k) {
-        uint32_t acc = tmem_base;
-        int dy = w.tap0 / w.taps_x, dx = w.tap0 % w.taps_x;
-        for (int tap = w.tap0; tap < tap_end; ++tap, acc += w.C) {
-          const int shift = dy * w.grid_w + dx;
-          umma_f16_lh(acc, a_st + k * 128, b_st + (uint32_t)shift * 8 + k * 128, idesc, (i > 0 || k > 0) ? 1u : 0u);
-          if (++dx == w.taps_x) { dx = 0; ++dy; }
-        }
+#pragma unroll
+        for (int j = 0; j < MAX_RUNS; ++j)
+          if (j < n_runs)
+            umma_f16_lh(tmem_base + r_acc[j], a_st + k * 128, b_st + r_off[j] + k * 128, r_idesc[j], (i > 0 || k > 0) ? 1u : 0u);
       }
       umma_commit(&empty[s]);
     }
