@@ -46,6 +46,10 @@ SIGNATURES = {
     "b2rl_act_bwd_bias_grad_bf16": [c_p, c_p, c_i64, c_i32, c_i32, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_p],
     "b2rl_conv_gemm_bf16": [c_i32, c_p, c_i64, c_i32, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i64, c_p, c_i32, c_i32,
                             c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
+    "b2rl_conv_gemm_dual_bf16": [c_p, c_p, c_i64, c_i32, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_i64, c_p, c_p,
+                                 c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
+    "b2rl_gemm_dual_bf16": [c_p, c_p, c_i64, c_p, c_p, c_i64, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_p, c_p, c_i32, c_i32,
+                            c_i32, c_p],
     "b2rl_gemm_bf16": [c_p, c_i32, c_i64, c_p, c_i32, c_i64, c_p, c_i64, c_i32, c_i32, c_i32, c_p, c_i32, c_i32, c_i32, c_i32,
                        c_p],
     "b2rl_nature_pack_weights": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_f32, c_p, c_p, c_p, c_p, c_p, c_p, c_p],

@@ -152,6 +152,11 @@ struct GemmParams {
   // output row mapping (rows of the GEMM are positions of a G x G grid per image)
   int out_map;             // 0: identity; 1: G-grid -> space-to-depth(2) rows, valid V x V; 2: G-grid -> compact V x V
   int G, V;
+  // dual launch: the same GEMM for two independent operand sets (online / target network) in ONE grid -- the first half of
+  // the CTAs works on (tmA, tmB, D, bias), the second half on (tmA2, tmB2, D2, bias2); halves the per-kernel fixed cost
+  int dual;
+  void* D2;
+  const float* bias2;
 };
 
 __device__ __forceinline__ int tap_shift(const GemmParams& p, int tap) {
@@ -298,7 +303,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                        const __grid_constant__ CUtensorMap tmB,
-                                                                       const GemmParams p) {
+                                                                       const __grid_constant__ CUtensorMap tmA2,
+                                                                       const __grid_constant__ CUtensorMap tmB2,
+                                                                       const GemmParams p0) {
+  const int n_cta = p0.dual ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const bool second = p0.dual && (int)blockIdx.x >= n_cta;
+  const int cta = second ? (int)blockIdx.x - n_cta : (int)blockIdx.x;
+  const CUtensorMap* mA = second ? &tmA2 : &tmA;
+  const CUtensorMap* mB = second ? &tmB2 : &tmB;
+  GemmParams p = p0;
+  if (second) { p.D = p0.D2; p.bias = p0.bias2; }
   constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2, B_BYTES = BN * GEMM_BK * 2;
   constexpr int ACC = 1;     // partial accumulators per tile: measured, independent chains do not raise the MMA rate
   constexpr uint32_t TMEM_COLS = 2 * ACC * BN < 32 ? 32 : 2 * ACC * BN;   // two accumulator stages
@@ -324,8 +338,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     for (int s = 0; s < STAGES; ++s) { mb_init(&full[s], 1); mb_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mb_init(&tmem_full[s], 1); mb_init(&tmem_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(mA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(mB) : "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)), "n"(TMEM_COLS));
@@ -340,7 +354,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   if (warp == 0 && n_kt > 0 && elect_one()) {
     // ---------------------------------------------------------------------- TMA producer
     uint32_t it = 0;                                         // global k-iteration counter across tiles
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (int tile = cta; tile < tiles; tile += n_cta) {
       const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
       const int m0 = mt * GEMM_BM, n0 = nt * BN;
       int b_shift = 0, b_col = n0;
@@ -363,17 +377,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             ak = (g - tap * p.a_tap_tiles) * GEMM_BK;
             arow = m0 + tap_shift(p, tap);
           }
-          tma_load_2d(a, &tmA, &full[s], ak, arow);                       // box [128 rows][64 k]
+          tma_load_2d(a, mA, &full[s], ak, arow);                       // box [128 rows][64 k]
         } else {
-          tma_load_2d(a, &tmA, &full[s], m0, g * GEMM_BK);                // 2 boxes [64 k][64 m]
-          tma_load_2d(a + 8192, &tmA, &full[s], m0 + 64, g * GEMM_BK);
+          tma_load_2d(a, mA, &full[s], m0, g * GEMM_BK);                // 2 boxes [64 k][64 m]
+          tma_load_2d(a + 8192, mA, &full[s], m0 + 64, g * GEMM_BK);
         }
         if (!p.b_mn) {
-          tma_load_2d(b, &tmB, &full[s], g * GEMM_BK, n0);                // box [BN rows][64 k]
+          tma_load_2d(b, mB, &full[s], g * GEMM_BK, n0);                // box [BN rows][64 k]
         } else {
 #pragma unroll
           for (int q = 0; q < (BN + 63) / 64; ++q)
-            tma_load_2d(b + q * 8192, &tmB, &full[s], b_col + q * 64, g * GEMM_BK + b_shift);
+            tma_load_2d(b + q * 8192, mB, &full[s], b_col + q * 64, g * GEMM_BK + b_shift);
         }
       }
     }
@@ -384,7 +398,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     const uint32_t a_lo0 = desc_lo(s2u(sA), p.a_mn ? 8192 : 16), b_lo0 = desc_lo(s2u(sB), p.b_mn ? 8192 : 16);
     const uint32_t a_step = p.a_mn ? 128 : 2, b_step = p.b_mn ? 128 : 2;
     uint32_t it = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tcount) {
+    for (int tile = cta; tile < tiles; tile += n_cta, ++tcount) {
       const uint32_t as = tcount & 1;
       mb_wait(&tmem_empty[as], ((tcount >> 1) & 1) ^ 1);     // epilogue drained this accumulator stage
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -412,7 +426,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     const int q = warp & 3;
     const uint32_t grp = (uint32_t)(warp - 2) >> 2;
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tcount) {
+    for (int tile = cta; tile < tiles; tile += n_cta, ++tcount) {
       if ((tcount & 1) != grp) continue;
       const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
       const int m0 = mt * GEMM_BM, n0 = nt * BN;
@@ -448,8 +462,16 @@ struct SlabParams {
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                             const __grid_constant__ CUtensorMap tmB,
+                                                                            const __grid_constant__ CUtensorMap tmA2,
+                                                                            const __grid_constant__ CUtensorMap tmB2,
                                                                             const SlabParams sp) {
-  const GemmParams& p = sp.g;
+  const int n_cta = sp.g.dual ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const bool second = sp.g.dual && (int)blockIdx.x >= n_cta;
+  const int cta = second ? (int)blockIdx.x - n_cta : (int)blockIdx.x;
+  const CUtensorMap* mA = second ? &tmA2 : &tmA;
+  const CUtensorMap* mB = second ? &tmB2 : &tmB;
+  GemmParams p = sp.g;
+  if (second) { p.D = sp.g.D2; p.bias = sp.g.bias2; }
   if (threadIdx.x == 0) B2RL_TRACE_AT(3, 0, 0);
   constexpr uint32_t W_TILE = BN * 128;                               // one 64-wide k-tile of the weights
   constexpr int ACC = 1;
@@ -477,8 +499,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
     for (int s = 0; s < 2; ++s) { mb_init(&tmem_full[s], 1); mb_init(&tmem_empty[s], 4); }
     mb_init(w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(mA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(mB) : "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)), "n"(TMEM_COLS));
@@ -494,16 +516,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
     // ---------------------------------------------------------------------- TMA producer
     B2RL_TRACE_AT(3, 0, 1);
     mb_expect_tx(w_full, (uint32_t)k_tiles * W_TILE);
-    for (int kt = 0; kt < k_tiles; ++kt) tma_load_2d(sW + (size_t)kt * W_TILE, &tmB, w_full, kt * GEMM_BK, 0);
+    for (int kt = 0; kt < k_tiles; ++kt) tma_load_2d(sW + (size_t)kt * W_TILE, mB, w_full, kt * GEMM_BK, 0);
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    for (int tile = cta; tile < tiles; tile += n_cta, ++it) {
       const int s = it % sp.stages;
       B2RL_TRACE_AT(0, it, 0);
       mb_wait(&empty[s], ((it / sp.stages) & 1) ^ 1);
       B2RL_TRACE_AT(0, it, 1);
       mb_expect_tx(&full[s], slab_bytes);
       for (int cb = 0; cb < sp.col_blocks; ++cb)
-        tma_load_2d(sS + (size_t)s * slab_bytes + (size_t)cb * slab_block, &tmA, &full[s], cb * GEMM_BK,
+        tma_load_2d(sS + (size_t)s * slab_bytes + (size_t)cb * slab_block, mA, &full[s], cb * GEMM_BK,
                     tile * GEMM_BM + sp.min_shift);
     }
   } else if (warp == 1 && elect_one()) {
@@ -514,7 +536,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
     const uint32_t slab_lo0 = desc_lo(s2u(sS), 16), w_lo0 = desc_lo(s2u(sW), 16);
     const int taps_y = sp.taps / p.taps_x;
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    for (int tile = cta; tile < tiles; tile += n_cta, ++it) {
       const uint32_t as = it & 1;
       const int s = it % sp.stages;
       B2RL_TRACE_AT(1, it, 0);
@@ -553,7 +575,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(cons
     const int q = warp & 3;
     const uint32_t grp = (uint32_t)(warp - 2) >> 2;                    // accumulator stage this warp group drains
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it)
+    for (int tile = cta; tile < tiles; tile += n_cta, ++it)
       if ((it & 1) == grp)
         epilogue_tile<BN, ACC>(p, tile * GEMM_BM, 0, q, lane, tmem_base, it & 1, (it >> 1) & 1, true, tmem_full, tmem_empty, it);
   }
@@ -760,7 +782,8 @@ static int sm_count() {
 }
 
 template <int BN, int STAGES>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int splits, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
+                       const GemmParams& p, int splits, cudaStream_t st) {
   constexpr size_t smem = 1024 + (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + (2 * STAGES + 4) * 8 + 16;
   auto k = gemm_tcgen05_kernel<BN, STAGES>;
   static bool attr_set = false;
@@ -769,18 +792,18 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     attr_set = true;
   }
   const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN);
-  int ctas = sm_count() / splits;
+  int ctas = sm_count() / splits / (p.dual ? 2 : 1);                 // per operand set
   if (ctas < 1) ctas = 1;
   if (ctas > tiles) ctas = tiles;
-  dim3 grid(ctas, 1, splits);
-  launch_pdl(k, dim3(grid), dim3(GEMM_THREADS), smem, st, ta, tb, p);
+  dim3 grid(p.dual ? 2 * ctas : ctas, 1, splits);
+  launch_pdl(k, dim3(grid), dim3(GEMM_THREADS), smem, st, ta, tb, ta2, tb2, p);
   return check_launch("b2rl_gemm_bf16");
 }
 
 static int gemm_dispatch(const uint16_t* A, int a_mn, int64_t lda, int64_t a_rows, int64_t a_cols, const uint16_t* B,
                          int b_mn, int64_t ldb, int64_t b_rows, int64_t b_cols, GemmParams p, int splits, int block_n,
-                         cudaStream_t st) {
-  CUtensorMap ta, tb;
+                         cudaStream_t st, const uint16_t* A2 = nullptr, const uint16_t* B2 = nullptr) {
+  CUtensorMap ta, tb, ta2, tb2;
   int rc;
   // the tensor map describes the matrix AS STORED: [a_rows][a_cols]; box = [128|64 rows][64 cols]
   rc = make_map(&ta, A, a_cols, a_rows, lda, a_mn ? 64 : GEMM_BM);
@@ -791,13 +814,21 @@ static int gemm_dispatch(const uint16_t* A, int a_mn, int64_t lda, int64_t a_row
   if (splits > kt_total) splits = kt_total;
   p.k_tiles_per_split = (kt_total + splits - 1) / splits;
   splits = (kt_total + p.k_tiles_per_split - 1) / p.k_tiles_per_split;
-  if (block_n == 32) return launch_gemm<32, 6>(ta, tb, p, splits, st);
-  if (block_n == 64) return launch_gemm<64, 6>(ta, tb, p, splits, st);
-  return launch_gemm<128, 5>(ta, tb, p, splits, st);
+  ta2 = ta, tb2 = tb;
+  if (p.dual) {                                                      // second operand set: same shapes and strides
+    rc = make_map(&ta2, A2, a_cols, a_rows, lda, a_mn ? 64 : GEMM_BM);
+    if (rc) return rc;
+    rc = make_map(&tb2, B2, b_cols, b_rows, ldb, b_mn ? 64 : block_n);
+    if (rc) return rc;
+  }
+  if (block_n == 32) return launch_gemm<32, 6>(ta, tb, ta2, tb2, p, splits, st);
+  if (block_n == 64) return launch_gemm<64, 6>(ta, tb, ta2, tb2, p, splits, st);
+  return launch_gemm<128, 5>(ta, tb, ta2, tb2, p, splits, st);
 }
 
 template <int BN>
-static int launch_slab(const CUtensorMap& ta, const CUtensorMap& tb, SlabParams sp, cudaStream_t st) {
+static int launch_slab(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
+                       SlabParams sp, cudaStream_t st) {
   const size_t w_bytes = (size_t)sp.taps * sp.col_blocks * BN * 128;
   const size_t slab_bytes = (size_t)sp.slab_rows * 128 * sp.col_blocks;
   const size_t budget = 200 * 1024;
@@ -813,9 +844,9 @@ static int launch_slab(const CUtensorMap& ta, const CUtensorMap& tb, SlabParams 
     attr = smem;
   }
   const int tiles = (sp.g.M + GEMM_BM - 1) / GEMM_BM;
-  int ctas = sm_count();
+  int ctas = sp.g.dual ? sm_count() / 2 : sm_count();                // per operand set
   if (ctas > tiles) ctas = tiles;
-  launch_pdl(k, dim3(ctas), dim3(GEMM_THREADS), smem, st, ta, tb, sp);
+  launch_pdl(k, dim3(sp.g.dual ? 2 * ctas : ctas), dim3(GEMM_THREADS), smem, st, ta, tb, ta2, tb2, sp);
   return check_launch("b2rl_conv_gemm_bf16(slab)");
 }
 
@@ -896,10 +927,11 @@ extern "C" int b2rl_gemm_bf16(const uint16_t* A, int32_t a_mn, int64_t lda, cons
 //        X: [rows][C] bf16 (C multiple of 64), W: [N][taps*C] bf16 K-major, shift(tap) = sign*((tap/taps_x)*grid_w + tap%taps_x)
 //   mode 1 (wgrad):            D[n, tap*C + c] (+)= sum_r G[r, n] * X[r + shift(tap), c]
 //        G: [rows][N_out] bf16, X: [rows][C] bf16 (C multiple of block_n), D: fp32 [N_out][taps*C], atomic accumulation
-extern "C" int b2rl_conv_gemm_bf16(int32_t mode, const uint16_t* X, int64_t rows, int32_t C, const uint16_t* W_or_G,
-                                   int32_t n_out, int32_t taps, int32_t taps_x, int32_t grid_w, int32_t shift_sign,
-                                   void* D, int64_t ldd, const float* bias, int32_t relu, int32_t out_mode,
-                                   int32_t out_map, int32_t G, int32_t V, int32_t splits, int32_t block_n, void* stream) {
+static int conv_gemm_impl(int32_t mode, const uint16_t* X, int64_t rows, int32_t C, const uint16_t* W_or_G, int32_t n_out,
+                          int32_t taps, int32_t taps_x, int32_t grid_w, int32_t shift_sign, void* D, int64_t ldd,
+                          const float* bias, int32_t relu, int32_t out_mode, int32_t out_map, int32_t G, int32_t V,
+                          int32_t splits, int32_t block_n, void* stream, const uint16_t* X2 = nullptr,
+                          const uint16_t* W2 = nullptr, void* D2 = nullptr, const float* bias2 = nullptr) {
   B2RL_REQUIRE(mode == 0 || mode == 1, "mode 0 (forward/dgrad) or 1 (wgrad)");
   B2RL_REQUIRE(rows > 0 && C > 0 && taps > 0 && taps_x > 0 && n_out > 0, "bad shape");
   B2RL_REQUIRE(out_map >= 0 && out_map <= 2, "bad out_map");
@@ -907,6 +939,7 @@ extern "C" int b2rl_conv_gemm_bf16(int32_t mode, const uint16_t* X, int64_t rows
   p.relu = relu; p.out_mode = out_mode; p.bias = bias; p.D = D; p.ldd = (int)ldd;
   p.taps_x = taps_x; p.grid_w = grid_w; p.shift_sign = shift_sign;
   p.out_map = out_map; p.G = G; p.V = V;
+  p.dual = X2 != nullptr; p.D2 = D2; p.bias2 = bias2;
   if (mode == 0) {
     B2RL_REQUIRE(C % 64 == 0, "forward/dgrad needs channels in multiples of 64");
     const int K = taps * C;
@@ -921,19 +954,27 @@ extern "C" int b2rl_conv_gemm_bf16(int32_t mode, const uint16_t* X, int64_t rows
       sp.min_shift = shift_sign > 0 ? 0 : -max_shift;
       sp.base_offset_mode = g_use_slab;
       if (sp.slab_rows <= 256) {
-        CUtensorMap ta, tb;
+        CUtensorMap ta, tb, ta2, tb2;
         rc = make_map(&ta, X, C, rows, C, sp.slab_rows);            // box [slab_rows][64]
         if (rc) return rc;
         rc = make_map(&tb, W_or_G, K, n_out, K, block_n);           // box [block_n][64]
         if (rc) return rc;
-        int r2 = block_n == 32 ? launch_slab<32>(ta, tb, sp, (cudaStream_t)stream)
-                 : block_n == 64 ? launch_slab<64>(ta, tb, sp, (cudaStream_t)stream)
-                                 : launch_slab<128>(ta, tb, sp, (cudaStream_t)stream);
+        ta2 = ta, tb2 = tb;
+        if (p.dual) {
+          rc = make_map(&ta2, X2, C, rows, C, sp.slab_rows);
+          if (rc) return rc;
+          rc = make_map(&tb2, W2, K, n_out, K, block_n);
+          if (rc) return rc;
+        }
+        int r2 = block_n == 32 ? launch_slab<32>(ta, tb, ta2, tb2, sp, (cudaStream_t)stream)
+                 : block_n == 64 ? launch_slab<64>(ta, tb, ta2, tb2, sp, (cudaStream_t)stream)
+                                 : launch_slab<128>(ta, tb, ta2, tb2, sp, (cudaStream_t)stream);
         if (r2 <= 0) return r2;                                      // launched (0) or failed (<0); 1 = does not fit
       }
     }
-    return gemm_dispatch(X, 0, C, rows, C, W_or_G, 0, K, n_out, K, p, splits, block_n, (cudaStream_t)stream);
+    return gemm_dispatch(X, 0, C, rows, C, W_or_G, 0, K, n_out, K, p, splits, block_n, (cudaStream_t)stream, X2, W2);
   }
+  B2RL_REQUIRE(!p.dual, "the dual launch is for forward / dgrad GEMMs");
   B2RL_REQUIRE(C % block_n == 0, "wgrad needs channels in multiples of block_n");
   B2RL_REQUIRE(n_out % 8 == 0, "wgrad needs n_out in multiples of 8");
   int rc = check_common(W_or_G, X, D, n_out, C, n_out, taps * C, (int)rows, out_mode, splits, block_n, 1, relu);
@@ -967,6 +1008,47 @@ extern "C" int b2rl_conv_gemm_bf16(int32_t mode, const uint16_t* X, int64_t rows
   }
   p.M = n_out; p.N = taps * C; p.K = (int)rows; p.a_mn = 1; p.b_mn = 1; p.b_tap_tiles = C / block_n;
   return gemm_dispatch(W_or_G, 1, n_out, rows, n_out, X, 1, C, rows, C, p, splits, block_n, (cudaStream_t)stream);
+}
+
+extern "C" int b2rl_conv_gemm_bf16(int32_t mode, const uint16_t* X, int64_t rows, int32_t C, const uint16_t* W_or_G,
+                                   int32_t n_out, int32_t taps, int32_t taps_x, int32_t grid_w, int32_t shift_sign,
+                                   void* D, int64_t ldd, const float* bias, int32_t relu, int32_t out_mode,
+                                   int32_t out_map, int32_t G, int32_t V, int32_t splits, int32_t block_n, void* stream) {
+  return conv_gemm_impl(mode, X, rows, C, W_or_G, n_out, taps, taps_x, grid_w, shift_sign, D, ldd, bias, relu, out_mode,
+                        out_map, G, V, splits, block_n, stream);
+}
+
+// The same forward / dgrad convolution for TWO independent operand sets (online and target network) in one launch:
+// D = conv(X, W) + bias and D2 = conv(X2, W2) + bias2, identical shapes.  Half of the CTAs work on each set.
+extern "C" int b2rl_conv_gemm_dual_bf16(const uint16_t* X, const uint16_t* X2, int64_t rows, int32_t C, const uint16_t* W,
+                                        const uint16_t* W2, int32_t n_out, int32_t taps, int32_t taps_x, int32_t grid_w,
+                                        int32_t shift_sign, void* D, void* D2, int64_t ldd, const float* bias,
+                                        const float* bias2, int32_t relu, int32_t out_mode, int32_t out_map, int32_t G,
+                                        int32_t V, int32_t block_n, void* stream) {
+  B2RL_REQUIRE(X2 && W2 && D2, "null pointer in the second operand set");
+  B2RL_REQUIRE((reinterpret_cast<uintptr_t>(X2) | reinterpret_cast<uintptr_t>(W2)) % 16 == 0, "operands must be 16-byte aligned");
+  B2RL_REQUIRE((bias == nullptr) == (bias2 == nullptr), "both or neither bias");
+  return conv_gemm_impl(0, X, rows, C, W, n_out, taps, taps_x, grid_w, shift_sign, D, ldd, bias, relu, out_mode, out_map, G,
+                        V, 1, block_n, stream, X2, W2, D2, bias2);
+}
+
+// D = A B^T + bias and D2 = A2 B2^T + bias2 (K-major operands, identical shapes) in one launch
+extern "C" int b2rl_gemm_dual_bf16(const uint16_t* A, const uint16_t* A2, int64_t lda, const uint16_t* B, const uint16_t* B2,
+                                   int64_t ldb, void* D, void* D2, int64_t ldd, int32_t M, int32_t N, int32_t K,
+                                   const float* bias, const float* bias2, int32_t relu, int32_t out_mode, int32_t block_n,
+                                   void* stream) {
+  int rc = check_common(A, B, D, lda, ldb, M, N, K, out_mode, 1, block_n, 0, relu);
+  if (rc) return rc;
+  B2RL_REQUIRE(A2 && B2 && D2, "null pointer in the second operand set");
+  B2RL_REQUIRE((reinterpret_cast<uintptr_t>(A2) | reinterpret_cast<uintptr_t>(B2)) % 16 == 0, "operands must be 16-byte aligned");
+  B2RL_REQUIRE(out_mode != 2, "the dual launch stores (bf16 or fp32), it does not accumulate");
+  B2RL_REQUIRE((bias == nullptr) == (bias2 == nullptr), "both or neither bias");
+  GemmParams p = {};
+  p.M = M; p.N = N; p.K = K; p.ldd = (int)ldd;
+  p.relu = relu; p.out_mode = out_mode; p.bias = bias; p.D = D;
+  p.taps_x = 1; p.shift_sign = 1;
+  p.dual = 1; p.D2 = D2; p.bias2 = bias2;
+  return gemm_dispatch(A, 0, lda, M, K, B, 0, ldb, N, K, p, 1, block_n, (cudaStream_t)stream, A2, B2);
 }
 
 // Weight gradient as split-K PARTIALS: partial i (one per CTA, n_partials_host of them, at most 148) is stored at

@@ -229,6 +229,18 @@ int b2rl_conv_gemm_bf16(int32_t mode, const uint16_t* X, int64_t rows, int32_t C
                         const float* bias, int32_t relu, int32_t out_mode, int32_t out_map, int32_t G, int32_t V,
                         int32_t splits, int32_t block_n, void* stream);
 
+/* Dual launches: the same GEMM / convolution for TWO independent operand sets of identical shape (online network on the
+ * sampled states, target network on the next states -- DQN_agent.py:84-99 evaluates both every update) in ONE grid;
+ * half of the CTAs work on each set, so the per-kernel fixed cost (launch, prologue, weight load, drain) is paid once. */
+int b2rl_conv_gemm_dual_bf16(const uint16_t* X, const uint16_t* X2, int64_t rows, int32_t C, const uint16_t* W,
+                             const uint16_t* W2, int32_t n_out, int32_t taps, int32_t taps_x, int32_t grid_w,
+                             int32_t shift_sign, void* D, void* D2, int64_t ldd, const float* bias, const float* bias2,
+                             int32_t relu, int32_t out_mode, int32_t out_map, int32_t G, int32_t V, int32_t block_n,
+                             void* stream);
+int b2rl_gemm_dual_bf16(const uint16_t* A, const uint16_t* A2, int64_t lda, const uint16_t* B, const uint16_t* B2,
+                        int64_t ldb, void* D, void* D2, int64_t ldd, int32_t M, int32_t N, int32_t K, const float* bias,
+                        const float* bias2, int32_t relu, int32_t out_mode, int32_t block_n, void* stream);
+
 /* NatureConvBody weights (network_bodies.py:13-20) between the reference's parameter layouts and the tap-major bf16
  * operands of the grid-GEMM stack: w1 [32,c1,8,8] -> w1f [32][4 taps][16*c1] (times `scale` = ImageNormalizer's 1/255);
  * w2 [64,32,4,4] -> w2f [64][4][128], w2d [128][4][64]; w3 [64,64,3,3] -> w3f [64][9][64], w3d [64][9][64];
