@@ -42,16 +42,18 @@ __device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mb_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the waiting thread sleeps in hardware until the phase completes instead of polling
+// the barrier word -- eight epilogue warps spinning on shared memory measurably slow the tensor pipe's operand reads
 __device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra LAB_DONE;\n"
       "bra LAB_WAIT;\n"
       "LAB_DONE:\n"
-      "}\n" ::"r"(s2u(bar)), "r"(parity)
+      "}\n" ::"r"(s2u(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -603,12 +605,19 @@ struct WgradParams {
   float* D;
   int ldd;
   int64_t partial_stride;   // 0: atomically accumulate into D; > 0: CTA i stores its partial sums at D + i*partial_stride
+  // MMAs of one k16 step, built on the host (launch_wgrad): with one 64-channel column block per tap (C == 64) the taps of
+  // one grid row (dx = 0..taps_x-1) are ONE MMA -- their windows start 1 row = 128 bytes apart in the slab, which is an
+  // MN-major B operand of N = run*64 columns whose 64-element groups are LBO = 128 bytes apart (the 128-byte swizzle is a
+  // function of the address, so overlapping groups read the right bytes) with adjacent TMEM accumulator columns.
+  int n_runs;
+  uint32_t run_off[9], run_acc[9], run_n[9];   // slab window offset (16-byte units), accumulator column, N of the MMA
 };
 
 template <int TMEM_COLS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmG,
                                                                              const __grid_constant__ CUtensorMap tmX,
                                                                              const WgradParams w) {
+  if (threadIdx.x == 0) B2RL_TRACE_AT(3, 0, 0);
   constexpr int MAX_STAGES = 6;
   constexpr uint32_t A_BYTES = 2 * 8192;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -642,9 +651,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
   pdl_sync();   // everything above (barriers, tensor-map prefetch, TMEM allocation) overlaps the previous kernel's tail
 
   if (warp == 0 && elect_one()) {
+    B2RL_TRACE_AT(3, 0, 1);
     for (int i = 0; i < n_kt; ++i) {
       const int s = i % w.stages;
+      B2RL_TRACE_AT(0, i, 0);
       mb_wait(&empty[s], ((i / w.stages) & 1) ^ 1);
+      B2RL_TRACE_AT(0, i, 1);
       mb_expect_tx(&full[s], (uint32_t)w.a_boxes * 8192 + slab_bytes);
       uint8_t* st = smem + (size_t)s * stage_bytes;
       const int k0 = (kt_begin + i) * GEMM_BK;
@@ -654,59 +666,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
     }
   } else if (warp == 1 && n_kt > 0 && elect_one()) {
     const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(GEMM_BM >> 4) << 24);
-    // With one 64-channel column block per tap (C == 64) the taps of one grid row (dx = 0..taps_x-1) are ONE MMA: their
-    // windows start 1 row = 128 bytes apart in the slab, which is exactly an MN-major B operand of N = run*64 columns
-    // whose 64-element groups are LBO = 128 bytes apart (the 128-byte swizzle is a function of the address, so overlapping
-    // groups read the right bytes), and their accumulators are adjacent TMEM columns.  The tensor pipe takes
-    // max(53, N/2) cycles per MMA, so a run of 3 taps costs 96 cycles instead of 3 x 53.
     const bool merge = w.C == 64;
     const uint32_t a_lo0 = desc_lo(s2u(smem), 8192), b_lo0 = desc_lo(s2u(smem + A_BYTES), merge ? 128u : slab_block);
-    const int tap_end = w.tap0 + w.ntaps;
-    // the (window offset, accumulator column, instruction descriptor) of every MMA of a k16 step, computed once
-    constexpr int MAX_RUNS = 16;
-    uint32_t r_off[MAX_RUNS], r_acc[MAX_RUNS], r_idesc[MAX_RUNS];
-    int n_runs = 0;
-    {
-      int tap = w.tap0;
-      uint32_t acc = 0;
-#pragma unroll
-      for (int j = 0; j < MAX_RUNS; ++j) {
-        r_off[j] = r_acc[j] = r_idesc[j] = 0;
-        if (tap < tap_end) {
-          const int dy = tap / w.taps_x, dx = tap - dy * w.taps_x;
-          int run = 1;
-          if (merge) {
-            run = w.taps_x - dx;
-            if (run > tap_end - tap) run = tap_end - tap;
-          }
-          r_off[j] = (uint32_t)(dy * w.grid_w + dx) * 8;
-          r_acc[j] = acc;
-          r_idesc[j] = idesc0 | ((uint32_t)((run * w.C) >> 3) << 17);
-          acc += run * w.C;
-          tap += run;
-          n_runs = j + 1;
-        }
-      }
-    }
     for (int i = 0; i < n_kt; ++i) {
       const int s = i % w.stages;
+      B2RL_TRACE_AT(1, i, 0);
       mb_wait(&full[s], (i / w.stages) & 1);
+      B2RL_TRACE_AT(1, i, 2);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_st = a_lo0 + (uint32_t)s * (stage_bytes >> 4), b_st = b_lo0 + (uint32_t)s * (stage_bytes >> 4);
+      // runs outer (table in the constant bank, not unrolled), k16 steps inner: the issuing thread must stay lean --
+      // a fully unrolled predicated table cost ~190 cycles of bookkeeping per MMA
+      const uint32_t first = i > 0 ? 1u : 0u;
+#pragma unroll 1
+      for (int j = 0; j < w.n_runs; ++j) {
+        const uint32_t acc = tmem_base + w.run_acc[j], idesc = idesc0 | ((w.run_n[j] >> 3) << 17);
+        const uint32_t b_j = b_st + w.run_off[j];
+        umma_f16_lh(acc, a_st, b_j, idesc, first);
 #pragma unroll
-      for (int k = 0; k < GEMM_BK / 16; ++k) {
-#pragma unroll
-        for (int j = 0; j < MAX_RUNS; ++j)
-          if (j < n_runs)
-            umma_f16_lh(tmem_base + r_acc[j], a_st + k * 128, b_st + r_off[j] + k * 128, r_idesc[j], (i > 0 || k > 0) ? 1u : 0u);
+        for (int k = 1; k < GEMM_BK / 16; ++k) umma_f16_lh(acc, a_st + k * 128, b_j + k * 128, idesc, 1u);
       }
       umma_commit(&empty[s]);
+      B2RL_TRACE_AT(1, i, 3);
     }
     umma_commit(tmem_full);
   } else if (warp >= 2 && n_kt > 0) {
     const int q = warp & 3;
     const int n = q * 32 + lane;
+    if (warp == 4 && lane == 0) B2RL_TRACE_AT(2, 0, 0);
     mb_wait(tmem_full, 0);
+    if (warp == 4 && lane == 0) B2RL_TRACE_AT(2, 0, 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int cols = w.ntaps * w.C;
     for (int c = ((warp - 2) >> 2) * 32; c < cols; c += 64) {         // the two warp groups take alternate 32-column chunks
@@ -734,6 +723,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (warp == 4 && lane == 0) B2RL_TRACE_AT(2, 0, 3);
+  if (threadIdx.x == 0) B2RL_TRACE_AT(3, 0, 3);
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
@@ -863,6 +854,28 @@ static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, WgradParam
   if (attr < smem) {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = smem;
+  }
+  {
+    const bool merge = w.C == 64;
+    int tap = w.tap0, n = 0;
+    uint32_t acc = 0;
+    const int tap_end = w.tap0 + w.ntaps;
+    while (tap < tap_end && n < 9) {
+      const int dy = tap / w.taps_x, dx = tap - dy * w.taps_x;
+      int run = 1;
+      if (merge) {
+        run = w.taps_x - dx;
+        if (run > tap_end - tap) run = tap_end - tap;
+      }
+      w.run_off[n] = (uint32_t)(dy * w.grid_w + dx) * 8;
+      w.run_acc[n] = acc;
+      w.run_n[n] = (uint32_t)(run * w.C);
+      acc += run * w.C;
+      tap += run;
+      ++n;
+    }
+    if (tap < tap_end) return 1;
+    w.n_runs = n;
   }
   const int kt_total = (w.rows + GEMM_BK - 1) / GEMM_BK;
   // split-K over all SMs (the MMAs are shared-memory-read bound per SM, so the work must be spread); every CTA ends with

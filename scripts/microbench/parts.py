@@ -93,3 +93,66 @@ opt = ops.FlatOptimizer([torch.nn.Parameter(torch.randn(n, device=dev))], kind="
 opt.grad.normal_()
 timed("clip + RMSprop(centered) over %d params (2 launches)" % n, lambda: opt.step(max_norm=10.0))
 print("done")
+
+# ---------------------------------------------------------------------------------------------- convolution GEMMs
+import ctypes  # noqa: E402
+from deeprl_b200.network import nature_tc  # noqa: E402
+
+x0 = torch.randint(0, 255, (B * 441, 64), device=dev).to(bf)
+w1 = (torch.randn(32, 256, device=dev) * 0.01).to(bf)
+b1 = torch.randn(32, device=dev)
+x1 = torch.empty(B * 100, 128, device=dev, dtype=bf)
+w2 = (torch.randn(64, 512, device=dev) * 0.01).to(bf)
+b2 = torch.randn(64, device=dev)
+y2 = torch.empty(B * 100, 64, device=dev, dtype=bf)
+w3 = (torch.randn(64, 576, device=dev) * 0.01).to(bf)
+y3b = torch.empty(B * 49, 64, device=dev, dtype=bf)
+g1 = torch.randn(B * 441, 32, device=dev).to(bf)
+g2 = torch.randn(B * 100, 64, device=dev).to(bf)
+w2d = (torch.randn(128, 256, device=dev) * 0.01).to(bf)
+gy1 = torch.empty(B * 100, 128, device=dev, dtype=bf)
+timed("conv1 fwd", lambda: nature_tc.conv_gemm(0, x0, w1, 32, 4, 2, 21, 1, x1, bias=b1, relu=True, out_map=1, G=21, V=20, block_n=32))
+timed("conv2 fwd", lambda: nature_tc.conv_gemm(0, x1, w2, 64, 4, 2, 10, 1, y2, bias=b2, relu=True, block_n=64))
+timed("conv3 fwd", lambda: nature_tc.conv_gemm(0, y2, w3, 64, 9, 3, 10, 1, y3b, bias=b2, relu=True, out_map=2, G=10, V=7, block_n=64))
+timed("conv3 dgrad", lambda: nature_tc.conv_gemm(0, g2, w3, 64, 9, 3, 10, -1, y2, block_n=64))
+timed("conv2 dgrad", lambda: nature_tc.conv_gemm(0, g2, w2d, 128, 4, 2, 10, -1, gy1, block_n=128))
+timed("conv3 wgrad (partials)", lambda: nature_tc.wgrad_partials(y2, g2, 64, 9, 3, 10))
+timed("conv2 wgrad (partials)", lambda: nature_tc.wgrad_partials(x1, g2, 64, 4, 2, 10))
+timed("conv1 wgrad (partials)", lambda: nature_tc.wgrad_partials(x0, g1, 32, 4, 2, 21))
+
+# dual launches: two operand sets in one grid, checked against two single launches
+x0b = torch.randint(0, 255, (B * 441, 64), device=dev).to(bf)
+w1b = (torch.randn(32, 256, device=dev) * 0.01).to(bf)
+b1b = torch.randn(32, device=dev)
+x1a, x1b, x1r = torch.zeros_like(x1), torch.zeros_like(x1), torch.zeros_like(x1)
+
+
+def dual_conv1():
+    _lib.call("b2rl_conv_gemm_dual_bf16", _lib.ptr(x0), _lib.ptr(x0b), B * 441, 64, _lib.ptr(w1), _lib.ptr(w1b), 32, 4, 2, 21, 1,
+              _lib.ptr(x1a), _lib.ptr(x1b), 128, _lib.ptr(b1), _lib.ptr(b1b), 1, 0, 1, 21, 20, 32, _lib.stream())
+
+
+dual_conv1()
+nature_tc.conv_gemm(0, x0b, w1b, 32, 4, 2, 21, 1, x1r, bias=b1b, relu=True, out_map=1, G=21, V=20, block_n=32)
+nature_tc.conv_gemm(0, x0, w1, 32, 4, 2, 21, 1, x1, bias=b1, relu=True, out_map=1, G=21, V=20, block_n=32)
+torch.cuda.synchronize()
+print("dual conv1 == two single launches:", bool(torch.equal(x1a, x1)), bool(torch.equal(x1b, x1r)))
+timed("conv1 fwd DUAL (both nets)", dual_conv1)
+y4a, y4b = torch.empty(B, 512, device=dev, dtype=bf), torch.empty(B, 512, device=dev, dtype=bf)
+y3x = torch.randn(B, 3136, device=dev).to(bf)
+w4x = (torch.randn(512, 3136, device=dev) * 0.02).to(bf)
+
+
+def dual_fc4(bn):
+    _lib.call("b2rl_gemm_dual_bf16", _lib.ptr(y3), _lib.ptr(y3x), 3136, _lib.ptr(w4), _lib.ptr(w4x), 3136, _lib.ptr(y4a),
+              _lib.ptr(y4b), 512, B, 512, 3136, _lib.ptr(b4), _lib.ptr(b4), 1, 0, bn, _lib.stream())
+
+
+dual_fc4(64)
+ref_a = ops.gemm_bf16(y3, w4, bias=b4, relu=True, block_n=64)
+ref_b = ops.gemm_bf16(y3x, w4x, bias=b4, relu=True, block_n=64)
+torch.cuda.synchronize()
+print("dual fc4 == two single launches:", bool(torch.equal(y4a, ref_a)), bool(torch.equal(y4b, ref_b)))
+for bn in (32, 64, 128):
+    timed("fc4 fwd DUAL, fused bias+ReLU, BN=%d" % bn, lambda bn=bn: dual_fc4(bn))
+print("done")

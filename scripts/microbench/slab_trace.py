@@ -42,6 +42,10 @@ if __name__ == "__main__":
         "conv3 fwd (BN=64, 400 tiles)": lambda: nature_tc.conv_gemm(
             0, y2, w3, 64, 9, 3, 10, 1, y3, bias=b2, relu=True, out_map=2, G=10, V=7, block_n=64),
     }
+    g1 = torch.randn(B * 441, 32, device=dev).to(bf)
+    g2 = torch.randn(B * 100, 64, device=dev).to(bf)
+    cases["conv1 wgrad (147 CTAs x ~24 k-tiles)"] = lambda: nature_tc.wgrad_partials(x0, g1, 32, 4, 2, 21)
+    cases["conv2 wgrad"] = lambda: nature_tc.wgrad_partials(x1, g2, 64, 4, 2, 10)
     x0 = torch.randint(0, 255, (B * 441, 64), device=dev).to(bf)
     w1 = (torch.randn(32, 256, device=dev) * 0.01).to(bf)
     b1 = torch.zeros(32, device=dev)

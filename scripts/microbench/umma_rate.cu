@@ -7,7 +7,8 @@
 
 __device__ __forceinline__ uint32_t s2u(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(128, 1) k(int N, int a_mn, int b_mn, int nacc, int reps, long long* out) {
+__global__ void __launch_bounds__(128, 1) k(int N, int a_mn, int b_mn, int nacc, int reps, long long* out, int b_off_rows = 0,
+                                            int b_lbo16 = 0) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t bar;
@@ -31,7 +32,10 @@ __global__ void __launch_bounds__(128, 1) k(int N, int a_mn, int b_mn, int nacc,
                            ((uint32_t)(N >> 3) << 17) | (8u << 24);
     const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     const uint32_t a_lo = ((s2u(smem) >> 4) & 0x3FFF) | ((a_mn ? 512u : 1u) << 16);
-    const uint32_t b_lo = ((s2u(smem + 32768) >> 4) & 0x3FFF) | ((b_mn ? 512u : 1u) << 16);
+    // b_off_rows: start the B window that many 128-byte rows into the swizzled tile (a shifted slab window);
+    // b_lbo16: override the MN-group stride (in 16-byte units), e.g. 8 = groups one row apart (merged taps)
+    const uint32_t b_lo = (((s2u(smem + 32768) >> 4) + (uint32_t)b_off_rows * 8) & 0x3FFF) |
+                          ((b_lbo16 ? (uint32_t)b_lbo16 : (b_mn ? 512u : 1u)) << 16);
     long long t0 = clock64();
 #pragma unroll 8
     for (int r = 0; r < reps; ++r) {
@@ -74,5 +78,19 @@ int main() {
         if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
         printf("%4d %5d %5d %5d %12.1f %12.1f\n", N, mn, mn, nacc, (double)h[0] / reps, (double)h[1] / reps);
       }
+  printf("\nMN-major B windows that start off the 8-row swizzle atom (slab wgrad), a_mn = b_mn = 1\n");
+  printf("%4s %9s %7s %12s\n", "N", "off_rows", "lbo16", "total cyc/mma");
+  int N2[] = {64, 128, 192};
+  for (int N : N2)
+    for (int off : {0, 1, 5, 8, 21})
+      for (int lbo : {0, 8}) {
+        if (lbo == 8 && N == 64) continue;
+        k<<<1, 128, 100 * 1024>>>(N, 1, 1, 1, reps, d, off, lbo);
+        long long h[2];
+        cudaError_t e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+        printf("%4d %9d %7d %12.1f\n", N, off, lbo, (double)h[1] / reps);
+      }
+  printf("\nK-major A windows off the atom (slab forward), b K-major\n");
   return 0;
 }
