@@ -16,13 +16,14 @@ from . import _lib, ops
 from .component.replay import PrioritizedReplay
 from .network import nature_tc
 from .network.fused import frame_scale
+from .utils.config import Config
 
 
 class GraphedDQNLearner:
     def __init__(self, network, target_network, optimizer, replay, kind="dqn", discount=0.99, n_step=1, double_q=False,
                  gradient_clip=5.0, feeds_per_update=4, compute_dtype=torch.bfloat16, state_scale=1.0 / 255,
                  replay_eps=0.01, replay_alpha=0.5, categorical=(-10.0, 10.0), world_size=1, target_sync_every=10000,
-                 prefetch=False):
+                 prefetch=False, dual=True):
         self.net, self.tgt, self.opt, self.replay = network, target_network, optimizer, replay
         self.kind, self.gamma_n, self.double_q = kind, discount ** n_step, double_q
         self.clip, self.feeds = gradient_clip, feeds_per_update
@@ -62,6 +63,7 @@ class GraphedDQNLearner:
         # trains on the batch sampled during update k-1 while a third branch of the graph feeds + samples batch k+1
         # into the other buffer set.  Two graphs (one per buffer parity) are captured and replayed alternately.
         self.prefetch = bool(prefetch)
+        self.dual = bool(dual)          # one launch per body layer for online(s) + target(s') (nature_tc.forward_dual)
         self._batch = [None, None]
         self._parity = 0
         self.updates = 0
@@ -117,17 +119,29 @@ class GraphedDQNLearner:
         else:
             t = self._sample(0)
         per = dict(is_prob=t.sampling_prob, eps=self.eps, alpha=self.alpha, beta_dev=self.d_beta) if self.per else {}
-        # the target forward on s' and the online forward on s are independent: fork them onto two streams (two parallel
-        # branches of the captured graph) so that the prologue / tail of one chain overlaps the other
-        side.wait_stream(cur)
-        with torch.cuda.stream(side), frame_scale(fs), torch.no_grad():
-            nxt_t = self.tgt(t.next_state)
-        cur.wait_event(self._packed_ev)
-        with frame_scale(fs):
-            with torch.no_grad():
-                nxt_o = self.net(t.next_state) if self.double_q else None
-            out = self.net(t.state)
-        cur.wait_stream(side)
+        body_a, body_b = getattr(self.net, "body", None), getattr(self.tgt, "body", None)
+        if (self.dual and self.dtype == torch.bfloat16 and Config.DENSE_BACKEND == "tcgen05"
+                and hasattr(body_a, "repack") and hasattr(body_b, "repack")):
+            # online(s) and target(s') share every launch of the convolutional body (nature_tc.forward_dual): the grid of
+            # each kernel is split between the two networks, so the per-launch fixed cost is paid once
+            cur.wait_event(self._packed_ev)
+            with nature_tc.dual_forward(body_a, body_b, t.next_state), frame_scale(fs):
+                out = self.net(t.state)
+                with torch.no_grad():
+                    nxt_t = self.tgt(t.next_state)
+                    nxt_o = self.net(t.next_state) if self.double_q else None
+        else:
+            # the target forward on s' and the online forward on s are independent: fork them onto two streams (two
+            # parallel branches of the captured graph) so that the prologue / tail of one chain overlaps the other
+            side.wait_stream(cur)
+            with torch.cuda.stream(side), frame_scale(fs), torch.no_grad():
+                nxt_t = self.tgt(t.next_state)
+            cur.wait_event(self._packed_ev)
+            with frame_scale(fs):
+                with torch.no_grad():
+                    nxt_o = self.net(t.next_state) if self.double_q else None
+                out = self.net(t.state)
+            cur.wait_stream(side)
         if self.kind == "dqn":
             head = out["q"]
             r = ops.dqn_loss_fused(head.detach(), nxt_t["q"], nxt_o["q"] if nxt_o else None, t.action, t.reward, t.mask,

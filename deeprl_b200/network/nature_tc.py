@@ -146,11 +146,50 @@ def forward_only(x0, packed, b1, b2, b3, b4):
     return y4, (x0m, x1, y2, y3)
 
 
+def conv_gemm_dual(X, X2, W, W2, n_out, taps, taps_x, grid_w, out, out2, bias, bias2, out_map=0, G=0, V=0, block_n=64):
+    rows, C = X.shape
+    _lib.call("b2rl_conv_gemm_dual_bf16", _lib.ptr(X), _lib.ptr(X2), int(rows), int(C), _lib.ptr(W), _lib.ptr(W2), int(n_out),
+              int(taps), int(taps_x), int(grid_w), 1, _lib.ptr(out), _lib.ptr(out2), out.stride(0), _lib.ptr(bias),
+              _lib.ptr(bias2), 1, 0, int(out_map), int(G), int(V), int(block_n), _lib.stream())
+
+
+def forward_dual(x0, packed, biases, x0_b, packed_b, biases_b):
+    """``forward_only`` for TWO networks of the same shape (online on the states, target on the next states --
+    DQN_agent.py:84-99) with ONE launch per layer: every kernel's grid is split between the two operand sets, so the
+    per-launch fixed cost (launch, prologue, weight load, pipeline fill and drain -- most of the time of these
+    3-tiles-per-CTA kernels) is paid once.  Returns (y4, saved activations of the first network, y4 of the second)."""
+    w1f, w2f, _, w3f, _, w4p = packed
+    v1f, v2f, _, v3f, _, v4p = packed_b
+    b1, b2, b3, b4 = biases
+    c1, c2, c3, c4 = biases_b
+    B, dev = x0.shape[0], x0.device
+    e = lambda *shape: torch.empty(shape, dtype=_bf16, device=dev)
+    x0m = x0.permute(0, 2, 3, 1).reshape(B * 441, x0.shape[1])
+    x0n = x0_b.permute(0, 2, 3, 1).reshape(B * 441, x0_b.shape[1])
+    x1, z1 = e(B * 100, 128), e(B * 100, 128)
+    conv_gemm_dual(x0m, x0n, w1f, v1f, 32, 4, 2, 21, x1, z1, b1, c1, out_map=1, G=21, V=20, block_n=32)
+    y2, z2 = e(B * 100, 64), e(B * 100, 64)
+    conv_gemm_dual(x1, z1, w2f, v2f, 64, 4, 2, 10, y2, z2, b2, c2, block_n=64)
+    y3, z3 = e(B * 49, 64), e(B * 49, 64)
+    conv_gemm_dual(y2, z2, w3f, v3f, 64, 9, 3, 10, y3, z3, b3, c3, out_map=2, G=10, V=7, block_n=64)
+    n4 = w4p.shape[0]
+    y4, z4 = e(B, n4), e(B, n4)
+    _lib.call("b2rl_gemm_dual_bf16", _lib.ptr(y3), _lib.ptr(z3), 3136, _lib.ptr(w4p), _lib.ptr(v4p), 3136, _lib.ptr(y4),
+              _lib.ptr(z4), n4, B, n4, 3136, _lib.ptr(b4), _lib.ptr(c4), 1, 0, 64, _lib.stream())
+    return y4, (x0m, x1, y2, y3), z4
+
+
 class _NatureBody(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x0, w1, b1, w2, b2, w3, b3, w4, b4, scale, packed):
+    def forward(ctx, x0, w1, b1, w2, b2, w3, b3, w4, b4, scale, packed, companion=None):
         pk = packed.tensors()
-        y4, (x0m, x1, y2, y3) = forward_only(x0, pk, b1.detach(), b2.detach(), b3.detach(), b4.detach())
+        biases = (b1.detach(), b2.detach(), b3.detach(), b4.detach())
+        if companion is None:
+            y4, (x0m, x1, y2, y3) = forward_only(x0, pk, *biases)
+        else:                                   # (x0 of the other network, its packed weights, its biases): one launch per layer
+            x0_b, packed_b, biases_b, _ = companion
+            y4, (x0m, x1, y2, y3), z4 = forward_dual(x0, pk, biases, x0_b, packed_b.tensors(), biases_b)
+            companion[3].append(z4)
         ctx.save_for_backward(x0m, x1, y2, y3, y4, pk[2], pk[4], pk[5])
         ctx.scale, ctx.c1 = scale, w1.shape[1]
         ctx.params = (w1, b1, w2, b2, w3, b3, w4, b4)
@@ -189,10 +228,30 @@ class _NatureBody(torch.autograd.Function):
                       _lib.ptr(db2), _lib.ptr(db3), _lib.ptr(db4), ctx.c1, w4.shape[0], float(ctx.scale), _lib.ptr(w1.grad),
                       _lib.ptr(w2.grad), _lib.ptr(w3.grad), _lib.ptr(w4.grad), _lib.ptr(b1.grad), _lib.ptr(b2.grad),
                       _lib.ptr(b3.grad), _lib.ptr(b4.grad), p1, p2, p3, _lib.stream())
-            return (None,) * 11
+            return (None,) * 12
         gw1f, gw2f, gw3f = gw1p[:p1].sum(0), gw2p[:p2].sum(0), gw3p[:p3].sum(0)
         g1w, g2w, g3w, g4w = unpack_grads(gw1f, gw2f, gw3f, gw4p, ctx.scale, ctx.c1)
-        return None, g1w, db1, g2w, db2, g3w, db3, g4w, db4, None, None
+        return None, g1w, db1, g2w, db2, g3w, db3, g4w, db4, None, None, None
+
+
+class dual_forward:
+    """``with dual_forward(online_body, target_body, next_states):`` -- inside the context the first call of
+    ``online_body`` also evaluates ``target_body(next_states)`` (one launch per layer for both networks, see
+    ``forward_dual``) and the following call ``target_body(next_states)`` returns those features instead of
+    recomputing them.  Used by the graph learner; everything else calls the bodies separately."""
+    current = None
+
+    def __init__(self, primary, companion, x_companion):
+        self.primary, self.companion, self.x = primary, companion, x_companion
+        self.features = []
+
+    def __enter__(self):
+        dual_forward.current = self
+        return self
+
+    def __exit__(self, *exc):
+        dual_forward.current = None
+        return False
 
 
 def nature_body(body, x0, scale):
@@ -207,8 +266,21 @@ def nature_body(body, x0, scale):
     if getattr(body, "auto_repack", True) or pk.scale != float(scale):
         repack(body, scale)
     c1, c2, c3, f4 = body.conv1, body.conv2, body.conv3, body.fc4
+    d = dual_forward.current
+    companion = None
+    if d is not None:
+        if body is d.companion and d.features and x0.data_ptr() == d.x.data_ptr():
+            return d.features[0]                                   # computed alongside the primary network
+        if body is d.primary and not d.features and torch.is_grad_enabled():
+            o = d.companion
+            xb = d.x if d.x.is_contiguous(memory_format=torch.channels_last) else d.x.contiguous(memory_format=torch.channels_last)
+            pb = getattr(o, "_packed", None)
+            if pb is None or getattr(o, "auto_repack", True) or pb.scale != float(scale):
+                pb = repack(o, scale)
+            if xb.shape == x0.shape and pb.n4 == pk.n4:
+                companion = (xb, pb, tuple(m.bias.detach() for m in (o.conv1, o.conv2, o.conv3, o.fc4)), d.features)
     return _NatureBody.apply(x0, c1.weight, c1.bias, c2.weight, c2.bias, c3.weight, c3.bias, f4.weight, f4.bias,
-                             float(scale), pk)
+                             float(scale), pk, companion)
 
 
 def repack(body, scale):

@@ -81,7 +81,7 @@ def test_graph_replay_equals_eager_update(env, workload, prefetch):
     np.testing.assert_allclose(params(b).cpu().numpy(), params(a).cpu().numpy(), rtol=0, atol=2e-6)
     assert a.replay.ring_state.cpu().tolist()[:4] == b.replay.ring_state.cpu().tolist()[:4]
     if a.per:                                              # same leaves updated, priorities equal to forward-pass noise
-        np.testing.assert_allclose(a.replay.tree.tree.cpu().numpy(), b.replay.tree.tree.cpu().numpy(), rtol=1e-3)
+        np.testing.assert_allclose(a.replay.tree.tree.cpu().numpy(), b.replay.tree.tree.cpu().numpy(), rtol=1e-2)
     # and a second update, now from (almost) identical state: same batch, loss within bf16-activation noise
     a._main(), a._opt()
     b.update()
@@ -121,3 +121,37 @@ def test_update_from_host_feeds_the_ring(env):
     got = lr.replay.frames[rows].cpu().numpy().reshape(4, -1)
     assert np.array_equal(got, frames)
     assert lr.replay.action[rows].cpu().tolist() == [0, 1, 2, 3]
+
+
+def test_dual_forward_matches_separate_forwards(env):
+    """nature_tc.dual_forward: online(s) and target(s') evaluated with one launch per layer give the features, Q values and
+    parameter gradients of two separate forwards (convolutions bit-identical; fc4 differs by its summation order: split-K
+    with fp32 atomics vs one pass, i.e. bf16 rounding of the 512 features)."""
+    bench, rl = env
+    from deeprl_b200.network import nature_tc
+    from deeprl_b200.network.fused import frame_scale
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(3)
+    net = rl.VanillaNet(4, rl.NatureConvBody(in_channels=4))
+    tgt = rl.VanillaNet(4, rl.NatureConvBody(in_channels=4))          # different weights
+    s = torch.randint(0, 256, (64, 64, 21, 21), device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    s2 = torch.randint(0, 256, (64, 64, 21, 21), device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    with frame_scale(1.0 / 255):
+        q_ref = net(s)["q"]
+        q_ref.sum().backward()
+        g_ref = [p.grad.clone() for p in net.parameters()]
+        net.zero_grad()
+        with torch.no_grad():
+            t_ref = tgt(s2)["q"]
+        with nature_tc.dual_forward(net.body, tgt.body, s2) as d:
+            q = net(s)["q"]
+            assert len(d.features) == 1                                  # the target features were computed alongside
+            with torch.no_grad():
+                t = tgt(s2)["q"]
+        q.sum().backward()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(q.detach().cpu().numpy(), q_ref.detach().cpu().numpy(), rtol=2e-2, atol=2e-3)
+    np.testing.assert_allclose(t.cpu().numpy(), t_ref.cpu().numpy(), rtol=2e-2, atol=2e-3)
+    for g, r in zip([p.grad for p in net.parameters()], g_ref):
+        scale = float(r.abs().max()) + 1e-12
+        assert float((g - r).abs().max()) <= 3e-2 * scale
