@@ -274,7 +274,9 @@ def run_b2rl(args):
                 achieved=round(ach, 1), peak=hbm, unit="GB/s", frac=round(ach / hbm, 4),
                 peak_source="MEASURED_PEAKS.json hbm_gbs (burst)" if "hbm_gbs" in pk else "fallback 6650",
                 us_per_launch=round(gt["bf16_s2d"] * 1e3, 2), algorithmic_bytes_per_launch=B * ALGO_BYTES_BF16,
-                traffic=None,
+                traffic=22_051_840,
+                traffic_source="profiles/r01_ncu_summary.txt: dram__bytes_read.sum 18.29 MB + dram__bytes_write.sum 3.76 MB per launch "
+                               "(ncu --set full): frames read once; the 57.8 MB bf16 output stays in L2 for conv1",
                 raw_u8_variant=dict(kernel="gather_raw_tma_kernel (uint8 stacks, SURVEY 8d: 91 728 B/sample)",
                                     achieved=round(ach_u8, 1), frac=round(ach_u8 / hbm, 4),
                                     us_per_launch=round(gt["u8"] * 1e3, 2), algorithmic_bytes_per_launch=B * ALGO_BYTES_U8))
