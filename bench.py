@@ -182,6 +182,8 @@ def run_b2rl(args):
     rl.Config.COMPUTE_DTYPE = torch.bfloat16
     torch.backends.cudnn.benchmark = True
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"             # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     learner = build_learner(rl, args.workload, dev, rank, world, prefetch=(args.replay == "async"))
@@ -299,7 +301,7 @@ def run_b2rl(args):
                     replay=("async_replay=True (examples.py:16,60 default; ReplayWrapper replay.py:214-262): batch k+1 is fed + sampled "
                             "on a parallel graph branch while update k trains on the batch sampled during update k-1"
                             if learner.prefetch else "async_replay=False: feed -> sample -> update in sequence (examples.py:646)"),
-                    cuda_graph=True),
+                    cuda_graph=True, nccl_in_graph=bool(world > 1 and learner.g_opt is None)),
         e2e=dict(value=round(e2e, 1), unit="updates/s", h2d_bytes_per_step=learner.h2d_bytes, d2h_bytes_per_step=4,
                  ms_per_step=round(e2e_ms / K, 4)),
         gpu_launches=int(launches_per_update * K), gpu_launches_per_step=int(launches_per_update),

@@ -8,6 +8,9 @@ Multi-GPU: one learner per rank, rank-local replay shard, parameters
 gradients are summed with ONE NCCL all-reduce of the flat gradient arena between the two graphs and scaled by
 1 / world_size inside the clip kernel.
 """
+import os
+import sys
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -201,17 +204,22 @@ class GraphedDQNLearner:
                 self._opt()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        self.g_main = []
-        for parity in ((0, 1) if self.prefetch else (None,)):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=self.g_main[0].pool() if self.g_main else None):
-                if with_h2d:
-                    self._h2d()
-                self._main(parity)
-                if self.world == 1:                      # single GPU: the whole update is ONE graph
-                    self._opt()
-            self.g_main.append(g)
-        if self.world > 1:                               # multi GPU: [sample..backward] | NCCL all-reduce | [clip+opt]
+        self.g_main, self.g_opt = [], None
+        # multi GPU: the NCCL all-reduce is captured INSIDE the update graph (one graph replay per update, no host gap
+        # around the collective); B2RL_NCCL_IN_GRAPH=0, or a capture failure, falls back to
+        # [sample..backward] graph | eager all-reduce | [clip + optimizer] graph
+        one_graph = self.world == 1 or os.environ.get("B2RL_NCCL_IN_GRAPH", "1") != "0"
+        try:
+            self._capture_main(with_h2d, one_graph)
+        except Exception as e:                            # noqa: BLE001 -- any capture error: use the split form
+            if self.world == 1 or not one_graph:
+                raise
+            print("b2rl: NCCL capture failed (%s); using the split-graph form" % str(e).splitlines()[0], file=sys.stderr)
+            torch.cuda.synchronize()
+            one_graph = False
+            self.g_main = []
+            self._capture_main(with_h2d, False)
+        if not one_graph:                                # [sample..backward] | NCCL all-reduce | [clip+opt]
             self.g_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g_opt):
                 self._opt()
@@ -220,6 +228,18 @@ class GraphedDQNLearner:
         self.replay.pos, self.replay._size = int(st[0]), int(st[1])
         self.launches_per_update = None
         return self
+
+    def _capture_main(self, with_h2d, one_graph):
+        for parity in ((0, 1) if self.prefetch else (None,)):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self.g_main[0].pool() if self.g_main else None):
+                if with_h2d:
+                    self._h2d()
+                self._main(parity)
+                if one_graph:
+                    self._allreduce()
+                    self._opt()
+            self.g_main.append(g)
 
     def _allreduce(self):
         if self.world > 1:
@@ -232,7 +252,7 @@ class GraphedDQNLearner:
             self._parity = 1 - self._parity
         else:
             self.g_main[0].replay()
-        if self.world > 1:
+        if self.g_opt is not None:
             self._allreduce()
             self.g_opt.replay()
         self.updates += 1
