@@ -182,8 +182,7 @@ def run_b2rl(args):
     rl.Config.COMPUTE_DTYPE = torch.bfloat16
     torch.backends.cudnn.benchmark = True
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"             # keep stdout to the one JSON line (NCCL prints its version there)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL logs its version there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     learner = build_learner(rl, args.workload, dev, rank, world, prefetch=(args.replay == "async"))

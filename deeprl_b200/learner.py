@@ -205,10 +205,10 @@ class GraphedDQNLearner:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.g_main, self.g_opt = [], None
-        # multi GPU: the NCCL all-reduce is captured INSIDE the update graph (one graph replay per update, no host gap
-        # around the collective); B2RL_NCCL_IN_GRAPH=0, or a capture failure, falls back to
-        # [sample..backward] graph | eager all-reduce | [clip + optimizer] graph
-        one_graph = self.world == 1 or os.environ.get("B2RL_NCCL_IN_GRAPH", "1") != "0"
+        # multi GPU: [sample..backward] graph | eager NCCL all-reduce | [clip + optimizer] graph.  Capturing the collective
+        # INSIDE the update graph (B2RL_NCCL_IN_GRAPH=1) was measured at 2 x B200: 6 232 vs 6 718 updates/s for the split
+        # form, and the process group then hung at teardown -- so the split form is the default.
+        one_graph = self.world == 1 or os.environ.get("B2RL_NCCL_IN_GRAPH", "0") == "1"
         try:
             self._capture_main(with_h2d, one_graph)
         except Exception as e:                            # noqa: BLE001 -- any capture error: use the split form
