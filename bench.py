@@ -215,6 +215,14 @@ def run_b2rl(args):
     ms_total = float(ms)
     loss_value = float(learner.loss)
 
+    if args.quick:                                        # A/B runs: the resident-input number only
+        if rank == 0:
+            print(json.dumps(dict(quick=True, value=round(world * K / (ms_total * 1e-3), 1), ms_per_step=round(ms_total / K, 4),
+                                  loss=loss_value)), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- launches of OUR kernels per update (count one eager update; graph replays do not pass through the C ABI)
     rl._lib.reset_launch_count()
     learner._main(), learner._allreduce(), learner._opt()
@@ -314,6 +322,55 @@ def run_b2rl(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------- PPO (BASELINE configs[3])
+def run_ppo(args):
+    """PPO on synthetic HalfCheetah-shaped states (17-dim obs, 6-dim action): 2048-step x 16-worker rollout, GAE(0.95),
+    10 epochs x 64-sample minibatches (examples.py:496-522).  One "step" = one PPO iteration (rollout + GAE + advantage
+    normalisation + 5 120 minibatch updates); the envs step on the host (north_star), everything else on the device.
+    Extra workload next to the headline DQN metric: the line names its own metric."""
+    import deeprl_b200 as rl
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --workload ppo needs a CUDA device")
+    rl.select_device(0)
+    rl.Config.COMPUTE_DTYPE = torch.float32
+    torch.manual_seed(0), np.random.seed(0)
+    c = rl.Config()
+    c.merge(dict(tag=None))
+    c.num_workers = 16
+    c.task_fn = lambda: rl.Task("SyntheticCheetah-v0", num_envs=16, seed=0)
+    c.eval_env = rl.Task("SyntheticCheetah-v0", seed=0)
+    c.network_fn = lambda: rl.GaussianActorCriticNet(c.state_dim, c.action_dim, actor_body=rl.FCBody(c.state_dim, gate=torch.tanh),
+                                                     critic_body=rl.FCBody(c.state_dim, gate=torch.tanh))
+    c.actor_opt_fn = lambda p: torch.optim.Adam(p, 3e-4)
+    c.critic_opt_fn = lambda p: torch.optim.Adam(p, 1e-3)
+    c.discount, c.use_gae, c.gae_tau, c.gradient_clip = 0.99, True, 0.95, 0.5
+    c.rollout_length, c.optimization_epochs, c.mini_batch_size, c.ppo_ratio_clip, c.target_kl = 2048, 10, 64, 0.2, 0.01
+    c.state_normalizer = rl.MeanStdNormalizer()
+    ag = rl.PPOAgent(c)
+    K, W = max(1, min(args.steps, 3)), 1
+    for _ in range(W):
+        ag.step()
+    torch.cuda.synchronize()
+    rl._lib.reset_launch_count()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        ag.step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / K
+    mb = c.optimization_epochs * (c.rollout_length * c.num_workers // c.mini_batch_size)
+    print(json.dumps(dict(
+        metric="PPO minibatch updates/sec (17-dim obs, 2048 x 16 rollout, GAE 0.95, 10 epochs x 64)", value=round(mb / dt, 1),
+        unit="updates/s", n_gpus=1, steps=K, warmup=W, ms_per_step=round(dt * 1e3, 1), higher_is_better=True, scaling="weak",
+        vs_baseline=None, dtype="f32", data="synthetic",
+        config=dict(workload="PPO synthetic HalfCheetah-shape 17-dim obs, 2048-step x 16-worker rollout, GAE 0.95, 10 epochs x 64 "
+                             "minibatch (BASELINE configs[3]); one step = one PPO iteration incl. the host env rollout",
+                    minibatch_updates_per_iteration=mb, env_steps_per_iteration=c.rollout_length * c.num_workers,
+                    timing="wall clock around whole iterations (host envs + eager launches), torch.cuda.synchronize on both sides"),
+        env_steps_per_s=round(c.rollout_length * c.num_workers / dt, 1),
+        gpu_launches=int(rl._lib.launch_count()), gpu_launches_per_step=int(rl._lib.launch_count() // K))), flush=True)
+    ag.close()
+
+
 # --------------------------------------------------------------------------------------------- CPU arm (oracle port)
 def make_cpu_agent(workload, capacity=20_000):
     """The reference's CPU path as restated in oracle/ (pinned against the reference by tests/test_oracle_golden.py):
@@ -379,6 +436,9 @@ def cpu_baseline(workload, seconds=20.0):
 
 
 def run_reference(args):
+    if args.workload == "ppo":
+        print(json.dumps(dict(impl="reference", unavailable="the CPU reference arm times the DQN-family update only")), flush=True)
+        return
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -415,9 +475,15 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b2rl", choices=["b2rl", "reference"])
-    ap.add_argument("--workload", default="dqn", choices=["dqn", "per", "c51", "qr"])
+    ap.add_argument("--workload", default="dqn", choices=["dqn", "per", "c51", "qr", "ppo"])
     ap.add_argument("--replay", default="async", choices=["async", "sync"],
                     help="async_replay of the reference's launchers (examples.py:16 default True; :646 runs False); the other "
                          "mode is timed as well and reported under other_replay_mode")
+    ap.add_argument("--quick", action="store_true", help="developer A/B runs: print the resident-input value only")
     a = ap.parse_args()
-    run_reference(a) if a.impl == "reference" else run_b2rl(a)
+    if a.impl == "reference":
+        run_reference(a)
+    elif a.workload == "ppo":
+        run_ppo(a)
+    else:
+        run_b2rl(a)

@@ -23,6 +23,7 @@
 //                            overlapped with the next tile's MMAs; warp 2 also owns TMEM alloc / dealloc
 // sm_100a only.
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace b2rl {
@@ -882,6 +883,12 @@ static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, WgradParam
   // n_out x cols / 4 vector reductions (red.global.add.v4.f32) into the same small D
   int ctas = kt_total / 4;
   if (ctas > sm_count()) ctas = sm_count();
+  static int cap = -1;                                               // tunable: B2RL_WGRAD_CTAS caps the split-K width
+  if (cap < 0) {
+    const char* e = getenv("B2RL_WGRAD_CTAS");
+    cap = e ? atoi(e) : 0;
+  }
+  if (cap > 0 && ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
   w.k_tiles_per_cta = (kt_total + ctas - 1) / ctas;
   ctas = (kt_total + w.k_tiles_per_cta - 1) / w.k_tiles_per_cta;
