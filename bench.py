@@ -346,12 +346,25 @@ def run_ppo(args):
     c.discount, c.use_gae, c.gae_tau, c.gradient_clip = 0.99, True, 0.95, 0.5
     c.rollout_length, c.optimization_epochs, c.mini_batch_size, c.ppo_ratio_clip, c.target_kl = 2048, 10, 64, 0.2, 0.01
     c.state_normalizer = rl.MeanStdNormalizer()
+    c.graph_minibatch = args.replay != "sync"             # --replay sync: the eager minibatch loop (for comparison)
     ag = rl.PPOAgent(c)
+    sgd = [0.0]
+    if c.graph_minibatch:                                 # time the minibatch phase on its own as well
+        inner = ag._graphed_epochs
+
+        def timed_epochs(entries):
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            inner(entries)
+            torch.cuda.synchronize()
+            sgd[0] += time.perf_counter() - t
+        ag._graphed_epochs = timed_epochs
     K, W = max(1, min(args.steps, 3)), 1
     for _ in range(W):
         ag.step()
     torch.cuda.synchronize()
     rl._lib.reset_launch_count()
+    sgd[0] = 0.0
     t0 = time.perf_counter()
     for _ in range(K):
         ag.step()
@@ -367,6 +380,9 @@ def run_ppo(args):
                     minibatch_updates_per_iteration=mb, env_steps_per_iteration=c.rollout_length * c.num_workers,
                     timing="wall clock around whole iterations (host envs + eager launches), torch.cuda.synchronize on both sides"),
         env_steps_per_s=round(c.rollout_length * c.num_workers / dt, 1),
+        minibatch_phase=(dict(updates_per_s=round(mb * K / sgd[0], 1), seconds_per_iteration=round(sgd[0] / K, 3),
+                              form="one CUDA-graph replay per minibatch (GraphedPPOLearner), KL gate on the device")
+                         if c.graph_minibatch else dict(form="eager loop (PPOAgent._minibatch)")),
         gpu_launches=int(rl._lib.launch_count()), gpu_launches_per_step=int(rl._lib.launch_count() // K))), flush=True)
     ag.close()
 

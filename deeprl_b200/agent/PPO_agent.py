@@ -125,6 +125,32 @@ class PPOAgent(BaseAgent):
         self._normalize(entries)
         if config.shared_repr:
             self.lr_scheduler.step(self.total_steps)
+        rows = entries.state.size(0)
+        if (getattr(config, "graph_minibatch", False) and entries.state.is_cuda and not config.shared_repr
+                and rows % config.mini_batch_size == 0):
+            self._graphed_epochs(entries)                  # same updates, one CUDA-graph replay each (learner.py)
+            return
         for _ in range(config.optimization_epochs):
-            for batch_indices in random_sample(np.arange(entries.state.size(0)), config.mini_batch_size):
+            for batch_indices in random_sample(np.arange(rows), config.mini_batch_size):
                 self._minibatch(entries, batch_indices)
+
+    def _graphed_epochs(self, entries):
+        """``config.graph_minibatch = True``: the minibatch loop of PPO_agent.py:68-99 through ``GraphedPPOLearner``.  The
+        torch optimizers built by ``actor_opt_fn`` / ``critic_opt_fn`` are replaced by flat-arena Adam with the same
+        hyper-parameters on first use; the permutations come from ``np.random.permutation`` exactly as ``random_sample``."""
+        from ..learner import GraphedPPOLearner
+        config = self.config
+        rows, mb = entries.state.size(0), config.mini_batch_size
+        if getattr(self, "_graph", None) is None:
+            a = ops.FlatOptimizer.from_torch(self.actor_opt, self.network.actor_params)
+            c = ops.FlatOptimizer.from_torch(self.critic_opt, self.network.critic_params)
+            self._graph = GraphedPPOLearner(self.network, a, c, rows, entries.state.shape[1], entries.action.shape[1], mb,
+                                            config.ppo_ratio_clip, config.entropy_weight, config.target_kl,
+                                            config.optimization_epochs * (rows // mb))
+            self._graph.load(entries)
+            self._graph.capture()
+        g = self._graph
+        g.load(entries)
+        batches = [b for _ in range(config.optimization_epochs) for b in random_sample(np.arange(rows), mb)]
+        g.run(g.set_batches(batches))
+        self.last_stats = g.stats

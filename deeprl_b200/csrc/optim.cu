@@ -80,8 +80,10 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
                                                    float b1, float b2, float eps, const int64_t* __restrict__ step_dev,
                                                    const NormScratch* __restrict__ sc,
-                                                   __nv_bfloat16* __restrict__ shadow) {
+                                                   __nv_bfloat16* __restrict__ shadow, const float* __restrict__ gate,
+                                                   float gate_max) {
   pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
+  if (gate && !(*gate <= gate_max)) return;        // device-side `if approx_kl <= 1.5 * target_kl:` (PPO_agent.py:94)
   const float coef = sc->coef;
   const float t = (float)(*step_dev);
   const float bc1 = 1.0f - powf(b1, t), bc2 = 1.0f - powf(b2, t);
@@ -99,8 +101,9 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
-__global__ void bump_step_kernel(int64_t* step) {
+__global__ void bump_step_kernel(int64_t* step, const float* gate, float gate_max) {
   pdl_sync();
+  if (gate && !(*gate <= gate_max)) return;
   *step += 1;
 }
 
@@ -136,21 +139,39 @@ extern "C" int b2rl_clip_rmsprop(float* param, const float* grad, float* square_
   return check_launch("b2rl_clip_rmsprop");
 }
 
-extern "C" int b2rl_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                              float max_norm, float lr, float beta1, float beta2, float eps, int64_t* step_dev,
-                              float grad_scale, void* norm_scratch, uint16_t* bf16_shadow, void* stream) {
+static int clip_adam_impl(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float max_norm,
+                          float lr, float beta1, float beta2, float eps, int64_t* step_dev, float grad_scale,
+                          void* norm_scratch, uint16_t* bf16_shadow, const float* gate, float gate_max, void* stream) {
   B2RL_REQUIRE(param && grad && exp_avg && exp_avg_sq && step_dev && norm_scratch, "null pointer");
   B2RL_REQUIRE(n > 0 && (reinterpret_cast<uintptr_t>(grad) % 16 == 0), "bad size / gradient arena must be 16B aligned");
   cudaStream_t st = (cudaStream_t)stream;
   int rc = norm_pass(grad, n, grad_scale, max_norm, norm_scratch, st);
   if (rc) return rc;
-  launch_pdl(bump_step_kernel, dim3(1), dim3(1), 0, st, step_dev);
+  launch_pdl(bump_step_kernel, dim3(1), dim3(1), 0, st, step_dev, gate, gate_max);
   rc = check_launch("adam/step");
   if (rc) return rc;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   launch_pdl(adam_kernel, dim3(blocks), dim3(256), 0, st, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step_dev,
-                                      reinterpret_cast<NormScratch*>(norm_scratch),
-                                      reinterpret_cast<__nv_bfloat16*>(bf16_shadow));
+             reinterpret_cast<NormScratch*>(norm_scratch), reinterpret_cast<__nv_bfloat16*>(bf16_shadow), gate, gate_max);
   return check_launch("b2rl_clip_adam");
+}
+
+extern "C" int b2rl_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                              float max_norm, float lr, float beta1, float beta2, float eps, int64_t* step_dev,
+                              float grad_scale, void* norm_scratch, uint16_t* bf16_shadow, void* stream) {
+  return clip_adam_impl(param, grad, exp_avg, exp_avg_sq, n, max_norm, lr, beta1, beta2, eps, step_dev, grad_scale,
+                        norm_scratch, bf16_shadow, nullptr, 0.0f, stream);
+}
+
+// The same step, taken only if the DEVICE scalar *gate <= gate_max (moments, step count and parameters untouched otherwise):
+// the KL gate of the PPO actor update (`if approx_kl <= 1.5 * target_kl:` PPO_agent.py:94) without a host round trip, so the
+// minibatch update can live in a CUDA graph.
+extern "C" int b2rl_clip_adam_gated(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                    float max_norm, float lr, float beta1, float beta2, float eps, int64_t* step_dev,
+                                    float grad_scale, void* norm_scratch, uint16_t* bf16_shadow, const float* gate,
+                                    float gate_max, void* stream) {
+  B2RL_REQUIRE(gate, "null gate");
+  return clip_adam_impl(param, grad, exp_avg, exp_avg_sq, n, max_norm, lr, beta1, beta2, eps, step_dev, grad_scale,
+                        norm_scratch, bf16_shadow, gate, gate_max, stream);
 }

@@ -278,3 +278,91 @@ class GraphedDQNLearner:
     @property
     def h2d_bytes(self):
         return self.h_pack.numel()
+
+
+class GraphedPPOLearner:
+    """The PPO minibatch update (PPO_agent.py:73-99, non-shared representation) as ONE captured graph replayed once per
+    minibatch: row gather by a device-resident index matrix, network forward, ``b2rl_ppo_loss`` (clipped surrogate, value
+    loss, approx-KL and their gradients in one launch), backward, KL-GATED actor Adam step (``b2rl_clip_adam_gated``: the
+    reference's ``if approx_kl <= 1.5 * target_kl`` decided on the device) and the critic Adam step.  An iteration of
+    examples.py:496-522 is 5 120 such updates of an 11 k-parameter MLP: eager, each costs ~1.8 ms of Python and launch
+    latency; as a graph replay the host cost is one ``cudaGraphLaunch``.
+
+    The rollout rows live in persistent device buffers (``load``); the minibatch index rows of ALL epochs are uploaded
+    once per iteration (``set_batches``) and consumed through a device cursor."""
+
+    KEYS = ("state", "action", "log_pi_a", "ret", "advantage")
+
+    def __init__(self, network, actor_opt, critic_opt, rows, state_dim, action_dim, mini_batch_size, ppo_ratio_clip,
+                 entropy_weight, target_kl, max_batches):
+        self.net, self.actor_opt, self.critic_opt = network, actor_opt, critic_opt
+        self.mb, self.clip, self.ent_w, self.target_kl = int(mini_batch_size), ppo_ratio_clip, entropy_weight, target_kl
+        dev = actor_opt.flat.device
+        f = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+        self.buf = dict(state=f(rows, state_dim), action=f(rows, action_dim), log_pi_a=f(rows, 1), ret=f(rows, 1),
+                        advantage=f(rows, 1))
+        self.perm = torch.zeros((max_batches, self.mb), dtype=torch.int64, device=dev)
+        self.cursor = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.stats = torch.zeros(4, dtype=torch.float32, device=dev)      # policy loss, value loss, approx KL of the last update
+        self.graph = None
+        self.dev = dev
+
+    def load(self, entries):
+        for k in self.KEYS:
+            self.buf[k].copy_(getattr(entries, k).reshape(self.buf[k].shape))
+
+    def set_batches(self, index_rows):
+        rows = np.stack([np.asarray(r, dtype=np.int64) for r in index_rows])
+        assert rows.shape[1] == self.mb and rows.shape[0] <= self.perm.shape[0]
+        self.perm[:rows.shape[0]].copy_(torch.from_numpy(rows), non_blocking=False)
+        self.cursor.zero_()
+        return rows.shape[0]
+
+    def _step(self):
+        idx = self.perm.index_select(0, self.cursor).view(-1)
+        e = {k: v.index_select(0, idx) for k, v in self.buf.items()}
+        pred = self.net(e["state"], e["action"])
+        r = ops.ppo_loss_fused(pred["log_pi_a"].detach(), pred["entropy"].detach(), pred["v"].detach(), e["log_pi_a"],
+                               e["advantage"], e["ret"], self.clip, self.ent_w)
+        shape = pred["v"].shape
+        self.actor_opt.zero_grad()
+        torch.autograd.backward([pred["log_pi_a"], pred["entropy"]], [r["dlogp"].view(shape), r["dent"].view(shape)])
+        self.actor_opt.step(gate=r["out"][2:3], gate_max=1.5 * self.target_kl)        # PPO_agent.py:94-97
+        self.critic_opt.zero_grad()
+        pred["v"].backward(r["dv"].view(shape))
+        self.critic_opt.step()                                                        # PPO_agent.py:98-99
+        self.stats.copy_(r["out"])
+        self.cursor.add_(1)
+
+    def _state(self):
+        return [t for o in (self.actor_opt, self.critic_opt) for t in (o.flat, o.s1, o.s2, o.step_dev)]
+
+    def capture(self, warmup=3):
+        """Warm-up + capture run on whatever is in the buffers; parameters and optimizer state are restored afterwards."""
+        saved = [t.clone() for t in self._state()]
+        validate = torch.distributions.Distribution._validate_args
+        torch.distributions.Distribution.set_default_validate_args(False)     # argument checks synchronise: not capturable
+        try:
+            s = torch.cuda.Stream(device=self.dev)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(warmup):
+                    self.cursor.zero_()
+                    self._step()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.cursor.zero_()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._step()
+        finally:
+            torch.distributions.Distribution.set_default_validate_args(validate)
+        for t, v in zip(self._state(), saved):
+            t.copy_(v)
+        self.cursor.zero_()
+        torch.cuda.synchronize()
+        return self
+
+    def run(self, n_batches):
+        for _ in range(n_batches):
+            self.graph.replay()

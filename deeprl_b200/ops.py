@@ -249,10 +249,19 @@ class FlatOptimizer:
     def zero_grad(self):
         self.grad.zero_()
 
-    def step(self, max_norm=0.0, grad_scale=1.0):
+    def step(self, max_norm=0.0, grad_scale=1.0, gate=None, gate_max=0.0):
         """clip_grad_norm_(max_norm) (0 = no clip) then the update; ``grad_scale`` pre-multiplies the gradient
-        (1/world_size after an all-reduce sum)."""
+        (1/world_size after an all-reduce sum).  ``gate`` (Adam only): a float32 DEVICE scalar; the step is taken only if
+        ``gate <= gate_max`` (PPO's ``if approx_kl <= 1.5 * target_kl`` without a host round trip)."""
         sh = _lib.ptr(self.shadow)
+        if gate is not None:
+            if self.kind != "adam":
+                raise NotImplementedError("gated steps are implemented for Adam (the PPO actor optimizer)")
+            _lib.call("b2rl_clip_adam_gated", _lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.s1), _lib.ptr(self.s2),
+                      self.n, float(max_norm or 0.0), float(self.lr), float(self.betas[0]), float(self.betas[1]),
+                      float(self.eps), _lib.ptr(self.step_dev), float(grad_scale), _lib.ptr(self.scratch), sh, _lib.ptr(gate),
+                      float(gate_max), _lib.stream())
+            return
         if self.kind == "rmsprop":
             _lib.call("b2rl_clip_rmsprop", _lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.s1), _lib.ptr(self.s2),
                       self.n, float(max_norm or 0.0), float(self.lr), float(self.alpha), float(self.eps), int(self.centered),

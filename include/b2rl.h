@@ -183,6 +183,11 @@ int b2rl_clip_rmsprop(float* param, const float* grad, float* square_avg, float*
 int b2rl_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float max_norm,
                    float lr, float beta1, float beta2, float eps, int64_t* step_dev, float grad_scale,
                    void* norm_scratch, uint16_t* bf16_shadow, void* stream);
+/* b2rl_clip_adam taken only if the DEVICE scalar *gate <= gate_max (nothing is touched otherwise): the KL gate of the PPO
+ * actor step, `if approx_kl <= 1.5 * target_kl:` PPO_agent.py:94, decided on the device so the update can be graph-captured */
+int b2rl_clip_adam_gated(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float max_norm,
+                         float lr, float beta1, float beta2, float eps, int64_t* step_dev, float grad_scale,
+                         void* norm_scratch, uint16_t* bf16_shadow, const float* gate, float gate_max, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense-layer epilogues (network_bodies.py:27-33,70-73: y = relu(layer(x))), bf16 activations [rows][C] (NHWC

@@ -155,3 +155,62 @@ def test_dual_forward_matches_separate_forwards(env):
     for g, r in zip([p.grad for p in net.parameters()], g_ref):
         scale = float(r.abs().max()) + 1e-12
         assert float((g - r).abs().max()) <= 3e-2 * scale
+
+
+def test_graphed_ppo_minibatches_match_the_eager_loop(env):
+    """GraphedPPOLearner (one graph replay per minibatch, KL gate decided on the device by b2rl_clip_adam_gated) against
+    PPOAgent._minibatch (the eager loop with the host-side `if approx_kl <= 1.5 * target_kl`, PPO_agent.py:94) on the same
+    rollout rows and the same permutations.  fp32 throughout: parameters agree to 1e-5 after 16 updates, and both took
+    the same number of (gated) actor steps."""
+    bench, rl = env
+    from collections import namedtuple
+    from deeprl_b200.utils import random_sample
+    dev = torch.device("cuda", 0)
+    rl.Config.COMPUTE_DTYPE = torch.float32
+    try:
+        def agent(graph):
+            torch.manual_seed(11)
+            c = rl.Config()
+            c.merge(dict(tag=None))
+            c.num_workers = 2
+            c.task_fn = lambda: rl.Task("SyntheticCheetah-v0", num_envs=2, seed=1)
+            c.eval_env = rl.Task("SyntheticCheetah-v0", seed=1)
+            c.network_fn = lambda: rl.GaussianActorCriticNet(c.state_dim, c.action_dim,
+                                                             actor_body=rl.FCBody(c.state_dim, gate=torch.tanh),
+                                                             critic_body=rl.FCBody(c.state_dim, gate=torch.tanh))
+            c.actor_opt_fn = lambda p: torch.optim.Adam(p, 3e-4)
+            c.critic_opt_fn = lambda p: torch.optim.Adam(p, 1e-3)
+            c.discount, c.use_gae, c.gae_tau, c.gradient_clip = 0.99, True, 0.95, 0.5
+            c.rollout_length, c.optimization_epochs, c.mini_batch_size, c.ppo_ratio_clip = 8, 4, 64, 0.2
+            c.target_kl = 2e-4                                             # small: some actor steps are skipped
+            c.graph_minibatch = graph
+            return rl.PPOAgent(c)
+
+        a, b = agent(False), agent(True)
+        for pa, pb in zip(a.network.parameters(), b.network.parameters()):
+            assert torch.equal(pa, pb)
+        g = torch.Generator(device=dev).manual_seed(5)
+        rows = 256
+        state = torch.randn(rows, a.config.state_dim, device=dev, generator=g)
+        with torch.no_grad():
+            pred = a.network(state)
+        Entry = namedtuple("Entry", ["state", "action", "log_pi_a", "ret", "advantage"])
+        entries = Entry(state, pred["action"].contiguous(), pred["log_pi_a"].contiguous(),
+                        torch.randn(rows, 1, device=dev, generator=g), torch.randn(rows, 1, device=dev, generator=g))
+        np.random.seed(3)
+        for _ in range(a.config.optimization_epochs):
+            for idx in random_sample(np.arange(rows), 64):
+                a._minibatch(entries, idx)
+        np.random.seed(3)
+        b._graphed_epochs(entries)
+        torch.cuda.synchronize()
+        for (n, pa), pb in zip(a.network.named_parameters(), b.network.parameters()):
+            np.testing.assert_allclose(pb.detach().cpu().numpy(), pa.detach().cpu().numpy(), rtol=1e-4, atol=1e-5, err_msg=n)
+        steps_a = int(next(iter(a.actor_opt.state.values()))["step"])
+        steps_b = int(b._graph.actor_opt.step_dev)
+        assert steps_a == steps_b and 0 < steps_b < 16                     # the gate closed at least once, identically
+        assert int(b._graph.critic_opt.step_dev) == 16
+        np.testing.assert_allclose(b.last_stats.cpu().numpy()[:3], a.last_stats.cpu().numpy()[:3], rtol=1e-3, atol=1e-6)
+        a.close(), b.close()
+    finally:
+        rl.Config.COMPUTE_DTYPE = torch.bfloat16
