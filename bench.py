@@ -383,7 +383,8 @@ def run_ppo(args):
         minibatch_phase=(dict(updates_per_s=round(mb * K / sgd[0], 1), seconds_per_iteration=round(sgd[0] / K, 3),
                               form="one CUDA-graph replay per minibatch (GraphedPPOLearner), KL gate on the device")
                          if c.graph_minibatch else dict(form="eager loop (PPOAgent._minibatch)")),
-        gpu_launches=int(rl._lib.launch_count()), gpu_launches_per_step=int(rl._lib.launch_count() // K))), flush=True)
+        gpu_launches=int(rl._lib.launch_count() + (K * mb * ag._graph.launches_per_update if c.graph_minibatch else 0)),
+        gpu_launches_per_minibatch=(int(ag._graph.launches_per_update) if c.graph_minibatch else None))), flush=True)
     ag.close()
 
 

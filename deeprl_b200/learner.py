@@ -348,7 +348,9 @@ class GraphedPPOLearner:
             with torch.cuda.stream(s):
                 for _ in range(warmup):
                     self.cursor.zero_()
+                    _lib.reset_launch_count()
                     self._step()
+                    self.launches_per_update = _lib.launch_count()     # of OUR kernels (the MLP itself is torch / cuBLAS)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             self.cursor.zero_()
