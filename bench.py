@@ -20,6 +20,7 @@ Multi-GPU: launched by torchrun, one rank per GPU; each rank owns a replay shard
 gradients are all-reduced (NCCL) every step: weak scaling, value = ranks x updates/s.
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -169,6 +170,20 @@ def time_gather_kernel(rl, rp, iters=64, reps=5):
     return res
 
 
+@contextlib.contextmanager
+def stdout_to_stderr():
+    """Route file descriptor 1 to stderr for the duration (library banners), so that stdout carries the one JSON line."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        yield
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def run_b2rl(args):
     import torch.distributed as dist
     import deeprl_b200 as rl
@@ -181,10 +196,12 @@ def run_b2rl(args):
     rl.select_device(local)
     rl.Config.COMPUTE_DTYPE = torch.bfloat16
     torch.backends.cudnn.benchmark = True
-    if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL logs its version there)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    if world > 1:
+        with stdout_to_stderr():                           # NCCL prints its version banner on stdout at communicator creation
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
     learner = build_learner(rl, args.workload, dev, rank, world, prefetch=(args.replay == "async"))
     if world > 1:                                          # parameters identical on every rank
         dist.broadcast(learner.opt.flat, 0)

@@ -462,8 +462,10 @@ struct SlabParams {
   int base_offset_mode;    // 1: descriptor base_offset = (window start >> 7) & 7; 2: base_offset = 0 (address-based swizzle)
 };
 
+// BN = 32 (conv1, 12 tiles per SM, 16 KB of weights) compiles for two resident CTAs per SM: with many tiles the work can be
+// split over 2 x 148 CTAs whose waits interleave (launch_slab uses a <= 110 KB shared-memory budget then).
 template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) conv_slab_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(GEMM_THREADS, BN == 32 ? 2 : 1) conv_slab_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                             const __grid_constant__ CUtensorMap tmB,
                                                                             const __grid_constant__ CUtensorMap tmA2,
                                                                             const __grid_constant__ CUtensorMap tmB2,
@@ -823,7 +825,16 @@ static int launch_slab(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
                        SlabParams sp, cudaStream_t st) {
   const size_t w_bytes = (size_t)sp.taps * sp.col_blocks * BN * 128;
   const size_t slab_bytes = (size_t)sp.slab_rows * 128 * sp.col_blocks;
-  const size_t budget = 200 * 1024;
+  const int tiles = (sp.g.M + GEMM_BM - 1) / GEMM_BM;
+  static int two_cta = -1;                                           // B2RL_SLAB_2CTA=0 keeps one CTA per SM for BN = 32 too
+  if (two_cta < 0) {
+    const char* e = getenv("B2RL_SLAB_2CTA");
+    two_cta = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  // two CTAs per SM when the kernel was compiled for it, the tiles are plentiful and both fit (<= 110 KB each, >= 3 stages)
+  const bool pair = BN == 32 && two_cta && !sp.g.dual && tiles >= 4 * sm_count() &&
+                    w_bytes + 3 * slab_bytes + 2048 <= 110 * 1024;
+  const size_t budget = pair ? 110 * 1024 - 2048 : 200 * 1024;
   if (w_bytes + 2 * slab_bytes > budget) return 1;                   // does not fit: caller falls back to tap addressing
   int stages = (int)((budget - w_bytes) / slab_bytes);
   if (stages > 6) stages = 6;
@@ -835,8 +846,7 @@ static int launch_slab(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = smem;
   }
-  const int tiles = (sp.g.M + GEMM_BM - 1) / GEMM_BM;
-  int ctas = sp.g.dual ? sm_count() / 2 : sm_count();                // per operand set
+  int ctas = sp.g.dual ? sm_count() / 2 : (pair ? 2 * sm_count() : sm_count());   // per operand set
   if (ctas > tiles) ctas = tiles;
   launch_pdl(k, dim3(sp.g.dual ? 2 * ctas : ctas), dim3(GEMM_THREADS), smem, st, ta, tb, ta2, tb2, sp);
   return check_launch("b2rl_conv_gemm_bf16(slab)");
