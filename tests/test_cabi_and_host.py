@@ -229,3 +229,61 @@ def test_a2c_cpu_matches_oracle_trajectory(golden):
         ag.step()
         flat = np.concatenate([p.detach().numpy().ravel() for p in ag.network.parameters()])
         np.testing.assert_allclose(flat, g["a2c_params"][it], rtol=0, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------------ repository rules
+def _py_files(root):
+    for d, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py"):
+                yield os.path.join(d, f)
+
+
+def test_product_never_imports_the_oracle_or_reads_the_reference():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import it,
+    and nothing that runs on the GPU box may read /root/reference."""
+    import ast
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for path in _py_files(os.path.join(root, "deeprl_b200")):
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            assert not any(n == "oracle" or n.startswith("oracle.") for n in names), path
+        assert "/root/reference" not in open(path).read(), path
+    # bench.py: the oracle is imported inside the CPU arm only
+    tree = ast.parse(open(os.path.join(root, "bench.py")).read())
+    for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
+        uses = any(isinstance(n, ast.ImportFrom) and (n.module or "").startswith("oracle") for n in ast.walk(fn))
+        assert uses == (fn.name == "make_cpu_agent"), fn.name
+    entry = ast.parse(open(os.path.join(root, "__graft_entry__.py")).read())
+    for fn in [n for n in entry.body if isinstance(n, ast.FunctionDef)]:
+        uses = any(isinstance(n, ast.ImportFrom) and (n.module or "").startswith("oracle") for n in ast.walk(fn))
+        assert not uses or fn.name == "smoke", fn.name
+
+
+def test_bench_arms_on_a_cpu_only_host():
+    """No GPU here: the product arm must refuse loudly (no CPU fallback), the reference arm must print ONE JSON line
+    with the contract's keys and zero transfer bytes."""
+    import json
+    import subprocess
+    import sys
+    if torch.cuda.is_available():
+        pytest.skip("CPU-host behaviour")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "bench.py", "--steps", "1", "--warmup", "1"], cwd=root, capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1"], cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "updates/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["metric"].startswith("gradient-updates/sec")
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
