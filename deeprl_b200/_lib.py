@@ -149,10 +149,6 @@ def set_pdl(on):
     L.b2rl_set_pdl(int(on))
 
 
-def _unused():
-    pass
-
-
 def launch_count():
     return int(lib().b2rl_launch_count())
 
