@@ -18,9 +18,13 @@
 //
 // One persistent CTA per SM loops over output tiles (128 x BN):
 //   warp 0    TMA producer   cp.async.bulk.tensor into a STAGES-deep 128B-swizzled smem ring (mbarrier full/empty)
-//   warp 1    MMA issuer     one thread: tcgen05.mma.cta_group::1.kind::f16, accumulators double-buffered in TMEM
-//   warps 2-5 epilogue       tcgen05.ld (32 lanes x 32 columns per warp) -> bias / ReLU -> bf16 | fp32 | atomic fp32,
+//   warp 1    MMA issuer     one ELECTED thread (elect.sync, see elect_one): tcgen05.mma.cta_group::1.kind::f16,
+//                            accumulators double-buffered in TMEM
+//   warps 2-5 epilogue of even tiles, warps 6-9 epilogue of odd tiles (one group per accumulator stage):
+//                            tcgen05.ld (32 lanes x 32 columns per warp) -> bias / ReLU -> bf16 | fp32 | atomic fp32,
 //                            overlapped with the next tile's MMAs; warp 2 also owns TMEM alloc / dealloc
+// Every kernel runs its prologue (barrier init, tensor-map prefetch, TMEM allocation) before pdl_sync(): under
+// programmatic dependent launch that part overlaps the tail of the previous kernel (common.cuh).
 // sm_100a only.
 #include <cuda.h>
 #include <cstdlib>
@@ -598,8 +602,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, BN == 32 ? 2 : 1) conv_slab_tcge
 // Both operands are read as stored (MN-major, K = rows).  A CTA owns a contiguous range of 64-row k-tiles; per k-tile it
 // loads the gradient rows ONCE and ONE slab of 64 + max_shift activation rows, and issues every tap's MMAs on windows of
 // that slab (a K-row shift is a 128-byte step in the MN-major swizzled layout, address-based swizzle as above) into one
-// TMEM accumulator per tap (taps x C fp32 columns, <= 512).  At the end the accumulators are added to D with fp32
-// atomics (split-K across CTAs).
+// TMEM accumulator per tap (taps x C fp32 columns, <= 512).  At the end each CTA stores its partial sums plainly at
+// D + blockIdx.x * partial_stride (the consumer sums them: deterministic), or adds them to D with fp32 vector atomics
+// when partial_stride == 0.
 // ---------------------------------------------------------------------------------------------------------------
 struct WgradParams {
   int rows, n_out, C, col_blocks;
