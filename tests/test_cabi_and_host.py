@@ -287,3 +287,27 @@ def test_bench_arms_on_a_cpu_only_host():
     assert d["metric"].startswith("gradient-updates/sec")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_tcgen05_kernels_issue_mma_and_tma_directly():
+    """SASS-level guard (profiles/r01_microbench.txt 3a/3b): the tensor-core GEMM kernels must contain UTCHMMA (tcgen05.mma),
+    UTMALDG (TMA loads) and LDTM (TMEM loads), and the single-thread roles must be entered through elect.sync -- behind a
+    plain `lane == 0` test nvcc wraps every UTCHMMA in an ELECT / BRA.U.ANY loop, which doubled the per-MMA issue cost."""
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    kernels = {}
+    name = None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :")[1].strip()
+            kernels[name] = []
+        elif name is not None:
+            kernels[name].append(line)
+    tc = {k: "\n".join(v) for k, v in kernels.items() if "tcgen05_kernel" in k}
+    assert len(tc) >= 9, sorted(kernels)[:5]                    # gemm x3, slab x3, wgrad x4 instantiations
+    for k, body in tc.items():
+        assert "UTCHMMA" in body and "UTMALDG" in body and "LDTM" in body, k
+        assert "BRA.U.ANY" not in body, "%s: uniform-datapath instructions are wrapped in ELECT loops again" % k
+    assert "EF_CUDA_SM100" in sass
