@@ -9,10 +9,11 @@ timeout 900 python bench.py --steps 300 --warmup 20 > $OUT/bench_dqn_$TAG.json 2
 for w in per c51 qr; do
   timeout 900 python bench.py --workload $w --steps 100 --warmup 10 > $OUT/bench_${w}_$TAG.json 2> $OUT/bench_${w}_$TAG.err; echo "bench $w $?"
 done
+timeout 300 python bench.py --workload ppo --steps 2 > $OUT/bench_ppo_$TAG.json 2> $OUT/bench_ppo_$TAG.err; echo "bench ppo $?"
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "bench reference $?"
 python - <<PY
 import json
-for w in ("dqn", "per", "c51", "qr", "ref"):
+for w in ("dqn", "per", "c51", "qr", "ppo", "ref"):
     try:
         d = json.load(open("$OUT/bench_%s_$TAG.json" % w))
         print(w, d.get("value"), d.get("ms_per_step"), (d.get("e2e") or {}).get("value"), d.get("other_replay_mode"), d.get("gpu_launches_per_step"))
