@@ -214,3 +214,32 @@ def test_graphed_ppo_minibatches_match_the_eager_loop(env):
         a.close(), b.close()
     finally:
         rl.Config.COMPUTE_DTYPE = torch.bfloat16
+
+
+def test_fused_backward_epilogues_match_the_separate_passes(env):
+    """B2RL_FUSED_BWD: ReLU mask + bias gradient + grid scatter inside the dgrad GEMM epilogues against the three
+    b2rl_act_bwd_bias_grad_bf16 passes.  The masked gradients are the same bf16 values (masking commutes with rounding);
+    the bias gradients sum fp32 accumulators instead of bf16-rounded values."""
+    bench, rl = env
+    from deeprl_b200.network import nature_tc
+    from deeprl_b200.network.fused import frame_scale
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(5)
+    net = rl.VanillaNet(4, rl.NatureConvBody(in_channels=4))
+    s = torch.randint(0, 256, (96, 64, 21, 21), device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    grads = {}
+    for fused in (False, True):
+        nature_tc.FUSED_BWD = fused
+        try:
+            net.zero_grad()
+            with frame_scale(1.0 / 255):
+                q = net(s)["q"]
+                (q * torch.linspace(-1, 1, q.numel(), device=dev).view_as(q)).sum().backward()
+            torch.cuda.synchronize()
+            grads[fused] = {n: p.grad.detach().clone() for n, p in net.named_parameters()}
+        finally:
+            nature_tc.FUSED_BWD = False
+    for n, ref in grads[False].items():
+        got = grads[True][n]
+        scale = float(ref.abs().max()) + 1e-12
+        assert float((got - ref).abs().max()) <= 2e-2 * scale, n
