@@ -34,6 +34,8 @@ FC4_SPLITS = int(os.environ.get("B2RL_FC4_SPLITS", "4"))
 # b2rl_act_bwd_bias_grad_bf16 passes.  NOT YET VERIFIED ON A GPU (written after the round's GPU budget was spent): off.
 FUSED_BWD = os.environ.get("B2RL_FUSED_BWD", "0") == "1"
 _ZEROED = {}
+RELU_FEATURES = set()      # data_ptr of feature tensors y4 = relu(fc4(.)) produced by nature_body (for head_bwd_relu)
+PREMASKED = {}             # data_ptr of a feature gradient already masked by head_bwd_relu -> its column sums (= db4)
 
 
 def _zero_grid(key, shape, device):
@@ -48,7 +50,11 @@ def _zero_grid(key, shape, device):
 def _backward_fused(ctx, gy4):
     x0m, x1, y2, y3, y4, w2d, w3d, w4p = ctx.saved_tensors
     B, dev = y4.shape[0], y4.device
-    g4, db4 = act_bwd_bias_grad(gy4, y4, True)                                          # fc4's own ReLU / bias gradient
+    db4 = PREMASKED.pop(gy4.data_ptr(), None) if gy4.dtype == _bf16 and gy4.is_contiguous() else None
+    if db4 is not None:
+        g4 = gy4                                                                        # masked + summed by b2rl_head_bwd_relu
+    else:
+        g4, db4 = act_bwd_bias_grad(gy4, y4, True)                                      # fc4's own ReLU / bias gradient
     y3c = y3.view(B, 3136)
     gw4p = gemm_bf16(g4, y3c, a_major="mn", b_major="mn", out_dtype=_f32, block_n=128, stream=_fork())
     db = torch.zeros(32 + 64 + 64, dtype=_f32, device=dev)
@@ -334,8 +340,13 @@ def nature_body(body, x0, scale):
                 pb = repack(o, scale)
             if xb.shape == x0.shape and pb.n4 == pk.n4:
                 companion = (xb, pb, tuple(m.bias.detach() for m in (o.conv1, o.conv2, o.conv3, o.fc4)), d.features)
-    return _NatureBody.apply(x0, c1.weight, c1.bias, c2.weight, c2.bias, c3.weight, c3.bias, f4.weight, f4.bias,
-                             float(scale), pk, companion)
+    y4 = _NatureBody.apply(x0, c1.weight, c1.bias, c2.weight, c2.bias, c3.weight, c3.bias, f4.weight, f4.bias,
+                           float(scale), pk, companion)
+    if FUSED_BWD:
+        if len(RELU_FEATURES) > 256:
+            RELU_FEATURES.clear()
+        RELU_FEATURES.add(y4.data_ptr())
+    return y4
 
 
 def repack(body, scale):

@@ -289,6 +289,10 @@ int b2rl_head_fwd(const uint16_t* phi, const float* Wa, const float* ba, const f
                   int32_t K, int32_t A, float* q, void* stream);
 int b2rl_head_bwd(const float* gq, const uint16_t* phi, const float* Wa, const float* Wv, int32_t B, int32_t K, int32_t A,
                   uint16_t* gphi, float* gWa, float* gba, float* gWv, float* gbv, void* stream);
+/* b2rl_head_bwd when phi = relu(layer(.)) (NatureConvBody's fc4 output): gphi is masked (0 where phi <= 0) and
+ * relu_colsum[K] (fp32, zero it first) receives the column sums of the masked gphi = that layer's bias gradient. */
+int b2rl_head_bwd_relu(const float* gq, const uint16_t* phi, const float* Wa, const float* Wv, int32_t B, int32_t K, int32_t A,
+                       uint16_t* gphi, float* gWa, float* gba, float* gWv, float* gbv, float* relu_colsum, void* stream);
 
 /* Convolution weight gradient as split-K partials (no atomics): partial i of *n_partials_host (<= 148, written on the
  * HOST, deterministic for given shapes) is stored at partials + i * n_out*taps*C floats. */
