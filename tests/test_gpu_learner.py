@@ -243,3 +243,38 @@ def test_fused_backward_epilogues_match_the_separate_passes(env):
         got = grads[True][n]
         scale = float(ref.abs().max()) + 1e-12
         assert float((got - ref).abs().max()) <= 2e-2 * scale, n
+
+
+@pytest.mark.parametrize("replay_cls_name", ["UniformReplay", "PrioritizedReplay"])
+def test_dqn_agent_with_cuda_graph_option(env, replay_cls_name):
+    """config.cuda_graph: DQNAgent.step() drives GraphedDQNLearner (one graph replay per update) through the reference's
+    own agent API: transitions are fed by the agent, the update runs as a graph, the target is synchronised on schedule."""
+    bench, rl = env
+    c = rl.Config()
+    c.merge(dict(tag=None))
+    c.task_fn = lambda: rl.Task("SyntheticAtari-v0", seed=2)
+    c.eval_env = rl.Task("SyntheticAtari-v0", seed=2)
+    c.optimizer_fn = lambda p: torch.optim.RMSprop(p, lr=0.00025, alpha=0.95, eps=0.01, centered=True)
+    c.network_fn = lambda: rl.VanillaNet(c.action_dim, rl.NatureConvBody(in_channels=4))
+    c.random_action_prob = rl.LinearSchedule(1.0, 0.01, 1e6)
+    c.batch_size = 32
+    replay_cls = getattr(rl, replay_cls_name)
+    c.replay_fn = lambda: rl.ReplayWrapper(replay_cls, dict(memory_size=2000, batch_size=32, n_step=1, discount=0.99,
+                                                            history_length=4), async_=False)
+    c.replay_eps, c.replay_alpha, c.replay_beta = 0.01, 0.5, rl.LinearSchedule(0.4, 1.0, 1e5)
+    c.state_normalizer, c.reward_normalizer = rl.ImageNormalizer(), rl.SignNormalizer()
+    c.discount, c.history_length, c.double_q, c.n_step = 0.99, 4, False, 1
+    c.target_network_update_freq, c.exploration_steps, c.sgd_update_frequency, c.gradient_clip = 20, 200, 4, 5
+    c.async_actor = False
+    c.cuda_graph = True
+    ag = rl.DQNAgent(c)
+    before = None
+    for i in range(120):
+        ag.step()
+        if ag.total_steps == 204:
+            before = ag._flat.flat.clone()
+    torch.cuda.synchronize()
+    assert getattr(ag, "_learner", None) is not None and ag._learner.updates > 50
+    assert torch.isfinite(ag.last_loss).all()
+    assert not torch.equal(before, ag._flat.flat)
+    ag.close()
