@@ -50,6 +50,8 @@ SIGNATURES = {
                                  c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p],
     "b2rl_gemm_dual_bf16": [c_p, c_p, c_i64, c_p, c_p, c_i64, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_p, c_p, c_i32, c_i32,
                             c_i32, c_p],
+    "b2rl_conv_gemm_bwd_bf16": [c_p, c_i64, c_i32, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_i64, c_i32, c_i32, c_i32, c_p, c_i32, c_p],
+    "b2rl_gemm_bwd_bf16": [c_p, c_i64, c_p, c_i32, c_i64, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p],
     "b2rl_gemm_bf16": [c_p, c_i32, c_i64, c_p, c_i32, c_i64, c_p, c_i64, c_i32, c_i32, c_i32, c_p, c_i32, c_i32, c_i32, c_i32,
                        c_p],
     "b2rl_nature_pack_weights": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_f32, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
@@ -57,6 +59,7 @@ SIGNATURES = {
     "b2rl_conv_wgrad_partials": [c_p, c_i64, c_i32, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p],
     "b2rl_head_fwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p],
     "b2rl_head_bwd": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p],
+    "b2rl_head_bwd_relu": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "b2rl_clip_rmsprop": [c_p, c_p, c_p, c_p, c_i64, c_f32, c_f32, c_f32, c_f32, c_i32, c_f32, c_p, c_p, c_p],
     "b2rl_clip_adam": [c_p, c_p, c_p, c_p, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_p, c_f32, c_p, c_p, c_p],
     "b2rl_clip_adam_gated": [c_p, c_p, c_p, c_p, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_p, c_f32, c_p, c_p, c_p, c_f32, c_p],
@@ -64,6 +67,17 @@ SIGNATURES = {
 
 U8, F16, BF16, F32 = 0, 1, 2, 3
 DTYPE_CODE = {torch.uint8: U8, torch.float16: F16, torch.bfloat16: BF16, torch.float32: F32}
+
+
+class BwdEpilogue(ctypes.Structure):
+    """``b2rl_bwd_epilogue`` of include/b2rl.h: ReLU-gradient mask, bias-gradient accumulator, scatter-map channel count."""
+    _fields_ = [("mask", c_p), ("mask_ld", c_i64), ("dbias", c_p), ("dbias_mod", c_i32), ("sub_c", c_i32)]
+
+
+def bwd_epilogue(mask, dbias, dbias_mod, sub_c=0):
+    e = BwdEpilogue(ctypes.c_void_p(mask.data_ptr()), int(mask.stride(0)), ctypes.c_void_p(dbias.data_ptr()), int(dbias_mod),
+                    int(sub_c))
+    return e
 
 
 class B2RLError(RuntimeError):

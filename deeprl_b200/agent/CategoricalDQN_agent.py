@@ -31,6 +31,8 @@ class CategoricalDQNAgent(DQNAgent):
         self.atoms = tensor(config.atoms)
         self.delta_atom = (config.categorical_v_max - config.categorical_v_min) / float(config.categorical_n_atoms - 1)
 
+    _graph_kind = "c51"
+
     def _fused_owner(self):
         return CategoricalDQNAgent
 

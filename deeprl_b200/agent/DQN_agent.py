@@ -224,7 +224,9 @@ class DQNAgent(BaseAgent):
                 reward=[config.reward_normalizer(r) for r in rewards],
                 mask=1 - np.asarray(dones, dtype=np.int32)))
 
-        if self.total_steps > config.exploration_steps:
+        if self.total_steps > config.exploration_steps and self._graph_ok():
+            self._graph_update()                           # config.cuda_graph: the whole update is one graph replay
+        elif self.total_steps > config.exploration_steps:
             transitions = self._sample()
             if config.noisy_linear:
                 self.target_network.reset_noise()
@@ -236,4 +238,43 @@ class DQNAgent(BaseAgent):
                     self.last_loss = self._fused_update(transitions)
 
         if self.total_steps / config.sgd_update_frequency % config.target_network_update_freq == 0:
-            self.target_network.load_state_dict(self.network.state_dict())
+            if getattr(self, "_learner", None) is not None:
+                self._learner.sync_target()                # load_state_dict + re-pack of the target's bf16 operands
+            else:
+                self.target_network.load_state_dict(self.network.state_dict())
+
+    # ------------------------------------------------------------------ config.cuda_graph (opt-in)
+    _graph_kind = "dqn"
+
+    def _graph_ok(self):
+        """The captured update (learner.GraphedDQNLearner) serves the stock agents on a CUDA device with a synchronous uint8
+        image replay and the fused optimizer; everything else keeps the eager path."""
+        config = self.config
+        if not getattr(config, "cuda_graph", False) or self._flat is None or self._uses_reference_hooks():
+            return False
+        if config.noisy_linear or not _pre_normalized(config, self.replay):
+            return False
+        inner = getattr(self.replay, "replay", self.replay)
+        return len(getattr(inner, "item_shape", ())) == 2 and inner.size() >= inner.batch_size + 64
+
+    def _graph_update(self):
+        from ..learner import GraphedDQNLearner
+        config = self.config
+        lr = getattr(self, "_learner", None)
+        if lr is None:
+            inner = getattr(self.replay, "replay", self.replay)
+            lr = self._learner = GraphedDQNLearner(
+                self.network, self.target_network, self._flat, inner, kind=self._graph_kind, discount=config.discount,
+                n_step=config.n_step, double_q=bool(config.double_q), gradient_clip=config.gradient_clip or 0.0,
+                feeds_per_update=0, compute_dtype=Config.COMPUTE_DTYPE, state_scale=config.state_normalizer.coef,
+                replay_eps=getattr(config, "replay_eps", 0.01), replay_alpha=getattr(config, "replay_alpha", 0.5),
+                categorical=(getattr(config, "categorical_v_min", -10.0), getattr(config, "categorical_v_max", 10.0)),
+                target_sync_every=0, prefetch=False)
+            with config.lock:
+                lr.capture(warmup=1)                       # NOTE: the warm-up is one real (extra) gradient update
+        if lr.per:
+            lr.d_beta.fill_(float(config.replay_beta()))
+        with config.lock:                                  # the actor reads the shared parameters (DQN_agent.py:30,133)
+            lr.update()
+            lr._repack(self.network, lr.scale if lr.dtype == torch.bfloat16 else 1.0)   # the actor's next forward sees theta_k
+        self.last_loss = lr.loss

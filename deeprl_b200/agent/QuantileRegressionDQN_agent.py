@@ -30,6 +30,8 @@ class QuantileRegressionDQNAgent(DQNAgent):
         self.quantile_weight = 1.0 / config.num_quantiles
         self.cumulative_density = tensor((2 * np.arange(config.num_quantiles) + 1) / (2.0 * config.num_quantiles)).view(1, -1)
 
+    _graph_kind = "qr"
+
     def _fused_owner(self):
         return QuantileRegressionDQNAgent
 

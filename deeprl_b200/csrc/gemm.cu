@@ -164,6 +164,11 @@ struct GemmParams {
   int dual;
   void* D2;
   const float* bias2;
+  // backward extras (see epilogue_tile): ReLU-gradient mask, bias-gradient accumulation, grid scatter maps 3 / 4
+  const __nv_bfloat16* mask;
+  int64_t mask_ld;
+  float* dbias;
+  int dbias_mod, sub_c;
 };
 
 __device__ __forceinline__ int tap_shift(const GemmParams& p, int tap) {
@@ -189,17 +194,27 @@ __device__ unsigned long long* g_trace_buf = nullptr;
 // scripts/microbench/umma_rate.cu measured on B200: one issuing thread sustains one tcgen05.mma (M=128, K=16) every
 // max(53, N/2) cycles whatever the operand majors and whether consecutive MMAs hit the same accumulator or not, so
 // ACC = 1 is used; small-N tiles are bound by that 53-cycle issue floor, not by accumulator dependencies.
+// Backward extras (dgrad GEMMs): `mask` is the saved forward activation in the GEMM's own output coordinates -- the ReLU
+// gradient is applied in the epilogue (v = mask > 0 ? v : 0); `dbias` receives the column sums of the masked tile (the bias
+// gradient of the layer below) through a per-CTA shared accumulator `s_dbias`, index = column % dbias_mod.  Output row maps
+// 3 / 4 scatter the tile into the G x G grid matrix the next backward GEMMs read:
+//   map 3: rows are space-to-depth(2) positions [b][oy][ox] of an (V/2)^2 grid, columns are 4 sub-positions x sub_c channels
+//          -> grid row b*G*G + (2*oy + dy)*G + 2*ox + dx, column = channel           (conv2's input gradient -> conv1's grid)
+//   map 4: rows are images b, columns are V*V positions x sub_c channels
+//          -> grid row b*G*G + (pos / V)*G + pos % V, column = channel               (fc4's input gradient -> conv3's grid)
+// Grid rows that no tile covers keep whatever the destination holds: the caller keeps it zeroed (persistent buffer).
 template <int BN, int ACC>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n0, int q, int lane, uint32_t tmem_base,
                                               uint32_t as, uint32_t parity, bool has_acc, uint64_t* tmem_full,
-                                              uint64_t* tmem_empty, uint32_t trace_it = 1u << 30) {
+                                              uint64_t* tmem_empty, float* s_dbias, uint32_t trace_it = 1u << 30) {
   const bool tr = q == 0 && lane == 0;
   if (tr) B2RL_TRACE_AT(2, trace_it, 0);
   const int row = m0 + q * 32 + lane;
   bool valid = row < p.M;
   int64_t drow = row;
   int dcol0 = 0;
-  if (p.out_map != 0 && valid) {
+  int img = 0, sy = 0, sx = 0;                        // maps 3 / 4: image and source position of this row
+  if ((p.out_map == 1 || p.out_map == 2) && valid) {
     const int gg = p.G * p.G;
     const int b = row / gg, rem = row - b * gg;
     const int oy = rem / p.G, ox = rem - oy * p.G;
@@ -211,6 +226,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
     } else {
       drow = (int64_t)b * p.V * p.V + oy * p.V + ox;
     }
+  } else if (p.out_map == 3 && valid) {
+    const int h = p.V >> 1, hh = h * h;
+    img = row / hh;
+    const int rem = row - img * hh;
+    sy = rem / h, sx = rem - sy * h;
+  } else if (p.out_map == 4) {
+    img = row;
   }
   if (has_acc) {
     mb_wait(&tmem_full[as], parity);
@@ -240,7 +262,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
       if (lane == 0) mb_arrive(&tmem_empty[as]);
       if (tr) B2RL_TRACE_AT(2, trace_it, 2);
     }
-    if (valid && n0 + c < p.N) {
+    const bool live = valid && n0 + c < p.N;
+    if (live) {
       if (p.bias && blockIdx.z == 0) {
         const float* bp = p.bias + n0 + c;
         if (n0 + c + 32 <= p.N && (reinterpret_cast<uintptr_t>(bp) & 15) == 0) {
@@ -262,7 +285,50 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]), 0.0f));
       }
-      const int64_t off = drow * p.ldd + dcol0 + n0 + c;
+      if (p.mask) {                                                     // ReLU gradient: zero where the forward output was <= 0
+        const int4* mp = reinterpret_cast<const int4*>(p.mask + (int64_t)row * p.mask_ld + n0 + c);   // 32 bf16 = 64 bytes
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const int4 m4 = __ldg(mp + (j >> 3));
+          const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&m4);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 mf = __bfloat1622float2(mh[t]);
+            if (!(mf.x > 0.0f)) r[j + 2 * t] = 0;
+            if (!(mf.y > 0.0f)) r[j + 2 * t + 1] = 0;
+          }
+        }
+      }
+    }
+    if (p.dbias) {
+      // column sums over the 32 rows of this warp: 5-step register transpose-reduce (31 shuffles), lane l ends up with the
+      // total of column l; rows that are not live contribute zeros.  All 32 lanes take part.
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = live ? __uint_as_float(r[j]) : 0.0f;
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) {
+        const bool hi = (lane & s) != 0;
+#pragma unroll
+        for (int j = 0; j < s; ++j) {
+          const float send = hi ? v[j] : v[j + s];
+          const float keep = hi ? v[j + s] : v[j];
+          v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+      }
+      if (n0 + c + lane < p.N) atomicAdd(s_dbias + (n0 + c + lane) % p.dbias_mod, v[0]);
+    }
+    if (live) {
+      int64_t off;
+      if (p.out_map == 3) {
+        const int sub = (n0 + c) / p.sub_c, cc = (n0 + c) - sub * p.sub_c;
+        off = ((int64_t)img * p.G * p.G + (2 * sy + (sub >> 1)) * p.G + 2 * sx + (sub & 1)) * p.ldd + cc;
+      } else if (p.out_map == 4) {
+        const int pos = (n0 + c) / p.sub_c, cc = (n0 + c) - pos * p.sub_c;
+        off = ((int64_t)img * p.G * p.G + (pos / p.V) * p.G + pos % p.V) * p.ldd + cc;
+      } else {
+        off = drow * p.ldd + dcol0 + n0 + c;
+      }
       if (p.out_mode == 0) {
         __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + off;
         if (n0 + c + 32 <= p.N && (off % 8 == 0)) {
@@ -341,6 +407,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   const int kt_end = min(kt_total, kt_begin + p.k_tiles_per_split);
   const int n_kt = max(kt_end - kt_begin, 0);
 
+  __shared__ float s_dbias[128];                    // per-CTA bias-gradient accumulator (backward extras)
+  if (threadIdx.x < 128) s_dbias[threadIdx.x] = 0.0f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mb_init(&full[s], 1); mb_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mb_init(&tmem_full[s], 1); mb_init(&tmem_empty[s], 4); }
@@ -437,11 +505,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       if ((tcount & 1) != grp) continue;
       const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
       const int m0 = mt * GEMM_BM, n0 = nt * BN;
-      epilogue_tile<BN, ACC>(p, m0, n0, q, lane, tmem_base, tcount & 1, (tcount >> 1) & 1, n_kt > 0, tmem_full, tmem_empty);
+      epilogue_tile<BN, ACC>(p, m0, n0, q, lane, tmem_base, tcount & 1, (tcount >> 1) & 1, n_kt > 0, tmem_full, tmem_empty, s_dbias);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (p.dbias && (int)threadIdx.x < p.dbias_mod) atomicAdd(p.dbias + threadIdx.x, s_dbias[threadIdx.x]);
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
@@ -503,6 +572,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, BN == 32 ? 2 : 1) conv_slab_tcge
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
   const int tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
 
+  __shared__ float s_dbias[128];                    // per-CTA bias-gradient accumulator (backward extras)
+  if (threadIdx.x < 128) s_dbias[threadIdx.x] = 0.0f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) { mb_init(&full[s], 1); mb_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mb_init(&tmem_full[s], 1); mb_init(&tmem_empty[s], 4); }
@@ -586,10 +657,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, BN == 32 ? 2 : 1) conv_slab_tcge
     uint32_t it = 0;
     for (int tile = cta; tile < tiles; tile += n_cta, ++it)
       if ((it & 1) == grp)
-        epilogue_tile<BN, ACC>(p, tile * GEMM_BM, 0, q, lane, tmem_base, it & 1, (it >> 1) & 1, true, tmem_full, tmem_empty, it);
+        epilogue_tile<BN, ACC>(p, tile * GEMM_BM, 0, q, lane, tmem_base, it & 1, (it >> 1) & 1, true, tmem_full, tmem_empty, s_dbias, it);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (p.dbias && (int)threadIdx.x < p.dbias_mod) atomicAdd(p.dbias + threadIdx.x, s_dbias[threadIdx.x]);
   if (threadIdx.x == 0) B2RL_TRACE_AT(3, 0, 3);
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
@@ -962,19 +1034,38 @@ extern "C" int b2rl_gemm_bf16(const uint16_t* A, int32_t a_mn, int64_t lda, cons
 //        X: [rows][C] bf16 (C multiple of 64), W: [N][taps*C] bf16 K-major, shift(tap) = sign*((tap/taps_x)*grid_w + tap%taps_x)
 //   mode 1 (wgrad):            D[n, tap*C + c] (+)= sum_r G[r, n] * X[r + shift(tap), c]
 //        G: [rows][N_out] bf16, X: [rows][C] bf16 (C multiple of block_n), D: fp32 [N_out][taps*C], atomic accumulation
+static int apply_ext(GemmParams& p, const b2rl_bwd_epilogue* ext, int N) {
+  B2RL_REQUIRE(!ext->mask || (ext->mask_ld % 8 == 0 && reinterpret_cast<uintptr_t>(ext->mask) % 16 == 0 && N % 32 == 0),
+               "mask rows must be 16-byte aligned and N a multiple of 32");
+  B2RL_REQUIRE(!ext->dbias || (ext->dbias_mod > 0 && ext->dbias_mod <= 128), "dbias_mod must be in [1, 128]");
+  B2RL_REQUIRE(p.out_map < 3 || (ext->sub_c > 0 && ext->sub_c % 32 == 0 && N % ext->sub_c == 0),
+               "scatter maps need sub_c a multiple of 32 that divides N");
+  p.mask = reinterpret_cast<const __nv_bfloat16*>(ext->mask);
+  p.mask_ld = ext->mask_ld;
+  p.dbias = ext->dbias;
+  p.dbias_mod = ext->dbias_mod > 0 ? ext->dbias_mod : 1;
+  p.sub_c = ext->sub_c > 0 ? ext->sub_c : 32;
+  return B2RL_OK;
+}
+
 static int conv_gemm_impl(int32_t mode, const uint16_t* X, int64_t rows, int32_t C, const uint16_t* W_or_G, int32_t n_out,
                           int32_t taps, int32_t taps_x, int32_t grid_w, int32_t shift_sign, void* D, int64_t ldd,
                           const float* bias, int32_t relu, int32_t out_mode, int32_t out_map, int32_t G, int32_t V,
                           int32_t splits, int32_t block_n, void* stream, const uint16_t* X2 = nullptr,
-                          const uint16_t* W2 = nullptr, void* D2 = nullptr, const float* bias2 = nullptr) {
+                          const uint16_t* W2 = nullptr, void* D2 = nullptr, const float* bias2 = nullptr,
+                          const b2rl_bwd_epilogue* ext = nullptr) {
   B2RL_REQUIRE(mode == 0 || mode == 1, "mode 0 (forward/dgrad) or 1 (wgrad)");
   B2RL_REQUIRE(rows > 0 && C > 0 && taps > 0 && taps_x > 0 && n_out > 0, "bad shape");
-  B2RL_REQUIRE(out_map >= 0 && out_map <= 2, "bad out_map");
+  B2RL_REQUIRE(out_map >= 0 && out_map <= (ext ? 4 : 2), "bad out_map");
   GemmParams p = {};
   p.relu = relu; p.out_mode = out_mode; p.bias = bias; p.D = D; p.ldd = (int)ldd;
   p.taps_x = taps_x; p.grid_w = grid_w; p.shift_sign = shift_sign;
   p.out_map = out_map; p.G = G; p.V = V;
   p.dual = X2 != nullptr; p.D2 = D2; p.bias2 = bias2;
+  if (ext) {
+    int rc0 = apply_ext(p, ext, n_out);
+    if (rc0) return rc0;
+  }
   if (mode == 0) {
     B2RL_REQUIRE(C % 64 == 0, "forward/dgrad needs channels in multiples of 64");
     const int K = taps * C;
@@ -1084,6 +1175,35 @@ extern "C" int b2rl_gemm_dual_bf16(const uint16_t* A, const uint16_t* A2, int64_
   p.taps_x = 1; p.shift_sign = 1;
   p.dual = 1; p.D2 = D2; p.bias2 = bias2;
   return gemm_dispatch(A, 0, lda, M, K, B, 0, ldb, N, K, p, 1, block_n, (cudaStream_t)stream, A2, B2);
+}
+
+// dgrad convolution with the backward extras fused into the epilogue (ReLU mask, bias gradient, grid scatter): D = mask .*
+// conv_transpose(G_rows, W), see b2rl_bwd_epilogue in the header.  bf16 output.
+extern "C" int b2rl_conv_gemm_bwd_bf16(const uint16_t* G_rows, int64_t rows, int32_t C, const uint16_t* W, int32_t n_out,
+                                       int32_t taps, int32_t taps_x, int32_t grid_w, void* D, int64_t ldd, int32_t out_map,
+                                       int32_t G, int32_t V, const b2rl_bwd_epilogue* ext, int32_t block_n, void* stream) {
+  B2RL_REQUIRE(ext, "null epilogue description");
+  B2RL_REQUIRE(out_map == 0 || out_map == 3, "dgrad output map 0 (same grid) or 3 (space-to-depth(2) -> grid)");
+  return conv_gemm_impl(0, G_rows, rows, C, W, n_out, taps, taps_x, grid_w, -1, D, ldd, nullptr, 0, 0, out_map, G, V, 1,
+                        block_n, stream, nullptr, nullptr, nullptr, nullptr, ext);
+}
+
+// D = mask .* (A B^T) with A [M][K] K-major and B K-major ([N][K]) or MN-major ([K][N]); same epilogue extras (fc4 dgrad)
+extern "C" int b2rl_gemm_bwd_bf16(const uint16_t* A, int64_t lda, const uint16_t* B, int32_t b_mn, int64_t ldb, void* D,
+                                  int64_t ldd, int32_t M, int32_t N, int32_t K, int32_t out_map, int32_t G, int32_t V,
+                                  const b2rl_bwd_epilogue* ext, int32_t block_n, void* stream) {
+  B2RL_REQUIRE(ext, "null epilogue description");
+  B2RL_REQUIRE(out_map == 0 || out_map == 4, "output map 0 (plain) or 4 (per-image positions -> grid)");
+  int rc = check_common(A, B, D, lda, ldb, M, N, K, 0, 1, block_n, b_mn, 0);
+  if (rc) return rc;
+  GemmParams p = {};
+  p.M = M; p.N = N; p.K = K; p.ldd = (int)ldd;
+  p.a_mn = 0; p.b_mn = b_mn; p.out_mode = 0; p.D = D;
+  p.taps_x = 1; p.shift_sign = 1;
+  p.out_map = out_map; p.G = G; p.V = V;
+  rc = apply_ext(p, ext, N);
+  if (rc) return rc;
+  return gemm_dispatch(A, 0, lda, M, K, B, b_mn, ldb, b_mn ? K : N, b_mn ? N : K, p, 1, block_n, (cudaStream_t)stream);
 }
 
 // Weight gradient as split-K PARTIALS: partial i (one per CTA, n_partials_host of them, at most 148) is stored at

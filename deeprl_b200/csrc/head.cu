@@ -81,7 +81,11 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
                                                        const float* __restrict__ Wa, const float* __restrict__ Wv, int B,
                                                        int K, int A, __nv_bfloat16* __restrict__ gphi,
                                                        float* __restrict__ gWa, float* __restrict__ gba,
-                                                       float* __restrict__ gWv, float* __restrict__ gbv) {
+                                                       float* __restrict__ gWv, float* __restrict__ gbv,
+                                                       float* __restrict__ relu_colsum) {
+  // relu_colsum != NULL: phi is the output of a ReLU layer (NatureConvBody's fc4): the gradient is masked here (gphi = 0 where
+  // phi <= 0) and its column sums -- that layer's bias gradient -- are accumulated into relu_colsum[K] (zeroed by the caller),
+  // which replaces the separate mask / bias-gradient pass over gphi.
   pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
   __shared__ float geff[HB_ROWS][HEAD_MAX_OUT + 1];       // [row][a], last used column = value gradient (dueling)
   __shared__ float red[4][64][HEAD_MAX_OUT + 1];
@@ -109,6 +113,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     acc[n] = 0.0f;
     w[n] = (n < n_out && k < K) ? ((n < A) ? Wa[(int64_t)n * K + k] : Wv[k]) : 0.0f;
   }
+  float colsum = 0.0f;
   if (k < K) {
     float xs[HB_ROWS / 4];
 #pragma unroll
@@ -130,9 +135,13 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
           acc[n] = fmaf(ge, x, acc[n]);
         }
       }
-      gphi[(int64_t)(r0 + r) * K + k] = __float2bfloat16_rn(g);
+      if (relu_colsum && !(x > 0.0f)) g = 0.0f;
+      const __nv_bfloat16 gb = __float2bfloat16_rn(g);
+      colsum += __bfloat162float(gb);                  // the sum of the stored (bf16) values, as the separate pass computes it
+      gphi[(int64_t)(r0 + r) * K + k] = gb;
     }
   }
+  red[rg][threadIdx.x & 63][HEAD_MAX_OUT] = colsum;     // slot HEAD_MAX_OUT is free: n_out <= HEAD_MAX_OUT
 #pragma unroll
   for (int n = 0; n < HEAD_MAX_OUT + 1; ++n)
     if (n < n_out) red[rg][threadIdx.x & 63][n] = acc[n];
@@ -144,6 +153,12 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       const float s = red[0][c][n] + red[1][c][n] + red[2][c][n] + red[3][c][n];
       atomicAdd((n < A) ? gWa + (int64_t)n * K + kk : gWv + kk, s);
     }
+  }
+  if (relu_colsum && threadIdx.x < 64) {
+    const int kk = blockIdx.x * 64 + threadIdx.x;
+    if (kk < K)
+      atomicAdd(relu_colsum + kk, red[0][threadIdx.x][HEAD_MAX_OUT] + red[1][threadIdx.x][HEAD_MAX_OUT] +
+                                      red[2][threadIdx.x][HEAD_MAX_OUT] + red[3][threadIdx.x][HEAD_MAX_OUT]);
   }
   if (blockIdx.x == 0 && threadIdx.x < n_out) {      // bias gradients: sum of geff over this block's rows
     float s = 0.0f;
@@ -172,13 +187,28 @@ extern "C" int b2rl_head_fwd(const uint16_t* phi, const float* Wa, const float* 
   return check_launch("b2rl_head_fwd");
 }
 
-extern "C" int b2rl_head_bwd(const float* gq, const uint16_t* phi, const float* Wa, const float* Wv, int32_t B, int32_t K,
-                             int32_t A, uint16_t* gphi, float* gWa, float* gba, float* gWv, float* gbv, void* stream) {
+static int head_bwd_impl(const float* gq, const uint16_t* phi, const float* Wa, const float* Wv, int32_t B, int32_t K,
+                         int32_t A, uint16_t* gphi, float* gWa, float* gba, float* gWv, float* gbv, float* relu_colsum,
+                         void* stream) {
   B2RL_REQUIRE(gq && phi && Wa && gphi && gWa && gba && ((Wv == nullptr) == (gWv == nullptr)) && ((Wv == nullptr) == (gbv == nullptr)),
                "null pointer");
   B2RL_REQUIRE(B > 0 && K > 0 && A > 0 && A < HEAD_MAX_OUT, "need 0 < A < 32");
   dim3 grid((K + 63) / 64, (B + HB_ROWS - 1) / HB_ROWS);
   launch_pdl(head_bwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, gq, reinterpret_cast<const __nv_bfloat16*>(phi), Wa, Wv, B, K, A,
-                                                          reinterpret_cast<__nv_bfloat16*>(gphi), gWa, gba, gWv, gbv);
+                                                          reinterpret_cast<__nv_bfloat16*>(gphi), gWa, gba, gWv, gbv, relu_colsum);
   return check_launch("b2rl_head_bwd");
+}
+
+extern "C" int b2rl_head_bwd(const float* gq, const uint16_t* phi, const float* Wa, const float* Wv, int32_t B, int32_t K,
+                             int32_t A, uint16_t* gphi, float* gWa, float* gba, float* gWv, float* gbv, void* stream) {
+  return head_bwd_impl(gq, phi, Wa, Wv, B, K, A, gphi, gWa, gba, gWv, gbv, nullptr, stream);
+}
+
+// b2rl_head_bwd for features phi = relu(layer(.)): gphi is masked (0 where phi <= 0) and relu_colsum[K] += column sums of the
+// masked gphi (the bias gradient of that layer; zero it first) -- the ReLU backward of the body's last layer in the same pass
+extern "C" int b2rl_head_bwd_relu(const float* gq, const uint16_t* phi, const float* Wa, const float* Wv, int32_t B, int32_t K,
+                                  int32_t A, uint16_t* gphi, float* gWa, float* gba, float* gWv, float* gbv,
+                                  float* relu_colsum, void* stream) {
+  B2RL_REQUIRE(relu_colsum, "null relu_colsum");
+  return head_bwd_impl(gq, phi, Wa, Wv, B, K, A, gphi, gWa, gba, gWv, gbv, relu_colsum, stream);
 }

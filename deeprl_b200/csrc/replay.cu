@@ -11,6 +11,7 @@
 // The gather is the HBM-bound kernel of the path: per sampled transition it reads history+n_step
 // contiguous rows ONCE (valid indices never straddle the ring seam, replay.py:105-110) with one TMA
 // bulk copy into shared memory and writes the two overlapping stacks (state, next_state) from there.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace b2rl {
@@ -355,6 +356,79 @@ __global__ void __launch_bounds__(256) gather_cvt_kernel(const uint8_t* __restri
   }
 }
 
+// Space-to-depth gather with BULK stores (16-bit outputs): the converted stack of a sample is one contiguous range of
+// (H/4)*(W/4)*hl*16 elements, so instead of 16-byte stores from every thread (the L1->L2 store path is what holds the kernel
+// above at 0.60 of the copy peak while the raw uint8 variant, all bulk copies, reaches 0.76) the threads convert a third of
+// the positions at a time into a shared staging tile laid out exactly like the output and ONE thread hands the tile to the
+// copy engine (cp.async.bulk shared -> global); two tiles alternate so that conversion overlaps the previous tile's store.
+// NOT YET VERIFIED ON A GPU (selected with B2RL_GATHER_BULK=1).
+template <typename T>
+__global__ void __launch_bounds__(256) gather_s2d_bulk_kernel(const uint8_t* __restrict__ frames,
+                                                              const int32_t* __restrict__ action,
+                                                              const double* __restrict__ reward,
+                                                              const int32_t* __restrict__ mask, int64_t row_bytes,
+                                                              const int64_t* __restrict__ idx, int hl, int n,
+                                                              double discount, T* __restrict__ state_out,
+                                                              T* __restrict__ next_out, int64_t* a_out, float* r_out,
+                                                              float* m_out, int frame_w, int tile_pos) {
+  static_assert(sizeof(T) == 2, "16-bit outputs: one 16-byte piece = 2 image rows x 4 pixels of one frame");
+  pdl_sync();
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const int b = blockIdx.x;
+  const int64_t i = idx[b];
+  const int64_t span = (int64_t)(hl + n) * row_bytes, stack = (int64_t)hl * row_bytes;
+  const uint32_t span_al = ((uint32_t)span + 127u) & ~127u;
+  const uint32_t tile_bytes = (uint32_t)tile_pos * hl * 16 * sizeof(T);
+  uint8_t* stage0 = smem + span_al;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    mbar_expect_tx(&bar, (uint32_t)span);
+    bulk_g2s(smem, frames + (i - hl + 1) * row_bytes, (uint32_t)span, &bar);
+  }
+  if (threadIdx.x == 32) gather_scalars(action, reward, mask, i, n, discount, a_out, r_out, m_out, b);
+  __syncthreads();
+  mbar_wait(&bar, 0);
+  __syncthreads();
+  const int Wq = frame_w / 4, Hq = (int)(row_bytes / frame_w) / 4;
+  const int positions = Hq * Wq;
+  const int tiles = (positions + tile_pos - 1) / tile_pos;
+  int t_global = 0;
+  for (int which = 0; which < 2; ++which) {
+    T* out = which ? next_out : state_out;
+    if (!out) continue;
+    out += (int64_t)b * stack;
+    const uint8_t* src = smem + (which ? (int64_t)n * row_bytes : 0);
+    for (int t = 0; t < tiles; ++t, ++t_global) {
+      uint8_t* stage = stage0 + (size_t)(t_global & 1) * tile_bytes;
+      // the tile that used this staging buffer two rounds ago must have been read by the copy engine
+      if (t_global >= 2) {
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncthreads();
+      }
+      const int p0 = t * tile_pos, np = min(tile_pos, positions - p0);
+      const int pieces = np * hl * 2;                                   // 16-byte pieces: (position, frame, half)
+      for (int h = threadIdx.x; h < pieces; h += blockDim.x) {
+        const int u = h >> 1, half = h & 1;
+        const int pos = p0 + u / hl, f = u % hl;
+        const int Y = pos / Wq, X = pos - Y * Wq;
+        const uint8_t* base = src + (int64_t)f * row_bytes + (4 * Y + 2 * half) * frame_w + 4 * X;
+        __align__(16) T v[8];
+        cvt_word<T>(*reinterpret_cast<const uint32_t*>(base), nullptr, false, v);
+        cvt_word<T>(*reinterpret_cast<const uint32_t*>(base + frame_w), nullptr, false, v + 4);
+        *reinterpret_cast<int4*>(stage + (size_t)h * 16) = *reinterpret_cast<const int4*>(v);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the copy engine
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        bulk_s2g(out + (int64_t)p0 * hl * 16, stage, (uint32_t)np * hl * 16 * sizeof(T));
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // raw uint8 fallback when rows are not 16-byte multiples (feature vectors)
 __global__ void __launch_bounds__(128) gather_raw_generic_kernel(const uint8_t* __restrict__ frames,
                                                                  const int32_t* __restrict__ action,
@@ -391,10 +465,38 @@ static int launch_cvt1(dim3 grid, size_t smem, cudaStream_t st, const uint8_t* f
 }
 
 template <typename T>
+static int launch_s2d_bulk(dim3 grid, cudaStream_t st, const uint8_t* frames, const int32_t* action, const double* reward,
+                           const int32_t* mask, int64_t row_bytes, const int64_t* idx, int hl, int n, double discount,
+                           void* so, void* no, int64_t* a, float* r, float* m, int frame_w) {
+  const int positions = (frame_w / 4) * ((int)(row_bytes / frame_w) / 4);
+  const int tile_pos = (positions + 2) / 3;
+  const size_t span_al = ((size_t)(hl + n) * row_bytes + 127) & ~(size_t)127;
+  const size_t smem = span_al + 2 * (size_t)tile_pos * hl * 16 * sizeof(T);
+  if (smem > 200 * 1024) return 1;
+  auto k = gather_s2d_bulk_kernel<T>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  launch_ordered(k, dim3(grid), dim3(256), smem, st, frames, action, reward, mask, row_bytes, idx, hl, n, discount, (T*)so,
+                 (T*)no, a, r, m, frame_w, tile_pos);
+  return check_launch("b2rl_replay_gather(s2d bulk)");
+}
+
+template <typename T>
 static int launch_cvt(int layout, dim3 grid, size_t smem, cudaStream_t st, const uint8_t* frames, const int32_t* action,
                       const double* reward, const int32_t* mask, int64_t row_bytes, const int64_t* idx, int hl, int n,
                       double discount, const float* lut, void* so, void* no, int64_t* a, float* r, float* m,
                       int use_tma, int frame_w) {
+  if constexpr (sizeof(T) == 2) {
+    static int bulk = -1;                                            // B2RL_GATHER_BULK=1: bulk-store variant (unverified)
+    if (bulk < 0) {
+      const char* e = getenv("B2RL_GATHER_BULK");
+      bulk = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    if (layout == 2 && bulk && use_tma && lut == nullptr) {
+      int rc = launch_s2d_bulk<T>(grid, st, frames, action, reward, mask, row_bytes, idx, hl, n, discount, so, no, a, r, m,
+                                  frame_w);
+      if (rc <= 0) return rc;
+    }
+  }
   if (layout == 2)
     return launch_cvt1<T, 2>(grid, smem, st, frames, action, reward, mask, row_bytes, idx, hl, n, discount, lut, so, no,
                              a, r, m, use_tma, frame_w);

@@ -169,8 +169,19 @@ class _NarrowHead(torch.autograd.Function):
         else:
             z = lambda p: None if p is None else torch.zeros_like(p, dtype=torch.float32)
             gwa, gba, gwv, gbv = z(wa), z(ba), z(wv), z(bv)
-        _lib.call("b2rl_head_bwd", _lib.ptr(gq), _lib.ptr(phi), _lib.ptr(wa.detach()), _lib.ptr(None if wv is None else wv.detach()),
-                  B, K, A, _lib.ptr(gphi), _lib.ptr(gwa), _lib.ptr(gba), _lib.ptr(gwv), _lib.ptr(gbv), _lib.stream())
+        from . import nature_tc
+        if nature_tc.FUSED_BWD and phi.data_ptr() in nature_tc.RELU_FEATURES:
+            # phi = relu(fc4(.)) of a tcgen05 NatureConvBody: its ReLU backward and bias gradient ride along (the body's
+            # backward finds the column sums under the gradient's address and skips its own pass)
+            colsum = torch.zeros(K, dtype=torch.float32, device=phi.device)
+            _lib.call("b2rl_head_bwd_relu", _lib.ptr(gq), _lib.ptr(phi), _lib.ptr(wa.detach()),
+                      _lib.ptr(None if wv is None else wv.detach()), B, K, A, _lib.ptr(gphi), _lib.ptr(gwa), _lib.ptr(gba),
+                      _lib.ptr(gwv), _lib.ptr(gbv), _lib.ptr(colsum), _lib.stream())
+            nature_tc.PREMASKED[gphi.data_ptr()] = colsum
+        else:
+            _lib.call("b2rl_head_bwd", _lib.ptr(gq), _lib.ptr(phi), _lib.ptr(wa.detach()),
+                      _lib.ptr(None if wv is None else wv.detach()), B, K, A, _lib.ptr(gphi), _lib.ptr(gwa), _lib.ptr(gba),
+                      _lib.ptr(gwv), _lib.ptr(gbv), _lib.stream())
         if inplace:
             return gphi, None, None, None, None
         return gphi, gwa, gba, gwv, gbv

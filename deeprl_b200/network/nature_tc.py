@@ -30,6 +30,55 @@ _f32 = torch.float32
 # fc4 forward at small batch: split-K factor (zero fill + split-K GEMM with fp32 atomics + bias/ReLU pass, 3 launches) or 1 =
 # one GEMM launch with the fused bias/ReLU epilogue (measured per network at B = 512: 10.1 us vs 10.0 us in isolation)
 FC4_SPLITS = int(os.environ.get("B2RL_FC4_SPLITS", "4"))
+# backward: ReLU mask + bias gradient + re-layout fused into the dgrad GEMM epilogues (b2rl_*_bwd_bf16) instead of three
+# b2rl_act_bwd_bias_grad_bf16 passes.  NOT YET VERIFIED ON A GPU (written after the round's GPU budget was spent): off.
+FUSED_BWD = os.environ.get("B2RL_FUSED_BWD", "0") == "1"
+_ZEROED = {}
+RELU_FEATURES = set()      # data_ptr of feature tensors y4 = relu(fc4(.)) produced by nature_body (for head_bwd_relu)
+PREMASKED = {}             # data_ptr of a feature gradient already masked by head_bwd_relu -> its column sums (= db4)
+
+
+def _zero_grid(key, shape, device):
+    """Persistent zero-initialised destination of a scatter epilogue: the tiles overwrite exactly the same rows every time
+    and never touch the padding rows, so the buffer is zeroed once."""
+    k = (key, tuple(shape), str(device))
+    if k not in _ZEROED:
+        _ZEROED[k] = torch.zeros(shape, dtype=_bf16, device=device)
+    return _ZEROED[k]
+
+
+def _backward_fused(ctx, gy4):
+    x0m, x1, y2, y3, y4, w2d, w3d, w4p = ctx.saved_tensors
+    B, dev = y4.shape[0], y4.device
+    db4 = PREMASKED.pop(gy4.data_ptr(), None) if gy4.dtype == _bf16 and gy4.is_contiguous() else None
+    if db4 is not None:
+        g4 = gy4                                                                        # masked + summed by b2rl_head_bwd_relu
+    else:
+        g4, db4 = act_bwd_bias_grad(gy4, y4, True)                                      # fc4's own ReLU / bias gradient
+    y3c = y3.view(B, 3136)
+    gw4p = gemm_bf16(g4, y3c, a_major="mn", b_major="mn", out_dtype=_f32, block_n=128, stream=_fork())
+    db = torch.zeros(32 + 64 + 64, dtype=_f32, device=dev)
+    db1, db2, db3 = db[:32], db[32:96], db[96:160]
+    # fc4 dgrad -> conv3's output grid (10 x 10 per image), masked by relu(conv3) and summed into db3
+    g3 = _zero_grid("g3", (B * 100, 64), dev)
+    e3 = _lib.bwd_epilogue(y3c, db3, 64, 64)
+    _lib.call("b2rl_gemm_bwd_bf16", _lib.ptr(g4), g4.stride(0), _lib.ptr(w4p), 1, w4p.stride(0), _lib.ptr(g3), 64, B, 3136,
+              g4.shape[1], 4, 10, 7, ctypes.byref(e3), 128, _lib.stream())
+    gw3p, p3 = wgrad_partials(y2, g3, 64, 9, 3, 10, stream=_fork())
+    # conv3 dgrad on the 10-grid, masked by relu(conv2)
+    g2 = torch.empty((B * 100, 64), dtype=_bf16, device=dev)
+    e2 = _lib.bwd_epilogue(y2, db2, 64, 0)
+    _lib.call("b2rl_conv_gemm_bwd_bf16", _lib.ptr(g3), B * 100, 64, _lib.ptr(w3d), 64, 9, 3, 10, _lib.ptr(g2), 64, 0, 0, 0,
+              ctypes.byref(e2), 64, _lib.stream())
+    gw2p, p2 = wgrad_partials(x1, g2, 64, 4, 2, 10, stream=_fork())
+    # conv2 dgrad: space-to-depth(2) rows -> conv1's 21-grid, masked by relu(conv1)
+    g1 = _zero_grid("g1", (B * 441, 32), dev)
+    e1 = _lib.bwd_epilogue(x1, db1, 32, 32)
+    _lib.call("b2rl_conv_gemm_bwd_bf16", _lib.ptr(g2), B * 100, 64, _lib.ptr(w2d), 128, 4, 2, 10, _lib.ptr(g1), 32, 3, 21, 20,
+              ctypes.byref(e1), 128, _lib.stream())
+    gw1p, p1 = wgrad_partials(x0m, g1, 32, 4, 2, 21, stream=_fork())
+    _join()
+    return (gw1p, p1, gw2p, p2, gw3p, p3, gw4p), (db1, db2, db3, db4)
 
 
 _WGRAD = {"stream": None}
@@ -183,6 +232,32 @@ def forward_dual(x0, packed, biases, x0_b, packed_b, biases_b):
     return y4, (x0m, x1, y2, y3), z4
 
 
+def _backward_unfused(ctx, gy4):
+    x0m, x1, y2, y3, y4, w2d, w3d, w4p = ctx.saved_tensors
+    B = y4.shape[0]
+    dev = y4.device
+    # ---- fc4
+    g4, db4 = act_bwd_bias_grad(gy4, y4, True)                                        # [B, 512]
+    y3c = y3.view(B, 3136)
+    gw4p = gemm_bf16(g4, y3c, a_major="mn", b_major="mn", out_dtype=_f32, block_n=128, stream=_fork())  # [512, 3136]
+    gy3c = gemm_bf16(g4, w4p, a_major="k", b_major="mn", block_n=128)                  # [B, 3136] bf16
+    # ---- conv3: mask + bias grad, re-laid out from the compact 7x7 rows to the 10-grid
+    g3, db3 = act_bwd_bias_grad(gy3c.view(B * 49, 64), y3, True, row_map=1, G=10, V=7, out_rows=B * 100)
+    gw3p, p3 = wgrad_partials(y2, g3, 64, 9, 3, 10, stream=_fork())
+    gy2 = torch.empty((B * 100, 64), dtype=_bf16, device=dev)
+    conv_gemm(0, g3, w3d, 64, 9, 3, 10, -1, gy2, block_n=64)
+    # ---- conv2
+    g2, db2 = act_bwd_bias_grad(gy2, y2, True)                                        # rows 9 / cols 9 of gy2 are exact zeros
+    gw2p, p2 = wgrad_partials(x1, g2, 64, 4, 2, 10, stream=_fork())
+    gy1 = torch.empty((B * 100, 128), dtype=_bf16, device=dev)
+    conv_gemm(0, g2, w2d, 128, 4, 2, 10, -1, gy1, block_n=128)
+    # ---- conv1: mask + bias grad, re-laid out from space-to-depth(2) rows to the 21-grid of conv1's output positions
+    g1, db1 = act_bwd_bias_grad(gy1, x1, True, row_map=2, G=21, V=20, out_rows=B * 441)
+    gw1p, p1 = wgrad_partials(x0m, g1, 32, 4, 2, 21, stream=_fork())
+    _join()
+    return (gw1p, p1, gw2p, p2, gw3p, p3, gw4p), (db1, db2, db3, db4)
+
+
 class _NatureBody(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x0, w1, b1, w2, b2, w3, b3, w4, b4, scale, packed, companion=None):
@@ -201,28 +276,10 @@ class _NatureBody(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy4):
-        x0m, x1, y2, y3, y4, w2d, w3d, w4p = ctx.saved_tensors
-        B = y4.shape[0]
-        dev = y4.device
-        # ---- fc4
-        g4, db4 = act_bwd_bias_grad(gy4, y4, True)                                        # [B, 512]
-        y3c = y3.view(B, 3136)
-        gw4p = gemm_bf16(g4, y3c, a_major="mn", b_major="mn", out_dtype=_f32, block_n=128, stream=_fork())  # [512, 3136]
-        gy3c = gemm_bf16(g4, w4p, a_major="k", b_major="mn", block_n=128)                  # [B, 3136] bf16
-        # ---- conv3: mask + bias grad, re-laid out from the compact 7x7 rows to the 10-grid
-        g3, db3 = act_bwd_bias_grad(gy3c.view(B * 49, 64), y3, True, row_map=1, G=10, V=7, out_rows=B * 100)
-        gw3p, p3 = wgrad_partials(y2, g3, 64, 9, 3, 10, stream=_fork())
-        gy2 = torch.empty((B * 100, 64), dtype=_bf16, device=dev)
-        conv_gemm(0, g3, w3d, 64, 9, 3, 10, -1, gy2, block_n=64)
-        # ---- conv2
-        g2, db2 = act_bwd_bias_grad(gy2, y2, True)                                        # rows 9 / cols 9 of gy2 are exact zeros
-        gw2p, p2 = wgrad_partials(x1, g2, 64, 4, 2, 10, stream=_fork())
-        gy1 = torch.empty((B * 100, 128), dtype=_bf16, device=dev)
-        conv_gemm(0, g2, w2d, 128, 4, 2, 10, -1, gy1, block_n=128)
-        # ---- conv1: mask + bias grad, re-laid out from space-to-depth(2) rows to the 21-grid of conv1's output positions
-        g1, db1 = act_bwd_bias_grad(gy1, x1, True, row_map=2, G=21, V=20, out_rows=B * 441)
-        gw1p, p1 = wgrad_partials(x0m, g1, 32, 4, 2, 21, stream=_fork())
-        _join()
+        if FUSED_BWD and _lib.CONV_SLAB:
+            (gw1p, p1, gw2p, p2, gw3p, p3, gw4p), (db1, db2, db3, db4) = _backward_fused(ctx, gy4)
+        else:
+            (gw1p, p1, gw2p, p2, gw3p, p3, gw4p), (db1, db2, db3, db4) = _backward_unfused(ctx, gy4)
         params = ctx.params
         if all(p.grad is not None and p.grad.dtype == _f32 and p.grad.is_contiguous() for p in params):
             # accumulate straight into the .grad arena (reference layouts), one launch
@@ -283,8 +340,13 @@ def nature_body(body, x0, scale):
                 pb = repack(o, scale)
             if xb.shape == x0.shape and pb.n4 == pk.n4:
                 companion = (xb, pb, tuple(m.bias.detach() for m in (o.conv1, o.conv2, o.conv3, o.fc4)), d.features)
-    return _NatureBody.apply(x0, c1.weight, c1.bias, c2.weight, c2.bias, c3.weight, c3.bias, f4.weight, f4.bias,
-                             float(scale), pk, companion)
+    y4 = _NatureBody.apply(x0, c1.weight, c1.bias, c2.weight, c2.bias, c3.weight, c3.bias, f4.weight, f4.bias,
+                           float(scale), pk, companion)
+    if FUSED_BWD:
+        if len(RELU_FEATURES) > 256:
+            RELU_FEATURES.clear()
+        RELU_FEATURES.add(y4.data_ptr())
+    return y4
 
 
 def repack(body, scale):

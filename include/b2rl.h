@@ -246,6 +246,27 @@ int b2rl_gemm_dual_bf16(const uint16_t* A, const uint16_t* A2, int64_t lda, cons
                         int64_t ldb, void* D, void* D2, int64_t ldd, int32_t M, int32_t N, int32_t K, const float* bias,
                         const float* bias2, int32_t relu, int32_t out_mode, int32_t block_n, void* stream);
 
+/* Backward GEMMs with the element-wise backward pass fused into the epilogue (replaces b2rl_act_bwd_bias_grad_bf16 between the
+ * dgrad GEMMs of NatureConvBody).  mask: the saved forward activation (bf16) in the GEMM's own output coordinates,
+ * [M][mask_ld] -- the ReLU gradient D = mask > 0 ? D : 0; dbias: fp32 [dbias_mod], receives (atomically, zero it first) the
+ * column sums of the masked output, index = column % dbias_mod = the bias gradient of the layer below; sub_c: channels per
+ * position for the scatter maps.  out_map 3: rows are space-to-depth(2) positions of a (V/2)^2 grid with 4 x sub_c columns ->
+ * rows of the G x G grid; out_map 4: rows are images with V*V x sub_c columns -> rows of the G x G grid.  Grid rows that no
+ * tile covers are left untouched (keep the destination zeroed). */
+typedef struct {
+  const uint16_t* mask;
+  int64_t mask_ld;
+  float* dbias;
+  int32_t dbias_mod;
+  int32_t sub_c;
+} b2rl_bwd_epilogue;
+int b2rl_conv_gemm_bwd_bf16(const uint16_t* G_rows, int64_t rows, int32_t C, const uint16_t* W, int32_t n_out, int32_t taps,
+                            int32_t taps_x, int32_t grid_w, void* D, int64_t ldd, int32_t out_map, int32_t G, int32_t V,
+                            const b2rl_bwd_epilogue* ext, int32_t block_n, void* stream);
+int b2rl_gemm_bwd_bf16(const uint16_t* A, int64_t lda, const uint16_t* B, int32_t b_mn, int64_t ldb, void* D, int64_t ldd,
+                       int32_t M, int32_t N, int32_t K, int32_t out_map, int32_t G, int32_t V,
+                       const b2rl_bwd_epilogue* ext, int32_t block_n, void* stream);
+
 /* NatureConvBody weights (network_bodies.py:13-20) between the reference's parameter layouts and the tap-major bf16
  * operands of the grid-GEMM stack: w1 [32,c1,8,8] -> w1f [32][4 taps][16*c1] (times `scale` = ImageNormalizer's 1/255);
  * w2 [64,32,4,4] -> w2f [64][4][128], w2d [128][4][64]; w3 [64,64,3,3] -> w3f [64][9][64], w3d [64][9][64];
@@ -268,6 +289,10 @@ int b2rl_head_fwd(const uint16_t* phi, const float* Wa, const float* ba, const f
                   int32_t K, int32_t A, float* q, void* stream);
 int b2rl_head_bwd(const float* gq, const uint16_t* phi, const float* Wa, const float* Wv, int32_t B, int32_t K, int32_t A,
                   uint16_t* gphi, float* gWa, float* gba, float* gWv, float* gbv, void* stream);
+/* b2rl_head_bwd when phi = relu(layer(.)) (NatureConvBody's fc4 output): gphi is masked (0 where phi <= 0) and
+ * relu_colsum[K] (fp32, zero it first) receives the column sums of the masked gphi = that layer's bias gradient. */
+int b2rl_head_bwd_relu(const float* gq, const uint16_t* phi, const float* Wa, const float* Wv, int32_t B, int32_t K, int32_t A,
+                       uint16_t* gphi, float* gWa, float* gba, float* gWv, float* gbv, float* relu_colsum, void* stream);
 
 /* Convolution weight gradient as split-K partials (no atomics): partial i of *n_partials_host (<= 148, written on the
  * HOST, deterministic for given shapes) is stored at partials + i * n_out*taps*C floats. */

@@ -214,3 +214,67 @@ def test_graphed_ppo_minibatches_match_the_eager_loop(env):
         a.close(), b.close()
     finally:
         rl.Config.COMPUTE_DTYPE = torch.bfloat16
+
+
+def test_fused_backward_epilogues_match_the_separate_passes(env):
+    """B2RL_FUSED_BWD: ReLU mask + bias gradient + grid scatter inside the dgrad GEMM epilogues against the three
+    b2rl_act_bwd_bias_grad_bf16 passes.  The masked gradients are the same bf16 values (masking commutes with rounding);
+    the bias gradients sum fp32 accumulators instead of bf16-rounded values."""
+    bench, rl = env
+    from deeprl_b200.network import nature_tc
+    from deeprl_b200.network.fused import frame_scale
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(5)
+    net = rl.VanillaNet(4, rl.NatureConvBody(in_channels=4))
+    s = torch.randint(0, 256, (96, 64, 21, 21), device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    grads = {}
+    for fused in (False, True):
+        nature_tc.FUSED_BWD = fused
+        try:
+            net.zero_grad()
+            with frame_scale(1.0 / 255):
+                q = net(s)["q"]
+                (q * torch.linspace(-1, 1, q.numel(), device=dev).view_as(q)).sum().backward()
+            torch.cuda.synchronize()
+            grads[fused] = {n: p.grad.detach().clone() for n, p in net.named_parameters()}
+        finally:
+            nature_tc.FUSED_BWD = False
+    for n, ref in grads[False].items():
+        got = grads[True][n]
+        scale = float(ref.abs().max()) + 1e-12
+        assert float((got - ref).abs().max()) <= 2e-2 * scale, n
+
+
+@pytest.mark.parametrize("replay_cls_name", ["UniformReplay", "PrioritizedReplay"])
+def test_dqn_agent_with_cuda_graph_option(env, replay_cls_name):
+    """config.cuda_graph: DQNAgent.step() drives GraphedDQNLearner (one graph replay per update) through the reference's
+    own agent API: transitions are fed by the agent, the update runs as a graph, the target is synchronised on schedule."""
+    bench, rl = env
+    c = rl.Config()
+    c.merge(dict(tag=None))
+    c.task_fn = lambda: rl.Task("SyntheticAtari-v0", seed=2)
+    c.eval_env = rl.Task("SyntheticAtari-v0", seed=2)
+    c.optimizer_fn = lambda p: torch.optim.RMSprop(p, lr=0.00025, alpha=0.95, eps=0.01, centered=True)
+    c.network_fn = lambda: rl.VanillaNet(c.action_dim, rl.NatureConvBody(in_channels=4))
+    c.random_action_prob = rl.LinearSchedule(1.0, 0.01, 1e6)
+    c.batch_size = 32
+    replay_cls = getattr(rl, replay_cls_name)
+    c.replay_fn = lambda: rl.ReplayWrapper(replay_cls, dict(memory_size=2000, batch_size=32, n_step=1, discount=0.99,
+                                                            history_length=4), async_=False)
+    c.replay_eps, c.replay_alpha, c.replay_beta = 0.01, 0.5, rl.LinearSchedule(0.4, 1.0, 1e5)
+    c.state_normalizer, c.reward_normalizer = rl.ImageNormalizer(), rl.SignNormalizer()
+    c.discount, c.history_length, c.double_q, c.n_step = 0.99, 4, False, 1
+    c.target_network_update_freq, c.exploration_steps, c.sgd_update_frequency, c.gradient_clip = 20, 200, 4, 5
+    c.async_actor = False
+    c.cuda_graph = True
+    ag = rl.DQNAgent(c)
+    before = None
+    for i in range(120):
+        ag.step()
+        if ag.total_steps == 204:
+            before = ag._flat.flat.clone()
+    torch.cuda.synchronize()
+    assert getattr(ag, "_learner", None) is not None and ag._learner.updates > 50
+    assert torch.isfinite(ag.last_loss).all()
+    assert not torch.equal(before, ag._flat.flat)
+    ag.close()
