@@ -169,6 +169,11 @@ struct GemmParams {
   int64_t mask_ld;
   float* dbias;
   int dbias_mod, sub_c;
+  // out_mode 3: split-K with an in-kernel fix-up -- every split stores its fp32 partial tile to ws[split][row][col], the split
+  // that arrives last at counters[tile] adds the partials in split order (deterministic), applies bias / ReLU and stores bf16
+  float* ws;
+  int ws_rows, ws_ld;
+  int* counters;
 };
 
 __device__ __forceinline__ int tap_shift(const GemmParams& p, int tap) {
@@ -373,6 +378,87 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
   if (tr) B2RL_TRACE_AT(2, trace_it, 3);
 }
 
+// Epilogue of one tile of a split-K GEMM with in-kernel fix-up (out_mode 3; fc4 forward at batch 512: 32 output tiles cannot
+// fill 148 SMs, and the 196 dependent MMAs of one un-split tile take ~5 us at the 53-cycle issue floor).  Replaces
+// zero-fill + atomic split-K + bias/ReLU pass (three launches) by one launch.  One warp group (128 threads) per tile.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_fixup(const GemmParams& p, int tile, int m0, int n0, int q, int lane,
+                                                    uint32_t tmem_base, uint32_t as, uint32_t parity, bool has_acc,
+                                                    uint64_t* tmem_full, uint64_t* tmem_empty, int* s_flag, int grp) {
+  const int row = m0 + q * 32 + lane;
+  const int splits = (int)gridDim.z;
+  if (has_acc) {
+    mb_wait(&tmem_full[as], parity);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  float* wrow = p.ws + ((int64_t)blockIdx.z * p.ws_rows + row) * p.ws_ld + n0;
+#pragma unroll
+  for (int c = 0; c < BN; c += 32) {
+    uint32_t r[32];
+    if (has_acc) {
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c, r);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = 0;
+    }
+    if (c + 32 >= BN && has_acc) {
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (lane == 0) mb_arrive(&tmem_empty[as]);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      __stcg(reinterpret_cast<float4*>(wrow + c + j), make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                  __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+  }
+  __threadfence();
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+  if (q == 0 && lane == 0) s_flag[grp] = atomicAdd(p.counters + tile, 1) == splits - 1;
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+  if (!s_flag[grp]) return;
+  __threadfence();
+  if (q == 0 && lane == 0) p.counters[tile] = 0;                          // re-armed for the next launch
+  const bool valid = row < p.M;
+#pragma unroll
+  for (int c = 0; c < BN; c += 32) {
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.0f;
+    for (int sp = 0; sp < splits; ++sp) {
+      const float4* src = reinterpret_cast<const float4*>(p.ws + ((int64_t)sp * p.ws_rows + row) * p.ws_ld + n0 + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 v = __ldcg(src + j);
+        acc[4 * j] += v.x; acc[4 * j + 1] += v.y; acc[4 * j + 2] += v.z; acc[4 * j + 3] += v.w;
+      }
+    }
+    if (valid && n0 + c < p.N) {
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + c + j < p.N) acc[j] += __ldg(p.bias + n0 + c + j);
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.0f);
+      }
+      __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + (int64_t)row * p.ldd + n0 + c;
+      if (n0 + c + 32 <= p.N && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          int4 v;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(acc[j + 2 * t], acc[j + 2 * t + 1]);
+          *reinterpret_cast<int4*>(d + j) = v;
+        }
+      } else {
+        for (int j = 0; j < 32; ++j)
+          if (n0 + c + j < p.N) d[j] = __float2bfloat16_rn(acc[j]);
+      }
+    }
+  }
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                        const __grid_constant__ CUtensorMap tmB,
@@ -408,6 +494,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   const int n_kt = max(kt_end - kt_begin, 0);
 
   __shared__ float s_dbias[128];                    // per-CTA bias-gradient accumulator (backward extras)
+  __shared__ int s_fix[2];                          // out_mode 3: "this CTA arrived last" per epilogue warp group
   if (threadIdx.x < 128) s_dbias[threadIdx.x] = 0.0f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mb_init(&full[s], 1); mb_init(&empty[s], 1); }
@@ -505,7 +592,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       if ((tcount & 1) != grp) continue;
       const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
       const int m0 = mt * GEMM_BM, n0 = nt * BN;
-      epilogue_tile<BN, ACC>(p, m0, n0, q, lane, tmem_base, tcount & 1, (tcount >> 1) & 1, n_kt > 0, tmem_full, tmem_empty, s_dbias);
+      if (p.out_mode == 3)
+        epilogue_tile_fixup<BN>(p, tile, m0, n0, q, lane, tmem_base, tcount & 1, (tcount >> 1) & 1, n_kt > 0, tmem_full, tmem_empty,
+                                s_fix, (int)grp);
+      else
+        epilogue_tile<BN, ACC>(p, m0, n0, q, lane, tmem_base, tcount & 1, (tcount >> 1) & 1, n_kt > 0, tmem_full, tmem_empty, s_dbias);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1220,4 +1311,27 @@ extern "C" int b2rl_conv_wgrad_partials(const uint16_t* X, int64_t rows, int32_t
   g_wgrad_partials = 0;
   *n_partials_host = g_partial_count;
   return rc;
+}
+
+// D = act(A B^T + bias) in bf16 with split-K over `splits` CTAs per output tile and an in-kernel fix-up (out_mode 3): ONE
+// launch instead of zero-fill + atomic split-K + bias/activation pass.  A [M][K], B [N][K] K-major bf16.  ws: fp32
+// [splits][ceil(M/128)*128][ceil(N/block_n)*block_n] scratch; counters: int32 [tiles], zero-initialised once (the kernel
+// re-arms them).  Launches on different streams must not share ws / counters.  fc4 of NatureConvBody (network_bodies.py:33).
+extern "C" int b2rl_gemm_splitk_bf16(const uint16_t* A, int64_t lda, const uint16_t* B, int64_t ldb, void* D, int64_t ldd,
+                                     int32_t M, int32_t N, int32_t K, const float* bias, int32_t relu, int32_t splits,
+                                     int32_t block_n, float* ws, int32_t* counters, void* stream) {
+  B2RL_REQUIRE(A && B && D && ws && counters, "null pointer");
+  B2RL_REQUIRE(M > 0 && N > 0 && K > 0 && splits >= 1, "bad shape");
+  B2RL_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "operand row strides must be multiples of 8 elements (16 bytes)");
+  B2RL_REQUIRE((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(ws)) % 16 == 0,
+               "operands and scratch must be 16-byte aligned");
+  B2RL_REQUIRE(block_n == 32 || block_n == 64 || block_n == 128, "block_n must be 32, 64 or 128");
+  GemmParams p = {};
+  p.M = M; p.N = N; p.K = K; p.ldd = (int)ldd;
+  p.relu = relu; p.out_mode = 3; p.bias = bias; p.D = D;
+  p.taps_x = 1; p.shift_sign = 1;
+  p.ws = ws; p.counters = counters;
+  p.ws_rows = (M + GEMM_BM - 1) / GEMM_BM * GEMM_BM;
+  p.ws_ld = (N + block_n - 1) / block_n * block_n;
+  return gemm_dispatch(A, 0, lda, M, K, B, 0, ldb, N, K, p, splits, block_n, (cudaStream_t)stream);
 }

@@ -13,17 +13,15 @@ constexpr int HEAD_MAX_OUT = 32;       // A (+1 for the dueling value row)
 
 // one warp per batch row; the row of phi is read once (16-byte loads, 8 features per lane per 256-feature chunk) and
 // every output accumulates against it, so all weight loads of a chunk are independent and in flight together
+// dot products of one bf16 feature row against every output row of a head (A advantage / action rows + the dueling value
+// row): the row of phi is read once (16-byte loads, 8 features per lane per 256-feature chunk) and every output
+// accumulates against it, so all weight loads of a chunk are independent and in flight together.  On return every lane
+// holds, for n < n_out, the full dot product plus bias in acc[n].
 template <int NB>
-__global__ void __launch_bounds__(128) head_fwd_kernel(const __nv_bfloat16* __restrict__ phi, const float* __restrict__ Wa,
-                                                       const float* __restrict__ ba, const float* __restrict__ Wv,
-                                                       const float* __restrict__ bv, int B, int K, int A,
-                                                       float* __restrict__ q) {
-  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
-  const int lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b >= B) return;
-  const __nv_bfloat16* x = phi + (int64_t)b * K;
+__device__ __forceinline__ void head_row_dots(const __nv_bfloat16* __restrict__ x, const float* __restrict__ Wa,
+                                              const float* __restrict__ ba, const float* __restrict__ Wv,
+                                              const float* __restrict__ bv, int K, int A, int lane, float (&acc)[NB]) {
   const int n_out = A + (Wv ? 1 : 0);
-  float acc[NB];
 #pragma unroll
   for (int n = 0; n < NB; ++n) acc[n] = 0.0f;
   for (int k0 = lane * 8; k0 < K; k0 += 256) {
@@ -54,59 +52,71 @@ __global__ void __launch_bounds__(128) head_fwd_kernel(const __nv_bfloat16* __re
       acc[n] = s + ((n < A) ? ba[n] : bv[0]);
     }
   }
+}
+
+// q values of one row from the dot products: plain head q = acc, dueling q = value + (adv - mean(adv)) (network_heads.py:34-36)
+template <int NB>
+__device__ __forceinline__ void head_combine(float (&acc)[NB], int A, bool dueling) {
+  if (!dueling) return;
+  float mean = 0.0f, value = 0.0f;
+#pragma unroll
+  for (int n = 0; n < NB; ++n) {
+    if (n < A) mean += acc[n];
+    if (n == A) value = acc[n];
+  }
+  mean /= (float)A;
+#pragma unroll
+  for (int n = 0; n < NB; ++n)
+    if (n < A) acc[n] = value + (acc[n] - mean);
+}
+
+// one warp per batch row
+template <int NB>
+__global__ void __launch_bounds__(128) head_fwd_kernel(const __nv_bfloat16* __restrict__ phi, const float* __restrict__ Wa,
+                                                       const float* __restrict__ ba, const float* __restrict__ Wv,
+                                                       const float* __restrict__ bv, int B, int K, int A,
+                                                       float* __restrict__ q) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
+  const int lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float acc[NB];
+  head_row_dots<NB>(phi + (int64_t)b * K, Wa, ba, Wv, bv, K, A, lane, acc);
+  head_combine<NB>(acc, A, Wv != nullptr);
   if (lane == 0) {
-    if (Wv) {                                     // network_heads.py:34-36: q = value + (adv - adv.mean(1))
-      float mean = 0.0f, value = 0.0f;
 #pragma unroll
-      for (int n = 0; n < NB; ++n) {
-        if (n < A) mean += acc[n];
-        if (n == A) value = acc[n];
-      }
-      mean /= (float)A;
-#pragma unroll
-      for (int n = 0; n < NB; ++n)
-        if (n < A) q[(int64_t)b * A + n] = value + (acc[n] - mean);
-    } else {
-#pragma unroll
-      for (int n = 0; n < NB; ++n)
-        if (n < A) q[(int64_t)b * A + n] = acc[n];
-    }
+    for (int n = 0; n < NB; ++n)
+      if (n < A) q[(int64_t)b * A + n] = acc[n];
   }
 }
 
 // grid (K/64, ceil(B/HB_ROWS)); block 256 = 64 columns x 4 row groups of HB_ROWS/4 rows (many small CTAs: the kernel is
 // latency-bound, 16 rows per CTA puts 256 CTAs in flight at B = 512)
 constexpr int HB_ROWS = 16;
-__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ gq, const __nv_bfloat16* __restrict__ phi,
-                                                       const float* __restrict__ Wa, const float* __restrict__ Wv, int B,
-                                                       int K, int A, __nv_bfloat16* __restrict__ gphi,
-                                                       float* __restrict__ gWa, float* __restrict__ gba,
-                                                       float* __restrict__ gWv, float* __restrict__ gbv,
-                                                       float* __restrict__ relu_colsum) {
-  // relu_colsum != NULL: phi is the output of a ReLU layer (NatureConvBody's fc4): the gradient is masked here (gphi = 0 where
-  // phi <= 0) and its column sums -- that layer's bias gradient -- are accumulated into relu_colsum[K] (zeroed by the caller),
-  // which replaces the separate mask / bias-gradient pass over gphi.
-  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
-  __shared__ float geff[HB_ROWS][HEAD_MAX_OUT + 1];       // [row][a], last used column = value gradient (dueling)
-  __shared__ float red[4][64][HEAD_MAX_OUT + 1];
+
+struct HeadBwdShared {
+  float geff[HB_ROWS][HEAD_MAX_OUT + 1];       // [row][a], last used column = value gradient (dueling)
+  float red[4][64][HEAD_MAX_OUT + 1];
+};
+
+// effective output gradients of one row: dq mapped through the dueling combine (identity for a plain head)
+__device__ __forceinline__ float head_geff(const float* gr, int n, int A, bool dueling) {
+  if (!dueling) return gr[n];
+  float sum = 0.0f;
+  for (int a = 0; a < A; ++a) sum += gr[a];
+  return (n < A) ? gr[n] - sum / (float)A : sum;      // d/d adv_n and d/d value of q = v + adv - mean(adv)
+}
+
+// with sh.geff filled for the HB_ROWS rows of this CTA: dphi = geff W (masked by phi > 0 when relu_colsum is given), dW += geff^T
+// phi, db += sum geff, relu_colsum += column sums of the masked dphi.  grid (K/64, ceil(B/HB_ROWS)), 256 threads = 64 columns x
+// 4 row groups.
+__device__ __forceinline__ void head_bwd_body(HeadBwdShared& sh, const __nv_bfloat16* __restrict__ phi,
+                                              const float* __restrict__ Wa, const float* __restrict__ Wv, int B, int K, int A,
+                                              __nv_bfloat16* __restrict__ gphi, float* __restrict__ gWa,
+                                              float* __restrict__ gba, float* __restrict__ gWv, float* __restrict__ gbv,
+                                              float* __restrict__ relu_colsum) {
   const int k = blockIdx.x * 64 + (threadIdx.x & 63), rg = threadIdx.x >> 6;
   const int r0 = blockIdx.y * HB_ROWS;
   const int n_out = A + (Wv ? 1 : 0);
-  for (int e = threadIdx.x; e < HB_ROWS * n_out; e += blockDim.x) {
-    const int r = e / n_out, n = e - r * n_out;
-    float g = 0.0f;
-    if (r0 + r < B) {
-      const float* gr = gq + (int64_t)(r0 + r) * A;
-      if (!Wv) g = gr[n];
-      else {
-        float sum = 0.0f;
-        for (int a = 0; a < A; ++a) sum += gr[a];
-        g = (n < A) ? gr[n] - sum / (float)A : sum;   // d/d adv_n and d/d value of q = v + adv - mean(adv)
-      }
-    }
-    geff[r][n] = g;
-  }
-  __syncthreads();
   float w[HEAD_MAX_OUT + 1], acc[HEAD_MAX_OUT + 1];
 #pragma unroll
   for (int n = 0; n < HEAD_MAX_OUT + 1; ++n) {
@@ -130,7 +140,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
 #pragma unroll
       for (int n = 0; n < HEAD_MAX_OUT + 1; ++n) {
         if (n < n_out) {
-          const float ge = geff[r][n];
+          const float ge = sh.geff[r][n];
           g = fmaf(ge, w[n], g);
           acc[n] = fmaf(ge, x, acc[n]);
         }
@@ -141,30 +151,187 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       gphi[(int64_t)(r0 + r) * K + k] = gb;
     }
   }
-  red[rg][threadIdx.x & 63][HEAD_MAX_OUT] = colsum;     // slot HEAD_MAX_OUT is free: n_out <= HEAD_MAX_OUT
+  sh.red[rg][threadIdx.x & 63][HEAD_MAX_OUT] = colsum;     // slot HEAD_MAX_OUT is free: n_out <= HEAD_MAX_OUT
 #pragma unroll
   for (int n = 0; n < HEAD_MAX_OUT + 1; ++n)
-    if (n < n_out) red[rg][threadIdx.x & 63][n] = acc[n];
+    if (n < n_out) sh.red[rg][threadIdx.x & 63][n] = acc[n];
   __syncthreads();
   for (int e = threadIdx.x; e < 64 * n_out; e += blockDim.x) {
     const int c = e % 64, n = e / 64;
     const int kk = blockIdx.x * 64 + c;
     if (kk < K) {
-      const float s = red[0][c][n] + red[1][c][n] + red[2][c][n] + red[3][c][n];
+      const float s = sh.red[0][c][n] + sh.red[1][c][n] + sh.red[2][c][n] + sh.red[3][c][n];
       atomicAdd((n < A) ? gWa + (int64_t)n * K + kk : gWv + kk, s);
     }
   }
   if (relu_colsum && threadIdx.x < 64) {
     const int kk = blockIdx.x * 64 + threadIdx.x;
     if (kk < K)
-      atomicAdd(relu_colsum + kk, red[0][threadIdx.x][HEAD_MAX_OUT] + red[1][threadIdx.x][HEAD_MAX_OUT] +
-                                      red[2][threadIdx.x][HEAD_MAX_OUT] + red[3][threadIdx.x][HEAD_MAX_OUT]);
+      atomicAdd(relu_colsum + kk, sh.red[0][threadIdx.x][HEAD_MAX_OUT] + sh.red[1][threadIdx.x][HEAD_MAX_OUT] +
+                                      sh.red[2][threadIdx.x][HEAD_MAX_OUT] + sh.red[3][threadIdx.x][HEAD_MAX_OUT]);
   }
   if (blockIdx.x == 0 && threadIdx.x < n_out) {      // bias gradients: sum of geff over this block's rows
     float s = 0.0f;
-    for (int r = 0; r < HB_ROWS; ++r) s += geff[r][threadIdx.x];
+    for (int r = 0; r < HB_ROWS; ++r) s += sh.geff[r][threadIdx.x];
     atomicAdd((threadIdx.x < A) ? gba + threadIdx.x : gbv, s);
   }
+}
+
+// many small CTAs: the kernel is latency-bound, 16 rows per CTA puts 256 CTAs in flight at B = 512
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ gq, const __nv_bfloat16* __restrict__ phi,
+                                                       const float* __restrict__ Wa, const float* __restrict__ Wv, int B,
+                                                       int K, int A, __nv_bfloat16* __restrict__ gphi,
+                                                       float* __restrict__ gWa, float* __restrict__ gba,
+                                                       float* __restrict__ gWv, float* __restrict__ gbv,
+                                                       float* __restrict__ relu_colsum) {
+  // relu_colsum != NULL: phi is the output of a ReLU layer (NatureConvBody's fc4): the gradient is masked here (gphi = 0 where
+  // phi <= 0) and its column sums -- that layer's bias gradient -- are accumulated into relu_colsum[K] (zeroed by the caller),
+  // which replaces the separate mask / bias-gradient pass over gphi.
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
+  __shared__ HeadBwdShared sh;
+  const int r0 = blockIdx.y * HB_ROWS;
+  const int n_out = A + (Wv ? 1 : 0);
+  for (int e = threadIdx.x; e < HB_ROWS * n_out; e += blockDim.x) {
+    const int r = e / n_out, n = e - r * n_out;
+    sh.geff[r][n] = (r0 + r < B) ? head_geff(gq + (int64_t)(r0 + r) * A, n, A, Wv != nullptr) : 0.0f;
+  }
+  __syncthreads();
+  head_bwd_body(sh, phi, Wa, Wv, B, K, A, gphi, gWa, gba, gWv, gbv, relu_colsum);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// DQN update, head part, in ONE launch (DQN_agent.py:81-99 compute_loss, :120-127 PER block, :78-79 reduce_loss, and the
+// backward of the head): q = head(phi) for the online network on s, q_next = head_target(phi_t) on s' [, argmax from
+// head(phi_o) on s' for double-Q], delta / priorities / importance weights / loss exactly as csrc/losses.cu dqn_loss_kernel
+// computes them, dL/dq mapped through the dueling combine, then head_bwd_body: dphi (masked by the ReLU of fc4), head weight
+// and bias gradients and fc4's bias gradient.  Replaces 2-3 head_fwd launches + dqn_loss + head_bwd (+ a zero fill).
+// The 16 rows of a CTA are evaluated by its 8 warps (2 rows each); the K/64 CTAs of a row block repeat those few dot
+// products (16 x 3 x (A+1) rows of 512: negligible) instead of exchanging them.
+// ---------------------------------------------------------------------------------------------------------------
+struct DqnHeadArgs {
+  const __nv_bfloat16* phi; const __nv_bfloat16* phi_t; const __nv_bfloat16* phi_o;
+  const float* Wa; const float* ba; const float* Wv; const float* bv;
+  const float* Wa_t; const float* ba_t; const float* Wv_t; const float* bv_t;
+  const int64_t* action; const float* reward; const float* mask;
+  float gamma_n;
+  int B, K, A;
+  const float* is_prob; float beta; const float* beta_dev; float eps, alpha;
+  __nv_bfloat16* gphi; float* gWa; float* gba; float* gWv; float* gbv; float* relu_colsum;
+  float* q_out; float* delta_out; float* prio_out; float* loss_out; float* loss_partial; int* counter;
+};
+
+__device__ __forceinline__ float head_pow_like_torch(float x, float e) {      // csrc/losses.cu pow_like_torch
+  if (e == 0.5f) return sqrtf(x);
+  if (e == 1.0f) return x;
+  if (e == 2.0f) return x * x;
+  if (e == -0.5f) return 1.0f / sqrtf(x);
+  if (e == -1.0f) return 1.0f / x;
+  return powf(x, e);
+}
+__device__ __forceinline__ float head_per_raw_weight(float prob, int B, float beta) {
+  return head_pow_like_torch(__fadd_rn(__fmul_rn(prob, (float)B), 1e-6f), -beta);
+}
+
+template <int NB>
+__global__ void __launch_bounds__(256) dqn_head_fused_kernel(const DqnHeadArgs a) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
+  __shared__ HeadBwdShared sh;
+  __shared__ float s_red[32];
+  __shared__ float s_loss[HB_ROWS];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * HB_ROWS;
+  const int A = a.A, K = a.K, B = a.B;
+  const bool dueling = a.Wv != nullptr;
+  const int n_out = A + (dueling ? 1 : 0);
+  float beta = a.beta;
+  if (a.beta_dev) beta = *a.beta_dev;
+  float wmax = 1.0f;
+  if (a.is_prob) {
+    float m = 0.0f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) m = fmaxf(m, head_per_raw_weight(a.is_prob[b], B, beta));
+    wmax = block_reduce(m, OpMax(), 0.0f, s_red);
+  }
+  const float invB = 1.0f / (float)B;
+#pragma unroll
+  for (int rr = 0; rr < HB_ROWS / 8; ++rr) {
+    const int r = warp * (HB_ROWS / 8) + rr, b = r0 + r;
+    float loss_r = 0.0f;
+    float g_ab = 0.0f;
+    int a_b = -1;
+    if (b < B) {
+      float q[NB], qt[NB];
+      head_row_dots<NB>(a.phi + (int64_t)b * K, a.Wa, a.ba, a.Wv, a.bv, K, A, lane, q);
+      head_combine<NB>(q, A, dueling);
+      head_row_dots<NB>(a.phi_t + (int64_t)b * K, a.Wa_t, a.ba_t, a.Wv_t, a.bv_t, K, A, lane, qt);
+      head_combine<NB>(qt, A, a.Wv_t != nullptr);
+      float qnext;
+      if (a.phi_o) {                                   // DQN_agent.py:88-90: argmax (first max) of the ONLINE net on s'
+        float qo[NB];
+        head_row_dots<NB>(a.phi_o + (int64_t)b * K, a.Wa, a.ba, a.Wv, a.bv, K, A, lane, qo);
+        head_combine<NB>(qo, A, dueling);
+        int best = 0;
+        float bv = qo[0];
+#pragma unroll
+        for (int n = 1; n < NB; ++n)
+          if (n < A && qo[n] > bv) { bv = qo[n]; best = n; }
+        qnext = 0.0f;
+#pragma unroll
+        for (int n = 0; n < NB; ++n)
+          if (n == best) qnext = qt[n];
+      } else {                                         // :92
+        qnext = qt[0];
+#pragma unroll
+        for (int n = 1; n < NB; ++n)
+          if (n < A) qnext = fmaxf(qnext, qt[n]);
+      }
+      a_b = (int)a.action[b];
+      float q_ab = 0.0f;
+#pragma unroll
+      for (int n = 0; n < NB; ++n)
+        if (n == a_b) q_ab = q[n];
+      const float target = __fadd_rn(a.reward[b], __fmul_rn(__fmul_rn(a.gamma_n, qnext), a.mask[b]));   // :95
+      const float delta = __fsub_rn(target, q_ab);                                                    // :99
+      float w = 1.0f;
+      if (a.is_prob) w = __fdiv_rn(head_per_raw_weight(a.is_prob[b], B, beta), wmax);                 // :125-126
+      const float wl = __fmul_rn(delta, w);                                                           // :127
+      loss_r = __fmul_rn(__fmul_rn(wl, wl), 0.5f);                                                    // :79
+      g_ab = -wl * w * invB;                            // d/dq[a_b] of mean(0.5 * (w * (y - q))^2)
+      if (blockIdx.x == 0 && lane == 0) {
+        if (a.delta_out) a.delta_out[b] = delta;
+        if (a.prio_out && a.is_prob) a.prio_out[b] = head_pow_like_torch(__fadd_rn(fabsf(delta), a.eps), a.alpha);   // :121
+        if (a.q_out) {
+#pragma unroll
+          for (int n = 0; n < NB; ++n)
+            if (n < A) a.q_out[(int64_t)b * A + n] = q[n];
+        }
+      }
+    }
+    // geff of this row: dq has one non-zero entry (the taken action); the dueling combine spreads it
+    if (lane < n_out) {
+      float g;
+      if (!dueling) g = (lane == a_b) ? g_ab : 0.0f;
+      else g = (lane < A) ? ((lane == a_b ? g_ab : 0.0f) - g_ab / (float)A) : g_ab;
+      sh.geff[r][lane] = (b < B) ? g : 0.0f;
+    }
+    if (lane == 0) s_loss[r] = loss_r;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.loss_out) {
+    float t = 0.0f;
+    for (int r = 0; r < HB_ROWS; ++r) t += s_loss[r];
+    a.loss_partial[blockIdx.y] = t;
+    __threadfence();
+    s_last = atomicAdd(a.counter, 1) == (int)gridDim.y - 1;
+    if (s_last) {                                       // the last row block adds the partials in a fixed order
+      __threadfence();
+      float tot = 0.0f;
+      for (int i = 0; i < (int)gridDim.y; ++i) tot += __ldcg(a.loss_partial + i);
+      a.loss_out[0] = tot * invB;
+      *a.counter = 0;
+    }
+  }
+  head_bwd_body(sh, a.phi, a.Wa, a.Wv, B, K, A, a.gphi, a.gWa, a.gba, a.gWv, a.gbv, a.relu_colsum);
 }
 
 }  // namespace b2rl
@@ -211,4 +378,43 @@ extern "C" int b2rl_head_bwd_relu(const float* gq, const uint16_t* phi, const fl
                                   float* relu_colsum, void* stream) {
   B2RL_REQUIRE(relu_colsum, "null relu_colsum");
   return head_bwd_impl(gq, phi, Wa, Wv, B, K, A, gphi, gWa, gba, gWv, gbv, relu_colsum, stream);
+}
+
+
+// DQN head forward (online on s, target on s', optional online on s' for double-Q) + target / loss / PER block + head
+// backward in one launch; see dqn_head_fused_kernel.  phi* are bf16 [B][K] outputs of a ReLU layer; *_t = target network's
+// head.  relu_colsum [K] (zeroed by the caller) receives fc4's bias gradient.  scratch: float [>= ceil(B/16)] then one
+// int32 counter (zero-initialised once; the kernel re-arms it).  q_out / delta_out / prio_out / loss_out may be NULL.
+extern "C" int b2rl_dqn_head_fused(const uint16_t* phi, const uint16_t* phi_t, const uint16_t* phi_o, const float* Wa,
+                                   const float* ba, const float* Wv, const float* bv, const float* Wa_t, const float* ba_t,
+                                   const float* Wv_t, const float* bv_t, const int64_t* action, const float* reward,
+                                   const float* mask, float gamma_n, int32_t B, int32_t K, int32_t A, const float* is_prob,
+                                   float beta, const float* beta_dev, float eps, float alpha, uint16_t* gphi, float* gWa,
+                                   float* gba, float* gWv, float* gbv, float* relu_colsum, float* q_out, float* delta_out,
+                                   float* prio_out, float* loss_out, float* scratch, void* stream) {
+  B2RL_REQUIRE(phi && phi_t && Wa && ba && Wa_t && ba_t && action && reward && mask && gphi && gWa && gba && relu_colsum && scratch,
+               "null pointer");
+  B2RL_REQUIRE(((Wv == nullptr) == (bv == nullptr)) && ((Wv == nullptr) == (gWv == nullptr)) && ((Wv == nullptr) == (gbv == nullptr)) &&
+               ((Wv_t == nullptr) == (bv_t == nullptr)) && ((Wv == nullptr) == (Wv_t == nullptr)), "inconsistent dueling arguments");
+  B2RL_REQUIRE(B > 0 && K > 0 && K % 8 == 0 && A > 0 && A < HEAD_MAX_OUT, "need K % 8 == 0 and 0 < A < 32");
+  B2RL_REQUIRE((reinterpret_cast<uintptr_t>(phi) | reinterpret_cast<uintptr_t>(phi_t) | reinterpret_cast<uintptr_t>(phi_o) |
+                reinterpret_cast<uintptr_t>(Wa) | reinterpret_cast<uintptr_t>(Wv) | reinterpret_cast<uintptr_t>(Wa_t) |
+                reinterpret_cast<uintptr_t>(Wv_t)) % 16 == 0, "features and weights must be 16-byte aligned");
+  DqnHeadArgs a;
+  a.phi = reinterpret_cast<const __nv_bfloat16*>(phi); a.phi_t = reinterpret_cast<const __nv_bfloat16*>(phi_t);
+  a.phi_o = reinterpret_cast<const __nv_bfloat16*>(phi_o);
+  a.Wa = Wa; a.ba = ba; a.Wv = Wv; a.bv = bv; a.Wa_t = Wa_t; a.ba_t = ba_t; a.Wv_t = Wv_t; a.bv_t = bv_t;
+  a.action = action; a.reward = reward; a.mask = mask; a.gamma_n = gamma_n; a.B = B; a.K = K; a.A = A;
+  a.is_prob = is_prob; a.beta = beta; a.beta_dev = beta_dev; a.eps = eps; a.alpha = alpha;
+  a.gphi = reinterpret_cast<__nv_bfloat16*>(gphi); a.gWa = gWa; a.gba = gba; a.gWv = gWv; a.gbv = gbv; a.relu_colsum = relu_colsum;
+  a.q_out = q_out; a.delta_out = delta_out; a.prio_out = prio_out; a.loss_out = loss_out;
+  const int row_blocks = (B + HB_ROWS - 1) / HB_ROWS;
+  a.loss_partial = scratch; a.counter = reinterpret_cast<int*>(scratch + row_blocks);
+  const dim3 grid((K + 63) / 64, row_blocks);
+  const int n_out = A + (Wv ? 1 : 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_out <= 8) launch_pdl(dqn_head_fused_kernel<8>, dim3(grid), dim3(256), 0, st, a);
+  else if (n_out <= 19) launch_pdl(dqn_head_fused_kernel<19>, dim3(grid), dim3(256), 0, st, a);
+  else launch_pdl(dqn_head_fused_kernel<HEAD_MAX_OUT>, dim3(grid), dim3(256), 0, st, a);
+  return check_launch("b2rl_dqn_head_fused");
 }

@@ -123,6 +123,15 @@ static int norm_pass(const float* grad, int64_t n, float grad_scale, float max_n
   return check_launch("clip/sumsq");
 }
 
+// clip_grad_norm_'s coefficient on its own: norm_scratch[0] = total norm of grad * grad_scale, norm_scratch[1] = the factor
+// min(max_norm / (norm + 1e-6), 1) * grad_scale every gradient element is multiplied by (max_norm <= 0: grad_scale).  Used
+// after a gradient all-reduce, before b2rl_nature_fused_opt without unit partials.
+extern "C" int b2rl_grad_norm(const float* grad, int64_t n, float grad_scale, float max_norm, void* norm_scratch, void* stream) {
+  B2RL_REQUIRE(grad && norm_scratch, "null pointer");
+  B2RL_REQUIRE(n > 0 && (reinterpret_cast<uintptr_t>(grad) % 16 == 0), "bad size / gradient arena must be 16B aligned");
+  return norm_pass(grad, n, grad_scale, max_norm, norm_scratch, (cudaStream_t)stream);
+}
+
 extern "C" int b2rl_clip_rmsprop(float* param, const float* grad, float* square_avg, float* grad_avg, int64_t n,
                                  float max_norm, float lr, float alpha, float eps, int32_t centered, float grad_scale,
                                  void* norm_scratch, uint16_t* bf16_shadow, void* stream) {

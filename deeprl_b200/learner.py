@@ -74,6 +74,40 @@ class GraphedDQNLearner:
         self._parity = 0
         self.updates = 0
         self.with_h2d = False
+        self._tail = None                 # network/tail.py NatureTail (built on first use), False = not applicable
+        self.opt.zero_grad()              # the fused tail writes / re-zeroes the gradient arena itself: start from zeros
+
+    # ------------------------------------------------------------------ fused tail / fused head (csrc/tail.cu, csrc/head.cu)
+    def tail(self):
+        """The two-launch update tail (gradient reduce + clip / optimizer / operand pack) when the online network has a
+        tcgen05 NatureConvBody and the backward epilogues are fused; None otherwise (generic unpack + FlatOptimizer.step)."""
+        if self._tail is None:
+            from .network.tail import NatureTail
+            body = getattr(self.net, "body", None)
+            ok = (self.dtype == torch.bfloat16 and Config.DENSE_BACKEND == "tcgen05" and nature_tc.FUSED_BWD and _lib.CONV_SLAB
+                  and hasattr(body, "repack") and not getattr(body, "noisy_linear", False)
+                  and os.environ.get("B2RL_TAIL", "1") != "0" and self.opt.kind in ("rmsprop", "adam"))
+            if ok:
+                self._repack(self.net, self.scale)
+                self._tail = NatureTail(self.opt, body, self.scale)
+            else:
+                self._tail = False
+        return self._tail or None
+
+    def _heads(self):
+        """(online head modules, target head modules) when the DQN head can run in the fused head + loss + backward kernel."""
+        if self.kind != "dqn" or self.tail() is None or os.environ.get("B2RL_FUSED_HEAD", "1") == "0":
+            return None
+        out = []
+        for n in (self.net, self.tgt):
+            fa = getattr(n, "fc_head", None) or getattr(n, "fc_advantage", None)
+            fv = getattr(n, "fc_value", None) if hasattr(n, "fc_advantage") else None
+            if not isinstance(fa, torch.nn.Linear) or fa.out_features >= 32 or (fv is not None and not isinstance(fv, torch.nn.Linear)):
+                return None
+            if any(m is not None and m.weight.data_ptr() % 16 for m in (fa, fv)):
+                return None
+            out.append((fa, fv))
+        return out
 
     # ------------------------------------------------------------------ the update, as eager code
     def _h2d(self):
@@ -104,11 +138,14 @@ class GraphedDQNLearner:
             self._packed_ev, self._sampled_ev = torch.cuda.Event(), torch.cuda.Event()
         side, pre = self._side, self._pre
         fs = self.scale if self.dtype == torch.bfloat16 else 1.0
-        # online weights changed in the previous optimizer step: re-pack them on the side branch, next to feed + sample
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            self._repack(self.net, fs)
-            self._packed_ev.record(side)
+        tail = self.tail()
+        if tail is None:
+            # online weights changed in the previous optimizer step: re-pack them on the side branch, next to feed + sample
+            # (with the fused tail the optimizer kernel itself writes the packed bf16 operands)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self._repack(self.net, fs)
+                self._packed_ev.record(side)
         if self.prefetch:
             eager = parity is None
             if eager:
@@ -125,12 +162,19 @@ class GraphedDQNLearner:
         else:
             t = self._sample(0)
         per = dict(is_prob=t.sampling_prob, eps=self.eps, alpha=self.alpha, beta_dev=self.d_beta) if self.per else {}
+        heads = self._heads()
+        if heads is not None:
+            self._main_fused_head(t, per, heads, tail, fs)
+            if self.prefetch:
+                cur.wait_stream(pre)
+            return
         body_a, body_b = getattr(self.net, "body", None), getattr(self.tgt, "body", None)
         if (self.dual and self.dtype == torch.bfloat16 and Config.DENSE_BACKEND == "tcgen05"
                 and hasattr(body_a, "repack") and hasattr(body_b, "repack")):
             # online(s) and target(s') share every launch of the convolutional body (nature_tc.forward_dual): the grid of
             # each kernel is split between the two networks, so the per-launch fixed cost is paid once
-            cur.wait_event(self._packed_ev)
+            if tail is None:
+                cur.wait_event(self._packed_ev)
             with nature_tc.dual_forward(body_a, body_b, t.next_state), frame_scale(fs):
                 out = self.net(t.state)
                 with torch.no_grad():
@@ -142,7 +186,8 @@ class GraphedDQNLearner:
             side.wait_stream(cur)
             with torch.cuda.stream(side), frame_scale(fs), torch.no_grad():
                 nxt_t = self.tgt(t.next_state)
-            cur.wait_event(self._packed_ev)
+            if tail is None:
+                cur.wait_event(self._packed_ev)
             with frame_scale(fs):
                 with torch.no_grad():
                     nxt_o = self.net(t.next_state) if self.double_q else None
@@ -166,12 +211,37 @@ class GraphedDQNLearner:
             if self.prefetch:                            # the sum tree is read by the prefetch branch: update after it
                 cur.wait_event(self._sampled_ev)
             rp.update_priorities((t.idx, r["priority"]))
-        self.opt.zero_grad()
-        with nature_tc.wgrad_stream(side):           # weight-gradient GEMMs on the side branch, next to the dgrad chain
+        if tail is None:
+            self.opt.zero_grad()
+        with nature_tc.wgrad_stream(side), nature_tc.grad_sink(tail):   # weight-gradient GEMMs on the side branch
             head.backward(grad)
         self.loss.copy_(r["loss"])
         if self.prefetch:
             cur.wait_stream(pre)
+
+    def _main_fused_head(self, t, per, heads, tail, fs):
+        """DQN with a VanillaNet / DuelingNet head: bodies on the tcgen05 kernels, then ONE launch for the online / target
+        [/ double-Q] head forwards + target / loss / PER block + head backward (csrc/head.cu dqn_head_fused_kernel)."""
+        cur, side = torch.cuda.current_stream(), self._side
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), frame_scale(fs), torch.no_grad():
+            phi_t = self.tgt.body(t.next_state)
+        with frame_scale(fs):
+            with torch.no_grad():
+                phi_o = self.net.body(t.next_state) if self.double_q else None
+            phi = self.net.body(t.state)
+        cur.wait_stream(side)
+        r = ops.dqn_head_fused(phi.detach(), phi_t, phi_o, heads[0], heads[1], t.action, t.reward, t.mask, self.gamma_n,
+                               tail.db4, **per)
+        if self.per:
+            if self.prefetch:                            # the sum tree is read by the prefetch branch: update after it
+                cur.wait_event(self._sampled_ev)
+            self.replay.update_priorities((t.idx, r["priority"]))
+        gphi = r["gphi"]
+        nature_tc.PREMASKED[gphi.data_ptr()] = tail.db4  # already masked by relu(fc4); its column sums are in the tail's db4
+        with nature_tc.wgrad_stream(side), nature_tc.grad_sink(tail):
+            phi.backward(gphi)
+        self.loss.copy_(r["loss"])
 
     def _repack(self, net, fs):
         """tcgen05 backend: the learner owns the packed bf16 operands of both networks -- the online body is re-packed
@@ -186,13 +256,24 @@ class GraphedDQNLearner:
         self._repack(self.tgt, self.scale if self.dtype == torch.bfloat16 else 1.0)
 
     def _opt(self):
-        self.opt.step(max_norm=self.clip, grad_scale=1.0 / self.world)
+        tail = self.tail()
+        if tail is not None:
+            tail.step(max_norm=self.clip, grad_scale=1.0 / self.world, reduced_elsewhere=self.world > 1)
+        else:
+            self.opt.step(max_norm=self.clip, grad_scale=1.0 / self.world)
+
+    def refresh_packed(self):
+        """Re-derive the packed bf16 operands of both networks from the fp32 parameters (after the parameters were changed
+        from outside: load_state_dict, a broadcast, a copied arena)."""
+        fs = self.scale if self.dtype == torch.bfloat16 else 1.0
+        self._repack(self.net, fs)
+        self._repack(self.tgt, fs)
 
     # ------------------------------------------------------------------ capture / replay
     def capture(self, warmup=3, with_h2d=False):
         """Warm up eagerly on a side stream (cuDNN autotune, lazy allocations), then capture."""
         self.with_h2d = with_h2d
-        self._repack(self.tgt, self.scale if self.dtype == torch.bfloat16 else 1.0)
+        self.refresh_packed()
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):

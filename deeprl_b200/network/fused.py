@@ -173,7 +173,8 @@ class _NarrowHead(torch.autograd.Function):
         if nature_tc.FUSED_BWD and phi.data_ptr() in nature_tc.RELU_FEATURES:
             # phi = relu(fc4(.)) of a tcgen05 NatureConvBody: its ReLU backward and bias gradient ride along (the body's
             # backward finds the column sums under the gradient's address and skips its own pass)
-            colsum = torch.zeros(K, dtype=torch.float32, device=phi.device)
+            sink = nature_tc.SINK               # persistent accumulator (re-zeroed by the tail's kernel A) or a fresh one
+            colsum = sink.db4 if (sink is not None and sink.db4.numel() == K) else torch.zeros(K, dtype=torch.float32, device=phi.device)
             _lib.call("b2rl_head_bwd_relu", _lib.ptr(gq), _lib.ptr(phi), _lib.ptr(wa.detach()),
                       _lib.ptr(None if wv is None else wv.detach()), B, K, A, _lib.ptr(gphi), _lib.ptr(gwa), _lib.ptr(gba),
                       _lib.ptr(gwv), _lib.ptr(gbv), _lib.ptr(colsum), _lib.stream())

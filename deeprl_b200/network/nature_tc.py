@@ -22,7 +22,7 @@ import os
 import torch
 
 from .. import _lib
-from ..ops import gemm_bf16
+from ..ops import gemm_bf16, gemm_splitk_bf16
 from .fused import act_bwd_bias_grad
 
 _bf16 = torch.bfloat16
@@ -30,10 +30,13 @@ _f32 = torch.float32
 # fc4 forward at small batch: split-K factor (zero fill + split-K GEMM with fp32 atomics + bias/ReLU pass, 3 launches) or 1 =
 # one GEMM launch with the fused bias/ReLU epilogue (measured per network at B = 512: 10.1 us vs 10.0 us in isolation)
 FC4_SPLITS = int(os.environ.get("B2RL_FC4_SPLITS", "4"))
+# split-K with the in-kernel fix-up (one launch) instead of zero fill + atomic split-K + bias/ReLU pass (three)
+FC4_FIXUP = os.environ.get("B2RL_FC4_FIXUP", "1") == "1"
 # backward: ReLU mask + bias gradient + re-layout fused into the dgrad GEMM epilogues (b2rl_*_bwd_bf16) instead of three
-# b2rl_act_bwd_bias_grad_bf16 passes.  NOT YET VERIFIED ON A GPU (written after the round's GPU budget was spent): off.
-FUSED_BWD = os.environ.get("B2RL_FUSED_BWD", "0") == "1"
+# b2rl_act_bwd_bias_grad_bf16 passes (B2RL_FUSED_BWD=0 restores them).
+FUSED_BWD = os.environ.get("B2RL_FUSED_BWD", "1") == "1"
 _ZEROED = {}
+SINK = None                # network/tail.py NatureTail while ``grad_sink`` is active: backward hands it the GEMM-layout gradients
 RELU_FEATURES = set()      # data_ptr of feature tensors y4 = relu(fc4(.)) produced by nature_body (for head_bwd_relu)
 PREMASKED = {}             # data_ptr of a feature gradient already masked by head_bwd_relu -> its column sums (= db4)
 
@@ -47,9 +50,28 @@ def _zero_grid(key, shape, device):
     return _ZEROED[k]
 
 
+@contextlib.contextmanager
+def grad_sink(tail):
+    """Inside this context the backward pass of ``tail.body`` does not touch ``.grad`` itself: it hands the GEMM-layout
+    weight gradients (split-K partials) to ``tail.reduce`` (csrc/tail.cu kernel A) and accumulates the bias gradients in
+    the tail's persistent buffers."""
+    global SINK
+    old, SINK = SINK, tail
+    try:
+        yield tail
+    finally:
+        SINK = old
+
+
+def _sink_for(params):
+    t = SINK
+    return t if (t is not None and params[0] is t.body.conv1.weight) else None
+
+
 def _backward_fused(ctx, gy4):
     x0m, x1, y2, y3, y4, w2d, w3d, w4p = ctx.saved_tensors
     B, dev = y4.shape[0], y4.device
+    sink = _sink_for(ctx.params)
     db4 = PREMASKED.pop(gy4.data_ptr(), None) if gy4.dtype == _bf16 and gy4.is_contiguous() else None
     if db4 is not None:
         g4 = gy4                                                                        # masked + summed by b2rl_head_bwd_relu
@@ -57,8 +79,11 @@ def _backward_fused(ctx, gy4):
         g4, db4 = act_bwd_bias_grad(gy4, y4, True)                                      # fc4's own ReLU / bias gradient
     y3c = y3.view(B, 3136)
     gw4p = gemm_bf16(g4, y3c, a_major="mn", b_major="mn", out_dtype=_f32, block_n=128, stream=_fork())
-    db = torch.zeros(32 + 64 + 64, dtype=_f32, device=dev)
-    db1, db2, db3 = db[:32], db[32:96], db[96:160]
+    if sink is not None:                   # persistent accumulators, re-zeroed by the tail's kernel A
+        db1, db2, db3 = sink.db1, sink.db2, sink.db3
+    else:
+        db = torch.zeros(32 + 64 + 64, dtype=_f32, device=dev)
+        db1, db2, db3 = db[:32], db[32:96], db[96:160]
     # fc4 dgrad -> conv3's output grid (10 x 10 per image), masked by relu(conv3) and summed into db3
     g3 = _zero_grid("g3", (B * 100, 64), dev)
     e3 = _lib.bwd_epilogue(y3c, db3, 64, 64)
@@ -189,7 +214,10 @@ def forward_only(x0, packed, b1, b2, b3, b4):
     y3 = torch.empty((B * 49, 64), dtype=_bf16, device=dev)
     conv_gemm(0, y2, w3f, 64, 9, 3, 10, 1, y3, bias=b3, relu=True, out_map=2, G=10, V=7, block_n=64)
     n4 = w4p.shape[0]
-    if B <= 1024 and FC4_SPLITS > 1:
+    if B <= 1024 and FC4_SPLITS > 1 and FC4_FIXUP:
+        # few output tiles, long K (3136): split K over CTAs; the last split of a tile adds the partials, bias + ReLU + bf16
+        y4 = gemm_splitk_bf16(y3.view(B, 3136), w4p, bias=b4, relu=True, splits=FC4_SPLITS, block_n=64)
+    elif B <= 1024 and FC4_SPLITS > 1:
         # few output tiles, long K (3136): split K over CTAs, finish (bias + ReLU + bf16) in a streaming pass
         acc = gemm_bf16(y3.view(B, 3136), w4p, out_dtype=_f32, splits=FC4_SPLITS, block_n=64)
         y4 = torch.empty((B, n4), dtype=_bf16, device=dev)
@@ -281,6 +309,12 @@ class _NatureBody(torch.autograd.Function):
         else:
             (gw1p, p1, gw2p, p2, gw3p, p3, gw4p), (db1, db2, db3, db4) = _backward_unfused(ctx, gy4)
         params = ctx.params
+        sink = _sink_for(params)
+        if sink is not None and FUSED_BWD and _lib.CONV_SLAB:
+            if db4 is not sink.db4:
+                sink.db4.copy_(db4)
+            sink.reduce(gw1p, p1, gw2p, p2, gw3p, p3, gw4p)
+            return (None,) * 12
         if all(p.grad is not None and p.grad.dtype == _f32 and p.grad.is_contiguous() for p in params):
             # accumulate straight into the .grad arena (reference layouts), one launch
             w1, b1, w2, b2, w3, b3, w4, b4 = params

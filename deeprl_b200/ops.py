@@ -54,6 +54,41 @@ def dqn_loss_fused(q, q_next_target, q_next_online, action, reward, mask, gamma_
     return dict(delta=delta, priority=prio, loss=loss, dq=dq)
 
 
+def dqn_head_fused(phi, phi_t, phi_o, head, head_t, action, reward, mask, gamma_n, relu_colsum, is_prob=None, beta=0.0,
+                   eps=0.0, alpha=0.0, beta_dev=None, want_q=False):
+    """Head forward (online on s, target on s' [, online on s' for double-Q]) + ``dqn_loss_fused`` + head backward in ONE
+    launch (csrc/head.cu dqn_head_fused_kernel).  ``head`` / ``head_t`` = (fc_action_or_head, fc_value_or_None) modules of
+    the online / target network (VanillaNet / DuelingNet, network_heads.py:11-37); their weight and bias gradients are
+    accumulated into ``.grad`` (which must be fp32 contiguous tensors), ``relu_colsum`` [K] receives fc4's bias gradient.
+    Returns dict(gphi = dLoss/dphi masked by phi > 0 (bf16), delta, priority, loss, q)."""
+    B, K = phi.shape
+    fa, fv = head
+    ta, tv = head_t
+    A = fa.weight.shape[0]
+    dev = phi.device
+    assert phi.dtype == torch.bfloat16 and phi.is_contiguous() and phi_t.is_contiguous() and (phi_o is None or phi_o.is_contiguous())
+    for m in (fa, fv):
+        if m is not None:
+            assert all(p.grad is not None and p.grad.dtype == _f32 and p.grad.is_contiguous() for p in (m.weight, m.bias))
+    gphi = torch.empty_like(phi)
+    delta = torch.empty(B, dtype=_f32, device=dev)
+    prio = torch.empty(B, dtype=_f32, device=dev) if is_prob is not None else None
+    loss = torch.empty(1, dtype=_f32, device=dev)
+    q = torch.empty(B, A, dtype=_f32, device=dev) if want_q else None
+    scratch = _Scratch.get(dev, "dqn_head_scratch", (B + 15) // 16 + 8, _f32)
+    w = lambda m: None if m is None else m.weight.detach()
+    b = lambda m: None if m is None else m.bias.detach()
+    g = lambda t: None if t is None else t.grad
+    _lib.call("b2rl_dqn_head_fused", _lib.ptr(phi), _lib.ptr(phi_t), _lib.ptr(phi_o), _lib.ptr(w(fa)), _lib.ptr(b(fa)),
+              _lib.ptr(w(fv)), _lib.ptr(b(fv)), _lib.ptr(w(ta)), _lib.ptr(b(ta)), _lib.ptr(w(tv)), _lib.ptr(b(tv)),
+              _lib.ptr(_c(action, torch.int64)), _lib.ptr(_c(reward, _f32)), _lib.ptr(_c(mask, _f32)), float(gamma_n), B, K, A,
+              _lib.ptr(_c(is_prob, _f32)), float(beta), _lib.ptr(beta_dev), float(eps), float(alpha), _lib.ptr(gphi),
+              _lib.ptr(g(fa.weight)), _lib.ptr(g(fa.bias)), _lib.ptr(None if fv is None else g(fv.weight)),
+              _lib.ptr(None if fv is None else g(fv.bias)), _lib.ptr(relu_colsum), _lib.ptr(q), _lib.ptr(delta), _lib.ptr(prio),
+              _lib.ptr(loss), _lib.ptr(scratch), _lib.stream())
+    return dict(gphi=gphi, delta=delta, priority=prio, loss=loss, q=q)
+
+
 class _DQNDelta(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, q_next_target, q_next_online, action, reward, mask, gamma_n):
@@ -305,4 +340,24 @@ def gemm_bf16(a, b, a_major="k", b_major="k", bias=None, relu=False, out_dtype=t
     _lib.call("b2rl_gemm_bf16", _lib.ptr(a), int(a_mn), a.stride(0), _lib.ptr(b), int(b_mn), b.stride(0), _lib.ptr(out),
               out.stride(0), int(M), int(N), int(K), _lib.ptr(bias), int(relu), mode, int(splits), int(block_n),
               stream if stream is not None else _lib.stream())
+    return out
+
+
+def gemm_splitk_bf16(a, b, bias=None, relu=False, splits=4, block_n=64, out=None):
+    """``act(a @ b.T + bias)`` in bf16 with split-K and an in-kernel fix-up (csrc/gemm.cu out_mode 3): ONE launch where
+    ``gemm_bf16(splits > 1)`` needs a zero fill, the atomic split-K GEMM and a bias / activation pass.  ``a`` [M, K] and ``b``
+    [N, K] bf16 row-major.  The fp32 scratch and the tile counters are kept per (shape, stream): the online and the target
+    network run this concurrently on two streams."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() == 2 and b.dim() == 2
+    assert a.stride(1) == 1 and b.stride(1) == 1 and a.shape[1] == b.shape[1]
+    M, K = a.shape
+    N = b.shape[0]
+    rows, cols = (M + 127) // 128 * 128, (N + block_n - 1) // block_n * block_n
+    key = "splitk_%d_%d_%d_%d_%d" % (rows, cols, splits, block_n, torch.cuda.current_stream().cuda_stream)
+    ws = _Scratch.get(a.device, key + "_ws", splits * rows * cols, _f32)
+    counters = _Scratch.get(a.device, key + "_cnt", (rows // 128) * (cols // block_n), torch.int32)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    _lib.call("b2rl_gemm_splitk_bf16", _lib.ptr(a), a.stride(0), _lib.ptr(b), b.stride(0), _lib.ptr(out), out.stride(0), int(M),
+              int(N), int(K), _lib.ptr(bias), int(relu), int(splits), int(block_n), _lib.ptr(ws), _lib.ptr(counters), _lib.stream())
     return out

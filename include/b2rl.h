@@ -299,6 +299,56 @@ int b2rl_head_bwd_relu(const float* gq, const uint16_t* phi, const float* Wa, co
 int b2rl_conv_wgrad_partials(const uint16_t* X, int64_t rows, int32_t C, const uint16_t* G, int32_t n_out, int32_t taps,
                              int32_t taps_x, int32_t grid_w, float* partials, int32_t* n_partials_host, void* stream);
 
+/* D = act(A B^T + bias) (bf16 out) with split-K and an in-kernel fix-up: one launch instead of zero-fill + atomic split-K +
+ * bias/activation pass (fc4 of NatureConvBody at small batch, network_bodies.py:33).  A [M][K], B [N][K] bf16 K-major.
+ * ws: fp32 [splits][ceil(M/128)*128][ceil(N/block_n)*block_n]; counters: int32 [tiles], zeroed once (self re-arming).
+ * Concurrent launches (different streams) need their own ws / counters. */
+int b2rl_gemm_splitk_bf16(const uint16_t* A, int64_t lda, const uint16_t* B, int64_t ldb, void* D, int64_t ldd, int32_t M,
+                          int32_t N, int32_t K, const float* bias, int32_t relu, int32_t splits, int32_t block_n, float* ws,
+                          int32_t* counters, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tail of one gradient update for a NatureConvBody network on the tcgen05 path (csrc/tail.cu):
+ * loss.backward()'s last step + clip_grad_norm_ + optimizer.step (DQN_agent.py:131-134) in two launches.
+ * Work is described by unit tables (int32 x 4 per unit: arena offset, length, kind, row | segment << 16;
+ * kinds 0 plain, 1-4 one output row (or 256-element segment of it) of conv1 / conv2 / conv3 / fc4 weights,
+ * 5-8 their biases), built once by the host (deeprl_b200/network/tail.py).
+ *
+ * grad_reduce: sums the split-K partials of the conv weight gradients (g1p/g2p/g3p: [p][n_out][taps*C] fp32),
+ *   maps all four weight gradients from the GEMM layouts to the reference layouts and WRITES them into the flat
+ *   gradient arena, moves the bias gradients there (db1..db4 are re-zeroed), and leaves the sum of squares of the
+ *   gradient elements of unit i in unit_sumsq[i] (plain units: whatever the arena already holds, e.g. the head's
+ *   gradients).  step_dev (Adam) is incremented by one if not NULL.
+ * fused_opt: clip coefficient from the unit partials (NULL: from norm_scratch, see b2rl_grad_norm), RMSprop
+ *   (opt 0 plain, 1 centered; a_ = alpha) or Adam (opt 2; a_, b_ = betas) exactly as b2rl_clip_rmsprop / b2rl_clip_adam,
+ *   gradient re-zeroed when zero_grad != 0, and the updated conv / fc4 weights written to the bf16 tap-major GEMM
+ *   operands of b2rl_nature_pack_weights (all six pointers, or all NULL).
+ * ------------------------------------------------------------------------------------------- */
+int b2rl_nature_grad_reduce(const int32_t* units, int32_t n_units, const float* g1p, int32_t p1, const float* g2p, int32_t p2,
+                            const float* g3p, int32_t p3, const float* g4p, float* db1, float* db2, float* db3, float* db4,
+                            int32_t c1, int32_t n4, float scale, float* grad, float* unit_sumsq, int64_t* step_dev,
+                            void* stream);
+int b2rl_nature_fused_opt(const int32_t* units, int32_t n_units, float* param, float* grad, float* s1, float* s2, int32_t opt,
+                          float lr, float a_, float b_, float eps, float max_norm, float grad_scale, const float* unit_sumsq,
+                          int32_t n_sumsq, void* norm_scratch, const int64_t* step_dev, int32_t c1, int32_t n4, float scale,
+                          uint16_t* w1f, uint16_t* w2f, uint16_t* w2d, uint16_t* w3f, uint16_t* w3d, uint16_t* w4p,
+                          int32_t zero_grad, void* stream);
+/* clip_grad_norm_'s coefficient alone (torch.nn.utils.clip_grad_norm_): norm_scratch[0] = ||grad * grad_scale||,
+ * norm_scratch[1] = min(max_norm / (norm + 1e-6), 1) * grad_scale. */
+int b2rl_grad_norm(const float* grad, int64_t n, float grad_scale, float max_norm, void* norm_scratch, void* stream);
+
+/* DQN update, head part, in one launch (DQN_agent.py:78-99, 120-127 and the head's backward): q = head(phi) on s,
+ * q_next = target_head(phi_t) on s' [argmax from head(phi_o) for double-Q], delta / priorities / IS weights / loss as
+ * b2rl_dqn_loss, then the gradients of the head (accumulated into gWa / gba / gWv / gbv), dphi masked by phi > 0 and
+ * its column sums (fc4's bias gradient) accumulated into relu_colsum.  Heads: VanillaNet (Wv == NULL) or DuelingNet
+ * (network_heads.py:11-37).  scratch: float [ceil(B/16)] + int32 counter, zero-initialised once. */
+int b2rl_dqn_head_fused(const uint16_t* phi, const uint16_t* phi_t, const uint16_t* phi_o, const float* Wa, const float* ba,
+                        const float* Wv, const float* bv, const float* Wa_t, const float* ba_t, const float* Wv_t,
+                        const float* bv_t, const int64_t* action, const float* reward, const float* mask, float gamma_n,
+                        int32_t B, int32_t K, int32_t A, const float* is_prob, float beta, const float* beta_dev, float eps,
+                        float alpha, uint16_t* gphi, float* gWa, float* gba, float* gWv, float* gbv, float* relu_colsum,
+                        float* q_out, float* delta_out, float* prio_out, float* loss_out, float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

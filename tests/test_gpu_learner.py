@@ -39,7 +39,8 @@ def copy_state(dst, src):
     for a, b in ((do.flat, so.flat), (do.s1, so.s1), (do.s2, so.s2), (do.step_dev, so.step_dev), (do.scratch, so.scratch)):
         a.copy_(b)
     dst.tgt.load_state_dict(src.tgt.state_dict())
-    dst._repack(dst.tgt, dst.scale)
+    dst.opt.grad.copy_(src.opt.grad)
+    dst.refresh_packed()
     dr, sr = dst.replay, src.replay
     for name in ("frames", "action", "reward", "mask", "ring_state"):
         getattr(dr, name).copy_(getattr(sr, name))
