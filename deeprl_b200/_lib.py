@@ -62,7 +62,7 @@ SIGNATURES = {
     "b2rl_head_bwd": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p],
     "b2rl_head_bwd_relu": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "b2rl_nature_grad_reduce": [c_p, c_i32, c_p, c_i32, c_p, c_i32, c_p, c_i32, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_f32, c_p,
-                                c_p, c_p, c_p],
+                                c_p, c_p, c_p, c_f32, c_f32, c_p],
     "b2rl_nature_fused_opt": [c_p, c_i32, c_p, c_p, c_p, c_p, c_i32, c_f32, c_f32, c_f32, c_f32, c_f32, c_f32, c_p, c_i32, c_p,
                               c_p, c_i32, c_i32, c_f32, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_p],
     "b2rl_grad_norm": [c_p, c_i64, c_f32, c_f32, c_p, c_p],

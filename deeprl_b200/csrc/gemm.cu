@@ -208,7 +208,7 @@ __device__ unsigned long long* g_trace_buf = nullptr;
 //   map 4: rows are images b, columns are V*V positions x sub_c channels
 //          -> grid row b*G*G + (pos / V)*G + pos % V, column = channel               (fc4's input gradient -> conv3's grid)
 // Grid rows that no tile covers keep whatever the destination holds: the caller keeps it zeroed (persistent buffer).
-template <int BN, int ACC>
+template <int BN, int ACC, bool EXT>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n0, int q, int lane, uint32_t tmem_base,
                                               uint32_t as, uint32_t parity, bool has_acc, uint64_t* tmem_full,
                                               uint64_t* tmem_empty, float* s_dbias, uint32_t trace_it = 1u << 30) {
@@ -231,13 +231,24 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
     } else {
       drow = (int64_t)b * p.V * p.V + oy * p.V + ox;
     }
-  } else if (p.out_map == 3 && valid) {
+  } else if (EXT && p.out_map == 3 && valid) {
     const int h = p.V >> 1, hh = h * h;
     img = row / hh;
     const int rem = row - img * hh;
     sy = rem / h, sx = rem - sy * h;
-  } else if (p.out_map == 4) {
+  } else if (EXT && p.out_map == 4) {
     img = row;
+  }
+  // backward extras: the ReLU mask of this thread's row (the saved forward activation) does not depend on the accumulator --
+  // all of it is requested BEFORE the wait for the MMAs, so that its latency is hidden behind them
+  int4 mk[EXT ? BN / 8 : 1];
+  if constexpr (EXT) {
+    if (p.mask && valid) {
+      const int4* mp = reinterpret_cast<const int4*>(p.mask + (int64_t)row * p.mask_ld + n0);
+#pragma unroll
+      for (int j = 0; j < BN / 8; ++j)
+        if (n0 + 8 * j < p.N) mk[j] = __ldg(mp + j);
+    }
   }
   if (has_acc) {
     mb_wait(&tmem_full[as], parity);
@@ -290,22 +301,23 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]), 0.0f));
       }
-      if (p.mask) {                                                     // ReLU gradient: zero where the forward output was <= 0
-        const int4* mp = reinterpret_cast<const int4*>(p.mask + (int64_t)row * p.mask_ld + n0 + c);   // 32 bf16 = 64 bytes
+      if constexpr (EXT) {
+        if (p.mask) {                                                   // ReLU gradient: zero where the forward output was <= 0
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const int4 m4 = __ldg(mp + (j >> 3));
-          const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&m4);
+          for (int j = 0; j < 32; j += 8) {
+            const int4 m4 = mk[(c >> 3) + (j >> 3)];
+            const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&m4);
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float2 mf = __bfloat1622float2(mh[t]);
-            if (!(mf.x > 0.0f)) r[j + 2 * t] = 0;
-            if (!(mf.y > 0.0f)) r[j + 2 * t + 1] = 0;
+            for (int t = 0; t < 4; ++t) {
+              const float2 mf = __bfloat1622float2(mh[t]);
+              if (!(mf.x > 0.0f)) r[j + 2 * t] = 0;
+              if (!(mf.y > 0.0f)) r[j + 2 * t + 1] = 0;
+            }
           }
         }
       }
     }
-    if (p.dbias) {
+    if (EXT && p.dbias) {
       // column sums over the 32 rows of this warp: 5-step register transpose-reduce (31 shuffles), lane l ends up with the
       // total of column l; rows that are not live contribute zeros.  All 32 lanes take part.
       float v[32];
@@ -325,10 +337,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
     }
     if (live) {
       int64_t off;
-      if (p.out_map == 3) {
+      if (EXT && p.out_map == 3) {
         const int sub = (n0 + c) / p.sub_c, cc = (n0 + c) - sub * p.sub_c;
         off = ((int64_t)img * p.G * p.G + (2 * sy + (sub >> 1)) * p.G + 2 * sx + (sub & 1)) * p.ldd + cc;
-      } else if (p.out_map == 4) {
+      } else if (EXT && p.out_map == 4) {
         const int pos = (n0 + c) / p.sub_c, cc = (n0 + c) - pos * p.sub_c;
         off = ((int64_t)img * p.G * p.G + (pos / p.V) * p.G + pos % p.V) * p.ldd + cc;
       } else {
@@ -378,57 +390,74 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
   if (tr) B2RL_TRACE_AT(2, trace_it, 3);
 }
 
-// Epilogue of one tile of a split-K GEMM with in-kernel fix-up (out_mode 3; fc4 forward at batch 512: 32 output tiles cannot
-// fill 148 SMs, and the 196 dependent MMAs of one un-split tile take ~5 us at the 53-cycle issue floor).  Replaces
-// zero-fill + atomic split-K + bias/ReLU pass (three launches) by one launch.  One warp group (128 threads) per tile.
+// Epilogue of a split-K GEMM with in-kernel fix-up (out_mode 3; fc4 forward at batch 512: 32 output tiles cannot fill 148 SMs,
+// and the 196 dependent MMAs of one un-split tile take ~5 us at the 53-cycle issue floor).  Replaces zero-fill + atomic
+// split-K + bias/ReLU pass (three launches) by one launch.  Every CTA owns exactly ONE tile (the host sizes the grid so).
+// Warp group 0 (warps 2-5) drains the accumulator into the fp32 scratch; then all EIGHT epilogue warps of the CTA that arrived
+// last at the tile's counter add the `splits` partials -- each thread requests all its partials of a 32-column chunk before
+// adding them (in split order: deterministic), so the fix-up costs about one L2 round trip.
 template <int BN>
-__device__ __forceinline__ void epilogue_tile_fixup(const GemmParams& p, int tile, int m0, int n0, int q, int lane,
-                                                    uint32_t tmem_base, uint32_t as, uint32_t parity, bool has_acc,
-                                                    uint64_t* tmem_full, uint64_t* tmem_empty, int* s_flag, int grp) {
+__device__ __forceinline__ void epilogue_fixup(const GemmParams& p, int tile, int m0, int n0, int warp, int lane,
+                                               uint32_t tmem_base, bool has_acc, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                               int* s_flag) {
+  const int q = warp & 3, grp = (warp - 2) >> 2;
   const int row = m0 + q * 32 + lane;
   const int splits = (int)gridDim.z;
-  if (has_acc) {
-    mb_wait(&tmem_full[as], parity);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  }
-  float* wrow = p.ws + ((int64_t)blockIdx.z * p.ws_rows + row) * p.ws_ld + n0;
-#pragma unroll
-  for (int c = 0; c < BN; c += 32) {
-    uint32_t r[32];
+  if (grp == 0) {
     if (has_acc) {
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c, r);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] = 0;
+      mb_wait(&tmem_full[0], 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    if (c + 32 >= BN && has_acc) {
+    float* wrow = p.ws + ((int64_t)blockIdx.z * p.ws_rows + row) * p.ws_ld + n0;
+#pragma unroll
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      if (has_acc) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, r);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        __stcg(reinterpret_cast<float4*>(wrow + c + j), make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                    __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+    }
+    if (has_acc) {
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      if (lane == 0) mb_arrive(&tmem_empty[as]);
+      if (lane == 0) mb_arrive(&tmem_empty[0]);
     }
-#pragma unroll
-    for (int j = 0; j < 32; j += 4)
-      __stcg(reinterpret_cast<float4*>(wrow + c + j), make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                  __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+    __threadfence();
   }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (warp == 2 && lane == 0) *s_flag = atomicAdd(p.counters + tile, 1) == splits - 1;
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (!*s_flag) return;
   __threadfence();
-  asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-  if (q == 0 && lane == 0) s_flag[grp] = atomicAdd(p.counters + tile, 1) == splits - 1;
-  asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-  if (!s_flag[grp]) return;
-  __threadfence();
-  if (q == 0 && lane == 0) p.counters[tile] = 0;                          // re-armed for the next launch
+  if (warp == 2 && lane == 0) p.counters[tile] = 0;                       // re-armed for the next launch
   const bool valid = row < p.M;
-#pragma unroll
-  for (int c = 0; c < BN; c += 32) {
+  for (int c = grp * 32; c < BN; c += 64) {                                // the two warp groups take alternate 32-column chunks
     float acc[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = 0.0f;
-    for (int sp = 0; sp < splits; ++sp) {
-      const float4* src = reinterpret_cast<const float4*>(p.ws + ((int64_t)sp * p.ws_rows + row) * p.ws_ld + n0 + c);
+    for (int sp0 = 0; sp0 < splits; sp0 += 4) {                            // 4 splits x 8 float4 requested before any is added
+      float4 v[4][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 v = __ldcg(src + j);
-        acc[4 * j] += v.x; acc[4 * j + 1] += v.y; acc[4 * j + 2] += v.z; acc[4 * j + 3] += v.w;
+      for (int s4 = 0; s4 < 4; ++s4) {
+        if (sp0 + s4 < splits) {
+          const float4* src = reinterpret_cast<const float4*>(p.ws + ((int64_t)(sp0 + s4) * p.ws_rows + row) * p.ws_ld + n0 + c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[s4][j] = __ldcg(src + j);
+        }
+      }
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) {
+        if (sp0 + s4 < splits) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc[4 * j] += v[s4][j].x; acc[4 * j + 1] += v[s4][j].y; acc[4 * j + 2] += v[s4][j].z; acc[4 * j + 3] += v[s4][j].w;
+          }
+        }
       }
     }
     if (valid && n0 + c < p.N) {
@@ -445,11 +474,11 @@ __device__ __forceinline__ void epilogue_tile_fixup(const GemmParams& p, int til
       if (n0 + c + 32 <= p.N && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
-          int4 v;
-          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+          int4 o;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
           for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(acc[j + 2 * t], acc[j + 2 * t + 1]);
-          *reinterpret_cast<int4*>(d + j) = v;
+          *reinterpret_cast<int4*>(d + j) = o;
         }
       } else {
         for (int j = 0; j < 32; ++j)
@@ -459,7 +488,7 @@ __device__ __forceinline__ void epilogue_tile_fixup(const GemmParams& p, int til
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool EXT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                        const __grid_constant__ CUtensorMap tmB,
                                                                        const __grid_constant__ CUtensorMap tmA2,
@@ -494,7 +523,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   const int n_kt = max(kt_end - kt_begin, 0);
 
   __shared__ float s_dbias[128];                    // per-CTA bias-gradient accumulator (backward extras)
-  __shared__ int s_fix[2];                          // out_mode 3: "this CTA arrived last" per epilogue warp group
+  __shared__ int s_fix[2];                          // out_mode 3: "this CTA arrived last at the tile's counter"
   if (threadIdx.x < 128) s_dbias[threadIdx.x] = 0.0f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mb_init(&full[s], 1); mb_init(&empty[s], 1); }
@@ -584,24 +613,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     }
   } else if (warp >= 2) {
     // ---------------------------------------------------------------------- epilogue (warp%4 selects the TMEM lane quarter)
-    // two groups of four warps, one per accumulator stage: the epilogue of tile t overlaps that of tile t+1
-    const int q = warp & 3;
-    const uint32_t grp = (uint32_t)(warp - 2) >> 2;
-    uint32_t tcount = 0;
-    for (int tile = cta; tile < tiles; tile += n_cta, ++tcount) {
-      if ((tcount & 1) != grp) continue;
-      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
-      const int m0 = mt * GEMM_BM, n0 = nt * BN;
-      if (p.out_mode == 3)
-        epilogue_tile_fixup<BN>(p, tile, m0, n0, q, lane, tmem_base, tcount & 1, (tcount >> 1) & 1, n_kt > 0, tmem_full, tmem_empty,
-                                s_fix, (int)grp);
-      else
-        epilogue_tile<BN, ACC>(p, m0, n0, q, lane, tmem_base, tcount & 1, (tcount >> 1) & 1, n_kt > 0, tmem_full, tmem_empty, s_dbias);
+    if (!EXT && p.out_mode == 3) {
+      // split-K with in-kernel fix-up: one tile per CTA, all eight epilogue warps take part in the fix-up
+      if (cta < tiles) {
+        const int mt = cta / n_tiles, nt = cta - mt * n_tiles;
+        epilogue_fixup<BN>(p, cta, mt * GEMM_BM, nt * BN, warp, lane, tmem_base, n_kt > 0, tmem_full, tmem_empty, s_fix);
+      }
+    } else {
+      // two groups of four warps, one per accumulator stage: the epilogue of tile t overlaps that of tile t+1
+      const int q = warp & 3;
+      const uint32_t grp = (uint32_t)(warp - 2) >> 2;
+      uint32_t tcount = 0;
+      for (int tile = cta; tile < tiles; tile += n_cta, ++tcount) {
+        if ((tcount & 1) != grp) continue;
+        const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+        const int m0 = mt * GEMM_BM, n0 = nt * BN;
+        epilogue_tile<BN, ACC, EXT>(p, m0, n0, q, lane, tmem_base, tcount & 1, (tcount >> 1) & 1, n_kt > 0, tmem_full, tmem_empty, s_dbias);
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (p.dbias && (int)threadIdx.x < p.dbias_mod) atomicAdd(p.dbias + threadIdx.x, s_dbias[threadIdx.x]);
+  if (EXT && p.dbias && (int)threadIdx.x < p.dbias_mod) atomicAdd(p.dbias + threadIdx.x, s_dbias[threadIdx.x]);
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
@@ -628,7 +661,7 @@ struct SlabParams {
 
 // BN = 32 (conv1, 12 tiles per SM, 16 KB of weights) compiles for two resident CTAs per SM: with many tiles the work can be
 // split over 2 x 148 CTAs whose waits interleave (launch_slab uses a <= 110 KB shared-memory budget then).
-template <int BN>
+template <int BN, bool EXT>
 __global__ void __launch_bounds__(GEMM_THREADS, BN == 32 ? 2 : 1) conv_slab_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                             const __grid_constant__ CUtensorMap tmB,
                                                                             const __grid_constant__ CUtensorMap tmA2,
@@ -748,11 +781,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, BN == 32 ? 2 : 1) conv_slab_tcge
     uint32_t it = 0;
     for (int tile = cta; tile < tiles; tile += n_cta, ++it)
       if ((it & 1) == grp)
-        epilogue_tile<BN, ACC>(p, tile * GEMM_BM, 0, q, lane, tmem_base, it & 1, (it >> 1) & 1, true, tmem_full, tmem_empty, s_dbias, it);
+        epilogue_tile<BN, ACC, EXT>(p, tile * GEMM_BM, 0, q, lane, tmem_base, it & 1, (it >> 1) & 1, true, tmem_full, tmem_empty, s_dbias, it);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (p.dbias && (int)threadIdx.x < p.dbias_mod) atomicAdd(p.dbias + threadIdx.x, s_dbias[threadIdx.x]);
+  if (EXT && p.dbias && (int)threadIdx.x < p.dbias_mod) atomicAdd(p.dbias + threadIdx.x, s_dbias[threadIdx.x]);
   if (threadIdx.x == 0) B2RL_TRACE_AT(3, 0, 3);
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
@@ -943,11 +976,13 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int STAGES>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
-                       const GemmParams& p, int splits, cudaStream_t st) {
+static bool has_ext(const GemmParams& p) { return p.mask || p.dbias || p.out_map >= 3; }
+
+template <int BN, int STAGES, bool EXT>
+static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
+                         const GemmParams& p, int splits, cudaStream_t st) {
   constexpr size_t smem = 1024 + (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + (2 * STAGES + 4) * 8 + 16;
-  auto k = gemm_tcgen05_kernel<BN, STAGES>;
+  auto k = gemm_tcgen05_kernel<BN, STAGES, EXT>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -957,9 +992,22 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   int ctas = sm_count() / splits / (p.dual ? 2 : 1);                 // per operand set
   if (ctas < 1) ctas = 1;
   if (ctas > tiles) ctas = tiles;
+  if (p.out_mode == 3 && ctas != tiles) {
+    set_error("b2rl_gemm_splitk_bf16: tiles x splits (%d x %d) must fit one CTA per SM (%d) and splits <= 8", tiles, splits, sm_count());
+    return B2RL_ERR_ARG;
+  }
   dim3 grid(p.dual ? 2 * ctas : ctas, 1, splits);
   launch_pdl(k, dim3(grid), dim3(GEMM_THREADS), smem, st, ta, tb, ta2, tb2, p);
   return check_launch("b2rl_gemm_bf16");
+}
+
+// the backward extras (mask / bias gradient / scatter maps) are compiled into their own instantiation: the forward and
+// weight-gradient kernels keep the lean epilogue (102 instead of 168 registers)
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
+                       const GemmParams& p, int splits, cudaStream_t st) {
+  return has_ext(p) ? launch_gemm_t<BN, STAGES, true>(ta, tb, ta2, tb2, p, splits, st)
+                    : launch_gemm_t<BN, STAGES, false>(ta, tb, ta2, tb2, p, splits, st);
 }
 
 static int gemm_dispatch(const uint16_t* A, int a_mn, int64_t lda, int64_t a_rows, int64_t a_cols, const uint16_t* B,
@@ -988,9 +1036,9 @@ static int gemm_dispatch(const uint16_t* A, int a_mn, int64_t lda, int64_t a_row
   return launch_gemm<128, 5>(ta, tb, ta2, tb2, p, splits, st);
 }
 
-template <int BN>
-static int launch_slab(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
-                       SlabParams sp, cudaStream_t st) {
+template <int BN, bool EXT>
+static int launch_slab_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
+                         SlabParams sp, cudaStream_t st) {
   const size_t w_bytes = (size_t)sp.taps * sp.col_blocks * BN * 128;
   const size_t slab_bytes = (size_t)sp.slab_rows * 128 * sp.col_blocks;
   const int tiles = (sp.g.M + GEMM_BM - 1) / GEMM_BM;
@@ -1008,7 +1056,7 @@ static int launch_slab(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   if (stages > 6) stages = 6;
   sp.stages = stages;
   const size_t smem = 1024 + w_bytes + stages * slab_bytes + (2 * 6 + 5) * 8 + 16;
-  auto k = conv_slab_tcgen05_kernel<BN>;
+  auto k = conv_slab_tcgen05_kernel<BN, EXT>;
   static size_t attr = 0;
   if (attr < smem) {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1018,6 +1066,12 @@ static int launch_slab(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   if (ctas > tiles) ctas = tiles;
   launch_pdl(k, dim3(sp.g.dual ? 2 * ctas : ctas), dim3(GEMM_THREADS), smem, st, ta, tb, ta2, tb2, sp);
   return check_launch("b2rl_conv_gemm_bf16(slab)");
+}
+
+template <int BN>
+static int launch_slab(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
+                       SlabParams sp, cudaStream_t st) {
+  return has_ext(sp.g) ? launch_slab_t<BN, true>(ta, tb, ta2, tb2, sp, st) : launch_slab_t<BN, false>(ta, tb, ta2, tb2, sp, st);
 }
 
 template <int TMEM_COLS>
@@ -1321,7 +1375,7 @@ extern "C" int b2rl_gemm_splitk_bf16(const uint16_t* A, int64_t lda, const uint1
                                      int32_t M, int32_t N, int32_t K, const float* bias, int32_t relu, int32_t splits,
                                      int32_t block_n, float* ws, int32_t* counters, void* stream) {
   B2RL_REQUIRE(A && B && D && ws && counters, "null pointer");
-  B2RL_REQUIRE(M > 0 && N > 0 && K > 0 && splits >= 1, "bad shape");
+  B2RL_REQUIRE(M > 0 && N > 0 && K > 0 && splits >= 1 && splits <= 8, "bad shape (1 <= splits <= 8)");
   B2RL_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "operand row strides must be multiples of 8 elements (16 bytes)");
   B2RL_REQUIRE((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(ws)) % 16 == 0,
                "operands and scratch must be 16-byte aligned");

@@ -383,8 +383,8 @@ extern "C" int b2rl_head_bwd_relu(const float* gq, const uint16_t* phi, const fl
 
 // DQN head forward (online on s, target on s', optional online on s' for double-Q) + target / loss / PER block + head
 // backward in one launch; see dqn_head_fused_kernel.  phi* are bf16 [B][K] outputs of a ReLU layer; *_t = target network's
-// head.  relu_colsum [K] (zeroed by the caller) receives fc4's bias gradient.  scratch: float [>= ceil(B/16)] then one
-// int32 counter (zero-initialised once; the kernel re-arms it).  q_out / delta_out / prio_out / loss_out may be NULL.
+// head.  relu_colsum [K] (zeroed by the caller) receives fc4's bias gradient.  scratch: one int32 counter (zero-initialised once; the
+// kernel re-arms it), 12 bytes of padding, then float [>= ceil(B/16)].  q_out / delta_out / prio_out / loss_out may be NULL.
 extern "C" int b2rl_dqn_head_fused(const uint16_t* phi, const uint16_t* phi_t, const uint16_t* phi_o, const float* Wa,
                                    const float* ba, const float* Wv, const float* bv, const float* Wa_t, const float* ba_t,
                                    const float* Wv_t, const float* bv_t, const int64_t* action, const float* reward,
@@ -409,7 +409,7 @@ extern "C" int b2rl_dqn_head_fused(const uint16_t* phi, const uint16_t* phi_t, c
   a.gphi = reinterpret_cast<__nv_bfloat16*>(gphi); a.gWa = gWa; a.gba = gba; a.gWv = gWv; a.gbv = gbv; a.relu_colsum = relu_colsum;
   a.q_out = q_out; a.delta_out = delta_out; a.prio_out = prio_out; a.loss_out = loss_out;
   const int row_blocks = (B + HB_ROWS - 1) / HB_ROWS;
-  a.loss_partial = scratch; a.counter = reinterpret_cast<int*>(scratch + row_blocks);
+  a.counter = reinterpret_cast<int*>(scratch); a.loss_partial = scratch + 4;      // counter first: its place does not depend on B
   const dim3 grid((K + 63) / 64, row_blocks);
   const int n_out = A + (Wv ? 1 : 0);
   cudaStream_t st = (cudaStream_t)stream;

@@ -58,6 +58,8 @@ struct ReduceArgs {
   float* grad;                                                               // flat .grad arena
   float* unit_sumsq;                                                         // [gridDim.x]
   int64_t* step_dev;                                                         // Adam step counter (bumped by unit 0) or null
+  NormScratch* sc;                                                           // non-null: the CTA that finishes last turns the unit
+  float max_norm, grad_scale;                                                // partials into clip_grad_norm_'s coefficient
 };
 
 __device__ __forceinline__ void add4(float4& a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
@@ -140,9 +142,29 @@ __global__ void __launch_bounds__(TAIL_THREADS) nature_grad_reduce_kernel(const 
     }
   }
   ss = block_reduce(ss, OpAdd(), 0.0f, red);
+  __shared__ bool is_last;
   if (tid == 0) {
     a.unit_sumsq[blockIdx.x] = ss;
     if (blockIdx.x == 0 && a.step_dev) *a.step_dev += 1;
+    is_last = false;
+    if (a.sc) {
+      __threadfence();
+      is_last = atomicAdd(&a.sc->counter, 1) == (int)gridDim.x - 1;
+    }
+  }
+  __syncthreads();
+  if (is_last) {                                          // fixed summation order: the result does not depend on which CTA is last
+    __threadfence();
+    float t = 0.0f;
+    for (int i = tid; i < (int)gridDim.x; i += TAIL_THREADS) t += __ldcg(a.unit_sumsq + i);
+    t = block_reduce(t, OpAdd(), 0.0f, red);
+    if (tid == 0) {
+      const float norm = sqrtf(t) * a.grad_scale;
+      const float c = a.max_norm > 0.0f ? a.max_norm / (norm + 1e-6f) : 1.0f;
+      a.sc->sumsq = norm;                                 // total_norm (what clip_grad_norm_ returns)
+      a.sc->coef = fminf(c, 1.0f) * a.grad_scale;
+      a.sc->counter = 0;
+    }
   }
 }
 
@@ -268,7 +290,8 @@ using namespace b2rl;
 extern "C" int b2rl_nature_grad_reduce(const int32_t* units, int32_t n_units, const float* g1p, int32_t p1, const float* g2p,
                                        int32_t p2, const float* g3p, int32_t p3, const float* g4p, float* db1, float* db2,
                                        float* db3, float* db4, int32_t c1, int32_t n4, float scale, float* grad,
-                                       float* unit_sumsq, int64_t* step_dev, void* stream) {
+                                       float* unit_sumsq, int64_t* step_dev, void* norm_scratch, float max_norm,
+                                       float grad_scale, void* stream) {
   B2RL_REQUIRE(units && g1p && g2p && g3p && g4p && db1 && db2 && db3 && db4 && grad && unit_sumsq, "null pointer");
   B2RL_REQUIRE(n_units > 0 && p1 > 0 && p2 > 0 && p3 > 0, "bad counts");
   B2RL_REQUIRE(c1 > 0 && c1 <= 16 && c1 % 4 == 0 && n4 > 0, "conv1 input channels must be a multiple of 4, at most 16");
@@ -280,6 +303,7 @@ extern "C" int b2rl_nature_grad_reduce(const int32_t* units, int32_t n_units, co
   a.g1p = g1p; a.g2p = g2p; a.g3p = g3p; a.g4p = g4p; a.p1 = p1; a.p2 = p2; a.p3 = p3;
   a.db1 = db1; a.db2 = db2; a.db3 = db3; a.db4 = db4; a.c1 = c1; a.n4 = n4; a.scale = scale;
   a.grad = grad; a.unit_sumsq = unit_sumsq; a.step_dev = step_dev;
+  a.sc = reinterpret_cast<NormScratch*>(norm_scratch); a.max_norm = max_norm; a.grad_scale = grad_scale;
   launch_pdl(nature_grad_reduce_kernel, dim3(n_units), dim3(TAIL_THREADS), 0, (cudaStream_t)stream, a);
   return check_launch("b2rl_nature_grad_reduce");
 }

@@ -22,6 +22,24 @@ from .network.fused import frame_scale
 from .utils.config import Config
 
 
+class StepTrace:
+    """Timing events recorded INSIDE the captured update (``torch.cuda.Event(external=True)`` -> event-record nodes of the
+    graph): the real timeline of one graph replay, with the overlap between the branches, which neither the serialised ncu
+    launch list nor eager launches show.  ``scripts/trace_step.py`` prints it."""
+
+    def __init__(self):
+        self.marks = []
+
+    def mark(self, name, stream=None):
+        e = torch.cuda.Event(enable_timing=True, external=True)
+        e.record(stream if stream is not None else torch.cuda.current_stream())
+        self.marks.append((name, e))
+
+    def timeline(self):
+        t0 = self.marks[0][1]
+        return [(n, t0.elapsed_time(e) * 1e3) for n, e in self.marks]
+
+
 class GraphedDQNLearner:
     def __init__(self, network, target_network, optimizer, replay, kind="dqn", discount=0.99, n_step=1, double_q=False,
                  gradient_clip=5.0, feeds_per_update=4, compute_dtype=torch.bfloat16, state_scale=1.0 / 255,
@@ -90,13 +108,14 @@ class GraphedDQNLearner:
             if ok:
                 self._repack(self.net, self.scale)
                 self._tail = NatureTail(self.opt, body, self.scale)
+                self._tail.max_norm, self._tail.grad_scale = self.clip, 1.0 / self.world
             else:
                 self._tail = False
         return self._tail or None
 
     def _heads(self):
         """(online head modules, target head modules) when the DQN head can run in the fused head + loss + backward kernel."""
-        if self.kind != "dqn" or self.tail() is None or os.environ.get("B2RL_FUSED_HEAD", "1") == "0":
+        if self.kind != "dqn" or self.tail() is None or os.environ.get("B2RL_FUSED_HEAD", "0") == "0":
             return None
         out = []
         for n in (self.net, self.tgt):
@@ -132,11 +151,14 @@ class GraphedDQNLearner:
     def _main(self, parity=None):
         rp = self.replay
         cur = torch.cuda.current_stream()
+        nature_tc.mark("start")
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.dev)
             self._pre = torch.cuda.Stream(device=self.dev)
             self._packed_ev, self._sampled_ev = torch.cuda.Event(), torch.cuda.Event()
         side, pre = self._side, self._pre
+        if os.environ.get("B2RL_SINGLE_STREAM", "0") == "1":       # experiment: no parallel graph branches except the prefetch
+            side = cur
         fs = self.scale if self.dtype == torch.bfloat16 else 1.0
         tail = self.tail()
         if tail is None:
@@ -157,6 +179,7 @@ class GraphedDQNLearner:
             with torch.cuda.stream(pre):
                 self._batch[1 - parity] = self._sample(1 - parity)
                 self._sampled_ev.record(pre)
+                nature_tc.mark("sampled")
             if eager:
                 self._parity = 1 - parity
         else:
@@ -193,6 +216,7 @@ class GraphedDQNLearner:
                     nxt_o = self.net(t.next_state) if self.double_q else None
                 out = self.net(t.state)
             cur.wait_stream(side)
+        nature_tc.mark("fwd_joined")
         if self.kind == "dqn":
             head = out["q"]
             r = ops.dqn_loss_fused(head.detach(), nxt_t["q"], nxt_o["q"] if nxt_o else None, t.action, t.reward, t.mask,
@@ -211,10 +235,12 @@ class GraphedDQNLearner:
             if self.prefetch:                            # the sum tree is read by the prefetch branch: update after it
                 cur.wait_event(self._sampled_ev)
             rp.update_priorities((t.idx, r["priority"]))
+        nature_tc.mark("loss")
         if tail is None:
             self.opt.zero_grad()
-        with nature_tc.wgrad_stream(side), nature_tc.grad_sink(tail):   # weight-gradient GEMMs on the side branch
+        with nature_tc.wgrad_stream(None if side is cur else side), nature_tc.grad_sink(tail):   # weight-gradient GEMMs on the side branch
             head.backward(grad)
+        nature_tc.mark("bwd_done")
         self.loss.copy_(r["loss"])
         if self.prefetch:
             cur.wait_stream(pre)
@@ -231,6 +257,7 @@ class GraphedDQNLearner:
                 phi_o = self.net.body(t.next_state) if self.double_q else None
             phi = self.net.body(t.state)
         cur.wait_stream(side)
+        nature_tc.mark("fwd_joined")
         r = ops.dqn_head_fused(phi.detach(), phi_t, phi_o, heads[0], heads[1], t.action, t.reward, t.mask, self.gamma_n,
                                tail.db4, **per)
         if self.per:
@@ -238,6 +265,7 @@ class GraphedDQNLearner:
                 cur.wait_event(self._sampled_ev)
             self.replay.update_priorities((t.idx, r["priority"]))
         gphi = r["gphi"]
+        nature_tc.mark("head")
         nature_tc.PREMASKED[gphi.data_ptr()] = tail.db4  # already masked by relu(fc4); its column sums are in the tail's db4
         with nature_tc.wgrad_stream(side), nature_tc.grad_sink(tail):
             phi.backward(gphi)
@@ -259,8 +287,10 @@ class GraphedDQNLearner:
         tail = self.tail()
         if tail is not None:
             tail.step(max_norm=self.clip, grad_scale=1.0 / self.world, reduced_elsewhere=self.world > 1)
+            nature_tc.mark("opt")
         else:
             self.opt.step(max_norm=self.clip, grad_scale=1.0 / self.world)
+            nature_tc.mark("opt")
 
     def refresh_packed(self):
         """Re-derive the packed bf16 operands of both networks from the fp32 parameters (after the parameters were changed

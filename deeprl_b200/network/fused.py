@@ -179,6 +179,7 @@ class _NarrowHead(torch.autograd.Function):
                       _lib.ptr(None if wv is None else wv.detach()), B, K, A, _lib.ptr(gphi), _lib.ptr(gwa), _lib.ptr(gba),
                       _lib.ptr(gwv), _lib.ptr(gbv), _lib.ptr(colsum), _lib.stream())
             nature_tc.PREMASKED[gphi.data_ptr()] = colsum
+            nature_tc.mark("head_bwd")
         else:
             _lib.call("b2rl_head_bwd", _lib.ptr(gq), _lib.ptr(phi), _lib.ptr(wa.detach()),
                       _lib.ptr(None if wv is None else wv.detach()), B, K, A, _lib.ptr(gphi), _lib.ptr(gwa), _lib.ptr(gba),

@@ -36,6 +36,14 @@ FC4_FIXUP = os.environ.get("B2RL_FC4_FIXUP", "1") == "1"
 # b2rl_act_bwd_bias_grad_bf16 passes (B2RL_FUSED_BWD=0 restores them).
 FUSED_BWD = os.environ.get("B2RL_FUSED_BWD", "1") == "1"
 _ZEROED = {}
+TRACE = None               # learner.StepTrace while a traced capture is running: mark(name) records a timing event in the graph
+
+
+def mark(name, stream=None):
+    if TRACE is not None:
+        TRACE.mark(name, stream)
+
+
 SINK = None                # network/tail.py NatureTail while ``grad_sink`` is active: backward hands it the GEMM-layout gradients
 RELU_FEATURES = set()      # data_ptr of feature tensors y4 = relu(fc4(.)) produced by nature_body (for head_bwd_relu)
 PREMASKED = {}             # data_ptr of a feature gradient already masked by head_bwd_relu -> its column sums (= db4)
@@ -79,6 +87,7 @@ def _backward_fused(ctx, gy4):
         g4, db4 = act_bwd_bias_grad(gy4, y4, True)                                      # fc4's own ReLU / bias gradient
     y3c = y3.view(B, 3136)
     gw4p = gemm_bf16(g4, y3c, a_major="mn", b_major="mn", out_dtype=_f32, block_n=128, stream=_fork())
+    mark("w_fc4", _WGRAD["stream"])
     if sink is not None:                   # persistent accumulators, re-zeroed by the tail's kernel A
         db1, db2, db3 = sink.db1, sink.db2, sink.db3
     else:
@@ -89,19 +98,25 @@ def _backward_fused(ctx, gy4):
     e3 = _lib.bwd_epilogue(y3c, db3, 64, 64)
     _lib.call("b2rl_gemm_bwd_bf16", _lib.ptr(g4), g4.stride(0), _lib.ptr(w4p), 1, w4p.stride(0), _lib.ptr(g3), 64, B, 3136,
               g4.shape[1], 4, 10, 7, ctypes.byref(e3), 128, _lib.stream())
+    mark("d_fc4")
     gw3p, p3 = wgrad_partials(y2, g3, 64, 9, 3, 10, stream=_fork())
+    mark("w_conv3", _WGRAD["stream"])
     # conv3 dgrad on the 10-grid, masked by relu(conv2)
     g2 = torch.empty((B * 100, 64), dtype=_bf16, device=dev)
     e2 = _lib.bwd_epilogue(y2, db2, 64, 0)
     _lib.call("b2rl_conv_gemm_bwd_bf16", _lib.ptr(g3), B * 100, 64, _lib.ptr(w3d), 64, 9, 3, 10, _lib.ptr(g2), 64, 0, 0, 0,
               ctypes.byref(e2), 64, _lib.stream())
+    mark("d_conv3")
     gw2p, p2 = wgrad_partials(x1, g2, 64, 4, 2, 10, stream=_fork())
+    mark("w_conv2", _WGRAD["stream"])
     # conv2 dgrad: space-to-depth(2) rows -> conv1's 21-grid, masked by relu(conv1)
     g1 = _zero_grid("g1", (B * 441, 32), dev)
     e1 = _lib.bwd_epilogue(x1, db1, 32, 32)
     _lib.call("b2rl_conv_gemm_bwd_bf16", _lib.ptr(g2), B * 100, 64, _lib.ptr(w2d), 128, 4, 2, 10, _lib.ptr(g1), 32, 3, 21, 20,
               ctypes.byref(e1), 128, _lib.stream())
+    mark("d_conv2")
     gw1p, p1 = wgrad_partials(x0m, g1, 32, 4, 2, 21, stream=_fork())
+    mark("w_conv1", _WGRAD["stream"])
     _join()
     return (gw1p, p1, gw2p, p2, gw3p, p3, gw4p), (db1, db2, db3, db4)
 
@@ -209,10 +224,13 @@ def forward_only(x0, packed, b1, b2, b3, b4):
     x0m = x0.permute(0, 2, 3, 1).reshape(B * 441, x0.shape[1])                # free view of the NHWC memory
     x1 = torch.empty((B * 100, 128), dtype=_bf16, device=dev)
     conv_gemm(0, x0m, w1f, 32, 4, 2, 21, 1, x1, bias=b1, relu=True, out_map=1, G=21, V=20, block_n=32)
+    mark("f_conv1")
     y2 = torch.empty((B * 100, 64), dtype=_bf16, device=dev)
     conv_gemm(0, x1, w2f, 64, 4, 2, 10, 1, y2, bias=b2, relu=True, block_n=64)
+    mark("f_conv2")
     y3 = torch.empty((B * 49, 64), dtype=_bf16, device=dev)
     conv_gemm(0, y2, w3f, 64, 9, 3, 10, 1, y3, bias=b3, relu=True, out_map=2, G=10, V=7, block_n=64)
+    mark("f_conv3")
     n4 = w4p.shape[0]
     if B <= 1024 and FC4_SPLITS > 1 and FC4_FIXUP:
         # few output tiles, long K (3136): split K over CTAs; the last split of a tile adds the partials, bias + ReLU + bf16
@@ -224,6 +242,7 @@ def forward_only(x0, packed, b1, b2, b3, b4):
         _lib.call("b2rl_bias_act_f32_to_bf16", _lib.ptr(acc), _lib.ptr(b4), _lib.ptr(y4), B, n4, 1, _lib.stream())
     else:
         y4 = gemm_bf16(y3.view(B, 3136), w4p, bias=b4, relu=True, block_n=32 if B <= 1024 else 64)
+    mark("f_fc4")
     return y4, (x0m, x1, y2, y3)
 
 
@@ -314,6 +333,7 @@ class _NatureBody(torch.autograd.Function):
             if db4 is not sink.db4:
                 sink.db4.copy_(db4)
             sink.reduce(gw1p, p1, gw2p, p2, gw3p, p3, gw4p)
+            mark("reduce")
             return (None,) * 12
         if all(p.grad is not None and p.grad.dtype == _f32 and p.grad.is_contiguous() for p in params):
             # accumulate straight into the .grad arena (reference layouts), one launch

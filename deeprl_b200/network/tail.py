@@ -82,6 +82,9 @@ class NatureTail:
         self.db = torch.zeros(32 + 64 + 64 + self.n4, dtype=_f32, device=dev)
         self.db1, self.db2, self.db3, self.db4 = self.db[:32], self.db[32:96], self.db[96:160], self.db[160:]
         self.kind = {"rmsprop": 1 if opt.centered else 0, "adam": 2}[opt.kind]
+        # clip_grad_norm_'s arguments of the NEXT step(): kernel A's last CTA already turns its unit partials into the
+        # coefficient, so kernel B starts with one scalar load (set by the owner before the backward pass)
+        self.max_norm, self.grad_scale = 0.0, 1.0
 
     def packed(self):
         from . import nature_tc
@@ -95,20 +98,24 @@ class NatureTail:
         _lib.call("b2rl_nature_grad_reduce", _lib.ptr(self.a_units), self.n_a, _lib.ptr(gw1p), int(p1), _lib.ptr(gw2p), int(p2),
                   _lib.ptr(gw3p), int(p3), _lib.ptr(gw4p), _lib.ptr(self.db1), _lib.ptr(self.db2), _lib.ptr(self.db3),
                   _lib.ptr(self.db4), self.c1, self.n4, self.scale, _lib.ptr(o.grad), _lib.ptr(self.unit_sumsq),
-                  _lib.ptr(o.step_dev) if o.kind == "adam" else None, _lib.stream())
+                  _lib.ptr(o.step_dev) if o.kind == "adam" else None, _lib.ptr(o.scratch), float(self.max_norm or 0.0),
+                  float(self.grad_scale), _lib.stream())
 
     def step(self, max_norm=0.0, grad_scale=1.0, reduced_elsewhere=False):
         """Clip + optimizer + bf16 operand pack.  ``reduced_elsewhere``: the gradient arena was all-reduced after ``reduce``
-        (multi-GPU), so the norm is recomputed over the arena (one extra launch) instead of taken from the unit partials."""
+        (multi-GPU), so the norm is recomputed over the arena (one extra launch) instead of taken from the unit partials.
+        Otherwise ``max_norm`` / ``grad_scale`` must be what ``self.max_norm`` / ``self.grad_scale`` held during ``reduce``."""
         o = self.opt
         pk = self.packed()
+        if not reduced_elsewhere and (float(max_norm or 0.0), float(grad_scale)) != (float(self.max_norm or 0.0), float(self.grad_scale)):
+            raise _lib.B2RLError("NatureTail.step: set tail.max_norm / tail.grad_scale before the backward pass")
         if reduced_elsewhere:
             _lib.call("b2rl_grad_norm", _lib.ptr(o.grad), o.n, float(grad_scale), float(max_norm or 0.0), _lib.ptr(o.scratch),
                       _lib.stream())
         a, b = (o.betas if o.kind == "adam" else (o.alpha, 0.0))
         _lib.call("b2rl_nature_fused_opt", _lib.ptr(self.b_units), self.n_b, _lib.ptr(o.flat), _lib.ptr(o.grad), _lib.ptr(o.s1),
                   _lib.ptr(o.s2), self.kind, float(o.lr), float(a), float(b), float(o.eps), float(max_norm or 0.0),
-                  float(grad_scale), None if reduced_elsewhere else _lib.ptr(self.unit_sumsq), self.n_a, _lib.ptr(o.scratch),
+                  float(grad_scale), None, self.n_a, _lib.ptr(o.scratch),
                   _lib.ptr(o.step_dev), self.c1, self.n4, self.scale, _lib.ptr(pk.w1f), _lib.ptr(pk.w2f), _lib.ptr(pk.w2d),
                   _lib.ptr(pk.w3f), _lib.ptr(pk.w3d), _lib.ptr(pk.w4p), 1, _lib.stream())
         pk.scale = self.scale

@@ -318,7 +318,8 @@ int b2rl_gemm_splitk_bf16(const uint16_t* A, int64_t lda, const uint16_t* B, int
  *   maps all four weight gradients from the GEMM layouts to the reference layouts and WRITES them into the flat
  *   gradient arena, moves the bias gradients there (db1..db4 are re-zeroed), and leaves the sum of squares of the
  *   gradient elements of unit i in unit_sumsq[i] (plain units: whatever the arena already holds, e.g. the head's
- *   gradients).  step_dev (Adam) is incremented by one if not NULL.
+ *   gradients).  step_dev (Adam) is incremented by one if not NULL.  norm_scratch != NULL: the CTA that finishes last adds the
+ *   unit partials (fixed order) and leaves clip_grad_norm_'s total norm and coefficient there, as b2rl_grad_norm does.
  * fused_opt: clip coefficient from the unit partials (NULL: from norm_scratch, see b2rl_grad_norm), RMSprop
  *   (opt 0 plain, 1 centered; a_ = alpha) or Adam (opt 2; a_, b_ = betas) exactly as b2rl_clip_rmsprop / b2rl_clip_adam,
  *   gradient re-zeroed when zero_grad != 0, and the updated conv / fc4 weights written to the bf16 tap-major GEMM
@@ -327,7 +328,7 @@ int b2rl_gemm_splitk_bf16(const uint16_t* A, int64_t lda, const uint16_t* B, int
 int b2rl_nature_grad_reduce(const int32_t* units, int32_t n_units, const float* g1p, int32_t p1, const float* g2p, int32_t p2,
                             const float* g3p, int32_t p3, const float* g4p, float* db1, float* db2, float* db3, float* db4,
                             int32_t c1, int32_t n4, float scale, float* grad, float* unit_sumsq, int64_t* step_dev,
-                            void* stream);
+                            void* norm_scratch, float max_norm, float grad_scale, void* stream);
 int b2rl_nature_fused_opt(const int32_t* units, int32_t n_units, float* param, float* grad, float* s1, float* s2, int32_t opt,
                           float lr, float a_, float b_, float eps, float max_norm, float grad_scale, const float* unit_sumsq,
                           int32_t n_sumsq, void* norm_scratch, const int64_t* step_dev, int32_t c1, int32_t n4, float scale,
@@ -341,7 +342,8 @@ int b2rl_grad_norm(const float* grad, int64_t n, float grad_scale, float max_nor
  * q_next = target_head(phi_t) on s' [argmax from head(phi_o) for double-Q], delta / priorities / IS weights / loss as
  * b2rl_dqn_loss, then the gradients of the head (accumulated into gWa / gba / gWv / gbv), dphi masked by phi > 0 and
  * its column sums (fc4's bias gradient) accumulated into relu_colsum.  Heads: VanillaNet (Wv == NULL) or DuelingNet
- * (network_heads.py:11-37).  scratch: float [ceil(B/16)] + int32 counter, zero-initialised once. */
+ * (network_heads.py:11-37).  scratch: int32 counter (zero-initialised once, self re-arming) + 12 bytes
+ * padding + float [ceil(B/16)]. */
 int b2rl_dqn_head_fused(const uint16_t* phi, const uint16_t* phi_t, const uint16_t* phi_o, const float* Wa, const float* ba,
                         const float* Wv, const float* bv, const float* Wa_t, const float* ba_t, const float* Wv_t,
                         const float* bv_t, const int64_t* action, const float* reward, const float* mask, float gamma_n,
