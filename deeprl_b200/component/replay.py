@@ -198,7 +198,7 @@ class UniformReplay:
         return np.asarray(idx)
 
     # ------------------------------------------------------------------ sampling
-    LAYOUTS = {"nchw": 0, "nhwc": 1, "s2d": 2, False: 0, True: 1}
+    LAYOUTS = {"nchw": 0, "nhwc": 1, "s2d": 2, "ring": 3, False: 0, True: 1}
 
     def _buffers(self, B, out_dtype, layout, tag=0):
         layout = self.LAYOUTS[layout]
@@ -206,6 +206,8 @@ class UniformReplay:
         if key not in self._bufs:
             dev, hl = self.device, self.history_length
             shape = (B, self.row_bytes, hl) if layout else (B, hl, self.row_bytes)     # same byte count for s2d
+            if layout == 3:
+                shape = (0,)                                                           # the frames stay in the ring
             self._bufs[key] = dict(
                 idx=torch.empty(B, dtype=torch.int64, device=dev),
                 state=torch.empty(shape, dtype=out_dtype, device=dev), next_state=torch.empty(shape, dtype=out_dtype, device=dev),
@@ -227,6 +229,19 @@ class UniformReplay:
         n_cand = min(8192, max(2 * B, B + 256)) if candidates is None else min(8192, candidates.numel())
         _lib.call("b2rl_replay_select_uniform", _lib.ptr(self.ring_state), _lib.ptr(candidates), int(n_cand), self.seed,
                   self.history_length, self.n_step, int(B), _lib.ptr(idx_out), _lib.ptr(self._status), _lib.stream())
+
+    def ring_frames(self, idx, which):
+        """The (not materialised) frame stacks of ``idx``: ``which`` = 0 state, 1 next state (replay.py:124-125)."""
+        from ..network.nature_tc import RingFrames
+        hl = self.history_length
+        return RingFrames(self.frames, idx, which * self.n_step - (hl - 1), self.row_bytes, self.item_shape[-1], hl)
+
+    def gather_scalars(self, idx, B, bufs):
+        """action / n-step reward / mask of ``idx`` only (the frame stacks are read from the ring by the consumer)."""
+        _lib.call("b2rl_replay_gather", _lib.ptr(self.frames), _lib.ptr(self.action), _lib.ptr(self.reward),
+                  _lib.ptr(self.mask), self.memory_size, self.row_bytes, _lib.ptr(idx), int(B), self.history_length,
+                  self.n_step, self.discount, None, _lib.DTYPE_CODE[torch.uint8], 0, 0, None, None, _lib.ptr(bufs["action"]),
+                  _lib.ptr(bufs["reward"]), _lib.ptr(bufs["mask"]), _lib.stream())
 
     def gather(self, idx, B, bufs, out_dtype=torch.uint8, lut=None, layout="nchw"):
         frame_w = self.item_shape[-1] if len(getattr(self, "item_shape", ())) >= 2 else 0
@@ -277,7 +292,9 @@ class UniformReplay:
         ``out_dtype`` [B, history, H, W] (``layout="nhwc"``: same logical shape, channels_last memory) or, with
         ``layout="s2d"``, as the space-to-depth(4) tensor [B, 16*history, H/4, W/4] (channels_last memory).
         ``scale=None`` emits the exact integers 0..255 (the consumer folds 1/255 into its first layer, see
-        ``network.frame_scale``); otherwise ``float32(float64(v) * scale)`` rounded to ``out_dtype``."""
+        ``network.frame_scale``); otherwise ``float32(float64(v) * scale)`` rounded to ``out_dtype``.
+        ``layout="ring"`` (K1): nothing is gathered -- state / next_state are ``RingFrames`` (ring + indices) that the tcgen05
+        ``NatureConvBody`` reads directly; they are valid until the ring rows are overwritten."""
         if channels_last is not None:
             layout = "nhwc" if channels_last else "nchw"
         B = self.batch_size if batch_size is None else int(batch_size)
@@ -287,6 +304,10 @@ class UniformReplay:
         if candidates is not None and not isinstance(candidates, torch.Tensor):
             candidates = torch.as_tensor(np.asarray(candidates, dtype=np.int64), device=self.device)
         self.select(B, bufs["idx"], candidates)
+        if layout == "ring":             # K1: no batch is materialised, conv1 reads the ring through the sampled indices
+            self.gather_scalars(bufs["idx"], B, bufs)
+            return Transition(self.ring_frames(bufs["idx"], 0), bufs["action"], bufs["reward"], self.ring_frames(bufs["idx"], 1),
+                              bufs["mask"])
         self.gather(bufs["idx"], B, bufs, out_dtype, None if scale is None else self.lut(scale), layout)
         return Transition(self._image_view(bufs["state"], B, layout), bufs["action"], bufs["reward"],
                           self._image_view(bufs["next_state"], B, layout), bufs["mask"])
@@ -375,6 +396,10 @@ class PrioritizedReplay(UniformReplay):
         B = self.batch_size if batch_size is None else int(batch_size)
         bufs = self._buffers(B, out_dtype, layout, tag)
         self._select_per(B, bufs, uniforms, fills)
+        if layout == "ring":
+            self.gather_scalars(bufs["idx"], B, bufs)
+            return PrioritizedTransition(self.ring_frames(bufs["idx"], 0), bufs["action"], bufs["reward"],
+                                         self.ring_frames(bufs["idx"], 1), bufs["mask"], bufs["prob"], bufs["tree_idx"])
         self.gather(bufs["idx"], B, bufs, out_dtype, None if scale is None else self.lut(scale), layout)
         return PrioritizedTransition(self._image_view(bufs["state"], B, layout), bufs["action"], bufs["reward"],
                                      self._image_view(bufs["next_state"], B, layout), bufs["mask"], bufs["prob"],

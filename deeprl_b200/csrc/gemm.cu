@@ -650,6 +650,87 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 // results, 0 gives the right ones).  The weights (all taps) are loaded once per CTA and stay resident.  Activation traffic drops by the
 // number of taps (4x conv1/conv2, 9x conv3) and the weight traffic per tile to zero.
 // ---------------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------
+// K1: fused replay gather -> exact u8->bf16 -> conv1 operand.  Instead of reading a materialised bf16 space-to-depth matrix
+// (57.8 MB per batch-512 stack, written by the gather kernel and re-read here), conv1's forward and weight-gradient kernels
+// build their activation slabs themselves from the uint8 frame ring: four converter warps read, for every slab row
+// (b, gy, gx) and 16-byte chunk j (8 channels = frame j/2, pixel rows 4gy + 2(j&1) + {0,1}, pixel columns 4gx..4gx+3), two
+// aligned 32-bit words of the ring, convert the eight pixels exactly (integers 0..255 are representable in bf16; the 1/255
+// of ImageNormalizer is folded into conv1's weights) and store one 16-byte chunk at the 128-byte-swizzled position
+// (chunk ^ (row & 7)) the TMA would have written.  Reference chain replaced: replay.py:124-134 (frame-stack gather),
+// normalizer.py:58-61, network_bodies.py:27.
+// ---------------------------------------------------------------------------------------------------------------
+struct U8Src {
+  const uint8_t* frames;     // ring [capacity][row_bytes]
+  const int64_t* idx;        // sampled ring indices [batch]
+  int64_t row_bytes;         // bytes per ring row (84 * 84)
+  int first;                 // ring row of channel-frame 0 relative to idx[b]: -(history-1) for s, n_step-(history-1) for s'
+  int frame_w;               // pixels per frame row (84)
+  int G;                     // grid width = frame_w / 4 (21); slab rows are (b, gy, gx) over G x G positions per image
+  int rows;                  // batch * G * G
+};
+
+__device__ __forceinline__ int4 cvt8_u8_bf16(uint32_t w0, uint32_t w1) {
+  // exact u8 -> bf16 without I2F: 0x4B0000vv is the float 2^23 + v; subtract 2^23; the top 16 bits are the bf16
+  const float m = 8388608.0f;
+  uint32_t f[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    f[k] = __float_as_uint(__uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7540 + k)) - m);
+    f[4 + k] = __float_as_uint(__uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7540 + k)) - m);
+  }
+  int4 o;
+  o.x = (int)__byte_perm(f[0], f[1], 0x7632);
+  o.y = (int)__byte_perm(f[2], f[3], 0x7632);
+  o.z = (int)__byte_perm(f[4], f[5], 0x7632);
+  o.w = (int)__byte_perm(f[6], f[7], 0x7632);
+  return o;
+}
+
+// 128 threads (tid 0..127, named barrier `bar_id`) fill one swizzled slab of `slab_rows` rows x 64 channels whose first row is
+// grid-matrix row R0; rows outside [0, rows) are zero (what the TMA's out-of-bounds fill gave).  On return every thread's
+// stores are fenced towards the async proxy (tcgen05.mma reads shared memory through it) and all 128 threads have arrived.
+__device__ __forceinline__ void fill_slab_u8(const U8Src& u, uint8_t* slab, int R0, int slab_rows, long long* rowinfo, int tid,
+                                             int bar_id) {
+  const int gg = u.G * u.G;
+  for (int rl = tid; rl < slab_rows; rl += 128) {
+    const int r = R0 + rl;
+    long long o = -1;
+    if (r >= 0 && r < u.rows) {
+      const int b = r / gg, pos = r - b * gg, gy = pos / u.G, gx = pos - gy * u.G;
+      o = (__ldg(u.idx + b) + u.first) * u.row_bytes + (long long)(4 * gy) * u.frame_w + 4 * gx;
+    }
+    rowinfo[rl] = o;
+  }
+  asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+  const int units = slab_rows * 8;                        // unit = (chunk j, slab row): consecutive threads -> consecutive rows
+  for (int u0 = tid; u0 < units; u0 += 128 * 4) {         // 4 units = 8 independent 32-bit loads in flight per thread
+    uint32_t w[4][2];
+    int dst[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int uu = u0 + k * 128;
+      w[k][0] = w[k][1] = 0;
+      dst[k] = -1;
+      if (uu < units) {
+        const int j = uu / slab_rows, rl = uu - j * slab_rows;
+        dst[k] = rl * 128 + ((j ^ (rl & 7)) << 4);
+        const long long o = rowinfo[rl];
+        if (o >= 0) {
+          const uint8_t* src = u.frames + o + (long long)(j >> 1) * u.row_bytes + (2 * (j & 1)) * u.frame_w;
+          w[k][0] = __ldg(reinterpret_cast<const uint32_t*>(src));
+          w[k][1] = __ldg(reinterpret_cast<const uint32_t*>(src + u.frame_w));
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (dst[k] >= 0) *reinterpret_cast<int4*>(slab + dst[k]) = cvt8_u8_bf16(w[k][0], w[k][1]);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+}
+
 struct SlabParams {
   GemmParams g;            // M, N, ldd, relu, out_mode, bias, D, taps_x, grid_w, shift_sign, out_map, G, V
   int taps, col_blocks;    // taps, channels / 64
@@ -657,11 +738,12 @@ struct SlabParams {
   int min_shift;           // row offset of the slab start relative to m0 (0 for forward, -max_shift for dgrad)
   int stages;
   int base_offset_mode;    // 1: descriptor base_offset = (window start >> 7) & 7; 2: base_offset = 0 (address-based swizzle)
+  U8Src u8;                // U8 kernels: the activation slabs are built from the uint8 frame ring (K1), tmA is unused
 };
 
 // BN = 32 (conv1, 12 tiles per SM, 16 KB of weights) compiles for two resident CTAs per SM: with many tiles the work can be
 // split over 2 x 148 CTAs whose waits interleave (launch_slab uses a <= 110 KB shared-memory budget then).
-template <int BN, bool EXT>
+template <int BN, bool EXT, bool U8>
 __global__ void __launch_bounds__(GEMM_THREADS, BN == 32 ? 2 : 1) conv_slab_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                             const __grid_constant__ CUtensorMap tmB,
                                                                             const __grid_constant__ CUtensorMap tmA2,
@@ -692,6 +774,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, BN == 32 ? 2 : 1) conv_slab_tcge
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* w_full = tmem_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  __shared__ long long s_rowinfo[U8 ? 256 : 1];    // U8: ring byte offset of every slab row of the tile being converted
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
   const int tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
@@ -722,15 +805,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, BN == 32 ? 2 : 1) conv_slab_tcge
     mb_expect_tx(w_full, (uint32_t)k_tiles * W_TILE);
     for (int kt = 0; kt < k_tiles; ++kt) tma_load_2d(sW + (size_t)kt * W_TILE, mB, w_full, kt * GEMM_BK, 0);
     uint32_t it = 0;
+    if (!U8) {
+      for (int tile = cta; tile < tiles; tile += n_cta, ++it) {
+        const int s = it % sp.stages;
+        B2RL_TRACE_AT(0, it, 0);
+        mb_wait(&empty[s], ((it / sp.stages) & 1) ^ 1);
+        B2RL_TRACE_AT(0, it, 1);
+        mb_expect_tx(&full[s], slab_bytes);
+        for (int cb = 0; cb < sp.col_blocks; ++cb)
+          tma_load_2d(sS + (size_t)s * slab_bytes + (size_t)cb * slab_block, mA, &full[s], cb * GEMM_BK,
+                      tile * GEMM_BM + sp.min_shift);
+      }
+    }
+  } else if (U8 && warp >= 6) {
+    // ---------------------------------------------------------------------- K1 converters (warps 6-9): uint8 ring -> slab
+    const int tid = (int)threadIdx.x - 6 * 32;
+    uint32_t it = 0;
     for (int tile = cta; tile < tiles; tile += n_cta, ++it) {
       const int s = it % sp.stages;
-      B2RL_TRACE_AT(0, it, 0);
       mb_wait(&empty[s], ((it / sp.stages) & 1) ^ 1);
-      B2RL_TRACE_AT(0, it, 1);
-      mb_expect_tx(&full[s], slab_bytes);
-      for (int cb = 0; cb < sp.col_blocks; ++cb)
-        tma_load_2d(sS + (size_t)s * slab_bytes + (size_t)cb * slab_block, mA, &full[s], cb * GEMM_BK,
-                    tile * GEMM_BM + sp.min_shift);
+      fill_slab_u8(sp.u8, sS + (size_t)s * slab_bytes, tile * GEMM_BM + sp.min_shift, sp.slab_rows, s_rowinfo, tid, 2);
+      if (tid == 0) mb_arrive(&full[s]);
     }
   } else if (warp == 1 && elect_one()) {
     // ---------------------------------------------------------------------- MMA issuer
@@ -778,9 +873,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, BN == 32 ? 2 : 1) conv_slab_tcge
   } else if (warp >= 2) {
     const int q = warp & 3;
     const uint32_t grp = (uint32_t)(warp - 2) >> 2;                    // accumulator stage this warp group drains
-    uint32_t it = 0;
+    uint32_t it = 0;                                                   // (U8: warps 2-5 drain both stages, warps 6-9 convert)
     for (int tile = cta; tile < tiles; tile += n_cta, ++it)
-      if ((it & 1) == grp)
+      if (U8 || (it & 1) == grp)
         epilogue_tile<BN, ACC, EXT>(p, tile * GEMM_BM, 0, q, lane, tmem_base, it & 1, (it >> 1) & 1, true, tmem_full, tmem_empty, s_dbias, it);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -815,9 +910,10 @@ struct WgradParams {
   // function of the address, so overlapping groups read the right bytes) with adjacent TMEM accumulator columns.
   int n_runs;
   uint32_t run_off[9], run_acc[9], run_n[9];   // slab window offset (16-byte units), accumulator column, N of the MMA
+  U8Src u8;                                    // U8 kernels: the activation slabs come from the uint8 frame ring (K1)
 };
 
-template <int TMEM_COLS>
+template <int TMEM_COLS, bool U8>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmG,
                                                                              const __grid_constant__ CUtensorMap tmX,
                                                                              const WgradParams w) {
@@ -832,13 +928,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
   uint64_t* empty = full + MAX_STAGES;
   uint64_t* tmem_full = empty + MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  __shared__ long long s_rowinfo[U8 ? 256 : 1];
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
   const int kt_total = (w.rows + GEMM_BK - 1) / GEMM_BK;
   const int kt_begin = blockIdx.x * w.k_tiles_per_cta;
   const int n_kt = max(min(kt_total, kt_begin + w.k_tiles_per_cta) - kt_begin, 0);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < MAX_STAGES; ++s) { mb_init(&full[s], 1); mb_init(&empty[s], 1); }
+    for (int s = 0; s < MAX_STAGES; ++s) { mb_init(&full[s], U8 ? 2 : 1); mb_init(&empty[s], 1); }   // U8: TMA + converters
     mb_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
@@ -861,12 +958,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
       B2RL_TRACE_AT(0, i, 0);
       mb_wait(&empty[s], ((i / w.stages) & 1) ^ 1);
       B2RL_TRACE_AT(0, i, 1);
-      mb_expect_tx(&full[s], (uint32_t)w.a_boxes * 8192 + slab_bytes);
+      mb_expect_tx(&full[s], (uint32_t)w.a_boxes * 8192 + (U8 ? 0u : slab_bytes));
       uint8_t* st = smem + (size_t)s * stage_bytes;
       const int k0 = (kt_begin + i) * GEMM_BK;
       for (int g = 0; g < w.a_boxes; ++g) tma_load_2d(st + g * 8192, &tmG, &full[s], g * 64, k0);       // [64 k][64 n]
-      for (int cb = 0; cb < w.col_blocks; ++cb)
-        tma_load_2d(st + A_BYTES + (size_t)cb * slab_block, &tmX, &full[s], cb * GEMM_BK, k0);           // [slab_rows][64 c]
+      if (!U8) {
+        for (int cb = 0; cb < w.col_blocks; ++cb)
+          tma_load_2d(st + A_BYTES + (size_t)cb * slab_block, &tmX, &full[s], cb * GEMM_BK, k0);         // [slab_rows][64 c]
+      }
     }
   } else if (warp == 1 && n_kt > 0 && elect_one()) {
     const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(GEMM_BM >> 4) << 24);
@@ -895,6 +994,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
     }
     umma_commit(tmem_full);
   } else if (warp >= 2 && n_kt > 0) {
+    if (U8 && warp >= 6) {
+      // K1 converters (warps 6-9): the activation slab of every k-tile from the uint8 ring; they join the epilogue afterwards
+      const int tid = (int)threadIdx.x - 6 * 32;
+      for (int i = 0; i < n_kt; ++i) {
+        const int s = i % w.stages;
+        mb_wait(&empty[s], ((i / w.stages) & 1) ^ 1);
+        fill_slab_u8(w.u8, smem + (size_t)s * stage_bytes + A_BYTES, (kt_begin + i) * GEMM_BK, w.slab_rows, s_rowinfo, tid, 2);
+        if (tid == 0) mb_arrive(&full[s]);
+      }
+    }
     const int q = warp & 3;
     const int n = q * 32 + lane;
     if (warp == 4 && lane == 0) B2RL_TRACE_AT(2, 0, 0);
@@ -1036,7 +1145,7 @@ static int gemm_dispatch(const uint16_t* A, int a_mn, int64_t lda, int64_t a_row
   return launch_gemm<128, 5>(ta, tb, ta2, tb2, p, splits, st);
 }
 
-template <int BN, bool EXT>
+template <int BN, bool EXT, bool U8>
 static int launch_slab_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
                          SlabParams sp, cudaStream_t st) {
   const size_t w_bytes = (size_t)sp.taps * sp.col_blocks * BN * 128;
@@ -1056,7 +1165,7 @@ static int launch_slab_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
   if (stages > 6) stages = 6;
   sp.stages = stages;
   const size_t smem = 1024 + w_bytes + stages * slab_bytes + (2 * 6 + 5) * 8 + 16;
-  auto k = conv_slab_tcgen05_kernel<BN, EXT>;
+  auto k = conv_slab_tcgen05_kernel<BN, EXT, U8>;
   static size_t attr = 0;
   if (attr < smem) {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1071,10 +1180,18 @@ static int launch_slab_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
 template <int BN>
 static int launch_slab(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
                        SlabParams sp, cudaStream_t st) {
-  return has_ext(sp.g) ? launch_slab_t<BN, true>(ta, tb, ta2, tb2, sp, st) : launch_slab_t<BN, false>(ta, tb, ta2, tb2, sp, st);
+  if (sp.u8.frames) {                                                // K1: conv1 forward straight from the uint8 ring
+    if constexpr (BN == 32) {
+      if (!has_ext(sp.g) && !sp.g.dual && sp.col_blocks == 1) return launch_slab_t<32, false, true>(ta, tb, ta2, tb2, sp, st);
+    }
+    set_error("the uint8-ring producer serves block_n 32, 64 channels, no backward extras, no dual launch");
+    return B2RL_ERR_ARG;
+  }
+  return has_ext(sp.g) ? launch_slab_t<BN, true, false>(ta, tb, ta2, tb2, sp, st)
+                       : launch_slab_t<BN, false, false>(ta, tb, ta2, tb2, sp, st);
 }
 
-template <int TMEM_COLS>
+template <int TMEM_COLS, bool U8 = false>
 static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, WgradParams w, cudaStream_t st, int* n_ctas = nullptr) {
   const size_t slab_bytes = (size_t)w.slab_rows * 128 * w.col_blocks, stage = 16384 + slab_bytes;
   int stages = (int)((200 * 1024) / stage);
@@ -1082,7 +1199,7 @@ static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, WgradParam
   if (stages < 2) return 1;
   w.stages = stages;
   const size_t smem = 1024 + stages * stage + (2 * 6 + 2) * 8 + 16;
-  auto k = conv_wgrad_tcgen05_kernel<TMEM_COLS>;
+  auto k = conv_wgrad_tcgen05_kernel<TMEM_COLS, U8>;
   static size_t attr = 0;
   if (attr < smem) {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1388,4 +1505,86 @@ extern "C" int b2rl_gemm_splitk_bf16(const uint16_t* A, int64_t lda, const uint1
   p.ws_rows = (M + GEMM_BM - 1) / GEMM_BM * GEMM_BM;
   p.ws_ld = (N + block_n - 1) / block_n * block_n;
   return gemm_dispatch(A, 0, lda, M, K, B, 0, ldb, N, K, p, splits, block_n, (cudaStream_t)stream);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1 entry points: conv1 of NatureConvBody (network_bodies.py:27; 8x8 / stride 4 over `history` stacked frames = 2x2 taps
+// over the space-to-depth(4) grid) reading the sampled frame stacks STRAIGHT FROM THE uint8 REPLAY RING (replay.py:124-134)
+// -- no materialised batch.  frames: ring [capacity][row_bytes]; idx: int64 [batch] sampled ring indices; `first`: ring row
+// of the oldest stacked frame relative to idx[b] (-(history-1) for the state, n_step-(history-1) for the next state).
+// The frame values enter as exact integers 0..255; ImageNormalizer's 1/255 is folded into W (b2rl_nature_pack_weights).
+// ---------------------------------------------------------------------------------------------------------------
+static int u8_src(U8Src& u, const uint8_t* frames, const int64_t* idx, int32_t first, int64_t row_bytes, int32_t frame_w,
+                  int32_t batch, int32_t history) {
+  B2RL_REQUIRE(frames && idx, "null pointer");
+  B2RL_REQUIRE(history == 4, "the uint8-ring producer packs 4 frames x 16 pixels into the 64 channels of one slab column block");
+  B2RL_REQUIRE(frame_w > 0 && frame_w % 4 == 0 && row_bytes % frame_w == 0 && row_bytes / frame_w == frame_w,
+               "square frames with a side that is a multiple of 4");
+  B2RL_REQUIRE(reinterpret_cast<uintptr_t>(frames) % 4 == 0 && row_bytes % 4 == 0, "ring rows must be 4-byte aligned");
+  B2RL_REQUIRE(batch > 0 && (int64_t)batch * (frame_w / 4) * (frame_w / 4) < (1LL << 31), "bad batch");
+  u.frames = frames; u.idx = idx; u.row_bytes = row_bytes; u.first = first; u.frame_w = frame_w; u.G = frame_w / 4;
+  u.rows = batch * u.G * u.G;
+  return B2RL_OK;
+}
+
+// D = act(conv1(frames) + bias): rows (b, gy, gx) of the G x G grid, n_out <= 32 output channels, bf16, through the output row
+// maps of b2rl_conv_gemm_bf16 (out_map 1 = space-to-depth(2) rows for conv2, valid V x V).  W: [n_out][4 taps * 64] bf16.
+extern "C" int b2rl_conv1_u8_fwd(const uint8_t* frames, const int64_t* idx, int32_t first, int64_t row_bytes, int32_t frame_w,
+                                 int32_t batch, int32_t history, const uint16_t* W, int32_t n_out, void* D, int64_t ldd,
+                                 const float* bias, int32_t relu, int32_t out_map, int32_t V, void* stream) {
+  SlabParams sp = {};
+  int rc = u8_src(sp.u8, frames, idx, first, row_bytes, frame_w, batch, history);
+  if (rc) return rc;
+  B2RL_REQUIRE(W && D, "null pointer");
+  B2RL_REQUIRE(n_out > 0 && n_out <= 32 && out_map >= 0 && out_map <= 2, "n_out <= 32, out_map 0..2");
+  B2RL_REQUIRE(reinterpret_cast<uintptr_t>(W) % 16 == 0, "operands must be 16-byte aligned");
+  const int G = sp.u8.G, C = 64, taps = 4, K = taps * C;
+  GemmParams p = {};
+  p.M = sp.u8.rows; p.N = n_out; p.K = K; p.ldd = (int)ldd;
+  p.relu = relu; p.out_mode = 0; p.bias = bias; p.D = D;
+  p.taps_x = 2; p.grid_w = G; p.shift_sign = 1; p.a_tap_tiles = 1;
+  p.out_map = out_map; p.G = G; p.V = V;
+  const int max_shift = G + 1;
+  sp.g = p; sp.taps = taps; sp.col_blocks = 1;
+  sp.slab_rows = (GEMM_BM + max_shift + 7) / 8 * 8;
+  sp.min_shift = 0;
+  sp.base_offset_mode = 2;
+  B2RL_REQUIRE(sp.slab_rows <= 256, "frame too wide for one slab");
+  CUtensorMap tb;
+  rc = make_map(&tb, W, K, n_out, K, 32);
+  if (rc) return rc;
+  int r2 = launch_slab<32>(tb, tb, tb, tb, sp, (cudaStream_t)stream);
+  if (r2 > 0) { set_error("b2rl_conv1_u8_fwd: the slab does not fit in shared memory"); return B2RL_ERR_ARG; }
+  return r2;
+}
+
+// split-K partials of conv1's weight gradient dW[n][tap*64 + c] = sum_r G[r][n] * x[r + shift(tap)][c] with x read from the
+// ring as above (G_rows: bf16 [batch*G*G][n_out], the masked output gradient on conv1's grid).  Same output contract as
+// b2rl_conv_wgrad_partials.
+extern "C" int b2rl_conv1_u8_wgrad_partials(const uint8_t* frames, const int64_t* idx, int32_t first, int64_t row_bytes,
+                                            int32_t frame_w, int32_t batch, int32_t history, const uint16_t* G_rows,
+                                            int32_t n_out, float* partials, int32_t* n_partials_host, void* stream) {
+  WgradParams w = {};
+  int rc = u8_src(w.u8, frames, idx, first, row_bytes, frame_w, batch, history);
+  if (rc) return rc;
+  B2RL_REQUIRE(G_rows && partials && n_partials_host, "null pointer");
+  B2RL_REQUIRE(n_out > 0 && n_out <= 64 && n_out % 8 == 0, "n_out <= 64, multiple of 8");
+  B2RL_REQUIRE(reinterpret_cast<uintptr_t>(G_rows) % 16 == 0, "operands must be 16-byte aligned");
+  const int G = w.u8.G, C = 64, taps = 4;
+  const int max_shift = G + 1;
+  w.rows = w.u8.rows; w.n_out = n_out; w.C = C; w.col_blocks = 1; w.taps_x = 2; w.grid_w = G;
+  w.slab_rows = (GEMM_BK + max_shift + 7) / 8 * 8;
+  w.a_boxes = 1;
+  w.D = partials; w.ldd = taps * C; w.partial_stride = (int64_t)n_out * taps * C;
+  w.tap0 = 0; w.ntaps = taps;
+  B2RL_REQUIRE(w.slab_rows <= 256, "frame too wide for one slab");
+  CUtensorMap tg;
+  rc = make_map(&tg, G_rows, n_out, w.rows, n_out, 64);
+  if (rc) return rc;
+  int n = 0;
+  int r2 = launch_wgrad<256, true>(tg, tg, w, (cudaStream_t)stream, &n);
+  if (r2 > 0) { set_error("b2rl_conv1_u8_wgrad_partials: the slab does not fit in shared memory"); return B2RL_ERR_ARG; }
+  *n_partials_host = n;
+  return r2;
 }

@@ -192,6 +192,16 @@ __device__ __forceinline__ void gather_scalars(const int32_t* action, const doub
   if (m_out) m_out[b] = (float)cum_m;
 }
 
+// scalars only (action, n-step reward, mask): the frame stacks stay in the ring and are read by conv1 itself (K1, csrc/gemm.cu)
+__global__ void __launch_bounds__(128) gather_scalars_kernel(const int32_t* __restrict__ action, const double* __restrict__ reward,
+                                                             const int32_t* __restrict__ mask, const int64_t* __restrict__ idx,
+                                                             int B, int n, double discount, int64_t* a_out, float* r_out,
+                                                             float* m_out) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) gather_scalars(action, reward, mask, idx[b], n, discount, a_out, r_out, m_out, b);
+}
+
 // raw uint8 stacks, [B][hl][row_bytes]: pure TMA bulk copies, issued by one thread per CTA.
 __global__ void __launch_bounds__(32) gather_raw_tma_kernel(const uint8_t* __restrict__ frames,
                                                             const int32_t* __restrict__ action,
@@ -550,6 +560,11 @@ extern "C" int b2rl_replay_gather(const uint8_t* frames, const int32_t* action, 
   B2RL_REQUIRE(layout != 2 || (frame_w > 0 && frame_w % 4 == 0 && row_bytes % frame_w == 0 && (row_bytes / frame_w) % 4 == 0),
                "space-to-depth needs frame_w and frame height multiples of 4");
   cudaStream_t st = (cudaStream_t)stream;
+  if (!state_out && !next_out) {                                     // scalars only: the consumer reads the frames from the ring
+    launch_pdl(gather_scalars_kernel, dim3((B + 127) / 128), dim3(128), 0, st, action, reward, mask, idx, B, n_step, discount,
+               action_out, reward_out, mask_out);
+    return check_launch("b2rl_replay_gather(scalars)");
+  }
   const size_t span = (size_t)(history + n_step) * row_bytes;
   B2RL_REQUIRE(span <= 200 * 1024, "history+n_step rows do not fit in shared memory");
   const bool aligned = row_bytes % 16 == 0 && reinterpret_cast<uintptr_t>(frames) % 16 == 0;

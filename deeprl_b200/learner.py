@@ -93,6 +93,10 @@ class GraphedDQNLearner:
         self.updates = 0
         self.with_h2d = False
         self._tail = None                 # network/tail.py NatureTail (built on first use), False = not applicable
+        body = getattr(network, "body", None)
+        self.ring = (not self.prefetch and not self.dual and compute_dtype == torch.bfloat16 and Config.DENSE_BACKEND == "tcgen05"
+                     and hasattr(body, "repack") and not getattr(body, "noisy_linear", False) and replay.history_length == 4
+                     and tuple(getattr(replay, "item_shape", ())) == (84, 84) and os.environ.get("B2RL_K1", "1") != "0")
         self.opt.zero_grad()              # the fused tail writes / re-zeroes the gradient arena itself: start from zeros
 
     # ------------------------------------------------------------------ fused tail / fused head (csrc/tail.cu, csrc/head.cu)
@@ -144,8 +148,10 @@ class GraphedDQNLearner:
             if self.per:
                 rp.tree.add_n(self.feeds, rp.max_priority_dev)
         if self.dtype == torch.bfloat16:
-            # exact integer frames, space-to-depth layout; ImageNormalizer's scale is folded into conv1's weights
-            return rp.sample_normalized(out_dtype=self.dtype, scale=None, layout="s2d", tag=tag)
+            # exact integer frames, space-to-depth layout; ImageNormalizer's scale is folded into conv1's weights.
+            # K1 (self.ring): no batch at all -- conv1 reads the sampled stacks from the uint8 ring (synchronous replay only:
+            # a prefetched index could be overwritten by the next update's feeds before its frames are read)
+            return rp.sample_normalized(out_dtype=self.dtype, scale=None, layout="ring" if self.ring else "s2d", tag=tag)
         return rp.sample_normalized(out_dtype=self.dtype, scale=self.scale, layout="nchw", tag=tag)
 
     def _main(self, parity=None):

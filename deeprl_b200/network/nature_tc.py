@@ -49,6 +49,37 @@ RELU_FEATURES = set()      # data_ptr of feature tensors y4 = relu(fc4(.)) produ
 PREMASKED = {}             # data_ptr of a feature gradient already masked by head_bwd_relu -> its column sums (= db4)
 
 
+class RingFrames:
+    """A batch of frame stacks that is NOT materialised: (uint8 replay ring, sampled indices, offset of the oldest stacked
+    frame).  ``UniformReplay.sample_normalized(layout="ring")`` returns these as ``state`` / ``next_state``; conv1's forward
+    and weight-gradient kernels read the ring themselves (K1: csrc/gemm.cu ``fill_slab_u8``)."""
+
+    def __init__(self, frames, idx, first, row_bytes, frame_w, history):
+        self.frames, self.idx, self.first = frames, idx, int(first)
+        self.row_bytes, self.frame_w, self.history = int(row_bytes), int(frame_w), int(history)
+        self.batch = idx.shape[0]
+        self.grid = self.frame_w // 4
+        self.device = frames.device
+
+    is_cuda = True
+    dtype = torch.uint8
+
+    @property
+    def shape(self):
+        return (self.batch, 16 * self.history, self.grid, self.grid)
+
+    def materialize(self):
+        """The bf16 space-to-depth tensor [B, 16*history, G, G] (channels_last) this object stands for (tests, fallbacks)."""
+        rows = (self.idx + self.first).view(-1, 1) + torch.arange(self.history, device=self.device).view(1, -1)
+        x = self.frames.view(-1, self.frame_w, self.frame_w)[rows.view(-1)].view(self.batch, self.history, self.frame_w, self.frame_w)
+        g = self.grid
+        x = x.view(self.batch, self.history, g, 4, g, 4).permute(0, 2, 4, 1, 3, 5).reshape(self.batch, g, g, 16 * self.history)
+        return x.to(_bf16).permute(0, 3, 1, 2)
+
+    def args(self):
+        return (_lib.ptr(self.frames), _lib.ptr(self.idx), self.first, self.row_bytes, self.frame_w, self.batch, self.history)
+
+
 def _zero_grid(key, shape, device):
     """Persistent zero-initialised destination of a scatter epilogue: the tiles overwrite exactly the same rows every time
     and never touch the padding rows, so the buffer is zeroed once."""
@@ -115,7 +146,10 @@ def _backward_fused(ctx, gy4):
     _lib.call("b2rl_conv_gemm_bwd_bf16", _lib.ptr(g2), B * 100, 64, _lib.ptr(w2d), 128, 4, 2, 10, _lib.ptr(g1), 32, 3, 21, 20,
               ctypes.byref(e1), 128, _lib.stream())
     mark("d_conv2")
-    gw1p, p1 = wgrad_partials(x0m, g1, 32, 4, 2, 21, stream=_fork())
+    if ctx.ring is not None:
+        gw1p, p1 = wgrad_partials_ring(ctx.ring, g1, 32, stream=_fork())
+    else:
+        gw1p, p1 = wgrad_partials(x0m, g1, 32, 4, 2, 21, stream=_fork())
     mark("w_conv1", _WGRAD["stream"])
     _join()
     return (gw1p, p1, gw2p, p2, gw3p, p3, gw4p), (db1, db2, db3, db4)
@@ -163,6 +197,15 @@ def wgrad_partials(X, G_rows, n_out, taps, taps_x, grid_w, stream=None):
     n = ctypes.c_int32(0)
     _lib.call("b2rl_conv_wgrad_partials", _lib.ptr(X), int(rows), int(C), _lib.ptr(G_rows), int(n_out), int(taps), int(taps_x),
               int(grid_w), _lib.ptr(buf), ctypes.byref(n), stream if stream is not None else _lib.stream())
+    return buf, int(n.value)
+
+
+def wgrad_partials_ring(ring, G_rows, n_out, stream=None):
+    """conv1's split-K partial weight gradients with the activations read from the uint8 ring (K1)."""
+    buf = torch.empty((148, n_out, 4 * 16 * ring.history), dtype=_f32, device=G_rows.device)
+    n = ctypes.c_int32(0)
+    _lib.call("b2rl_conv1_u8_wgrad_partials", *ring.args(), _lib.ptr(G_rows), int(n_out), _lib.ptr(buf), ctypes.byref(n),
+              stream if stream is not None else _lib.stream())
     return buf, int(n.value)
 
 
@@ -221,9 +264,14 @@ def forward_only(x0, packed, b1, b2, b3, b4):
     w1f, w2f, _, w3f, _, w4p = packed
     B = x0.shape[0]
     dev = x0.device
-    x0m = x0.permute(0, 2, 3, 1).reshape(B * 441, x0.shape[1])                # free view of the NHWC memory
     x1 = torch.empty((B * 100, 128), dtype=_bf16, device=dev)
-    conv_gemm(0, x0m, w1f, 32, 4, 2, 21, 1, x1, bias=b1, relu=True, out_map=1, G=21, V=20, block_n=32)
+    if isinstance(x0, RingFrames):                                             # K1: conv1 reads the uint8 ring itself
+        x0m = x0
+        _lib.call("b2rl_conv1_u8_fwd", *x0.args(), _lib.ptr(w1f), 32, _lib.ptr(x1), x1.stride(0), _lib.ptr(b1), 1, 1, 20,
+                  _lib.stream())
+    else:
+        x0m = x0.permute(0, 2, 3, 1).reshape(B * 441, x0.shape[1])            # free view of the NHWC memory
+        conv_gemm(0, x0m, w1f, 32, 4, 2, 21, 1, x1, bias=b1, relu=True, out_map=1, G=21, V=20, block_n=32)
     mark("f_conv1")
     y2 = torch.empty((B * 100, 64), dtype=_bf16, device=dev)
     conv_gemm(0, x1, w2f, 64, 4, 2, 10, 1, y2, bias=b2, relu=True, block_n=64)
@@ -300,7 +348,10 @@ def _backward_unfused(ctx, gy4):
     conv_gemm(0, g2, w2d, 128, 4, 2, 10, -1, gy1, block_n=128)
     # ---- conv1: mask + bias grad, re-laid out from space-to-depth(2) rows to the 21-grid of conv1's output positions
     g1, db1 = act_bwd_bias_grad(gy1, x1, True, row_map=2, G=21, V=20, out_rows=B * 441)
-    gw1p, p1 = wgrad_partials(x0m, g1, 32, 4, 2, 21, stream=_fork())
+    if ctx.ring is not None:
+        gw1p, p1 = wgrad_partials_ring(ctx.ring, g1, 32, stream=_fork())
+    else:
+        gw1p, p1 = wgrad_partials(x0m, g1, 32, 4, 2, 21, stream=_fork())
     _join()
     return (gw1p, p1, gw2p, p2, gw3p, p3, gw4p), (db1, db2, db3, db4)
 
@@ -316,7 +367,8 @@ class _NatureBody(torch.autograd.Function):
             x0_b, packed_b, biases_b, _ = companion
             y4, (x0m, x1, y2, y3), z4 = forward_dual(x0, pk, biases, x0_b, packed_b.tensors(), biases_b)
             companion[3].append(z4)
-        ctx.save_for_backward(x0m, x1, y2, y3, y4, pk[2], pk[4], pk[5])
+        ctx.ring = x0m if isinstance(x0m, RingFrames) else None
+        ctx.save_for_backward(y4 if ctx.ring is not None else x0m, x1, y2, y3, y4, pk[2], pk[4], pk[5])
         ctx.scale, ctx.c1 = scale, w1.shape[1]
         ctx.params = (w1, b1, w2, b2, w3, b3, w4, b4)
         return y4
@@ -373,7 +425,10 @@ def nature_body(body, x0, scale):
     """``relu(fc4(flatten(relu(conv3(relu(conv2(relu(conv1(x * scale)))))))))`` for space-to-depth bf16 frames ``x0``.
     ``body`` is the NatureConvBody; its packed bf16 operands are refreshed here unless the owner manages them
     (``body.auto_repack = False`` + ``body.repack(scale)`` after every parameter change)."""
-    if not x0.is_contiguous(memory_format=torch.channels_last):
+    if isinstance(x0, RingFrames):
+        if not (_lib.CONV_SLAB and x0.history == 4 and x0.grid == 21 and dual_forward.current is None):
+            x0 = x0.materialize()
+    if not isinstance(x0, RingFrames) and not x0.is_contiguous(memory_format=torch.channels_last):
         x0 = x0.contiguous(memory_format=torch.channels_last)
     pk = getattr(body, "_packed", None)
     if pk is None:

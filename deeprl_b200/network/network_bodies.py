@@ -50,6 +50,11 @@ class NatureConvBody(nn.Module):
         """``x``: [B, C, 84, 84] images, or the space-to-depth(4) tensor [B, 16*C, 21, 21] the fused replay gather
         emits (conv1 then runs as a 2x2 / stride-1 convolution over 16*C channels: same arithmetic, tensor-core
         friendly).  bf16 CUDA inputs take the fused path (``network/fused.py``)."""
+        if type(x).__name__ == "RingFrames":              # frame stacks still in the uint8 replay ring (K1)
+            if Config.DENSE_BACKEND == "tcgen05" and Config.COMPUTE_DTYPE == torch.bfloat16 and not self.noisy_linear:
+                from . import nature_tc
+                return nature_tc.nature_body(self, x, fused.current_frame_scale())
+            x = x.materialize()
         if x.is_cuda and x.dtype == torch.bfloat16 and Config.COMPUTE_DTYPE == torch.bfloat16 and not self.noisy_linear:
             return self._forward_fused(x)
         if x.dim() == 4 and x.shape[1] == 16 * self.conv1.in_channels and x.shape[-1] * 4 == 84:

@@ -15,6 +15,8 @@ from .network_utils import BaseNet, NoisyLinear, layer_init
 
 
 def _phi(body, x):
+    if type(x).__name__ == "RingFrames":                  # not-materialised frame stacks (K1): the body reads the ring
+        return body(x)
     x = tensor(x)
     if x.dtype == torch.uint8:
         x = x.float()

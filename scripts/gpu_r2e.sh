@@ -1,16 +1,19 @@
 #!/bin/bash
-# round 2, call E: lean forward epilogues, 8-warp split-K fix-up, coef in kernel A; stream experiments
+# round 2, call E: lean forward epilogues, 8-warp split-K fix-up, coef in kernel A, K1 (conv1 from the uint8 ring); A/B benches
 cd "$(dirname "$0")/.."
 OUT=gpurun_out; mkdir -p $OUT
+timeout 600 python -m pytest tests/test_gpu_k1.py -m gpu -q --timeout=300 > $OUT/r2e_pytest_k1.log 2>&1; echo "pytest k1 exit $?"; grep -E "^(FAILED|ERROR)|passed|failed|^E  " $OUT/r2e_pytest_k1.log | head -30
 timeout 900 python -m pytest tests/test_gpu_tail.py tests/test_gpu_learner.py -m gpu -q --timeout=300 > $OUT/r2e_pytest_a.log 2>&1; echo "pytest tail+learner exit $?"; grep -E "^(FAILED|ERROR)|passed|failed|^E  " $OUT/r2e_pytest_a.log | head -30
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout=300 -k "gemm or conv or fused or head or agent" > $OUT/r2e_pytest_b.log 2>&1; echo "pytest parity subset exit $?"; grep -E "^(FAILED|ERROR)|passed|failed|^E  " $OUT/r2e_pytest_b.log | head -30
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout=300 -k "gemm or conv or fused or head or agent or replay or gather" > $OUT/r2e_pytest_b.log 2>&1; echo "pytest parity subset exit $?"; grep -E "^(FAILED|ERROR)|passed|failed|^E  " $OUT/r2e_pytest_b.log | head -30
 run() { echo "== $1 $2"; env $1 timeout 300 python bench.py --quick --steps 300 --warmup 20 $2 2>> $OUT/r2e_bench.err | tee -a $OUT/r2e_bench.jsonl; }
 run "B2RL_X=1"
-run "B2RL_X=1"
+run "B2RL_X=1" "--replay sync"
+run "B2RL_K1=0" "--replay sync"
 run "B2RL_SINGLE_STREAM=1"
+run "B2RL_SINGLE_STREAM=1" "--replay sync"
 run "B2RL_FC4_FIXUP=0"
 run "B2RL_FC4_SPLITS=2"
 run "B2RL_FC4_SPLITS=8"
 run "B2RL_TAIL=0"
-run "B2RL_X=1" "--replay sync"
-run "B2RL_SINGLE_STREAM=1" "--replay sync"
+run "B2RL_FC4_FIXUP=0" "--replay sync"
+echo "=== trace sync (K1)"; timeout 300 python scripts/trace_step.py --replay sync 2>&1 | grep -v Warning | tail -30
