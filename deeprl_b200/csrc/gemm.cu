@@ -687,45 +687,101 @@ __device__ __forceinline__ int4 cvt8_u8_bf16(uint32_t w0, uint32_t w1) {
   return o;
 }
 
-// 128 threads (tid 0..127, named barrier `bar_id`) fill one swizzled slab of `slab_rows` rows x 64 channels whose first row is
-// grid-matrix row R0; rows outside [0, rows) are zero (what the TMA's out-of-bounds fill gave).  On return every thread's
-// stores are fenced towards the async proxy (tcgen05.mma reads shared memory through it) and all 128 threads have arrived.
-__device__ __forceinline__ void fill_slab_u8(const U8Src& u, uint8_t* slab, int R0, int slab_rows, long long* rowinfo, int tid,
-                                             int bar_id) {
-  const int gg = u.G * u.G;
-  for (int rl = tid; rl < slab_rows; rl += 128) {
-    const int r = R0 + rl;
-    long long o = -1;
-    if (r >= 0 && r < u.rows) {
-      const int b = r / gg, pos = r - b * gg, gy = pos / u.G, gx = pos - gy * u.G;
-      o = (__ldg(u.idx + b) + u.first) * u.row_bytes + (long long)(4 * gy) * u.frame_w + 4 * gx;
-    }
-    rowinfo[rl] = o;
+// The uint8 pixels travel ring -> shared memory by the copy engine (cp.async.bulk, one copy per (image segment, frame) of a
+// tile: the 4 pixel rows of one grid row of one frame are 4 * frame_w contiguous bytes, consecutive grid rows of an image are
+// contiguous), U8_STAGES tiles ahead of the converters, so that no thread ever waits on a global load.
+//   staging layout of one tile: [frame f][slot = grid-row index q - q0][4 * frame_w bytes], q = b * G + gy = row / G
+constexpr int U8_STAGES = 3;
+__host__ __device__ inline int u8_slots(int slab_rows, int G) { return (slab_rows + G - 2) / G + 1; }
+__host__ __device__ inline int u8_stage_bytes(int slab_rows, int G, int frame_w) {
+  return (4 * u8_slots(slab_rows, G) * 4 * frame_w + 127) & ~127;
+}
+__device__ __forceinline__ void bulk_g2s_u8(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s2u(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(s2u(bar))
+               : "memory");
+}
+
+// geometry of the copies of the tile whose slab starts at grid-matrix row R0, for lane L < 8 (segment L >> 2 = first / second
+// image the slab touches, frame L & 3): image b, first grid row qa, n grid rows (0: nothing to copy); total = bytes of all copies
+struct U8Plan { int b, qa, n, q0; uint32_t total; };
+__device__ __forceinline__ U8Plan u8_plan(const U8Src& u, int R0, int slab_rows, int lane) {
+  U8Plan pl;
+  const int totalq = u.rows / u.G;
+  pl.q0 = R0 / u.G;
+  int q1 = (R0 + slab_rows - 1) / u.G;
+  if (q1 > totalq - 1) q1 = totalq - 1;
+  pl.b = 0; pl.qa = 0; pl.n = 0; pl.total = 0;
+  if (q1 >= pl.q0) {
+    const int b0 = pl.q0 / u.G, b1 = q1 / u.G;
+    const int e0 = min(q1, b0 * u.G + u.G - 1);
+    const int n0 = e0 - pl.q0 + 1, n1 = b1 > b0 ? q1 - b1 * u.G + 1 : 0;
+    pl.total = (uint32_t)(4 * (n0 + n1) * 4 * u.frame_w);
+    const int seg = lane >> 2;
+    pl.b = seg ? b1 : b0;
+    pl.qa = seg ? b1 * u.G : pl.q0;
+    pl.n = lane < 8 ? (seg ? n1 : n0) : 0;
   }
-  asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-  const int units = slab_rows * 8;                        // unit = (chunk j, slab row): consecutive threads -> consecutive rows
-  for (int u0 = tid; u0 < units; u0 += 128 * 4) {         // 4 units = 8 independent 32-bit loads in flight per thread
-    uint32_t w[4][2];
-    int dst[4];
+  return pl;
+}
+// one full warp: arm `bar` with the tile's byte count and issue the copies (lane L < 8 issues copy L); idx_b = idx[pl.b]
+__device__ __forceinline__ void u8_issue(const U8Src& u, const U8Plan& pl, long long idx_b, uint8_t* stage, uint64_t* bar,
+                                         int slots, int lane) {
+  const int rowb = 4 * u.frame_w;
+  if (lane == 0) {
+    if (pl.total) mb_expect_tx(bar, pl.total);
+    else mb_arrive(bar);
+  }
+  __syncwarp();
+  if (pl.n > 0) {
+    const int f = lane & 3;
+    const uint8_t* src = u.frames + (idx_b + u.first + f) * u.row_bytes + (long long)(pl.qa - pl.b * u.G) * rowb;
+    bulk_g2s_u8(stage + (f * slots + (pl.qa - pl.q0)) * rowb, src, (uint32_t)(pl.n * rowb), bar);
+  }
+}
+
+__device__ __forceinline__ void u8_store_chunks(const uint8_t* stage, uint8_t* slab, int rl, int so, int fstride, int frame_w) {
+  // the 8 chunks (16 bytes = 8 channels each) of slab row rl; so = staging offset of pixel (4gy, 4gx) of frame 0, or -1: zeros
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int uu = u0 + k * 128;
-      w[k][0] = w[k][1] = 0;
-      dst[k] = -1;
-      if (uu < units) {
-        const int j = uu / slab_rows, rl = uu - j * slab_rows;
-        dst[k] = rl * 128 + ((j ^ (rl & 7)) << 4);
-        const long long o = rowinfo[rl];
-        if (o >= 0) {
-          const uint8_t* src = u.frames + o + (long long)(j >> 1) * u.row_bytes + (2 * (j & 1)) * u.frame_w;
-          w[k][0] = __ldg(reinterpret_cast<const uint32_t*>(src));
-          w[k][1] = __ldg(reinterpret_cast<const uint32_t*>(src + u.frame_w));
-        }
-      }
+  for (int j = 0; j < 8; ++j) {
+    uint32_t w0 = 0, w1 = 0;
+    if (so >= 0) {
+      const uint8_t* src = stage + (j >> 1) * fstride + so + (2 * (j & 1)) * frame_w;
+      w0 = *reinterpret_cast<const uint32_t*>(src);
+      w1 = *reinterpret_cast<const uint32_t*>(src + frame_w);
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (dst[k] >= 0) *reinterpret_cast<int4*>(slab + dst[k]) = cvt8_u8_bf16(w[k][0], w[k][1]);
+    *reinterpret_cast<int4*>(slab + rl * 128 + ((j ^ (rl & 7)) << 4)) = cvt8_u8_bf16(w0, w1);
+  }
+}
+
+// 128 threads (tid 0..127, named barrier `bar_id`) convert one staged tile into the swizzled bf16 slab of `slab_rows` rows x 64
+// channels whose first row is grid-matrix row R0; rows >= u.rows are zero (what the TMA's out-of-bounds fill gave).  Thread t
+// owns slab row t (consecutive threads -> consecutive pixels of the staging rows and the 8 distinct swizzle positions of a
+// 128-byte window: conflict-free both ways); rows beyond 128 are shared out chunk-wise.  On return every thread's stores are
+// fenced towards the async proxy (tcgen05.mma reads shared memory through it) and all 128 threads have arrived.
+__device__ __forceinline__ void u8_convert(const U8Src& u, const uint8_t* stage, uint8_t* slab, int R0, int slab_rows, int slots,
+                                           int tid, int bar_id) {
+  const int rowb = 4 * u.frame_w, fstride = slots * rowb;
+  const int q0 = R0 / u.G;
+  if (tid < slab_rows) {
+    const int r = R0 + tid;
+    int so = -1;
+    if (r < u.rows) {
+      const int q = r / u.G;
+      so = (q - q0) * rowb + 4 * (r - q * u.G);
+    }
+    u8_store_chunks(stage, slab, tid, so, fstride, u.frame_w);
+  }
+  for (int e = tid; e < (slab_rows - 128) * 8; e += 128) {
+    const int rl = 128 + (e >> 3), j = e & 7, r = R0 + rl;
+    uint32_t w0 = 0, w1 = 0;
+    if (r < u.rows) {
+      const int q = r / u.G;
+      const uint8_t* src = stage + (j >> 1) * fstride + (q - q0) * rowb + 4 * (r - q * u.G) + (2 * (j & 1)) * u.frame_w;
+      w0 = *reinterpret_cast<const uint32_t*>(src);
+      w1 = *reinterpret_cast<const uint32_t*>(src + u.frame_w);
+    }
+    *reinterpret_cast<int4*>(slab + rl * 128 + ((j ^ (rl & 7)) << 4)) = cvt8_u8_bf16(w0, w1);
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
@@ -774,7 +830,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, BN == 32 ? 2 : 1) conv_slab_tcge
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* w_full = tmem_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
-  __shared__ long long s_rowinfo[U8 ? 256 : 1];    // U8: ring byte offset of every slab row of the tile being converted
+  // U8 (K1): uint8 staging tiles + their full / empty barriers live behind the slab ring (launch_slab_t sizes the allocation)
+  const int u8_slots_ = U8 ? u8_slots(sp.slab_rows, sp.u8.G) : 0;
+  const int u8_bytes = U8 ? u8_stage_bytes(sp.slab_rows, sp.u8.G, sp.u8.frame_w) : 0;
+  uint8_t* sU = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~uintptr_t(127));
+  uint64_t* u8_full = reinterpret_cast<uint64_t*>(sU + (size_t)U8_STAGES * u8_bytes);
+  uint64_t* u8_empty = u8_full + U8_STAGES;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
   const int tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
@@ -785,6 +846,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, BN == 32 ? 2 : 1) conv_slab_tcge
     for (int s = 0; s < MAX_STAGES; ++s) { mb_init(&full[s], 1); mb_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mb_init(&tmem_full[s], 1); mb_init(&tmem_empty[s], 4); }
     mb_init(w_full, 1);
+    if (U8) {
+      for (int s = 0; s < U8_STAGES; ++s) { mb_init(&u8_full[s], 1); mb_init(&u8_empty[s], 1); }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(mA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(mB) : "memory");
@@ -799,7 +863,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, BN == 32 ? 2 : 1) conv_slab_tcge
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();   // everything above (barriers, tensor-map prefetch, TMEM allocation) overlaps the previous kernel's tail
 
-  if (warp == 0 && elect_one()) {
+  if (U8 && warp == 0) {
+    // ---------------------------------------------------------------------- K1 producer (whole warp): weights by TMA, then
+    // the uint8 pixels of every tile by bulk copies, U8_STAGES tiles ahead; idx[] of the next tile is requested one tile early
+    if (elect_one()) {
+      mb_expect_tx(w_full, (uint32_t)k_tiles * W_TILE);
+      for (int kt = 0; kt < k_tiles; ++kt) tma_load_2d(sW + (size_t)kt * W_TILE, mB, w_full, kt * GEMM_BK, 0);
+    }
+    __syncwarp();
+    U8Plan pl = u8_plan(sp.u8, cta * GEMM_BM + sp.min_shift, sp.slab_rows, lane);
+    long long idx_b = (cta < tiles && pl.n > 0) ? __ldg(sp.u8.idx + pl.b) : 0;
+    uint32_t it = 0;
+    for (int tile = cta; tile < tiles; tile += n_cta, ++it) {
+      const U8Plan cur = pl;
+      const long long cur_idx = idx_b;
+      if (tile + n_cta < tiles) {
+        pl = u8_plan(sp.u8, (tile + n_cta) * GEMM_BM + sp.min_shift, sp.slab_rows, lane);
+        idx_b = pl.n > 0 ? __ldg(sp.u8.idx + pl.b) : 0;
+      }
+      const int us = it % U8_STAGES;
+      mb_wait(&u8_empty[us], ((it / U8_STAGES) & 1) ^ 1);
+      u8_issue(sp.u8, cur, cur_idx, sU + (size_t)us * u8_bytes, &u8_full[us], u8_slots_, lane);
+    }
+  } else if (warp == 0 && elect_one()) {
     // ---------------------------------------------------------------------- TMA producer
     B2RL_TRACE_AT(3, 0, 1);
     mb_expect_tx(w_full, (uint32_t)k_tiles * W_TILE);
@@ -822,10 +908,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, BN == 32 ? 2 : 1) conv_slab_tcge
     const int tid = (int)threadIdx.x - 6 * 32;
     uint32_t it = 0;
     for (int tile = cta; tile < tiles; tile += n_cta, ++it) {
-      const int s = it % sp.stages;
+      const int s = it % sp.stages, us = it % U8_STAGES;
       mb_wait(&empty[s], ((it / sp.stages) & 1) ^ 1);
-      fill_slab_u8(sp.u8, sS + (size_t)s * slab_bytes, tile * GEMM_BM + sp.min_shift, sp.slab_rows, s_rowinfo, tid, 2);
-      if (tid == 0) mb_arrive(&full[s]);
+      mb_wait(&u8_full[us], (it / U8_STAGES) & 1);
+      u8_convert(sp.u8, sU + (size_t)us * u8_bytes, sS + (size_t)s * slab_bytes, tile * GEMM_BM + sp.min_shift, sp.slab_rows,
+                 u8_slots_, tid, 2);
+      if (tid == 0) { mb_arrive(&full[s]); mb_arrive(&u8_empty[us]); }
     }
   } else if (warp == 1 && elect_one()) {
     // ---------------------------------------------------------------------- MMA issuer
@@ -928,7 +1016,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
   uint64_t* empty = full + MAX_STAGES;
   uint64_t* tmem_full = empty + MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  __shared__ long long s_rowinfo[U8 ? 256 : 1];
+  // U8 (K1): uint8 staging tiles + their full / empty barriers behind the operand ring (launch_wgrad sizes the allocation)
+  const int u8_slots_ = U8 ? u8_slots(w.slab_rows, w.u8.G) : 0;
+  const int u8_bytes = U8 ? u8_stage_bytes(w.slab_rows, w.u8.G, w.u8.frame_w) : 0;
+  uint8_t* sU = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~uintptr_t(127));
+  uint64_t* u8_full = reinterpret_cast<uint64_t*>(sU + (size_t)U8_STAGES * u8_bytes);
+  uint64_t* u8_empty = u8_full + U8_STAGES;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
   const int kt_total = (w.rows + GEMM_BK - 1) / GEMM_BK;
   const int kt_begin = blockIdx.x * w.k_tiles_per_cta;
@@ -937,6 +1030,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) { mb_init(&full[s], U8 ? 2 : 1); mb_init(&empty[s], 1); }   // U8: TMA + converters
     mb_init(tmem_full, 1);
+    if (U8) {
+      for (int s = 0; s < U8_STAGES; ++s) { mb_init(&u8_full[s], 1); mb_init(&u8_empty[s], 1); }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
@@ -951,7 +1047,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();   // everything above (barriers, tensor-map prefetch, TMEM allocation) overlaps the previous kernel's tail
 
-  if (warp == 0 && elect_one()) {
+  if (U8 && warp == 0) {
+    // K1 producer (whole warp): the uint8 pixels of every k-tile by bulk copies (U8_STAGES ahead, idx[] one k-tile early),
+    // the gradient rows by TMA
+    U8Plan pl = u8_plan(w.u8, kt_begin * GEMM_BK, w.slab_rows, lane);
+    long long idx_b = (n_kt > 0 && pl.n > 0) ? __ldg(w.u8.idx + pl.b) : 0;
+    for (int i = 0; i < n_kt; ++i) {
+      const U8Plan cur = pl;
+      const long long cur_idx = idx_b;
+      if (i + 1 < n_kt) {
+        pl = u8_plan(w.u8, (kt_begin + i + 1) * GEMM_BK, w.slab_rows, lane);
+        idx_b = pl.n > 0 ? __ldg(w.u8.idx + pl.b) : 0;
+      }
+      const int us = i % U8_STAGES, s = i % w.stages;
+      mb_wait(&u8_empty[us], ((i / U8_STAGES) & 1) ^ 1);
+      u8_issue(w.u8, cur, cur_idx, sU + (size_t)us * u8_bytes, &u8_full[us], u8_slots_, lane);
+      mb_wait(&empty[s], ((i / w.stages) & 1) ^ 1);
+      if (elect_one()) {
+        mb_expect_tx(&full[s], (uint32_t)w.a_boxes * 8192);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        for (int g = 0; g < w.a_boxes; ++g) tma_load_2d(st + g * 8192, &tmG, &full[s], g * 64, (kt_begin + i) * GEMM_BK);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 0 && elect_one()) {
     B2RL_TRACE_AT(3, 0, 1);
     for (int i = 0; i < n_kt; ++i) {
       const int s = i % w.stages;
@@ -998,10 +1117,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
       // K1 converters (warps 6-9): the activation slab of every k-tile from the uint8 ring; they join the epilogue afterwards
       const int tid = (int)threadIdx.x - 6 * 32;
       for (int i = 0; i < n_kt; ++i) {
-        const int s = i % w.stages;
+        const int s = i % w.stages, us = i % U8_STAGES;
         mb_wait(&empty[s], ((i / w.stages) & 1) ^ 1);
-        fill_slab_u8(w.u8, smem + (size_t)s * stage_bytes + A_BYTES, (kt_begin + i) * GEMM_BK, w.slab_rows, s_rowinfo, tid, 2);
-        if (tid == 0) mb_arrive(&full[s]);
+        mb_wait(&u8_full[us], (i / U8_STAGES) & 1);
+        u8_convert(w.u8, sU + (size_t)us * u8_bytes, smem + (size_t)s * stage_bytes + A_BYTES, (kt_begin + i) * GEMM_BK,
+                   w.slab_rows, u8_slots_, tid, 2);
+        if (tid == 0) { mb_arrive(&full[s]); mb_arrive(&u8_empty[us]); }
       }
     }
     const int q = warp & 3;
@@ -1158,13 +1279,14 @@ static int launch_slab_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
   }
   // two CTAs per SM when the kernel was compiled for it, the tiles are plentiful and both fit (<= 110 KB each, >= 3 stages)
   const bool pair = BN == 32 && two_cta && !sp.g.dual && tiles >= 4 * sm_count() &&
-                    w_bytes + 3 * slab_bytes + 2048 <= 110 * 1024;
-  const size_t budget = pair ? 110 * 1024 - 2048 : 200 * 1024;
+                    w_bytes + 3 * slab_bytes + 2048 + (U8 ? 3 * 16 * 1024 : 0) <= 110 * 1024;
+  const size_t u8_extra = U8 ? (size_t)U8_STAGES * u8_stage_bytes(sp.slab_rows, sp.u8.G, sp.u8.frame_w) + 2 * U8_STAGES * 8 : 0;
+  const size_t budget = (pair ? 110 * 1024 - 2048 : 200 * 1024) - u8_extra;
   if (w_bytes + 2 * slab_bytes > budget) return 1;                   // does not fit: caller falls back to tap addressing
   int stages = (int)((budget - w_bytes) / slab_bytes);
   if (stages > 6) stages = 6;
   sp.stages = stages;
-  const size_t smem = 1024 + w_bytes + stages * slab_bytes + (2 * 6 + 5) * 8 + 16;
+  const size_t smem = 1024 + w_bytes + stages * slab_bytes + (2 * 6 + 5) * 8 + 16 + 144 + u8_extra;
   auto k = conv_slab_tcgen05_kernel<BN, EXT, U8>;
   static size_t attr = 0;
   if (attr < smem) {
@@ -1194,11 +1316,12 @@ static int launch_slab(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
 template <int TMEM_COLS, bool U8 = false>
 static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, WgradParams w, cudaStream_t st, int* n_ctas = nullptr) {
   const size_t slab_bytes = (size_t)w.slab_rows * 128 * w.col_blocks, stage = 16384 + slab_bytes;
-  int stages = (int)((200 * 1024) / stage);
+  const size_t u8_extra = U8 ? (size_t)U8_STAGES * u8_stage_bytes(w.slab_rows, w.u8.G, w.u8.frame_w) + 2 * U8_STAGES * 8 + 144 : 0;
+  int stages = (int)((200 * 1024 - u8_extra) / stage);
   if (stages > 6) stages = 6;
   if (stages < 2) return 1;
   w.stages = stages;
-  const size_t smem = 1024 + stages * stage + (2 * 6 + 2) * 8 + 16;
+  const size_t smem = 1024 + stages * stage + (2 * 6 + 2) * 8 + 16 + u8_extra;
   auto k = conv_wgrad_tcgen05_kernel<TMEM_COLS, U8>;
   static size_t attr = 0;
   if (attr < smem) {

@@ -31,7 +31,9 @@ _f32 = torch.float32
 # one GEMM launch with the fused bias/ReLU epilogue (measured per network at B = 512: 10.1 us vs 10.0 us in isolation)
 FC4_SPLITS = int(os.environ.get("B2RL_FC4_SPLITS", "4"))
 # split-K with the in-kernel fix-up (one launch) instead of zero fill + atomic split-K + bias/ReLU pass (three)
-FC4_FIXUP = os.environ.get("B2RL_FC4_FIXUP", "1") == "1"
+# (measured on B200, batch 512: 234 us / update with the three launches vs 242 us with the fix-up -- the last-arriver's L2 round
+# trips are exposed, the three small launches overlap with the other network's chain -- so the fix-up is off by default)
+FC4_FIXUP = os.environ.get("B2RL_FC4_FIXUP", "0") == "1"
 # backward: ReLU mask + bias gradient + re-layout fused into the dgrad GEMM epilogues (b2rl_*_bwd_bf16) instead of three
 # b2rl_act_bwd_bias_grad_bf16 passes (B2RL_FUSED_BWD=0 restores them).
 FUSED_BWD = os.environ.get("B2RL_FUSED_BWD", "1") == "1"

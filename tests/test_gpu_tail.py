@@ -158,7 +158,7 @@ def test_dqn_head_fused_matches_separate_kernels(rl, head, A, per, double_q, B):
     assert float(r2["loss"]) == float(r["loss"])
 
 
-@pytest.mark.parametrize("M,N,K,splits,block_n", [(512, 512, 3136, 4, 64), (512, 512, 3136, 7, 32), (37, 200, 3136, 4, 64),
+@pytest.mark.parametrize("M,N,K,splits,block_n", [(512, 512, 3136, 4, 64), (512, 512, 3136, 2, 32), (37, 200, 3136, 4, 64),
                                                   (256, 512, 512, 1, 128), (512, 512, 3136, 4, 128)])
 def test_splitk_fixup_gemm_vs_torch(rl, M, N, K, splits, block_n):
     """b2rl_gemm_splitk_bf16 (one launch: split-K partials + last-arriver fix-up with bias / ReLU) against fp32 torch on the
