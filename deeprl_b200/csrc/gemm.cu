@@ -740,10 +740,12 @@ __device__ __forceinline__ void u8_issue(const U8Src& u, const U8Plan& pl, long 
   }
 }
 
+template <int J0, int NJ>
 __device__ __forceinline__ void u8_store_chunks(const uint8_t* stage, uint8_t* slab, int rl, int so, int fstride, int frame_w) {
-  // the 8 chunks (16 bytes = 8 channels each) of slab row rl; so = staging offset of pixel (4gy, 4gx) of frame 0, or -1: zeros
+  // chunks J0 .. J0+NJ-1 (16 bytes = 8 channels each) of slab row rl; so = staging offset of pixel (4gy, 4gx) of frame 0, or -1: zeros
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int jj = 0; jj < NJ; ++jj) {
+    const int j = J0 + jj;
     uint32_t w0 = 0, w1 = 0;
     if (so >= 0) {
       const uint8_t* src = stage + (j >> 1) * fstride + so + (2 * (j & 1)) * frame_w;
@@ -754,25 +756,34 @@ __device__ __forceinline__ void u8_store_chunks(const uint8_t* stage, uint8_t* s
   }
 }
 
-// 128 threads (tid 0..127, named barrier `bar_id`) convert one staged tile into the swizzled bf16 slab of `slab_rows` rows x 64
-// channels whose first row is grid-matrix row R0; rows >= u.rows are zero (what the TMA's out-of-bounds fill gave).  Thread t
-// owns slab row t (consecutive threads -> consecutive pixels of the staging rows and the 8 distinct swizzle positions of a
-// 128-byte window: conflict-free both ways); rows beyond 128 are shared out chunk-wise.  On return every thread's stores are
-// fenced towards the async proxy (tcgen05.mma reads shared memory through it) and all 128 threads have arrived.
+// NT = 128 or 256 threads (tid 0..NT-1, named barrier `bar_id`) convert one staged tile into the swizzled bf16 slab of
+// `slab_rows` rows x 64 channels whose first row is grid-matrix row R0; rows >= u.rows are zero (what the TMA's out-of-bounds
+// fill gave).  Thread t owns slab row t & 127 (consecutive threads -> consecutive pixels of the staging rows and the 8 distinct
+// swizzle positions of a 128-byte window: conflict-free both ways) and, with 256 threads, one half of its 8 chunks; rows beyond
+// 128 are shared out chunk-wise.  On return every thread's stores are fenced towards the async proxy (tcgen05.mma reads shared
+// memory through it) and all NT threads have arrived.
+template <int NT>
 __device__ __forceinline__ void u8_convert(const U8Src& u, const uint8_t* stage, uint8_t* slab, int R0, int slab_rows, int slots,
                                            int tid, int bar_id) {
   const int rowb = 4 * u.frame_w, fstride = slots * rowb;
   const int q0 = R0 / u.G;
-  if (tid < slab_rows) {
-    const int r = R0 + tid;
+  const int rl0 = tid & 127;
+  if (rl0 < slab_rows) {
+    const int r = R0 + rl0;
     int so = -1;
     if (r < u.rows) {
       const int q = r / u.G;
       so = (q - q0) * rowb + 4 * (r - q * u.G);
     }
-    u8_store_chunks(stage, slab, tid, so, fstride, u.frame_w);
+    if (NT == 128) {
+      u8_store_chunks<0, 8>(stage, slab, rl0, so, fstride, u.frame_w);
+    } else if (tid < 128) {
+      u8_store_chunks<0, 4>(stage, slab, rl0, so, fstride, u.frame_w);
+    } else {
+      u8_store_chunks<4, 4>(stage, slab, rl0, so, fstride, u.frame_w);
+    }
   }
-  for (int e = tid; e < (slab_rows - 128) * 8; e += 128) {
+  for (int e = tid; e < (slab_rows - 128) * 8; e += NT) {
     const int rl = 128 + (e >> 3), j = e & 7, r = R0 + rl;
     uint32_t w0 = 0, w1 = 0;
     if (r < u.rows) {
@@ -784,7 +795,7 @@ __device__ __forceinline__ void u8_convert(const U8Src& u, const uint8_t* stage,
     *reinterpret_cast<int4*>(slab + rl * 128 + ((j ^ (rl & 7)) << 4)) = cvt8_u8_bf16(w0, w1);
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NT) : "memory");
 }
 
 struct SlabParams {
@@ -799,8 +810,9 @@ struct SlabParams {
 
 // BN = 32 (conv1, 12 tiles per SM, 16 KB of weights) compiles for two resident CTAs per SM: with many tiles the work can be
 // split over 2 x 148 CTAs whose waits interleave (launch_slab uses a <= 110 KB shared-memory budget then).
+constexpr int SLAB_U8_THREADS = GEMM_THREADS + 128;   // K1: four converter warps (10-13) behind the ten of the TMA version
 template <int BN, bool EXT, bool U8>
-__global__ void __launch_bounds__(GEMM_THREADS, BN == 32 ? 2 : 1) conv_slab_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(U8 ? SLAB_U8_THREADS : GEMM_THREADS, (BN == 32 && !U8) ? 2 : 1) conv_slab_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                             const __grid_constant__ CUtensorMap tmB,
                                                                             const __grid_constant__ CUtensorMap tmA2,
                                                                             const __grid_constant__ CUtensorMap tmB2,
@@ -903,16 +915,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, BN == 32 ? 2 : 1) conv_slab_tcge
                       tile * GEMM_BM + sp.min_shift);
       }
     }
-  } else if (U8 && warp >= 6) {
-    // ---------------------------------------------------------------------- K1 converters (warps 6-9): uint8 ring -> slab
-    const int tid = (int)threadIdx.x - 6 * 32;
+  } else if (U8 && warp >= 10) {
+    // ---------------------------------------------------------------------- K1 converters (warps 10-13): staged uint8 -> slab
+    const int tid = (int)threadIdx.x - GEMM_THREADS;
     uint32_t it = 0;
     for (int tile = cta; tile < tiles; tile += n_cta, ++it) {
       const int s = it % sp.stages, us = it % U8_STAGES;
       mb_wait(&empty[s], ((it / sp.stages) & 1) ^ 1);
       mb_wait(&u8_full[us], (it / U8_STAGES) & 1);
-      u8_convert(sp.u8, sU + (size_t)us * u8_bytes, sS + (size_t)s * slab_bytes, tile * GEMM_BM + sp.min_shift, sp.slab_rows,
-                 u8_slots_, tid, 2);
+      u8_convert<128>(sp.u8, sU + (size_t)us * u8_bytes, sS + (size_t)s * slab_bytes, tile * GEMM_BM + sp.min_shift,
+                      sp.slab_rows, u8_slots_, tid, 2);
       if (tid == 0) { mb_arrive(&full[s]); mb_arrive(&u8_empty[us]); }
     }
   } else if (warp == 1 && elect_one()) {
@@ -958,12 +970,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, BN == 32 ? 2 : 1) conv_slab_tcge
       umma_commit(&tmem_full[as]);
       B2RL_TRACE_AT(1, it, 3);
     }
-  } else if (warp >= 2) {
+  } else if (warp >= 2 && warp < 10) {
     const int q = warp & 3;
     const uint32_t grp = (uint32_t)(warp - 2) >> 2;                    // accumulator stage this warp group drains
-    uint32_t it = 0;                                                   // (U8: warps 2-5 drain both stages, warps 6-9 convert)
+    uint32_t it = 0;
     for (int tile = cta; tile < tiles; tile += n_cta, ++it)
-      if (U8 || (it & 1) == grp)
+      if ((it & 1) == grp)
         epilogue_tile<BN, ACC, EXT>(p, tile * GEMM_BM, 0, q, lane, tmem_base, it & 1, (it >> 1) & 1, true, tmem_full, tmem_empty, s_dbias, it);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1113,15 +1125,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
     }
     umma_commit(tmem_full);
   } else if (warp >= 2 && n_kt > 0) {
-    if (U8 && warp >= 6) {
-      // K1 converters (warps 6-9): the activation slab of every k-tile from the uint8 ring; they join the epilogue afterwards
-      const int tid = (int)threadIdx.x - 6 * 32;
+    if (U8) {
+      // K1 converters (all eight epilogue warps, idle until the accumulators are complete): the activation slab of every k-tile
+      // from the staged uint8 pixels
+      const int tid = (int)threadIdx.x - 2 * 32;
       for (int i = 0; i < n_kt; ++i) {
         const int s = i % w.stages, us = i % U8_STAGES;
         mb_wait(&empty[s], ((i / w.stages) & 1) ^ 1);
         mb_wait(&u8_full[us], (i / U8_STAGES) & 1);
-        u8_convert(w.u8, sU + (size_t)us * u8_bytes, smem + (size_t)s * stage_bytes + A_BYTES, (kt_begin + i) * GEMM_BK,
-                   w.slab_rows, u8_slots_, tid, 2);
+        u8_convert<256>(w.u8, sU + (size_t)us * u8_bytes, smem + (size_t)s * stage_bytes + A_BYTES, (kt_begin + i) * GEMM_BK,
+                        w.slab_rows, u8_slots_, tid, 2);
         if (tid == 0) { mb_arrive(&full[s]); mb_arrive(&u8_empty[us]); }
       }
     }
@@ -1295,7 +1308,7 @@ static int launch_slab_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
   }
   int ctas = sp.g.dual ? sm_count() / 2 : (pair ? 2 * sm_count() : sm_count());   // per operand set
   if (ctas > tiles) ctas = tiles;
-  launch_pdl(k, dim3(sp.g.dual ? 2 * ctas : ctas), dim3(GEMM_THREADS), smem, st, ta, tb, ta2, tb2, sp);
+  launch_pdl(k, dim3(sp.g.dual ? 2 * ctas : ctas), dim3(U8 ? SLAB_U8_THREADS : GEMM_THREADS), smem, st, ta, tb, ta2, tb2, sp);
   return check_launch("b2rl_conv_gemm_bf16(slab)");
 }
 
