@@ -668,6 +668,7 @@ struct U8Src {
   int frame_w;               // pixels per frame row (84)
   int G;                     // grid width = frame_w / 4 (21); slab rows are (b, gy, gx) over G x G positions per image
   int rows;                  // batch * G * G
+  int stages;                // uint8 staging tiles in flight (set by the launcher, <= U8_MAX_STAGES)
 };
 
 __device__ __forceinline__ int4 cvt8_u8_bf16(uint32_t w0, uint32_t w1) {
@@ -691,7 +692,8 @@ __device__ __forceinline__ int4 cvt8_u8_bf16(uint32_t w0, uint32_t w1) {
 // tile: the 4 pixel rows of one grid row of one frame are 4 * frame_w contiguous bytes, consecutive grid rows of an image are
 // contiguous), U8_STAGES tiles ahead of the converters, so that no thread ever waits on a global load.
 //   staging layout of one tile: [frame f][slot = grid-row index q - q0][4 * frame_w bytes], q = b * G + gy = row / G
-constexpr int U8_STAGES = 3;
+constexpr int U8_MAX_STAGES = 12;   // staging tiles in flight: the launchers give the uint8 ring most of the shared memory
+                                    // (a staging tile is held for the copy latency + the conversion; the bf16 slab ring needs 3)
 __host__ __device__ inline int u8_slots(int slab_rows, int G) { return (slab_rows + G - 2) / G + 1; }
 __host__ __device__ inline int u8_stage_bytes(int slab_rows, int G, int frame_w) {
   return (4 * u8_slots(slab_rows, G) * 4 * frame_w + 127) & ~127;
@@ -846,8 +848,9 @@ __global__ void __launch_bounds__(U8 ? SLAB_U8_THREADS : GEMM_THREADS, (BN == 32
   const int u8_slots_ = U8 ? u8_slots(sp.slab_rows, sp.u8.G) : 0;
   const int u8_bytes = U8 ? u8_stage_bytes(sp.slab_rows, sp.u8.G, sp.u8.frame_w) : 0;
   uint8_t* sU = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~uintptr_t(127));
+  const int U8_STAGES = U8 ? sp.u8.stages : 1;
   uint64_t* u8_full = reinterpret_cast<uint64_t*>(sU + (size_t)U8_STAGES * u8_bytes);
-  uint64_t* u8_empty = u8_full + U8_STAGES;
+  uint64_t* u8_empty = u8_full + U8_MAX_STAGES;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
   const int tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
@@ -1032,8 +1035,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
   const int u8_slots_ = U8 ? u8_slots(w.slab_rows, w.u8.G) : 0;
   const int u8_bytes = U8 ? u8_stage_bytes(w.slab_rows, w.u8.G, w.u8.frame_w) : 0;
   uint8_t* sU = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~uintptr_t(127));
+  const int U8_STAGES = U8 ? w.u8.stages : 1;
   uint64_t* u8_full = reinterpret_cast<uint64_t*>(sU + (size_t)U8_STAGES * u8_bytes);
-  uint64_t* u8_empty = u8_full + U8_STAGES;
+  uint64_t* u8_empty = u8_full + U8_MAX_STAGES;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
   const int kt_total = (w.rows + GEMM_BK - 1) / GEMM_BK;
   const int kt_begin = blockIdx.x * w.k_tiles_per_cta;
@@ -1293,8 +1297,19 @@ static int launch_slab_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
   // two CTAs per SM when the kernel was compiled for it, the tiles are plentiful and both fit (<= 110 KB each, >= 3 stages)
   const bool pair = BN == 32 && two_cta && !sp.g.dual && tiles >= 4 * sm_count() &&
                     w_bytes + 3 * slab_bytes + 2048 + (U8 ? 3 * 16 * 1024 : 0) <= 110 * 1024;
-  const size_t u8_extra = U8 ? (size_t)U8_STAGES * u8_stage_bytes(sp.slab_rows, sp.u8.G, sp.u8.frame_w) + 2 * U8_STAGES * 8 : 0;
-  const size_t budget = (pair ? 110 * 1024 - 2048 : 200 * 1024) - u8_extra;
+  size_t u8_extra = 0;
+  size_t budget = pair ? 110 * 1024 - 2048 : 200 * 1024;
+  if (U8) {
+    // K1: three bf16 slabs are enough (shared -> shared conversion); everything else goes to uint8 staging tiles, each of which
+    // is held for the copy latency plus the conversion
+    const size_t ub = u8_stage_bytes(sp.slab_rows, sp.u8.G, sp.u8.frame_w);
+    if (w_bytes + 3 * slab_bytes + 2 * ub + 512 > budget) return 1;
+    int us = (int)((budget - w_bytes - 3 * slab_bytes - 512) / ub);
+    if (us > U8_MAX_STAGES) us = U8_MAX_STAGES;
+    sp.u8.stages = us;
+    u8_extra = (size_t)us * ub + 2 * U8_MAX_STAGES * 8;
+    budget = w_bytes + 3 * slab_bytes;
+  }
   if (w_bytes + 2 * slab_bytes > budget) return 1;                   // does not fit: caller falls back to tap addressing
   int stages = (int)((budget - w_bytes) / slab_bytes);
   if (stages > 6) stages = 6;
@@ -1329,8 +1344,17 @@ static int launch_slab(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
 template <int TMEM_COLS, bool U8 = false>
 static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, WgradParams w, cudaStream_t st, int* n_ctas = nullptr) {
   const size_t slab_bytes = (size_t)w.slab_rows * 128 * w.col_blocks, stage = 16384 + slab_bytes;
-  const size_t u8_extra = U8 ? (size_t)U8_STAGES * u8_stage_bytes(w.slab_rows, w.u8.G, w.u8.frame_w) + 2 * U8_STAGES * 8 + 144 : 0;
-  int stages = (int)((200 * 1024 - u8_extra) / stage);
+  size_t u8_extra = 0;
+  int stages = (int)((200 * 1024) / stage);
+  if (U8) {                                                          // K1: four operand stages, the rest for uint8 staging tiles
+    const size_t ub = u8_stage_bytes(w.slab_rows, w.u8.G, w.u8.frame_w);
+    if (4 * stage + 2 * ub + 512 > 200 * 1024) return 1;
+    stages = 4;
+    int us = (int)((200 * 1024 - 4 * stage - 512) / ub);
+    if (us > U8_MAX_STAGES) us = U8_MAX_STAGES;
+    w.u8.stages = us;
+    u8_extra = (size_t)us * ub + 2 * U8_MAX_STAGES * 8 + 144;
+  }
   if (stages > 6) stages = 6;
   if (stages < 2) return 1;
   w.stages = stages;

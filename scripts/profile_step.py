@@ -13,11 +13,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--updates", type=int, default=3)
 ap.add_argument("--workload", default="dqn")
 ap.add_argument("--capacity", type=int, default=200_000)
+ap.add_argument("--replay", default="async")
 a = ap.parse_args()
 rl.select_device(0)
 rl.Config.COMPUTE_DTYPE = torch.bfloat16
 bench.CAP = a.capacity
-learner = bench.build_learner(rl, a.workload, torch.device("cuda", 0), 0, 1)
+learner = bench.build_learner(rl, a.workload, torch.device("cuda", 0), 0, 1, prefetch=(a.replay == "async"))
 learner._repack(learner.tgt, learner.scale)          # as capture() does: the target operands are packed at sync time only
 for _ in range(2):                                     # warm-up (cuDNN plan selection)
     learner._main(), learner._opt()
