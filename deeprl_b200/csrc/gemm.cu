@@ -688,58 +688,54 @@ __device__ __forceinline__ int4 cvt8_u8_bf16(uint32_t w0, uint32_t w1) {
   return o;
 }
 
-// The uint8 pixels travel ring -> shared memory by the copy engine (cp.async.bulk, one copy per (image segment, frame) of a
-// tile: the 4 pixel rows of one grid row of one frame are 4 * frame_w contiguous bytes, consecutive grid rows of an image are
-// contiguous), U8_STAGES tiles ahead of the converters, so that no thread ever waits on a global load.
-//   staging layout of one tile: [frame f][slot = grid-row index q - q0][4 * frame_w bytes], q = b * G + gy = row / G
-constexpr int U8_MAX_STAGES = 12;   // staging tiles in flight: the launchers give the uint8 ring most of the shared memory
-                                    // (a staging tile is held for the copy latency + the conversion; the bf16 slab ring needs 3)
+// The uint8 pixels travel ring -> shared memory by TMA, several tiles ahead of the converters, so that no thread ever waits on a
+// global load.  The ring is described to the TMA as a 3-D tensor of 32-bit words [capacity rows][G grid rows][frame_w words]
+// (the 4 pixel rows of one grid row of one frame are 4 * frame_w contiguous bytes = frame_w words): the pixels a slab needs from
+// ONE image are the box [4 frames][slots grid rows][frame_w words] at (word 0, grid row q0 - b*G, ring row idx[b] + first) --
+// one tensor load per image the slab touches (at most two), instead of one bulk copy per (image, frame) whose fixed cost
+// (~0.2 us each, serialised per SM) made the kernel twice as slow as the bf16 version.  Grid rows past the end of the image are
+// zero-filled by the TMA and never read.
+//   staging layout of one tile: [image segment 0 | 1][frame f][slot = grid-row index q - qseg][4 * frame_w bytes]
+constexpr int U8_MAX_STAGES = 8;
 __host__ __device__ inline int u8_slots(int slab_rows, int G) { return (slab_rows + G - 2) / G + 1; }
-__host__ __device__ inline int u8_stage_bytes(int slab_rows, int G, int frame_w) {
+__host__ __device__ inline int u8_box_bytes(int slab_rows, int G, int frame_w) {
   return (4 * u8_slots(slab_rows, G) * 4 * frame_w + 127) & ~127;
 }
-__device__ __forceinline__ void bulk_g2s_u8(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s2u(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"(s2u(bar))
-               : "memory");
+__host__ __device__ inline int u8_stage_bytes(int slab_rows, int G, int frame_w) { return 2 * u8_box_bytes(slab_rows, G, frame_w); }
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          s2u(smem_dst)),
+      "l"(map), "r"(s2u(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 
-// geometry of the copies of the tile whose slab starts at grid-matrix row R0, for lane L < 8 (segment L >> 2 = first / second
-// image the slab touches, frame L & 3): image b, first grid row qa, n grid rows (0: nothing to copy); total = bytes of all copies
-struct U8Plan { int b, qa, n, q0; uint32_t total; };
-__device__ __forceinline__ U8Plan u8_plan(const U8Src& u, int R0, int slab_rows, int lane) {
+// images a slab starting at grid-matrix row R0 touches: b0 (always, if any row is inside the batch) and b1 = b0 + 1 (n1 > 0)
+struct U8Plan { int b0, n0, n1, q0; };
+__device__ __forceinline__ U8Plan u8_plan(const U8Src& u, int R0, int slab_rows) {
   U8Plan pl;
   const int totalq = u.rows / u.G;
   pl.q0 = R0 / u.G;
   int q1 = (R0 + slab_rows - 1) / u.G;
   if (q1 > totalq - 1) q1 = totalq - 1;
-  pl.b = 0; pl.qa = 0; pl.n = 0; pl.total = 0;
+  pl.b0 = 0; pl.n0 = 0; pl.n1 = 0;
   if (q1 >= pl.q0) {
-    const int b0 = pl.q0 / u.G, b1 = q1 / u.G;
-    const int e0 = min(q1, b0 * u.G + u.G - 1);
-    const int n0 = e0 - pl.q0 + 1, n1 = b1 > b0 ? q1 - b1 * u.G + 1 : 0;
-    pl.total = (uint32_t)(4 * (n0 + n1) * 4 * u.frame_w);
-    const int seg = lane >> 2;
-    pl.b = seg ? b1 : b0;
-    pl.qa = seg ? b1 * u.G : pl.q0;
-    pl.n = lane < 8 ? (seg ? n1 : n0) : 0;
+    pl.b0 = pl.q0 / u.G;
+    const int b1 = q1 / u.G;
+    pl.n0 = min(q1, pl.b0 * u.G + u.G - 1) - pl.q0 + 1;
+    pl.n1 = b1 > pl.b0 ? q1 - b1 * u.G + 1 : 0;
   }
   return pl;
 }
-// one full warp: arm `bar` with the tile's byte count and issue the copies (lane L < 8 issues copy L); idx_b = idx[pl.b]
-__device__ __forceinline__ void u8_issue(const U8Src& u, const U8Plan& pl, long long idx_b, uint8_t* stage, uint64_t* bar,
-                                         int slots, int lane) {
-  const int rowb = 4 * u.frame_w;
-  if (lane == 0) {
-    if (pl.total) mb_expect_tx(bar, pl.total);
-    else mb_arrive(bar);
-  }
-  __syncwarp();
-  if (pl.n > 0) {
-    const int f = lane & 3;
-    const uint8_t* src = u.frames + (idx_b + u.first + f) * u.row_bytes + (long long)(pl.qa - pl.b * u.G) * rowb;
-    bulk_g2s_u8(stage + (f * slots + (pl.qa - pl.q0)) * rowb, src, (uint32_t)(pl.n * rowb), bar);
-  }
+// ONE thread: arm `bar` with the tile's byte count and issue its one or two tensor loads; i0 / i1 = idx[b0] / idx[b0 + 1]
+__device__ __forceinline__ void u8_issue(const U8Src& u, const CUtensorMap* map, const U8Plan& pl, long long i0, long long i1,
+                                         uint8_t* stage, uint64_t* bar, int slots) {
+  const uint32_t box = (uint32_t)(4 * slots * 4 * u.frame_w);          // bytes the TMA reports per box (zero fill included)
+  const int nb = (pl.n0 > 0) + (pl.n1 > 0);
+  if (nb == 0) { mb_arrive(bar); return; }
+  mb_expect_tx(bar, box * nb);
+  tma_load_3d(stage, map, bar, 0, pl.q0 - pl.b0 * u.G, (int)(i0 + u.first));
+  if (pl.n1 > 0) tma_load_3d(stage + ((box + 127) & ~127u), map, bar, 0, 0, (int)(i1 + u.first));
 }
 
 template <int J0, int NJ>
@@ -769,13 +765,15 @@ __device__ __forceinline__ void u8_convert(const U8Src& u, const uint8_t* stage,
                                            int tid, int bar_id) {
   const int rowb = 4 * u.frame_w, fstride = slots * rowb;
   const int q0 = R0 / u.G;
+  const int qb1 = (q0 / u.G + 1) * u.G;                   // first grid row of the second image the slab may touch
+  const int seg1 = (4 * fstride + 127) & ~127;            // its box sits behind the first image's
   const int rl0 = tid & 127;
   if (rl0 < slab_rows) {
     const int r = R0 + rl0;
     int so = -1;
     if (r < u.rows) {
       const int q = r / u.G;
-      so = (q - q0) * rowb + 4 * (r - q * u.G);
+      so = (q >= qb1 ? seg1 + (q - qb1) * rowb : (q - q0) * rowb) + 4 * (r - q * u.G);
     }
     if (NT == 128) {
       u8_store_chunks<0, 8>(stage, slab, rl0, so, fstride, u.frame_w);
@@ -790,7 +788,8 @@ __device__ __forceinline__ void u8_convert(const U8Src& u, const uint8_t* stage,
     uint32_t w0 = 0, w1 = 0;
     if (r < u.rows) {
       const int q = r / u.G;
-      const uint8_t* src = stage + (j >> 1) * fstride + (q - q0) * rowb + 4 * (r - q * u.G) + (2 * (j & 1)) * u.frame_w;
+      const uint8_t* src = stage + (j >> 1) * fstride + (q >= qb1 ? seg1 + (q - qb1) * rowb : (q - q0) * rowb) +
+                           4 * (r - q * u.G) + (2 * (j & 1)) * u.frame_w;
       w0 = *reinterpret_cast<const uint32_t*>(src);
       w1 = *reinterpret_cast<const uint32_t*>(src + u.frame_w);
     }
@@ -878,27 +877,26 @@ __global__ void __launch_bounds__(U8 ? SLAB_U8_THREADS : GEMM_THREADS, (BN == 32
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();   // everything above (barriers, tensor-map prefetch, TMEM allocation) overlaps the previous kernel's tail
 
-  if (U8 && warp == 0) {
-    // ---------------------------------------------------------------------- K1 producer (whole warp): weights by TMA, then
-    // the uint8 pixels of every tile by bulk copies, U8_STAGES tiles ahead; idx[] of the next tile is requested one tile early
-    if (elect_one()) {
-      mb_expect_tx(w_full, (uint32_t)k_tiles * W_TILE);
-      for (int kt = 0; kt < k_tiles; ++kt) tma_load_2d(sW + (size_t)kt * W_TILE, mB, w_full, kt * GEMM_BK, 0);
-    }
-    __syncwarp();
-    U8Plan pl = u8_plan(sp.u8, cta * GEMM_BM + sp.min_shift, sp.slab_rows, lane);
-    long long idx_b = (cta < tiles && pl.n > 0) ? __ldg(sp.u8.idx + pl.b) : 0;
+  if (U8 && warp == 0 && elect_one()) {
+    // ---------------------------------------------------------------------- K1 producer: weights, then the uint8 pixels of every
+    // tile (one tensor load per image the slab touches), up to sp.u8.stages tiles ahead; idx[] is requested one tile early
+    mb_expect_tx(w_full, (uint32_t)k_tiles * W_TILE);
+    for (int kt = 0; kt < k_tiles; ++kt) tma_load_2d(sW + (size_t)kt * W_TILE, mB, w_full, kt * GEMM_BK, 0);
+    const int nimg = sp.u8.rows / (sp.u8.G * sp.u8.G);
+    U8Plan pl = u8_plan(sp.u8, cta * GEMM_BM + sp.min_shift, sp.slab_rows);
+    long long i0 = 0, i1 = 0;
+    if (cta < tiles && pl.n0 > 0) { i0 = __ldg(sp.u8.idx + pl.b0); i1 = __ldg(sp.u8.idx + min(pl.b0 + 1, nimg - 1)); }
     uint32_t it = 0;
     for (int tile = cta; tile < tiles; tile += n_cta, ++it) {
       const U8Plan cur = pl;
-      const long long cur_idx = idx_b;
+      const long long c0 = i0, c1 = i1;
       if (tile + n_cta < tiles) {
-        pl = u8_plan(sp.u8, (tile + n_cta) * GEMM_BM + sp.min_shift, sp.slab_rows, lane);
-        idx_b = pl.n > 0 ? __ldg(sp.u8.idx + pl.b) : 0;
+        pl = u8_plan(sp.u8, (tile + n_cta) * GEMM_BM + sp.min_shift, sp.slab_rows);
+        if (pl.n0 > 0) { i0 = __ldg(sp.u8.idx + pl.b0); i1 = __ldg(sp.u8.idx + min(pl.b0 + 1, nimg - 1)); }
       }
       const int us = it % U8_STAGES;
       mb_wait(&u8_empty[us], ((it / U8_STAGES) & 1) ^ 1);
-      u8_issue(sp.u8, cur, cur_idx, sU + (size_t)us * u8_bytes, &u8_full[us], u8_slots_, lane);
+      u8_issue(sp.u8, mA, cur, c0, c1, sU + (size_t)us * u8_bytes, &u8_full[us], u8_slots_);
     }
   } else if (warp == 0 && elect_one()) {
     // ---------------------------------------------------------------------- TMA producer
@@ -1063,28 +1061,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();   // everything above (barriers, tensor-map prefetch, TMEM allocation) overlaps the previous kernel's tail
 
-  if (U8 && warp == 0) {
-    // K1 producer (whole warp): the uint8 pixels of every k-tile by bulk copies (U8_STAGES ahead, idx[] one k-tile early),
-    // the gradient rows by TMA
-    U8Plan pl = u8_plan(w.u8, kt_begin * GEMM_BK, w.slab_rows, lane);
-    long long idx_b = (n_kt > 0 && pl.n > 0) ? __ldg(w.u8.idx + pl.b) : 0;
+  if (U8 && warp == 0 && elect_one()) {
+    // K1 producer: the uint8 pixels of every k-tile (one tensor load per image its slab touches, up to w.u8.stages k-tiles ahead,
+    // idx[] one k-tile early) and the gradient rows
+    const int nimg = w.u8.rows / (w.u8.G * w.u8.G);
+    U8Plan pl = u8_plan(w.u8, kt_begin * GEMM_BK, w.slab_rows);
+    long long i0 = 0, i1 = 0;
+    if (n_kt > 0 && pl.n0 > 0) { i0 = __ldg(w.u8.idx + pl.b0); i1 = __ldg(w.u8.idx + min(pl.b0 + 1, nimg - 1)); }
     for (int i = 0; i < n_kt; ++i) {
       const U8Plan cur = pl;
-      const long long cur_idx = idx_b;
+      const long long c0 = i0, c1 = i1;
       if (i + 1 < n_kt) {
-        pl = u8_plan(w.u8, (kt_begin + i + 1) * GEMM_BK, w.slab_rows, lane);
-        idx_b = pl.n > 0 ? __ldg(w.u8.idx + pl.b) : 0;
+        pl = u8_plan(w.u8, (kt_begin + i + 1) * GEMM_BK, w.slab_rows);
+        if (pl.n0 > 0) { i0 = __ldg(w.u8.idx + pl.b0); i1 = __ldg(w.u8.idx + min(pl.b0 + 1, nimg - 1)); }
       }
       const int us = i % U8_STAGES, s = i % w.stages;
       mb_wait(&u8_empty[us], ((i / U8_STAGES) & 1) ^ 1);
-      u8_issue(w.u8, cur, cur_idx, sU + (size_t)us * u8_bytes, &u8_full[us], u8_slots_, lane);
+      u8_issue(w.u8, &tmX, cur, c0, c1, sU + (size_t)us * u8_bytes, &u8_full[us], u8_slots_);
       mb_wait(&empty[s], ((i / w.stages) & 1) ^ 1);
-      if (elect_one()) {
-        mb_expect_tx(&full[s], (uint32_t)w.a_boxes * 8192);
-        uint8_t* st = smem + (size_t)s * stage_bytes;
-        for (int g = 0; g < w.a_boxes; ++g) tma_load_2d(st + g * 8192, &tmG, &full[s], g * 64, (kt_begin + i) * GEMM_BK);
-      }
-      __syncwarp();
+      mb_expect_tx(&full[s], (uint32_t)w.a_boxes * 8192);
+      uint8_t* st = smem + (size_t)s * stage_bytes;
+      for (int g = 0; g < w.a_boxes; ++g) tma_load_2d(st + g * 8192, &tmG, &full[s], g * 64, (kt_begin + i) * GEMM_BK);
     }
   } else if (warp == 0 && elect_one()) {
     B2RL_TRACE_AT(3, 0, 1);
@@ -1675,13 +1672,29 @@ extern "C" int b2rl_gemm_splitk_bf16(const uint16_t* A, int64_t lda, const uint1
 // of the oldest stacked frame relative to idx[b] (-(history-1) for the state, n_step-(history-1) for the next state).
 // The frame values enter as exact integers 0..255; ImageNormalizer's 1/255 is folded into W (b2rl_nature_pack_weights).
 // ---------------------------------------------------------------------------------------------------------------
+// 3-D tensor map over the uint8 ring as 32-bit words: [capacity][G grid rows][frame_w words], box [4 frames][slots][frame_w]
+static int make_ring_map(CUtensorMap* m, const uint8_t* frames, int64_t capacity, int64_t row_bytes, int frame_w, int slots) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return B2RL_ERR_CUDA; }
+  cuuint64_t gdim[3] = {(cuuint64_t)frame_w, (cuuint64_t)(frame_w / 4), (cuuint64_t)capacity};
+  cuuint64_t gstr[2] = {(cuuint64_t)4 * frame_w, (cuuint64_t)row_bytes};
+  cuuint32_t box[3] = {(cuuint32_t)frame_w, (cuuint32_t)slots, 4u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(frames), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (uint8 ring) failed (%d)", (int)r); return B2RL_ERR_CUDA; }
+  return B2RL_OK;
+}
+
 static int u8_src(U8Src& u, const uint8_t* frames, const int64_t* idx, int32_t first, int64_t row_bytes, int32_t frame_w,
                   int32_t batch, int32_t history) {
   B2RL_REQUIRE(frames && idx, "null pointer");
   B2RL_REQUIRE(history == 4, "the uint8-ring producer packs 4 frames x 16 pixels into the 64 channels of one slab column block");
   B2RL_REQUIRE(frame_w > 0 && frame_w % 4 == 0 && row_bytes % frame_w == 0 && row_bytes / frame_w == frame_w,
                "square frames with a side that is a multiple of 4");
-  B2RL_REQUIRE(reinterpret_cast<uintptr_t>(frames) % 4 == 0 && row_bytes % 4 == 0, "ring rows must be 4-byte aligned");
+  B2RL_REQUIRE(reinterpret_cast<uintptr_t>(frames) % 16 == 0 && row_bytes % 16 == 0 && (4 * frame_w) % 16 == 0 && frame_w <= 256,
+               "ring rows and grid rows must be 16-byte aligned (TMA strides), frames at most 256 pixels wide");
   B2RL_REQUIRE(batch > 0 && (int64_t)batch * (frame_w / 4) * (frame_w / 4) < (1LL << 31), "bad batch");
   u.frames = frames; u.idx = idx; u.row_bytes = row_bytes; u.first = first; u.frame_w = frame_w; u.G = frame_w / 4;
   u.rows = batch * u.G * u.G;
@@ -1690,8 +1703,8 @@ static int u8_src(U8Src& u, const uint8_t* frames, const int64_t* idx, int32_t f
 
 // D = act(conv1(frames) + bias): rows (b, gy, gx) of the G x G grid, n_out <= 32 output channels, bf16, through the output row
 // maps of b2rl_conv_gemm_bf16 (out_map 1 = space-to-depth(2) rows for conv2, valid V x V).  W: [n_out][4 taps * 64] bf16.
-extern "C" int b2rl_conv1_u8_fwd(const uint8_t* frames, const int64_t* idx, int32_t first, int64_t row_bytes, int32_t frame_w,
-                                 int32_t batch, int32_t history, const uint16_t* W, int32_t n_out, void* D, int64_t ldd,
+extern "C" int b2rl_conv1_u8_fwd(const uint8_t* frames, int64_t capacity, const int64_t* idx, int32_t first, int64_t row_bytes,
+                                 int32_t frame_w, int32_t batch, int32_t history, const uint16_t* W, int32_t n_out, void* D, int64_t ldd,
                                  const float* bias, int32_t relu, int32_t out_map, int32_t V, void* stream) {
   SlabParams sp = {};
   int rc = u8_src(sp.u8, frames, idx, first, row_bytes, frame_w, batch, history);
@@ -1711,10 +1724,13 @@ extern "C" int b2rl_conv1_u8_fwd(const uint8_t* frames, const int64_t* idx, int3
   sp.min_shift = 0;
   sp.base_offset_mode = 2;
   B2RL_REQUIRE(sp.slab_rows <= 256, "frame too wide for one slab");
-  CUtensorMap tb;
+  B2RL_REQUIRE(capacity > 0, "bad capacity");
+  CUtensorMap tb, tr;
   rc = make_map(&tb, W, K, n_out, K, 32);
   if (rc) return rc;
-  int r2 = launch_slab<32>(tb, tb, tb, tb, sp, (cudaStream_t)stream);
+  rc = make_ring_map(&tr, frames, capacity, row_bytes, frame_w, u8_slots(sp.slab_rows, G));
+  if (rc) return rc;
+  int r2 = launch_slab<32>(tr, tb, tr, tb, sp, (cudaStream_t)stream);
   if (r2 > 0) { set_error("b2rl_conv1_u8_fwd: the slab does not fit in shared memory"); return B2RL_ERR_ARG; }
   return r2;
 }
@@ -1722,8 +1738,8 @@ extern "C" int b2rl_conv1_u8_fwd(const uint8_t* frames, const int64_t* idx, int3
 // split-K partials of conv1's weight gradient dW[n][tap*64 + c] = sum_r G[r][n] * x[r + shift(tap)][c] with x read from the
 // ring as above (G_rows: bf16 [batch*G*G][n_out], the masked output gradient on conv1's grid).  Same output contract as
 // b2rl_conv_wgrad_partials.
-extern "C" int b2rl_conv1_u8_wgrad_partials(const uint8_t* frames, const int64_t* idx, int32_t first, int64_t row_bytes,
-                                            int32_t frame_w, int32_t batch, int32_t history, const uint16_t* G_rows,
+extern "C" int b2rl_conv1_u8_wgrad_partials(const uint8_t* frames, int64_t capacity, const int64_t* idx, int32_t first,
+                                            int64_t row_bytes, int32_t frame_w, int32_t batch, int32_t history, const uint16_t* G_rows,
                                             int32_t n_out, float* partials, int32_t* n_partials_host, void* stream) {
   WgradParams w = {};
   int rc = u8_src(w.u8, frames, idx, first, row_bytes, frame_w, batch, history);
@@ -1739,11 +1755,14 @@ extern "C" int b2rl_conv1_u8_wgrad_partials(const uint8_t* frames, const int64_t
   w.D = partials; w.ldd = taps * C; w.partial_stride = (int64_t)n_out * taps * C;
   w.tap0 = 0; w.ntaps = taps;
   B2RL_REQUIRE(w.slab_rows <= 256, "frame too wide for one slab");
-  CUtensorMap tg;
+  B2RL_REQUIRE(capacity > 0, "bad capacity");
+  CUtensorMap tg, tr;
   rc = make_map(&tg, G_rows, n_out, w.rows, n_out, 64);
   if (rc) return rc;
+  rc = make_ring_map(&tr, frames, capacity, row_bytes, frame_w, u8_slots(w.slab_rows, G));
+  if (rc) return rc;
   int n = 0;
-  int r2 = launch_wgrad<256, true>(tg, tg, w, (cudaStream_t)stream, &n);
+  int r2 = launch_wgrad<256, true>(tg, tr, w, (cudaStream_t)stream, &n);
   if (r2 > 0) { set_error("b2rl_conv1_u8_wgrad_partials: the slab does not fit in shared memory"); return B2RL_ERR_ARG; }
   *n_partials_host = n;
   return r2;

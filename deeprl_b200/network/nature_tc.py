@@ -79,7 +79,8 @@ class RingFrames:
         return x.to(_bf16).permute(0, 3, 1, 2)
 
     def args(self):
-        return (_lib.ptr(self.frames), _lib.ptr(self.idx), self.first, self.row_bytes, self.frame_w, self.batch, self.history)
+        return (_lib.ptr(self.frames), int(self.frames.shape[0]), _lib.ptr(self.idx), self.first, self.row_bytes, self.frame_w,
+                self.batch, self.history)
 
 
 def _zero_grid(key, shape, device):

@@ -301,18 +301,18 @@ int b2rl_conv_wgrad_partials(const uint16_t* X, int64_t rows, int32_t C, const u
 
 /* K1 -- conv1 of NatureConvBody straight from the uint8 replay ring: the fused gather -> normalize -> conv1 of the
  * reference chain replay.py:124-134 (frame-stack gather) -> normalizer.py:58-61 -> network_bodies.py:27, with no
- * materialised batch.  frames: ring [capacity][row_bytes] uint8; idx: int64 [batch] sampled ring indices; first: ring row of
+ * materialised batch.  frames: ring [capacity][row_bytes] uint8 (16-byte aligned rows); idx: int64 [batch] sampled ring indices; first: ring row of
  * the oldest stacked frame relative to idx[b] (-(history-1) for the state, n_step-(history-1) for the next state);
  * history must be 4 (4 frames x 16 pixels = the 64 channels of one space-to-depth(4) position).  The pixels enter as
  * exact integers 0..255; ImageNormalizer's 1/255 is folded into W [n_out][4 taps * 64] (b2rl_nature_pack_weights).
  * fwd: D = act(conv1 + bias) over rows (b, gy, gx) of the (frame_w/4)^2 grid, bf16, output row maps of
  * b2rl_conv_gemm_bf16.  wgrad_partials: split-K partials of dW[n][tap*64+c] = sum_r G[r][n] * x[r + shift(tap)][c],
  * contract of b2rl_conv_wgrad_partials. */
-int b2rl_conv1_u8_fwd(const uint8_t* frames, const int64_t* idx, int32_t first, int64_t row_bytes, int32_t frame_w,
-                      int32_t batch, int32_t history, const uint16_t* W, int32_t n_out, void* D, int64_t ldd,
+int b2rl_conv1_u8_fwd(const uint8_t* frames, int64_t capacity, const int64_t* idx, int32_t first, int64_t row_bytes,
+                      int32_t frame_w, int32_t batch, int32_t history, const uint16_t* W, int32_t n_out, void* D, int64_t ldd,
                       const float* bias, int32_t relu, int32_t out_map, int32_t V, void* stream);
-int b2rl_conv1_u8_wgrad_partials(const uint8_t* frames, const int64_t* idx, int32_t first, int64_t row_bytes, int32_t frame_w,
-                                 int32_t batch, int32_t history, const uint16_t* G_rows, int32_t n_out, float* partials,
+int b2rl_conv1_u8_wgrad_partials(const uint8_t* frames, int64_t capacity, const int64_t* idx, int32_t first, int64_t row_bytes,
+                                 int32_t frame_w, int32_t batch, int32_t history, const uint16_t* G_rows, int32_t n_out, float* partials,
                                  int32_t* n_partials_host, void* stream);
 
 /* D = act(A B^T + bias) (bf16 out) with split-K and an in-kernel fix-up: one launch instead of zero-fill + atomic split-K +
