@@ -877,7 +877,8 @@ __global__ void __launch_bounds__(U8 ? SLAB_U8_THREADS : GEMM_THREADS, (BN == 32
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();   // everything above (barriers, tensor-map prefetch, TMEM allocation) overlaps the previous kernel's tail
 
-  if (U8 && warp == 0 && elect_one()) {
+  if (warp == 0 && elect_one()) {
+   if constexpr (U8) {
     // ---------------------------------------------------------------------- K1 producer: weights, then the uint8 pixels of every
     // tile (one tensor load per image the slab touches), up to sp.u8.stages tiles ahead; idx[] is requested one tile early
     mb_expect_tx(w_full, (uint32_t)k_tiles * W_TILE);
@@ -898,7 +899,7 @@ __global__ void __launch_bounds__(U8 ? SLAB_U8_THREADS : GEMM_THREADS, (BN == 32
       mb_wait(&u8_empty[us], ((it / U8_STAGES) & 1) ^ 1);
       u8_issue(sp.u8, mA, cur, c0, c1, sU + (size_t)us * u8_bytes, &u8_full[us], u8_slots_);
     }
-  } else if (warp == 0 && elect_one()) {
+   } else {
     // ---------------------------------------------------------------------- TMA producer
     B2RL_TRACE_AT(3, 0, 1);
     mb_expect_tx(w_full, (uint32_t)k_tiles * W_TILE);
@@ -916,6 +917,7 @@ __global__ void __launch_bounds__(U8 ? SLAB_U8_THREADS : GEMM_THREADS, (BN == 32
                       tile * GEMM_BM + sp.min_shift);
       }
     }
+   }
   } else if (U8 && warp >= 10) {
     // ---------------------------------------------------------------------- K1 converters (warps 10-13): staged uint8 -> slab
     const int tid = (int)threadIdx.x - GEMM_THREADS;
@@ -1061,7 +1063,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();   // everything above (barriers, tensor-map prefetch, TMEM allocation) overlaps the previous kernel's tail
 
-  if (U8 && warp == 0 && elect_one()) {
+  if (warp == 0 && elect_one()) {
+   if constexpr (U8) {
     // K1 producer: the uint8 pixels of every k-tile (one tensor load per image its slab touches, up to w.u8.stages k-tiles ahead,
     // idx[] one k-tile early) and the gradient rows
     const int nimg = w.u8.rows / (w.u8.G * w.u8.G);
@@ -1083,7 +1086,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
       uint8_t* st = smem + (size_t)s * stage_bytes;
       for (int g = 0; g < w.a_boxes; ++g) tma_load_2d(st + g * 8192, &tmG, &full[s], g * 64, (kt_begin + i) * GEMM_BK);
     }
-  } else if (warp == 0 && elect_one()) {
+   } else {
     B2RL_TRACE_AT(3, 0, 1);
     for (int i = 0; i < n_kt; ++i) {
       const int s = i % w.stages;
@@ -1099,6 +1102,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
           tma_load_2d(st + A_BYTES + (size_t)cb * slab_block, &tmX, &full[s], cb * GEMM_BK, k0);         // [slab_rows][64 c]
       }
     }
+   }
   } else if (warp == 1 && n_kt > 0 && elect_one()) {
     const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(GEMM_BM >> 4) << 24);
     const bool merge = w.C == 64;
