@@ -738,19 +738,36 @@ __device__ __forceinline__ void u8_issue(const U8Src& u, const CUtensorMap* map,
   if (pl.n1 > 0) tma_load_3d(stage + ((box + 127) & ~127u), map, bar, 0, 0, (int)(i1 + u.first));
 }
 
+// explicit shared-space accesses: the staging / slab pointers are carved out of the dynamic shared memory through integer
+// arithmetic, so the compiler only sees GENERIC pointers -- generic loads of shared memory go through the L1 path with ~10x the
+// latency of LDS (measured: the converters took 4 000 cycles per tile with them, long_scoreboard-bound)
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const int4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 template <int J0, int NJ>
-__device__ __forceinline__ void u8_store_chunks(const uint8_t* stage, uint8_t* slab, int rl, int so, int fstride, int frame_w) {
+__device__ __forceinline__ void u8_store_chunks(uint32_t stage, uint32_t slab, int rl, int so, int fstride, int frame_w) {
   // chunks J0 .. J0+NJ-1 (16 bytes = 8 channels each) of slab row rl; so = staging offset of pixel (4gy, 4gx) of frame 0, or -1: zeros
+  uint32_t w0[NJ], w1[NJ];
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj) {                       // all loads first, then the conversions
+    const int j = J0 + jj;
+    w0[jj] = w1[jj] = 0;
+    if (so >= 0) {
+      const uint32_t src = stage + (uint32_t)((j >> 1) * fstride + so + (2 * (j & 1)) * frame_w);
+      w0[jj] = lds32(src);
+      w1[jj] = lds32(src + frame_w);
+    }
+  }
 #pragma unroll
   for (int jj = 0; jj < NJ; ++jj) {
     const int j = J0 + jj;
-    uint32_t w0 = 0, w1 = 0;
-    if (so >= 0) {
-      const uint8_t* src = stage + (j >> 1) * fstride + so + (2 * (j & 1)) * frame_w;
-      w0 = *reinterpret_cast<const uint32_t*>(src);
-      w1 = *reinterpret_cast<const uint32_t*>(src + frame_w);
-    }
-    *reinterpret_cast<int4*>(slab + rl * 128 + ((j ^ (rl & 7)) << 4)) = cvt8_u8_bf16(w0, w1);
+    sts128(slab + (uint32_t)(rl * 128 + ((j ^ (rl & 7)) << 4)), cvt8_u8_bf16(w0[jj], w1[jj]));
   }
 }
 
@@ -761,8 +778,9 @@ __device__ __forceinline__ void u8_store_chunks(const uint8_t* stage, uint8_t* s
 // 128 are shared out chunk-wise.  On return every thread's stores are fenced towards the async proxy (tcgen05.mma reads shared
 // memory through it) and all NT threads have arrived.
 template <int NT>
-__device__ __forceinline__ void u8_convert(const U8Src& u, const uint8_t* stage, uint8_t* slab, int R0, int slab_rows, int slots,
-                                           int tid, int bar_id) {
+__device__ __forceinline__ void u8_convert(const U8Src& u, const uint8_t* stage_p, uint8_t* slab_p, int R0, int slab_rows,
+                                           int slots, int tid, int bar_id) {
+  const uint32_t stage = s2u(stage_p), slab = s2u(slab_p);
   const int rowb = 4 * u.frame_w, fstride = slots * rowb;
   const int q0 = R0 / u.G;
   const int qb1 = (q0 / u.G + 1) * u.G;                   // first grid row of the second image the slab may touch
@@ -788,12 +806,12 @@ __device__ __forceinline__ void u8_convert(const U8Src& u, const uint8_t* stage,
     uint32_t w0 = 0, w1 = 0;
     if (r < u.rows) {
       const int q = r / u.G;
-      const uint8_t* src = stage + (j >> 1) * fstride + (q >= qb1 ? seg1 + (q - qb1) * rowb : (q - q0) * rowb) +
-                           4 * (r - q * u.G) + (2 * (j & 1)) * u.frame_w;
-      w0 = *reinterpret_cast<const uint32_t*>(src);
-      w1 = *reinterpret_cast<const uint32_t*>(src + u.frame_w);
+      const uint32_t src = stage + (uint32_t)((j >> 1) * fstride + (q >= qb1 ? seg1 + (q - qb1) * rowb : (q - q0) * rowb) +
+                                              4 * (r - q * u.G) + (2 * (j & 1)) * u.frame_w);
+      w0 = lds32(src);
+      w1 = lds32(src + u.frame_w);
     }
-    *reinterpret_cast<int4*>(slab + rl * 128 + ((j ^ (rl & 7)) << 4)) = cvt8_u8_bf16(w0, w1);
+    sts128(slab + (uint32_t)(rl * 128 + ((j ^ (rl & 7)) << 4)), cvt8_u8_bf16(w0, w1));
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NT) : "memory");
