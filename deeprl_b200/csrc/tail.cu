@@ -75,11 +75,20 @@ __global__ void __launch_bounds__(TAIL_THREADS) nature_grad_reduce_kernel(const 
   if (kind == U_W4) {
     // one fc4 row: [hw][c] -> [c][hw] through shared memory (row pitch 65: conflict-free both ways)
     const float4* src = reinterpret_cast<const float4*>(a.g4p + (int64_t)row * 3136);
-    for (int v = tid; v < 784; v += TAIL_THREADS) {
-      const float4 x = __ldg(src + v);
-      const int k = 4 * v, hw = k >> 6, c = k & 63;
-      float* d = sbuf + hw * 65 + c;
-      d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
+    float4 x[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {                             // 784 float4 = 3.06 per thread: all requested before any is used
+      const int v = tid + t * TAIL_THREADS;
+      if (v < 784) x[t] = __ldg(src + v);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int v = tid + t * TAIL_THREADS;
+      if (v < 784) {
+        const int k = 4 * v, hw = k >> 6, c = k & 63;
+        float* d = sbuf + hw * 65 + c;
+        d[0] = x[t].x; d[1] = x[t].y; d[2] = x[t].z; d[3] = x[t].w;
+      }
     }
     __syncthreads();
     float4* dst = reinterpret_cast<float4*>(a.grad + off);
@@ -214,10 +223,21 @@ __global__ void __launch_bounds__(TAIL_THREADS) nature_fused_opt_kernel(const Op
   float4* g4 = reinterpret_cast<float4*>(a.grad + off);
   float4* s14 = reinterpret_cast<float4*>(a.s1 + off);
   float4* s24 = reinterpret_cast<float4*>(a.s2 + off);
-  for (int v = tid; v < (len >> 2); v += TAIL_THREADS) {
-    const float4 gv = g4[v], pv = p4[v], s1v = s14[v];
-    float4 s2v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (a.opt != 0) s2v = s24[v];
+  constexpr int MAXV = 4;                                      // a unit has at most 3136 / 4 = 784 float4 = 3.06 per thread
+  float4 gq[MAXV], pq[MAXV], s1q[MAXV], s2q[MAXV];
+#pragma unroll
+  for (int t = 0; t < MAXV; ++t) {                            // one round trip: every load of the unit is in flight together
+    const int v = tid + t * TAIL_THREADS;
+    if (v < (len >> 2)) {
+      gq[t] = g4[v]; pq[t] = p4[v]; s1q[t] = s14[v];
+      s2q[t] = a.opt != 0 ? s24[v] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < MAXV; ++t) {
+    const int v = tid + t * TAIL_THREADS;
+    if (v >= (len >> 2)) continue;
+    const float4 gv = gq[t], pv = pq[t], s1v = s1q[t], s2v = s2q[t];
     const float g[4] = {gv.x * coef, gv.y * coef, gv.z * coef, gv.w * coef};
     float p[4] = {pv.x, pv.y, pv.z, pv.w}, s1[4] = {s1v.x, s1v.y, s1v.z, s1v.w}, s2[4] = {s2v.x, s2v.y, s2v.z, s2v.w};
 #pragma unroll

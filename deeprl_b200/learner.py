@@ -93,6 +93,8 @@ class GraphedDQNLearner:
         self.updates = 0
         self.with_h2d = False
         self._tail = None                 # network/tail.py NatureTail (built on first use), False = not applicable
+        self._overlap = False             # multi-GPU: NCCL captured inside the update graph, fc4's all-reduce beside the backward
+        self._early_work = None
         body = getattr(network, "body", None)
         self.ring = (not self.prefetch and not self.dual and compute_dtype == torch.bfloat16 and Config.DENSE_BACKEND == "tcgen05"
                      and hasattr(body, "repack") and not getattr(body, "noisy_linear", False) and replay.history_length == 4
@@ -113,6 +115,11 @@ class GraphedDQNLearner:
                 self._repack(self.net, self.scale)
                 self._tail = NatureTail(self.opt, body, self.scale)
                 self._tail.max_norm, self._tail.grad_scale = self.clip, 1.0 / self.world
+                if self.world > 1:
+                    # fc4's gradient is reduced into the arena and all-reduced right after its GEMM (beside the convolution
+                    # backward); the small remainder follows the last weight-gradient GEMM
+                    self._tail.split = True
+                    self._tail.early = self._allreduce_early
             else:
                 self._tail = False
         return self._tail or None
@@ -310,6 +317,12 @@ class GraphedDQNLearner:
         """Warm up eagerly on a side stream (cuDNN autotune, lazy allocations), then capture."""
         self.with_h2d = with_h2d
         self.refresh_packed()
+        # multi GPU, default: the collectives are captured INSIDE the update graph -- fc4's slice of the gradient arena (95 % of
+        # the bytes) is all-reduced asynchronously right after its weight-gradient GEMM, beside the convolution backward, the
+        # small remainder after the last GEMM.  B2RL_NCCL_IN_GRAPH=0: [sample..backward] graph | eager all-reduce of the whole
+        # arena | [clip + optimizer] graph (the round-1 form: +54 us per update at 2 and 4 GPUs, +85 us at 8).
+        one_graph = self.world == 1 or os.environ.get("B2RL_NCCL_IN_GRAPH", "1") == "1"
+        self._overlap = self.world > 1 and one_graph and self.tail() is not None
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -322,10 +335,6 @@ class GraphedDQNLearner:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.g_main, self.g_opt = [], None
-        # multi GPU: [sample..backward] graph | eager NCCL all-reduce | [clip + optimizer] graph.  Capturing the collective
-        # INSIDE the update graph (B2RL_NCCL_IN_GRAPH=1) was measured at 2 x B200: 6 232 vs 6 718 updates/s for the split
-        # form, and the process group then hung at teardown -- so the split form is the default.
-        one_graph = self.world == 1 or os.environ.get("B2RL_NCCL_IN_GRAPH", "0") == "1"
         try:
             self._capture_main(with_h2d, one_graph)
         except Exception as e:                            # noqa: BLE001 -- any capture error: use the split form
@@ -334,6 +343,7 @@ class GraphedDQNLearner:
             print("b2rl: NCCL capture failed (%s); using the split-graph form" % str(e).splitlines()[0], file=sys.stderr)
             torch.cuda.synchronize()
             one_graph = False
+            self._overlap = False
             self.g_main = []
             self._capture_main(with_h2d, False)
         if not one_graph:                                # [sample..backward] | NCCL all-reduce | [clip+opt]
@@ -358,8 +368,25 @@ class GraphedDQNLearner:
                     self._opt()
             self.g_main.append(g)
 
+    def _allreduce_early(self):
+        """fc4's slice of the gradient arena, asynchronously (called on the weight-gradient branch right after kernel A4): the
+        convolution backward proceeds while NCCL runs; ``_allreduce`` waits for it."""
+        self._early_work = None
+        if self._overlap:
+            lo, hi = self._tail.early_slice
+            self._early_work = dist.all_reduce(self.opt.grad[lo:hi], async_op=True)
+
     def _allreduce(self):
-        if self.world > 1:
+        if self.world <= 1:
+            return
+        tail = self.tail()
+        if tail is not None and self._overlap:
+            for lo, hi in tail.late_slices:
+                dist.all_reduce(self.opt.grad[lo:hi])
+            if getattr(self, "_early_work", None) is not None:
+                self._early_work.wait()
+                self._early_work = None
+        else:
             dist.all_reduce(self.opt.grad)
 
     def update(self):

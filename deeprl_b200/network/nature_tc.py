@@ -122,6 +122,16 @@ def _backward_fused(ctx, gy4):
     y3c = y3.view(B, 3136)
     gw4p = gemm_bf16(g4, y3c, a_major="mn", b_major="mn", out_dtype=_f32, block_n=128, stream=_fork())
     mark("w_fc4", _WGRAD["stream"])
+    if sink is not None and sink.split:
+        # multi-GPU: fc4's gradient (95 % of the bytes) goes to the arena NOW, and its all-reduce (sink.early) runs beside the
+        # convolution backward instead of after it
+        if db4 is not sink.db4:
+            sink.db4.copy_(db4)
+        side = _WGRAD["stream"]
+        with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+            sink.reduce_w4(gw4p)
+            if sink.early is not None:
+                sink.early()
     if sink is not None:                   # persistent accumulators, re-zeroed by the tail's kernel A
         db1, db2, db3 = sink.db1, sink.db2, sink.db3
     else:
@@ -385,9 +395,12 @@ class _NatureBody(torch.autograd.Function):
         params = ctx.params
         sink = _sink_for(params)
         if sink is not None and FUSED_BWD and _lib.CONV_SLAB:
-            if db4 is not sink.db4:
-                sink.db4.copy_(db4)
-            sink.reduce(gw1p, p1, gw2p, p2, gw3p, p3, gw4p)
+            if sink.split:
+                sink.reduce_rest(gw1p, p1, gw2p, p2, gw3p, p3)
+            else:
+                if db4 is not sink.db4:
+                    sink.db4.copy_(db4)
+                sink.reduce(gw1p, p1, gw2p, p2, gw3p, p3, gw4p)
             mark("reduce")
             return (None,) * 12
         if all(p.grad is not None and p.grad.dtype == _f32 and p.grad.is_contiguous() for p in params):

@@ -71,12 +71,25 @@ class NatureTail:
                 b_units.append((ow[layer] + n * lens[layer], lens[layer], U_W1 + layer, n))
             b_units.append((ob[layer], pad4(nb[layer]), U_PLAIN, 0))
         plain = _plain_units(covered, opt.n)
+        # multi-GPU: the fc4 part (95 % of the gradient bytes, final right after the fc4 weight-gradient GEMM) is reduced into
+        # the arena early and all-reduced while the convolution backward still runs; everything else follows at the end
+        a4_units = [u for u in a_units if u[2] in (U_W4, U_B4)]
+        arest_units = [u for u in a_units if u[2] not in (U_W4, U_B4)] + plain
         a_units += plain
         b_units += plain
         assert sum(u[1] for u in b_units) == opt.n, "unit table does not tile the arena"
         to_dev = lambda u: torch.from_numpy(np.asarray(u, dtype=np.int32).reshape(-1, 4)).to(dev)
         self.a_units, self.b_units = to_dev(a_units), to_dev(b_units)
         self.n_a, self.n_b = len(a_units), len(b_units)
+        self.a4_units, self.arest_units = to_dev(a4_units), to_dev(arest_units)
+        self.n_a4, self.n_arest = len(a4_units), len(arest_units)
+        lo, hi = ow[3], ow[3] + self.n4 * 3136
+        if ob[3] == hi:                                  # fc4.bias follows fc4.weight in the arena (parameter order of the body)
+            hi = ob[3] + pad4(self.n4)
+        self.early_slice = (lo, hi)
+        self.late_slices = [(a, b) for a, b in ((0, lo), (hi, opt.n)) if b > a]
+        self.split = False               # set by the owner (world_size > 1): backward calls reduce_w4 / reduce_rest
+        self.early = None                # callable: the all-reduce of the early slice (enqueued right after reduce_w4)
         self.unit_sumsq = torch.zeros(self.n_a, dtype=_f32, device=dev)
         # bias-gradient accumulators of the dgrad epilogues / head backward: zero here, re-zeroed by kernel A after use
         self.db = torch.zeros(32 + 64 + 64 + self.n4, dtype=_f32, device=dev)
@@ -100,6 +113,25 @@ class NatureTail:
                   _lib.ptr(self.db4), self.c1, self.n4, self.scale, _lib.ptr(o.grad), _lib.ptr(self.unit_sumsq),
                   _lib.ptr(o.step_dev) if o.kind == "adam" else None, _lib.ptr(o.scratch), float(self.max_norm or 0.0),
                   float(self.grad_scale), _lib.stream())
+
+    def _reduce(self, units, n, gw1p, p1, gw2p, p2, gw3p, p3, gw4p, stream=None):
+        o = self.opt
+        d = self.unit_sumsq                              # any valid address for the sources a partial table does not touch
+        _lib.call("b2rl_nature_grad_reduce", _lib.ptr(units), n, _lib.ptr(d if gw1p is None else gw1p), int(p1 or 1),
+                  _lib.ptr(d if gw2p is None else gw2p), int(p2 or 1), _lib.ptr(d if gw3p is None else gw3p), int(p3 or 1),
+                  _lib.ptr(d if gw4p is None else gw4p), _lib.ptr(self.db1), _lib.ptr(self.db2), _lib.ptr(self.db3), _lib.ptr(self.db4),
+                  self.c1, self.n4, self.scale, _lib.ptr(o.grad), _lib.ptr(self.unit_sumsq), None, None, 0.0, 1.0,
+                  stream if stream is not None else _lib.stream())
+
+    def reduce_w4(self, gw4p, stream=None):
+        """Multi-GPU, early part: fc4's weight gradient (GEMM layout -> arena) and bias gradient."""
+        self._reduce(self.a4_units, self.n_a4, None, 1, None, 1, None, 1, gw4p, stream)
+
+    def reduce_rest(self, gw1p, p1, gw2p, p2, gw3p, p3):
+        """Multi-GPU, late part: the convolution layers' gradients (+ Adam's step counter)."""
+        self._reduce(self.arest_units, self.n_arest, gw1p, p1, gw2p, p2, gw3p, p3, None)
+        if self.opt.kind == "adam":
+            self.opt.step_dev.add_(1)
 
     def step(self, max_norm=0.0, grad_scale=1.0, reduced_elsewhere=False):
         """Clip + optimizer + bf16 operand pack.  ``reduced_elsewhere``: the gradient arena was all-reduced after ``reduce``
