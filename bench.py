@@ -258,6 +258,18 @@ def measure_learner(rl, workload, dev, rank, world, K, W, repeats, barrier, pref
     return learner, res
 
 
+def leave(world):
+    """End of a multi-rank run: every rank has printed / finished; a process group whose collectives were captured in CUDA
+    graphs can hang in its destructor (measured: the ranks never exit), so the ranks synchronise, flush and leave directly."""
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush(), sys.stderr.flush()
+        os._exit(0)
+
+
 def free(*objs):
     import gc
     for o in objs:
@@ -392,8 +404,7 @@ def run_b2rl(args):
         if rank == 0:
             print(json.dumps(dict(quick=True, value=res["value"], ms_per_step=res["ms_per_step"], loss=res["loss"],
                                   launches=res["gpu_launches_per_step"])), flush=True)
-        if world > 1:
-            dist.destroy_process_group()
+        leave(world)
         return
 
     with ClockSampler(local) as clocks:
@@ -421,9 +432,7 @@ def run_b2rl(args):
     if world > 1:
         barrier()
     if rank != 0:
-        if world > 1:
-            barrier()                                      # rank 0 finishes its single-rank extras (PPO, CPU baseline) first
-            dist.destroy_process_group()
+        leave(world)                                       # (its barrier waits for rank 0's single-rank extras: PPO, CPU baseline)
         return
     if not args.no_extras:
         try:
@@ -469,9 +478,7 @@ def run_b2rl(args):
         tensor_frac_of_sustained=(roof_t["whole_step"]["frac"] if roof_t and roof_t.get("whole_step") else None),
     )
     print(json.dumps(line), flush=True)
-    if world > 1:
-        barrier()
-        dist.destroy_process_group()
+    leave(world)
 
 
 WORKLOADS = {"dqn": "DQN synthetic 84x84x4 uint8 frames, 1M-transition uniform Replay, batch 512, NatureConvBody, 1 B200 (BASELINE configs[1])",

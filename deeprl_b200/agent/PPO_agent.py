@@ -126,8 +126,12 @@ class PPOAgent(BaseAgent):
         if config.shared_repr:
             self.lr_scheduler.step(self.total_steps)
         rows = entries.state.size(0)
+        # the graphed path keeps the actor's and the critic's parameters in two separate arenas: a shared phi_body (whose
+        # parameters the reference gives to BOTH optimizers, network_heads.py:186-189) or discrete (1-D) actions are served
+        # by the eager loop below
+        shared_phi = len(getattr(self.network, "phi_params", [])) > 0
         if (getattr(config, "graph_minibatch", False) and entries.state.is_cuda and not config.shared_repr
-                and rows % config.mini_batch_size == 0):
+                and rows % config.mini_batch_size == 0 and not shared_phi and entries.action.dim() == 2):
             self._graphed_epochs(entries)                  # same updates, one CUDA-graph replay each (learner.py)
             return
         for _ in range(config.optimization_epochs):

@@ -128,9 +128,9 @@ class UniformReplay:
         n = len(states)
         if n == 0:
             return
-        if n > 1024:
-            for s in range(0, n, 1024):
-                self.feed({k: v[s:s + 1024] for k, v in data.items()})
+        if n > 1024:                                     # chunked by the BASE implementation: a subclass's feed() bookkeeping
+            for s in range(0, n, 1024):                  # (PrioritizedReplay adds ONE tree leaf per feed call) must run once
+                UniformReplay.feed(self, {k: v[s:s + 1024] for k, v in data.items()})
             return
         if self.frames is None:
             self._allocate(states[0])
@@ -470,6 +470,12 @@ class ReplayWrapper:
         return out
 
     def update_priorities(self, info):
+        # the tensors were allocated on the caller's stream and may be released as soon as the caller returns: tell the
+        # caching allocator that the side stream still reads them
+        if isinstance(info, tuple) and len(info) == 2 and isinstance(info[0], torch.Tensor):
+            for t in info:
+                if t.is_cuda:
+                    t.record_stream(self._side)
         self._on_side(self.replay.update_priorities, info)
 
     def size(self):

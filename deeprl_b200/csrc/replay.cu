@@ -127,6 +127,17 @@ __global__ void __launch_bounds__(SEL_THREADS) select_uniform_kernel(int64_t* __
     }
   }
   __syncthreads();
+  // The candidate stream is finite; the reference keeps drawing (replay.py:97-100).  If it ran dry (status[0] < B: a tiny ring,
+  // or B close to the stream length) the unfilled tail must still hold VALID indices -- the consumers (gather, conv1's ring
+  // producer) read frames through them without a host check inside a captured graph -- so the accepted indices are cycled;
+  // with none at all every slot gets the smallest index that cannot read below the ring (hl - 1).  status[0] keeps the count.
+  {
+    __shared__ int s_total;
+    if (t == SEL_THREADS - 1) s_total = min(warp_tot[w] + incl, B);     // accepted = inclusive count of the last thread
+    __syncthreads();
+    const int total = s_total;
+    for (int j = total + t; j < B; j += SEL_THREADS) idx_out[j] = total > 0 ? idx_out[j % total] : (int64_t)(hl - 1);
+  }
   if (t == 0) {
     status[1] = last_used ? last_used : n_cand;       // candidates consumed (all of them if the stream ran dry)
     if (!cand) ring_state[4] = (int64_t)(ctr + (uint64_t)n_cand);

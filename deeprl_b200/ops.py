@@ -244,6 +244,11 @@ class FlatOptimizer:
         self.params = [p for p in params]
         dev = self.params[0].device
         _lib.require_cuda(dev)
+        for p in self.params:
+            # a parameter re-pointed into a second arena would leave the first optimizer with a stale copy and send its gradient
+            # to the wrong arena (e.g. the shared phi_body of an actor-critic network given to two FlatOptimizers)
+            if getattr(p, "_b2rl_flat_owner", None) is not None:
+                raise _lib.B2RLError("FlatOptimizer: a parameter already lives in another FlatOptimizer's arena")
         # every parameter starts on a 16-byte boundary of the arena (vector loads in the consumers); the padding
         # elements have zero gradient for ever, so they do not change the global norm or anything else
         offs, n = [], 0
@@ -260,6 +265,7 @@ class FlatOptimizer:
             self.flat[off:off + k].copy_(p.detach().reshape(-1))
             p.data = self.flat[off:off + k].view_as(p)
             p.grad = self.grad[off:off + k].view_as(p)
+            p._b2rl_flat_owner = id(self)
         self.kind, self.lr, self.alpha, self.eps, self.centered, self.betas = kind, lr, alpha, eps, centered, betas
         self.s1 = torch.zeros(pad, dtype=_f32, device=dev)      # square_avg / exp_avg
         self.s2 = torch.zeros(pad, dtype=_f32, device=dev)      # grad_avg   / exp_avg_sq
