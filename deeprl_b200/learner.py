@@ -181,6 +181,13 @@ class GraphedDQNLearner:
             with torch.cuda.stream(side):
                 self._repack(self.net, fs)
                 self._packed_ev.record(side)
+        # async replay: the batch of the NEXT update is fed + sampled on a parallel branch.  Uniform replay: that branch starts
+        # after the backward pass, beside the (small-footprint, L2-bound) update tail -- started beside the forward pass its 512
+        # gather CTAs held the shared memory the convolution kernels need and delayed them by ~20 us (in-graph timeline,
+        # profiles/r02_timeline.txt).  Prioritized replay keeps the early start: the reference's replay worker draws the next
+        # batch BEFORE this update's priorities arrive (replay.py:219-261), and the graph keeps that order.
+        late = (self.prefetch and not self.per and getattr(self, "_one_graph", True)
+                and os.environ.get("B2RL_PREFETCH_LATE", "1") == "1")
         if self.prefetch:
             eager = parity is None
             if eager:
@@ -188,11 +195,8 @@ class GraphedDQNLearner:
             if self._batch[parity] is None:                              # very first update: nothing prefetched yet
                 self._batch[parity] = self._sample(parity)
             t = self._batch[parity]
-            pre.wait_stream(cur)                                         # after the host->device copy of this update's feeds
-            with torch.cuda.stream(pre):
-                self._batch[1 - parity] = self._sample(1 - parity)
-                self._sampled_ev.record(pre)
-                nature_tc.mark("sampled")
+            if not late:
+                self._prefetch_branch(parity)
             if eager:
                 self._parity = 1 - parity
         else:
@@ -201,6 +205,8 @@ class GraphedDQNLearner:
         heads = self._heads()
         if heads is not None:
             self._main_fused_head(t, per, heads, tail, fs)
+            if late:
+                self._prefetch_branch(parity)
             if self.prefetch:
                 cur.wait_stream(pre)
             return
@@ -255,8 +261,19 @@ class GraphedDQNLearner:
             head.backward(grad)
         nature_tc.mark("bwd_done")
         self.loss.copy_(r["loss"])
-        if self.prefetch:
+        if late:
+            self._prefetch_branch(parity)
+            self._late_join = True                       # joined after the optimizer kernels (_opt)
+        elif self.prefetch:
             cur.wait_stream(pre)
+
+    def _prefetch_branch(self, parity):
+        cur, pre = torch.cuda.current_stream(), self._pre
+        pre.wait_stream(cur)                                             # after the host->device copy of this update's feeds
+        with torch.cuda.stream(pre):
+            self._batch[1 - parity] = self._sample(1 - parity)
+            self._sampled_ev.record(pre)
+            nature_tc.mark("sampled")
 
     def _main_fused_head(self, t, per, heads, tail, fs):
         """DQN with a VanillaNet / DuelingNet head: bodies on the tcgen05 kernels, then ONE launch for the online / target
@@ -297,6 +314,12 @@ class GraphedDQNLearner:
         self._repack(self.tgt, self.scale if self.dtype == torch.bfloat16 else 1.0)
 
     def _opt(self):
+        self._opt_kernels()
+        if getattr(self, "_late_join", False):           # the late prefetch branch ran beside the update tail
+            torch.cuda.current_stream().wait_stream(self._pre)
+            self._late_join = False
+
+    def _opt_kernels(self):
         tail = self.tail()
         if tail is not None:
             tail.step(max_norm=self.clip, grad_scale=1.0 / self.world, reduced_elsewhere=self.world > 1)
@@ -322,6 +345,7 @@ class GraphedDQNLearner:
         # small remainder after the last GEMM.  B2RL_NCCL_IN_GRAPH=0: [sample..backward] graph | eager all-reduce of the whole
         # arena | [clip + optimizer] graph (the round-1 form: +54 us per update at 2 and 4 GPUs, +85 us at 8).
         one_graph = self.world == 1 or os.environ.get("B2RL_NCCL_IN_GRAPH", "1") == "1"
+        self._one_graph = one_graph      # (the late prefetch branch is joined after the optimizer kernels: one graph only)
         self._overlap = self.world > 1 and one_graph and self.tail() is not None
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream())
@@ -343,6 +367,7 @@ class GraphedDQNLearner:
             print("b2rl: NCCL capture failed (%s); using the split-graph form" % str(e).splitlines()[0], file=sys.stderr)
             torch.cuda.synchronize()
             one_graph = False
+            self._one_graph = False
             self._overlap = False
             self.g_main = []
             self._capture_main(with_h2d, False)
