@@ -287,7 +287,7 @@ class UniformReplay:
                           bufs["mask"])
 
     def sample_normalized(self, batch_size=None, out_dtype=torch.float32, scale=1.0 / 255, layout="nchw", candidates=None,
-                          tag=0, channels_last=None):
+                          tag=0, channels_last=None, phase=None):
         """Fused gather -> normalize (``ImageNormalizer``) for uint8 frame rings.  state / next_state come back as
         ``out_dtype`` [B, history, H, W] (``layout="nhwc"``: same logical shape, channels_last memory) or, with
         ``layout="s2d"``, as the space-to-depth(4) tensor [B, 16*history, H/4, W/4] (channels_last memory).
@@ -303,7 +303,12 @@ class UniformReplay:
         bufs = self._buffers(B, out_dtype, layout, tag)
         if candidates is not None and not isinstance(candidates, torch.Tensor):
             candidates = torch.as_tensor(np.asarray(candidates, dtype=np.int64), device=self.device)
-        self.select(B, bufs["idx"], candidates)
+        # phase "select": draw the indices only; phase "gather": build the batch from the indices drawn before (the learner
+        # draws early, on tiny kernels, and gathers late, beside its update tail); None: both
+        if phase != "gather":
+            self.select(B, bufs["idx"], candidates)
+        if phase == "select":
+            return None
         if layout == "ring":             # K1: no batch is materialised, conv1 reads the ring through the sampled indices
             self.gather_scalars(bufs["idx"], B, bufs)
             return Transition(self.ring_frames(bufs["idx"], 0), bufs["action"], bufs["reward"], self.ring_frames(bufs["idx"], 1),

@@ -1031,6 +1031,13 @@ struct WgradParams {
   // function of the address, so overlapping groups read the right bytes) with adjacent TMEM accumulator columns.
   int n_runs;
   uint32_t run_off[9], run_acc[9], run_n[9];   // slab window offset (16-byte units), accumulator column, N of the MMA
+  // M-stacking (n_out <= 64): the A operand's second 64-row half holds the SAME gradient columns read `stack_delta` rows away
+  // (a second TMA box), so accumulator lanes 64-127 of a window at shift s hold the tap at shift s - stack_delta: with
+  // stack_delta = -grid_w the windows of tap row dy also produce tap row dy + 1 -- the last tap row costs no MMAs at all
+  // (conv2 / conv1: half the MMAs; conv3: 6 windows instead of 9 taps, 384 columns, ONE launch instead of two).
+  // run_low[j] = first output column of the lower half of run j, or -1 (a duplicate of an upper tap: dropped).
+  int stack_delta, stack_rows;
+  int run_low[9];
   U8Src u8;                                    // U8 kernels: the activation slabs come from the uint8 frame ring (K1)
 };
 
@@ -1102,7 +1109,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
       mb_wait(&empty[s], ((i / w.stages) & 1) ^ 1);
       mb_expect_tx(&full[s], (uint32_t)w.a_boxes * 8192);
       uint8_t* st = smem + (size_t)s * stage_bytes;
-      for (int g = 0; g < w.a_boxes; ++g) tma_load_2d(st + g * 8192, &tmG, &full[s], g * 64, (kt_begin + i) * GEMM_BK);
+      for (int g = 0; g < w.a_boxes; ++g)
+        tma_load_2d(st + g * 8192, &tmG, &full[s], w.stack_delta ? 0 : g * 64, (kt_begin + i) * GEMM_BK + (g ? w.stack_delta : 0));
     }
    } else {
     B2RL_TRACE_AT(3, 0, 1);
@@ -1114,7 +1122,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
       mb_expect_tx(&full[s], (uint32_t)w.a_boxes * 8192 + (U8 ? 0u : slab_bytes));
       uint8_t* st = smem + (size_t)s * stage_bytes;
       const int k0 = (kt_begin + i) * GEMM_BK;
-      for (int g = 0; g < w.a_boxes; ++g) tma_load_2d(st + g * 8192, &tmG, &full[s], g * 64, k0);       // [64 k][64 n]
+      for (int g = 0; g < w.a_boxes; ++g)                                                                 // [64 k][64 n]
+        tma_load_2d(st + g * 8192, &tmG, &full[s], w.stack_delta ? 0 : g * 64, k0 + (g ? w.stack_delta : 0));
       if (!U8) {
         for (int cb = 0; cb < w.col_blocks; ++cb)
           tma_load_2d(st + A_BYTES + (size_t)cb * slab_block, &tmX, &full[s], cb * GEMM_BK, k0);         // [slab_rows][64 c]
@@ -1168,11 +1177,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_wgrad_tcgen05_kernel(con
     if (warp == 4 && lane == 0) B2RL_TRACE_AT(2, 0, 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int cols = w.ntaps * w.C;
+    const bool low = w.stack_delta != 0 && q >= 2;                     // lanes 64-127: the stacked copy (warp-uniform)
+    const int nn = low ? n - 64 : n;
     for (int c = ((warp - 2) >> 2) * 32; c < cols; c += 64) {         // the two warp groups take alternate 32-column chunks
+      int oc = w.tap0 * w.C + c;
+      if (low) {
+        int j = 0;
+        while (j + 1 < w.n_runs && (uint32_t)c >= w.run_acc[j + 1]) ++j;
+        if (w.run_low[j] < 0) continue;                                // duplicate of a tap the upper half already holds
+        oc = w.run_low[j] + (c - (int)w.run_acc[j]);
+      }
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, r);
-      if (n < w.n_out) {
-        float* d = w.D + (int64_t)blockIdx.x * w.partial_stride + (int64_t)n * w.ldd + (int64_t)w.tap0 * w.C + c;
+      if (nn < w.n_out) {
+        float* d = w.D + (int64_t)blockIdx.x * w.partial_stride + (int64_t)nn * w.ldd + oc;
         if (w.partial_stride > 0) {
           // split-K partials are stored plainly (coalesced 16-byte stores) and summed by the consumer
 #pragma unroll
@@ -1399,6 +1417,7 @@ static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, WgradParam
       w.run_off[n] = (uint32_t)(dy * w.grid_w + dx) * 8;
       w.run_acc[n] = acc;
       w.run_n[n] = (uint32_t)(run * w.C);
+      w.run_low[n] = (w.stack_delta && dy == w.stack_rows - 2) ? ((dy + 1) * w.taps_x + dx) * w.C : -1;
       acc += run * w.C;
       tap += run;
       ++n;
@@ -1548,11 +1567,25 @@ static int conv_gemm_impl(int32_t mode, const uint16_t* X, int64_t rows, int32_t
   if (rc) return rc;
   B2RL_REQUIRE(out_mode == 2, "wgrad accumulates with out_mode 2");
   if (g_use_slab && C % 64 == 0 && C <= 128 && n_out <= 128 && shift_sign > 0) {
-    const int max_shift = ((taps - 1) / taps_x) * grid_w + (taps - 1) % taps_x;
+    int max_shift = ((taps - 1) / taps_x) * grid_w + (taps - 1) % taps_x;
     WgradParams w = {};
     w.rows = (int)rows; w.n_out = n_out; w.C = C; w.col_blocks = C / 64; w.taps_x = taps_x; w.grid_w = grid_w;
-    w.slab_rows = (GEMM_BK + max_shift + 7) / 8 * 8;
     w.a_boxes = n_out > 64 ? 2 : 1;
+    // M-stacking (see WgradParams): with at most 64 output channels the second half of the 128 accumulator lanes computes the
+    // last tap row from the windows of the row before it (B2RL_WGRAD_STACK=0: every tap its own window, as in round 1)
+    static int stack_on = -1;
+    if (stack_on < 0) {
+      const char* e = getenv("B2RL_WGRAD_STACK");
+      stack_on = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    const int taps_y = taps / taps_x;
+    int win_taps = taps;
+    if (stack_on && n_out <= 64 && taps_y >= 2 && taps_y * taps_x == taps) {
+      w.stack_delta = -grid_w; w.stack_rows = taps_y; w.a_boxes = 2;
+      win_taps = (taps_y - 1) * taps_x;
+      max_shift = (taps_y - 2) * grid_w + taps_x - 1;
+    }
+    w.slab_rows = (GEMM_BK + max_shift + 7) / 8 * 8;
     w.D = reinterpret_cast<float*>(D); w.ldd = (int)ldd;
     if (g_wgrad_partials) { w.D = g_partial_buf; w.partial_stride = g_partial_stride; }
     CUtensorMap tg, tx;
@@ -1561,10 +1594,16 @@ static int conv_gemm_impl(int32_t mode, const uint16_t* X, int64_t rows, int32_t
     rc = make_map(&tx, X, C, rows, C, w.slab_rows);                 // activation slab: box [slab_rows][64 c]
     if (rc) return rc;
     const int per_launch = 512 / C;                                 // taps whose accumulators fit in TMEM together
+    if (w.stack_delta && win_taps > per_launch) {                   // (does not happen for the NatureConvBody shapes)
+      w.stack_delta = 0; w.stack_rows = 0; w.a_boxes = 1; win_taps = taps;
+      w.slab_rows = (GEMM_BK + ((taps - 1) / taps_x) * grid_w + (taps - 1) % taps_x + 7) / 8 * 8;
+      rc = make_map(&tx, X, C, rows, C, w.slab_rows);
+      if (rc) return rc;
+    }
     int r2 = 0;
-    for (int t0 = 0; t0 < taps && r2 == 0; t0 += per_launch) {
+    for (int t0 = 0; t0 < win_taps && r2 == 0; t0 += per_launch) {
       w.tap0 = t0;
-      w.ntaps = taps - t0 < per_launch ? taps - t0 : per_launch;
+      w.ntaps = win_taps - t0 < per_launch ? win_taps - t0 : per_launch;
       const int cols = w.ntaps * C;
       r2 = cols <= 64 ? launch_wgrad<64>(tg, tx, w, (cudaStream_t)stream, &g_partial_count)
            : cols <= 128 ? launch_wgrad<128>(tg, tx, w, (cudaStream_t)stream, &g_partial_count)
@@ -1770,12 +1809,12 @@ extern "C" int b2rl_conv1_u8_wgrad_partials(const uint8_t* frames, int64_t capac
   B2RL_REQUIRE(n_out > 0 && n_out <= 64 && n_out % 8 == 0, "n_out <= 64, multiple of 8");
   B2RL_REQUIRE(reinterpret_cast<uintptr_t>(G_rows) % 16 == 0, "operands must be 16-byte aligned");
   const int G = w.u8.G, C = 64, taps = 4;
-  const int max_shift = G + 1;
   w.rows = w.u8.rows; w.n_out = n_out; w.C = C; w.col_blocks = 1; w.taps_x = 2; w.grid_w = G;
-  w.slab_rows = (GEMM_BK + max_shift + 7) / 8 * 8;
-  w.a_boxes = 1;
+  // M-stacking (WgradParams): windows of tap row 0 only; accumulator lanes 64-127 (gradient rows read G rows earlier) give row 1
+  w.stack_delta = -G; w.stack_rows = 2; w.a_boxes = 2;
+  w.slab_rows = (GEMM_BK + 1 + 7) / 8 * 8;
   w.D = partials; w.ldd = taps * C; w.partial_stride = (int64_t)n_out * taps * C;
-  w.tap0 = 0; w.ntaps = taps;
+  w.tap0 = 0; w.ntaps = 2;
   B2RL_REQUIRE(w.slab_rows <= 256, "frame too wide for one slab");
   B2RL_REQUIRE(capacity > 0, "bad capacity");
   CUtensorMap tg, tr;
@@ -1784,7 +1823,7 @@ extern "C" int b2rl_conv1_u8_wgrad_partials(const uint8_t* frames, int64_t capac
   rc = make_ring_map(&tr, frames, capacity, row_bytes, frame_w, u8_slots(w.slab_rows, G));
   if (rc) return rc;
   int n = 0;
-  int r2 = launch_wgrad<256, true>(tg, tr, w, (cudaStream_t)stream, &n);
+  int r2 = launch_wgrad<128, true>(tg, tr, w, (cudaStream_t)stream, &n);
   if (r2 > 0) { set_error("b2rl_conv1_u8_wgrad_partials: the slab does not fit in shared memory"); return B2RL_ERR_ARG; }
   *n_partials_host = n;
   return r2;

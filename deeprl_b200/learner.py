@@ -143,12 +143,13 @@ class GraphedDQNLearner:
     def _h2d(self):
         self.d_pack.copy_(self.h_pack, non_blocking=True)
 
-    def _sample(self, tag=0):
-        """feeds of this update + one sampled batch into buffer set ``tag`` (on the current stream)."""
+    def _sample(self, tag=0, phase=None):
+        """feeds of this update + one sampled batch into buffer set ``tag`` (on the current stream).  ``phase`` "select" =
+        feed + index draw only, "gather" = the batch from those indices (uniform replay), None = everything."""
         rp = self.replay
         # DQN_agent.py:104-112 calls feed() once per env transition; `feeds` single-item calls are exactly one multi-item
         # call with each item in its own slot (reference_feed_quirk off) plus `feeds` tree.add(max_priority) -- one launch
-        if self.feeds:
+        if self.feeds and phase != "gather":
             quirk, rp.quirk = rp.quirk, False
             rp.feed_device(self.d_frames, self.d_action, self.d_reward, self.d_mask, self.feeds)
             rp.quirk = quirk
@@ -158,8 +159,10 @@ class GraphedDQNLearner:
             # exact integer frames, space-to-depth layout; ImageNormalizer's scale is folded into conv1's weights.
             # K1 (self.ring): no batch at all -- conv1 reads the sampled stacks from the uint8 ring (synchronous replay only:
             # a prefetched index could be overwritten by the next update's feeds before its frames are read)
-            return rp.sample_normalized(out_dtype=self.dtype, scale=None, layout="ring" if self.ring else "s2d", tag=tag)
-        return rp.sample_normalized(out_dtype=self.dtype, scale=self.scale, layout="nchw", tag=tag)
+            kw = dict(phase=phase) if phase else {}
+            return rp.sample_normalized(out_dtype=self.dtype, scale=None, layout="ring" if self.ring else "s2d", tag=tag, **kw)
+        kw = dict(phase=phase) if phase else {}
+        return rp.sample_normalized(out_dtype=self.dtype, scale=self.scale, layout="nchw", tag=tag, **kw)
 
     def _main(self, parity=None):
         rp = self.replay
@@ -195,7 +198,9 @@ class GraphedDQNLearner:
             if self._batch[parity] is None:                              # very first update: nothing prefetched yet
                 self._batch[parity] = self._sample(parity)
             t = self._batch[parity]
-            if not late:
+            if late:
+                self._prefetch_branch(parity, "select")  # feed + index draw now (two one-CTA kernels), the gather later
+            else:
                 self._prefetch_branch(parity)
             if eager:
                 self._parity = 1 - parity
@@ -206,7 +211,7 @@ class GraphedDQNLearner:
         if heads is not None:
             self._main_fused_head(t, per, heads, tail, fs)
             if late:
-                self._prefetch_branch(parity)
+                self._prefetch_branch(parity, "gather")
             if self.prefetch:
                 cur.wait_stream(pre)
             return
@@ -262,18 +267,20 @@ class GraphedDQNLearner:
         nature_tc.mark("bwd_done")
         self.loss.copy_(r["loss"])
         if late:
-            self._prefetch_branch(parity)
+            self._prefetch_branch(parity, "gather")
             self._late_join = True                       # joined after the optimizer kernels (_opt)
         elif self.prefetch:
             cur.wait_stream(pre)
 
-    def _prefetch_branch(self, parity):
+    def _prefetch_branch(self, parity, phase=None):
         cur, pre = torch.cuda.current_stream(), self._pre
         pre.wait_stream(cur)                                             # after the host->device copy of this update's feeds
         with torch.cuda.stream(pre):
-            self._batch[1 - parity] = self._sample(1 - parity)
-            self._sampled_ev.record(pre)
-            nature_tc.mark("sampled")
+            b = self._sample(1 - parity, phase)
+            if phase != "select":
+                self._batch[1 - parity] = b
+                self._sampled_ev.record(pre)
+                nature_tc.mark("sampled")
 
     def _main_fused_head(self, t, per, heads, tail, fs):
         """DQN with a VanillaNet / DuelingNet head: bodies on the tcgen05 kernels, then ONE launch for the online / target
