@@ -176,6 +176,31 @@ class UniformReplay:
         self.pos, self._size = int(pos), self.memory_size
         self.ring_state[0], self.ring_state[1] = self.pos, self._size
 
+    # ------------------------------------------------------------------ checkpoint (absent upstream)
+    def state_dict(self):
+        """Everything needed to resume: the HBM ring (frames + scalars, host copies), the device cursor / Philox counter and the
+        host mirrors.  ``torch.save``-able."""
+        if self.frames is None:
+            return dict(empty=True)
+        st = self.ring_state.cpu()
+        return dict(empty=False, frames=self.frames.cpu(), action=self.action.cpu(), reward=self.reward.cpu(), mask=self.mask.cpu(),
+                    ring_state=st, item_shape=tuple(self.item_shape), item_dtype=np.dtype(self.item_dtype).str,
+                    memory_size=self.memory_size, n_step=self.n_step, history_length=self.history_length)
+
+    def load_state_dict(self, sd):
+        if sd.get("empty"):
+            return
+        if sd["memory_size"] != self.memory_size or sd["history_length"] != self.history_length:
+            raise ValueError("checkpoint of a different replay geometry")
+        self.item_shape, self.item_dtype = tuple(sd["item_shape"]), np.dtype(sd["item_dtype"])
+        self.row_bytes = int(sd["frames"].shape[1])
+        self._torch_dtype = torch.from_numpy(np.zeros(1, self.item_dtype)).dtype
+        self.frames = sd["frames"].to(self.device)
+        self.action.copy_(sd["action"]), self.reward.copy_(sd["reward"]), self.mask.copy_(sd["mask"])
+        self.ring_state.copy_(sd["ring_state"])
+        self.pos, self._size = int(sd["ring_state"][0]), int(sd["ring_state"][1])
+        self._bufs = {}
+
     def size(self):
         return self._size
 
@@ -375,6 +400,20 @@ class PrioritizedReplay(UniformReplay):
                 t[idx] = t[2 * idx + 1] + t[2 * idx + 2]
         self.ring_state[3] = self.pos
         self.tree.n_entries = cap
+
+    def state_dict(self):
+        sd = super().state_dict()
+        if not sd.get("empty"):
+            sd.update(tree=self.tree.tree.cpu(), pending=self.tree.pending.cpu(), max_priority=self.max_priority_dev.cpu(),
+                      n_entries=self.tree.n_entries)
+        return sd
+
+    def load_state_dict(self, sd):
+        super().load_state_dict(sd)
+        if not sd.get("empty"):
+            self.tree.tree.copy_(sd["tree"]), self.tree.pending.copy_(sd["pending"])
+            self.max_priority_dev.copy_(sd["max_priority"])
+            self.tree.n_entries = int(sd["n_entries"])
 
     def sample(self, batch_size=None, uniforms=None, fills=None, check=True, tag=0):
         """replay.py:164-191 -> ``PrioritizedTransition`` (sampling_prob float32 = tensor(p / total), idx = TREE index)."""

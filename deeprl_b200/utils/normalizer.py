@@ -82,6 +82,8 @@ class MeanStdNormalizer(BaseNormalizer):
         return dict(mean=self.rms.mean, var=self.rms.var)
 
     def load_state_dict(self, saved):
+        if self.rms is None:                               # a fresh agent loading a checkpoint: the moments take the saved shape
+            self.rms = RunningMoments(shape=np.shape(saved["mean"]))    # (the reference dereferences None here, normalizer.py:47-51)
         for key in ("mean", "var"):
             setattr(self.rms, key, saved[key])
 
