@@ -333,7 +333,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int m0, int n
           v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
         }
       }
-      if (n0 + c + lane < p.N) atomicAdd(s_dbias + (n0 + c + lane) % p.dbias_mod, v[0]);
+      if (n0 + c + lane < p.N) {
+        if (p.dbias_mod > 0) atomicAdd(s_dbias + (n0 + c + lane) % p.dbias_mod, v[0]);
+        else atomicAdd(p.dbias + n0 + c + lane, v[0]);             // dbias_mod 0: one bias per output column, straight to global
+      }
     }
     if (live) {
       int64_t off;
@@ -634,7 +637,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (EXT && p.dbias && (int)threadIdx.x < p.dbias_mod) atomicAdd(p.dbias + threadIdx.x, s_dbias[threadIdx.x]);
+  if (EXT && p.dbias && p.dbias_mod > 0 && (int)threadIdx.x < p.dbias_mod) atomicAdd(p.dbias + threadIdx.x, s_dbias[threadIdx.x]);
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
@@ -1497,13 +1500,13 @@ extern "C" int b2rl_gemm_bf16(const uint16_t* A, int32_t a_mn, int64_t lda, cons
 static int apply_ext(GemmParams& p, const b2rl_bwd_epilogue* ext, int N) {
   B2RL_REQUIRE(!ext->mask || (ext->mask_ld % 8 == 0 && reinterpret_cast<uintptr_t>(ext->mask) % 16 == 0 && N % 32 == 0),
                "mask rows must be 16-byte aligned and N a multiple of 32");
-  B2RL_REQUIRE(!ext->dbias || (ext->dbias_mod > 0 && ext->dbias_mod <= 128), "dbias_mod must be in [1, 128]");
+  B2RL_REQUIRE(!ext->dbias || (ext->dbias_mod >= 0 && ext->dbias_mod <= 128), "dbias_mod must be in [0, 128] (0: one bias per column)");
   B2RL_REQUIRE(p.out_map < 3 || (ext->sub_c > 0 && ext->sub_c % 32 == 0 && N % ext->sub_c == 0),
                "scatter maps need sub_c a multiple of 32 that divides N");
   p.mask = reinterpret_cast<const __nv_bfloat16*>(ext->mask);
   p.mask_ld = ext->mask_ld;
   p.dbias = ext->dbias;
-  p.dbias_mod = ext->dbias_mod > 0 ? ext->dbias_mod : 1;
+  p.dbias_mod = ext->dbias ? ext->dbias_mod : 1;
   p.sub_c = ext->sub_c > 0 ? ext->sub_c : 32;
   return B2RL_OK;
 }

@@ -190,6 +190,7 @@ struct OptArgs {
   float scale;
   __nv_bfloat16* w1f; __nv_bfloat16* w2f; __nv_bfloat16* w2d; __nv_bfloat16* w3f; __nv_bfloat16* w3d; __nv_bfloat16* w4p;
   int zero_grad;
+  __nv_bfloat16* shadow;        // bf16 copy of the whole arena at the same offsets, or null (the GEMM operands of the heads)
 };
 
 __global__ void __launch_bounds__(TAIL_THREADS) nature_fused_opt_kernel(const OptArgs a) {
@@ -269,6 +270,12 @@ __global__ void __launch_bounds__(TAIL_THREADS) nature_fused_opt_kernel(const Op
     s14[v] = make_float4(s1[0], s1[1], s1[2], s1[3]);
     if (a.opt != 0) s24[v] = make_float4(s2[0], s2[1], s2[2], s2[3]);
     if (a.zero_grad) g4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.shadow) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(p[0], p[1]), hi = __floats2bfloat162_rn(p[2], p[3]);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&lo); o.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(a.shadow + off + 4 * v) = o;
+    }
     if (packs) {
       float* d = sbuf + 4 * v;
       d[0] = p[0]; d[1] = p[1]; d[2] = p[2]; d[3] = p[3];
@@ -332,7 +339,8 @@ extern "C" int b2rl_nature_fused_opt(const int32_t* units, int32_t n_units, floa
                                      int32_t opt, float lr, float a_, float b_, float eps, float max_norm, float grad_scale,
                                      const float* unit_sumsq, int32_t n_sumsq, void* norm_scratch, const int64_t* step_dev,
                                      int32_t c1, int32_t n4, float scale, uint16_t* w1f, uint16_t* w2f, uint16_t* w2d,
-                                     uint16_t* w3f, uint16_t* w3d, uint16_t* w4p, int32_t zero_grad, void* stream) {
+                                     uint16_t* w3f, uint16_t* w3d, uint16_t* w4p, int32_t zero_grad, uint16_t* bf16_shadow,
+                                     void* stream) {
   B2RL_REQUIRE(units && param && grad && s1 && norm_scratch, "null pointer");
   B2RL_REQUIRE(opt >= 0 && opt <= 2 && (opt == 0 || s2) && (opt != 2 || step_dev), "bad optimizer description");
   B2RL_REQUIRE(n_units > 0 && (!unit_sumsq || n_sumsq > 0), "bad counts");
@@ -349,6 +357,7 @@ extern "C" int b2rl_nature_fused_opt(const int32_t* units, int32_t n_units, floa
   a.w2d = reinterpret_cast<__nv_bfloat16*>(w2d); a.w3f = reinterpret_cast<__nv_bfloat16*>(w3f);
   a.w3d = reinterpret_cast<__nv_bfloat16*>(w3d); a.w4p = reinterpret_cast<__nv_bfloat16*>(w4p);
   a.zero_grad = zero_grad;
+  a.shadow = reinterpret_cast<__nv_bfloat16*>(bf16_shadow);
   launch_pdl(nature_fused_opt_kernel, dim3(n_units), dim3(TAIL_THREADS), 0, (cudaStream_t)stream, a);
   return check_launch("b2rl_nature_fused_opt");
 }

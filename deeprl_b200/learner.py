@@ -115,6 +115,7 @@ class GraphedDQNLearner:
                 self._repack(self.net, self.scale)
                 self._tail = NatureTail(self.opt, body, self.scale)
                 self._tail.max_norm, self._tail.grad_scale = self.clip, 1.0 / self.world
+                self._refresh_head_operands(True)
                 if self.world > 1:
                     # fc4's gradient is reduced into the arena and all-reduced right after its GEMM (beside the convolution
                     # backward); the small remainder follows the last weight-gradient GEMM
@@ -319,6 +320,7 @@ class GraphedDQNLearner:
     def sync_target(self):
         self.tgt.load_state_dict(self.net.state_dict())        # DQN_agent.py:136-138
         self._repack(self.tgt, self.scale if self.dtype == torch.bfloat16 else 1.0)
+        self._refresh_head_operands(False)
 
     def _opt(self):
         self._opt_kernels()
@@ -341,6 +343,29 @@ class GraphedDQNLearner:
         fs = self.scale if self.dtype == torch.bfloat16 else 1.0
         self._repack(self.net, fs)
         self._repack(self.tgt, fs)
+        self._refresh_head_operands(True)
+
+    def _dist_fc(self, net):
+        return getattr(net, "fc_categorical", None) or getattr(net, "fc_quantiles", None)
+
+    def _refresh_head_operands(self, online):
+        """Distributional heads (C51 / QR-DQN) on the tcgen05 GEMM: the online head reads its bf16 weight from the optimizer's
+        arena-wide bf16 shadow (written by the fused optimizer kernel), the target head from a copy refreshed at target sync."""
+        if self.kind not in ("c51", "qr") or self.tail() is None or os.environ.get("B2RL_DIST_HEAD", "1") == "0":
+            return
+        fa, ft = self._dist_fc(self.net), self._dist_fc(self.tgt)
+        if not isinstance(fa, torch.nn.Linear) or not isinstance(ft, torch.nn.Linear) or fa.weight.data_ptr() % 16:
+            return
+        o = self.opt
+        if o.shadow is None:
+            o.shadow = torch.zeros(o.n, dtype=torch.bfloat16, device=o.flat.device)
+        if online:
+            o.shadow.copy_(o.flat)
+            off = (fa.weight.data_ptr() - o.flat.data_ptr()) // 4
+            fa._w16 = o.shadow[off:off + fa.weight.numel()].view_as(fa.weight)
+        if getattr(ft, "_w16", None) is None:
+            ft._w16 = torch.empty_like(ft.weight, dtype=torch.bfloat16)
+        ft._w16.copy_(ft.weight.detach())
 
     # ------------------------------------------------------------------ capture / replay
     def capture(self, warmup=3, with_h2d=False):

@@ -199,3 +199,81 @@ def narrow_head_ok(phi, fc_action, fc_value=None):
     aligned = all(m is None or m.weight.data_ptr() % 16 == 0 for m in (fc_action, fc_value))
     return (phi.is_cuda and phi.dtype == _bf16 and phi.dim() == 2 and phi.shape[1] % 8 == 0 and aligned
             and isinstance(fc_action, torch.nn.Linear) and fc_action.out_features < 32)
+
+
+class _DistHead(torch.autograd.Function):
+    """Distributional head (CategoricalNet / QuantileNet, network_heads.py:40-55, 89-102) on bf16 features with no cuBLAS / ATen
+    kernel: logits = phi W^T + b on the tcgen05 GEMM, softmax + log_softmax in one launch (csrc/disthead.cu), and in the backward
+    pass the log_softmax gradient, the bf16 operand and the bias gradient in one launch followed by the two GEMMs
+    (dW = g^T phi, dphi = relu_mask(g W) with fc4's bias gradient from the same epilogue)."""
+
+    @staticmethod
+    def forward(ctx, phi, weight, bias, w16, A, N, softmax):
+        from ..ops import gemm_bf16
+        B, K = phi.shape
+        AN = A * N
+        logits = gemm_bf16(phi, w16, bias=bias.detach(), out_dtype=torch.float32, block_n=64)
+        ctx.dims = (A, N, bool(softmax))
+        ctx.params = (weight, bias)
+        if softmax:
+            prob = torch.empty((B, A, N), dtype=torch.float32, device=phi.device)
+            logp = torch.empty((B, A, N), dtype=torch.float32, device=phi.device)
+            _lib.call("b2rl_dist_softmax", _lib.ptr(logits), B * A, N, _lib.ptr(prob), _lib.ptr(logp), _lib.stream())
+            ctx.save_for_backward(phi, w16, prob)
+            ctx.mark_non_differentiable(prob)
+            return logp, prob
+        ctx.save_for_backward(phi, w16)
+        none = torch.empty(0, device=phi.device)
+        ctx.mark_non_differentiable(none)
+        return logits.view(B, A, N), none
+
+    @staticmethod
+    def backward(ctx, gout, _unused):
+        import ctypes
+        from . import nature_tc
+        from ..ops import gemm_bf16
+        A, N, softmax = ctx.dims
+        weight, bias = ctx.params
+        saved = ctx.saved_tensors
+        phi, w16 = saved[0], saved[1]
+        prob = saved[2] if softmax else None
+        B, K = phi.shape
+        AN = A * N
+        ld = (AN + 7) // 8 * 8
+        gout = gout.contiguous().float()
+        g = torch.empty((B, ld), dtype=_bf16, device=phi.device)
+        inplace = all(p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous() for p in (weight, bias))
+        gb = bias.grad if inplace else torch.zeros_like(bias, dtype=torch.float32)
+        _lib.call("b2rl_dist_head_bwd_prep", _lib.ptr(gout), _lib.ptr(prob), B, A, N, _lib.ptr(g), ld, _lib.ptr(gb), _lib.stream())
+        gv = g[:, :AN]
+        # dW [A*N, K] = g^T phi (both operands MN-major: nothing is transposed in memory), accumulated into .grad when it exists
+        gw = gemm_bf16(gv, phi, a_major="mn", b_major="mn", out_dtype=torch.float32, block_n=128,
+                       out=weight.grad if inplace else None, accumulate=inplace)
+        # dphi = (g W) masked by relu(fc4) with fc4's bias gradient from the same epilogue
+        gphi = torch.empty_like(phi)
+        sink = nature_tc.SINK
+        relu = nature_tc.FUSED_BWD and phi.data_ptr() in nature_tc.RELU_FEATURES
+        if relu:
+            colsum = sink.db4 if (sink is not None and sink.db4.numel() == K) else torch.zeros(K, dtype=torch.float32, device=phi.device)
+            e = _lib.bwd_epilogue(phi, colsum, 0, 0)               # dbias_mod 0: one bias gradient per feature column
+            _lib.call("b2rl_gemm_bwd_bf16", _lib.ptr(gv), gv.stride(0), _lib.ptr(w16), 1, w16.stride(0), _lib.ptr(gphi), gphi.stride(0),
+                      B, K, AN, 0, 0, 0, ctypes.byref(e), 128, _lib.stream())
+            nature_tc.PREMASKED[gphi.data_ptr()] = colsum
+        else:
+            gemm_bf16(gv, w16, a_major="k", b_major="mn", out=gphi, block_n=128)
+        if inplace:
+            return gphi, None, None, None, None, None, None
+        return gphi, gw, gb, None, None, None, None
+
+
+def dist_head(phi, fc, A, N, softmax):
+    """``fc`` = the head's nn.Linear with a bf16 copy of its weight in ``fc._w16`` (kept current by the owner: the fused
+    optimizer's shadow for the online network, refreshed at target sync for the target network).  Returns (log_prob, prob)
+    [B, A, N] for C51 (``softmax``), (quantile, quantile) for QR-DQN."""
+    return _DistHead.apply(phi.contiguous(), fc.weight, fc.bias, fc._w16, A, N, softmax)
+
+
+def dist_head_ok(phi, fc):
+    w16 = getattr(fc, "_w16", None)
+    return (w16 is not None and phi.is_cuda and phi.dtype == _bf16 and phi.dim() == 2 and phi.shape[1] % 64 == 0
+            and isinstance(fc, torch.nn.Linear) and w16.dtype == _bf16 and tuple(w16.shape) == tuple(fc.weight.shape))

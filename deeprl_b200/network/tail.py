@@ -149,5 +149,5 @@ class NatureTail:
                   _lib.ptr(o.s2), self.kind, float(o.lr), float(a), float(b), float(o.eps), float(max_norm or 0.0),
                   float(grad_scale), None, self.n_a, _lib.ptr(o.scratch),
                   _lib.ptr(o.step_dev), self.c1, self.n4, self.scale, _lib.ptr(pk.w1f), _lib.ptr(pk.w2f), _lib.ptr(pk.w2d),
-                  _lib.ptr(pk.w3f), _lib.ptr(pk.w3d), _lib.ptr(pk.w4p), 1, _lib.stream())
+                  _lib.ptr(pk.w3f), _lib.ptr(pk.w3d), _lib.ptr(pk.w4p), 1, _lib.ptr(o.shadow), _lib.stream())
         pk.scale = self.scale

@@ -249,7 +249,8 @@ int b2rl_gemm_dual_bf16(const uint16_t* A, const uint16_t* A2, int64_t lda, cons
 /* Backward GEMMs with the element-wise backward pass fused into the epilogue (replaces b2rl_act_bwd_bias_grad_bf16 between the
  * dgrad GEMMs of NatureConvBody).  mask: the saved forward activation (bf16) in the GEMM's own output coordinates,
  * [M][mask_ld] -- the ReLU gradient D = mask > 0 ? D : 0; dbias: fp32 [dbias_mod], receives (atomically, zero it first) the
- * column sums of the masked output, index = column % dbias_mod = the bias gradient of the layer below; sub_c: channels per
+ * column sums of the masked output, index = column % dbias_mod (dbias_mod 0: index = column, dbias is [N]) = the bias gradient
+ * of the layer below; sub_c: channels per
  * position for the scatter maps.  out_map 3: rows are space-to-depth(2) positions of a (V/2)^2 grid with 4 x sub_c columns ->
  * rows of the G x G grid; out_map 4: rows are images with V*V x sub_c columns -> rows of the G x G grid.  Grid rows that no
  * tile covers are left untouched (keep the destination zeroed). */
@@ -339,7 +340,8 @@ int b2rl_gemm_splitk_bf16(const uint16_t* A, int64_t lda, const uint16_t* B, int
  * fused_opt: clip coefficient from the unit partials (NULL: from norm_scratch, see b2rl_grad_norm), RMSprop
  *   (opt 0 plain, 1 centered; a_ = alpha) or Adam (opt 2; a_, b_ = betas) exactly as b2rl_clip_rmsprop / b2rl_clip_adam,
  *   gradient re-zeroed when zero_grad != 0, and the updated conv / fc4 weights written to the bf16 tap-major GEMM
- *   operands of b2rl_nature_pack_weights (all six pointers, or all NULL).
+ *   operands of b2rl_nature_pack_weights (all six pointers, or all NULL); bf16_shadow != NULL: a bf16 copy of every updated
+ *   parameter at the same arena offset (the GEMM operands of the distributional heads).
  * ------------------------------------------------------------------------------------------- */
 int b2rl_nature_grad_reduce(const int32_t* units, int32_t n_units, const float* g1p, int32_t p1, const float* g2p, int32_t p2,
                             const float* g3p, int32_t p3, const float* g4p, float* db1, float* db2, float* db3, float* db4,
@@ -349,10 +351,18 @@ int b2rl_nature_fused_opt(const int32_t* units, int32_t n_units, float* param, f
                           float lr, float a_, float b_, float eps, float max_norm, float grad_scale, const float* unit_sumsq,
                           int32_t n_sumsq, void* norm_scratch, const int64_t* step_dev, int32_t c1, int32_t n4, float scale,
                           uint16_t* w1f, uint16_t* w2f, uint16_t* w2d, uint16_t* w3f, uint16_t* w3d, uint16_t* w4p,
-                          int32_t zero_grad, void* stream);
+                          int32_t zero_grad, uint16_t* bf16_shadow, void* stream);
 /* clip_grad_norm_'s coefficient alone (torch.nn.utils.clip_grad_norm_): norm_scratch[0] = ||grad * grad_scale||,
  * norm_scratch[1] = min(max_norm / (norm + 1e-6), 1) * grad_scale. */
 int b2rl_grad_norm(const float* grad, int64_t n, float grad_scale, float max_norm, void* norm_scratch, void* stream);
+
+/* Element-wise halves of the distributional heads (CategoricalNet / QuantileNet, network_heads.py:40-55, 89-102) around the
+ * tcgen05 GEMMs: softmax + log_softmax over the N atoms of every (b, a) row (either output may be NULL), and the backward
+ * preparation dlogits = dout - prob * sum_n dout (prob == NULL: dlogits = dout, QR-DQN) written as the bf16 GEMM operand
+ * g [B][ld] (ld >= A*N, multiple of 8; padding zeroed) with its column sums ADDED to dbias [A*N] (the bias gradient). */
+int b2rl_dist_softmax(const float* logits, int32_t rows, int32_t N, float* prob, float* log_prob, void* stream);
+int b2rl_dist_head_bwd_prep(const float* dout, const float* prob, int32_t B, int32_t A, int32_t N, uint16_t* g, int32_t ld,
+                            float* dbias, void* stream);
 
 /* DQN update, head part, in one launch (DQN_agent.py:78-99, 120-127 and the head's backward): q = head(phi) on s,
  * q_next = target_head(phi_t) on s' [argmax from head(phi_o) for double-Q], delta / priorities / IS weights / loss as

@@ -178,3 +178,35 @@ def test_splitk_fixup_gemm_vs_torch(rl, M, N, K, splits, block_n):
     # and without bias / activation
     got3 = ops.gemm_splitk_bf16(a, b, splits=splits, block_n=block_n)
     np.testing.assert_allclose(got3.float().cpu().numpy(), (a.float() @ b.float().t()).cpu().numpy(), rtol=1e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("kind,A,N", [("c51", 4, 51), ("qr", 4, 200), ("c51", 6, 51), ("qr", 18, 32)])
+def test_dist_head_vs_torch(rl, kind, A, N):
+    """Distributional head on the tcgen05 GEMM + csrc/disthead.cu (network/fused.py _DistHead) against fp32 torch on the same bf16
+    operands: prob / log_prob (C51) or quantiles (QR-DQN), and the gradients w.r.t. the features, weight and bias."""
+    from deeprl_b200.network import fused
+    dev = torch.device("cuda", 0)
+    B, K = 512, 512
+    g = torch.Generator(device=dev).manual_seed(A * N)
+    fc = torch.nn.Linear(K, A * N).to(dev)
+    fc._w16 = fc.weight.detach().to(torch.bfloat16)
+    phi = torch.relu(torch.randn(B, K, device=dev, generator=g)).to(torch.bfloat16).requires_grad_(True)
+    softmax = kind == "c51"
+    out, prob = fused.dist_head(phi, fc, A, N, softmax)
+    # reference: fp32 on the bf16 operands
+    phi_r = phi.detach().float().requires_grad_(True)
+    w_r = fc._w16.float().requires_grad_(True)
+    b_r = fc.bias.detach().clone().requires_grad_(True)
+    logits = (phi_r @ w_r.t() + b_r).view(B, A, N)
+    ref = torch.log_softmax(logits, -1) if softmax else logits
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().cpu().numpy(), rtol=2e-3, atol=2e-3)
+    if softmax:
+        np.testing.assert_allclose(prob.cpu().numpy(), torch.softmax(logits, -1).detach().cpu().numpy(), rtol=2e-3, atol=1e-5)
+    grad = torch.randn(B, A, N, device=dev, generator=g) / B
+    out.backward(grad)
+    ref.backward(grad)
+    torch.cuda.synchronize()
+    sc = lambda t: float(t.abs().max()) + 1e-12
+    assert float((phi.grad.float() - phi_r.grad).abs().max()) <= 2e-2 * sc(phi_r.grad)
+    assert float((fc.weight.grad - w_r.grad).abs().max()) <= 2e-2 * sc(w_r.grad)
+    assert float((fc.bias.grad - b_r.grad).abs().max()) <= 2e-2 * sc(b_r.grad)
