@@ -178,6 +178,20 @@ def a2c_pixel(**kwargs):
     run_steps(A2CAgent(config))
 
 
+def a2c_continuous(**kwargs):
+    """examples.py:384-404: A2C with a Gaussian policy over FC bodies (16 workers, rollout 5, RMSprop 7e-4)."""
+    config = _config(kwargs)
+    config.num_workers = kwargs.get("num_workers", 16)
+    config.task_fn = lambda: Task(config.game, num_envs=config.num_workers)
+    config.eval_env = Task(config.game)
+    config.optimizer_fn = lambda params: torch.optim.RMSprop(params, lr=0.0007)
+    config.network_fn = lambda: GaussianActorCriticNet(config.state_dim, config.action_dim, actor_body=FCBody(config.state_dim),
+                                                       critic_body=FCBody(config.state_dim))
+    _apply(config, dict(discount=0.99, use_gae=True, gae_tau=1.0, entropy_weight=0.01, rollout_length=5, gradient_clip=5,
+                        max_steps=int(2e7)))
+    run_steps(A2CAgent(config))
+
+
 # ------------------------------------------------------------------------------------------------ PPO (examples.py:496-550)
 def ppo_continuous(**kwargs):
     config = _config(kwargs)
