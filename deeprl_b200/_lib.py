@@ -71,6 +71,7 @@ SIGNATURES = {
     "b2rl_dist_head_bwd_prep": [c_p, c_p, c_i32, c_i32, c_i32, c_p, c_i32, c_p, c_p],
     "b2rl_grad_norm": [c_p, c_i64, c_f32, c_f32, c_p, c_p],
     "b2rl_dqn_head_fused": [c_p] * 14 + [c_f32, c_i32, c_i32, c_i32, c_p, c_f32, c_p, c_f32, c_f32] + [c_p] * 12,
+    "b2rl_dqn_head_two": [c_p] * 14 + [c_f32, c_i32, c_i32, c_i32, c_p, c_f32, c_p, c_f32, c_f32] + [c_p] * 13,
     "b2rl_clip_rmsprop": [c_p, c_p, c_p, c_p, c_i64, c_f32, c_f32, c_f32, c_f32, c_i32, c_f32, c_p, c_p, c_p],
     "b2rl_clip_adam": [c_p, c_p, c_p, c_p, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_p, c_f32, c_p, c_p, c_p],
     "b2rl_clip_adam_gated": [c_p, c_p, c_p, c_p, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_p, c_f32, c_p, c_p, c_p, c_f32, c_p],

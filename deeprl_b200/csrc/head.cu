@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
                                                        int K, int A, __nv_bfloat16* __restrict__ gphi,
                                                        float* __restrict__ gWa, float* __restrict__ gba,
                                                        float* __restrict__ gWv, float* __restrict__ gbv,
-                                                       float* __restrict__ relu_colsum) {
+                                                       float* __restrict__ relu_colsum, const float* __restrict__ geff_in) {
+  // geff_in != NULL: the effective output gradients [B][HEAD_MAX_OUT + 1] were already computed (dqn_head_loss_kernel).
   // relu_colsum != NULL: phi is the output of a ReLU layer (NatureConvBody's fc4): the gradient is masked here (gphi = 0 where
   // phi <= 0) and its column sums -- that layer's bias gradient -- are accumulated into relu_colsum[K] (zeroed by the caller),
   // which replaces the separate mask / bias-gradient pass over gphi.
@@ -193,7 +194,8 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
   const int n_out = A + (Wv ? 1 : 0);
   for (int e = threadIdx.x; e < HB_ROWS * n_out; e += blockDim.x) {
     const int r = e / n_out, n = e - r * n_out;
-    sh.geff[r][n] = (r0 + r < B) ? head_geff(gq + (int64_t)(r0 + r) * A, n, A, Wv != nullptr) : 0.0f;
+    if (r0 + r >= B) sh.geff[r][n] = 0.0f;
+    else sh.geff[r][n] = geff_in ? geff_in[(int64_t)(r0 + r) * (HEAD_MAX_OUT + 1) + n] : head_geff(gq + (int64_t)(r0 + r) * A, n, A, Wv != nullptr);
   }
   __syncthreads();
   head_bwd_body(sh, phi, Wa, Wv, B, K, A, gphi, gWa, gba, gWv, gbv, relu_colsum);
@@ -230,6 +232,100 @@ __device__ __forceinline__ float head_pow_like_torch(float x, float e) {      //
 }
 __device__ __forceinline__ float head_per_raw_weight(float prob, int B, float beta) {
   return head_pow_like_torch(__fadd_rn(__fmul_rn(prob, (float)B), 1e-6f), -beta);
+}
+
+// Two-launch form of the DQN head (the default): dqn_head_loss_kernel -- ONE WARP PER BATCH ROW (128 CTAs at B = 512) evaluates
+// the online head on s, the target head on s' [, the online head on s' for double-Q], the target / loss / PER block, and leaves
+// the effective output gradient of the row (through the dueling combine) in geff_out [B][HEAD_MAX_OUT + 1]; head_bwd_kernel then
+// reads geff directly.  The single-launch form below repeats the row dot products in every 64-column CTA of the backward grid,
+// which puts 4 dependent L2 round trips in front of the backward part of all 256 CTAs (measured 11 us slower per update).
+template <int NB>
+__global__ void __launch_bounds__(128) dqn_head_loss_kernel(const DqnHeadArgs a, float* __restrict__ geff_out) {
+  pdl_sync();   // PDL contract (common.cuh): before any global-memory access or return
+  __shared__ float s_red[32];
+  __shared__ float s_loss[4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int A = a.A, K = a.K, B = a.B;
+  const bool dueling = a.Wv != nullptr;
+  const int n_out = A + (dueling ? 1 : 0);
+  float beta = a.beta;
+  if (a.beta_dev) beta = *a.beta_dev;
+  float wmax = 1.0f;
+  if (a.is_prob) {
+    float m = 0.0f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) m = fmaxf(m, head_per_raw_weight(a.is_prob[b], B, beta));
+    wmax = block_reduce(m, OpMax(), 0.0f, s_red);
+  }
+  const float invB = 1.0f / (float)B;
+  const int b = blockIdx.x * 4 + warp;
+  float loss_r = 0.0f;
+  if (b < B) {
+    float q[NB], qt[NB];
+    head_row_dots<NB>(a.phi + (int64_t)b * K, a.Wa, a.ba, a.Wv, a.bv, K, A, lane, q);
+    head_row_dots<NB>(a.phi_t + (int64_t)b * K, a.Wa_t, a.ba_t, a.Wv_t, a.bv_t, K, A, lane, qt);
+    head_combine<NB>(q, A, dueling);
+    head_combine<NB>(qt, A, a.Wv_t != nullptr);
+    float qnext;
+    if (a.phi_o) {                                   // DQN_agent.py:88-90: argmax (first max) of the ONLINE net on s'
+      float qo[NB];
+      head_row_dots<NB>(a.phi_o + (int64_t)b * K, a.Wa, a.ba, a.Wv, a.bv, K, A, lane, qo);
+      head_combine<NB>(qo, A, dueling);
+      int best = 0;
+      float bv = qo[0];
+#pragma unroll
+      for (int n = 1; n < NB; ++n)
+        if (n < A && qo[n] > bv) { bv = qo[n]; best = n; }
+      qnext = 0.0f;
+#pragma unroll
+      for (int n = 0; n < NB; ++n)
+        if (n == best) qnext = qt[n];
+    } else {                                         // :92
+      qnext = qt[0];
+#pragma unroll
+      for (int n = 1; n < NB; ++n)
+        if (n < A) qnext = fmaxf(qnext, qt[n]);
+    }
+    const int a_b = (int)a.action[b];
+    float q_ab = 0.0f;
+#pragma unroll
+    for (int n = 0; n < NB; ++n)
+      if (n == a_b) q_ab = q[n];
+    const float target = __fadd_rn(a.reward[b], __fmul_rn(__fmul_rn(a.gamma_n, qnext), a.mask[b]));   // :95
+    const float delta = __fsub_rn(target, q_ab);                                                    // :99
+    float w = 1.0f;
+    if (a.is_prob) w = __fdiv_rn(head_per_raw_weight(a.is_prob[b], B, beta), wmax);                 // :125-126
+    const float wl = __fmul_rn(delta, w);                                                           // :127
+    loss_r = __fmul_rn(__fmul_rn(wl, wl), 0.5f);                                                    // :79
+    const float g_ab = -wl * w * invB;               // d/dq[a_b] of mean(0.5 * (w * (y - q))^2)
+    if (lane == 0) {
+      if (a.delta_out) a.delta_out[b] = delta;
+      if (a.prio_out && a.is_prob) a.prio_out[b] = head_pow_like_torch(__fadd_rn(fabsf(delta), a.eps), a.alpha);   // :121
+      if (a.q_out) {
+#pragma unroll
+        for (int n = 0; n < NB; ++n)
+          if (n < A) a.q_out[(int64_t)b * A + n] = q[n];
+      }
+    }
+    if (lane < n_out) {
+      float g;
+      if (!dueling) g = (lane == a_b) ? g_ab : 0.0f;
+      else g = (lane < A) ? ((lane == a_b ? g_ab : 0.0f) - g_ab / (float)A) : g_ab;
+      geff_out[(int64_t)b * (HEAD_MAX_OUT + 1) + lane] = g;
+    }
+  }
+  if (lane == 0) s_loss[warp] = loss_r;
+  __syncthreads();
+  if (threadIdx.x == 0 && a.loss_out) {
+    a.loss_partial[blockIdx.x] = (s_loss[0] + s_loss[1]) + (s_loss[2] + s_loss[3]);
+    __threadfence();
+    if (atomicAdd(a.counter, 1) == (int)gridDim.x - 1) {      // the last CTA adds the partials in a fixed order
+      __threadfence();
+      float tot = 0.0f;
+      for (int i = 0; i < (int)gridDim.x; ++i) tot += __ldcg(a.loss_partial + i);
+      a.loss_out[0] = tot * invB;
+      *a.counter = 0;
+    }
+  }
 }
 
 template <int NB>
@@ -356,13 +452,13 @@ extern "C" int b2rl_head_fwd(const uint16_t* phi, const float* Wa, const float* 
 
 static int head_bwd_impl(const float* gq, const uint16_t* phi, const float* Wa, const float* Wv, int32_t B, int32_t K,
                          int32_t A, uint16_t* gphi, float* gWa, float* gba, float* gWv, float* gbv, float* relu_colsum,
-                         void* stream) {
-  B2RL_REQUIRE(gq && phi && Wa && gphi && gWa && gba && ((Wv == nullptr) == (gWv == nullptr)) && ((Wv == nullptr) == (gbv == nullptr)),
+                         void* stream, const float* geff_in = nullptr) {
+  B2RL_REQUIRE((gq || geff_in) && phi && Wa && gphi && gWa && gba && ((Wv == nullptr) == (gWv == nullptr)) && ((Wv == nullptr) == (gbv == nullptr)),
                "null pointer");
   B2RL_REQUIRE(B > 0 && K > 0 && A > 0 && A < HEAD_MAX_OUT, "need 0 < A < 32");
   dim3 grid((K + 63) / 64, (B + HB_ROWS - 1) / HB_ROWS);
   launch_pdl(head_bwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, gq, reinterpret_cast<const __nv_bfloat16*>(phi), Wa, Wv, B, K, A,
-                                                          reinterpret_cast<__nv_bfloat16*>(gphi), gWa, gba, gWv, gbv, relu_colsum);
+                                                          reinterpret_cast<__nv_bfloat16*>(gphi), gWa, gba, gWv, gbv, relu_colsum, geff_in);
   return check_launch("b2rl_head_bwd");
 }
 
@@ -417,4 +513,43 @@ extern "C" int b2rl_dqn_head_fused(const uint16_t* phi, const uint16_t* phi_t, c
   else if (n_out <= 19) launch_pdl(dqn_head_fused_kernel<19>, dim3(grid), dim3(256), 0, st, a);
   else launch_pdl(dqn_head_fused_kernel<HEAD_MAX_OUT>, dim3(grid), dim3(256), 0, st, a);
   return check_launch("b2rl_dqn_head_fused");
+}
+
+
+// The same update as b2rl_dqn_head_fused in TWO launches (the default of the learner): a row kernel (one warp per batch row:
+// heads forward, target / loss / PER block, effective output gradient) and the head backward reading that gradient.
+// geff: float scratch [B][33].  scratch: int32 counter + 12 bytes + float [ceil(B/4)], zero-initialised once.
+extern "C" int b2rl_dqn_head_two(const uint16_t* phi, const uint16_t* phi_t, const uint16_t* phi_o, const float* Wa,
+                                 const float* ba, const float* Wv, const float* bv, const float* Wa_t, const float* ba_t,
+                                 const float* Wv_t, const float* bv_t, const int64_t* action, const float* reward,
+                                 const float* mask, float gamma_n, int32_t B, int32_t K, int32_t A, const float* is_prob,
+                                 float beta, const float* beta_dev, float eps, float alpha, uint16_t* gphi, float* gWa,
+                                 float* gba, float* gWv, float* gbv, float* relu_colsum, float* q_out, float* delta_out,
+                                 float* prio_out, float* loss_out, float* scratch, float* geff, void* stream) {
+  B2RL_REQUIRE(phi && phi_t && Wa && ba && Wa_t && ba_t && action && reward && mask && gphi && gWa && gba && relu_colsum && scratch && geff,
+               "null pointer");
+  B2RL_REQUIRE(((Wv == nullptr) == (bv == nullptr)) && ((Wv == nullptr) == (gWv == nullptr)) && ((Wv == nullptr) == (gbv == nullptr)) &&
+               ((Wv_t == nullptr) == (bv_t == nullptr)) && ((Wv == nullptr) == (Wv_t == nullptr)), "inconsistent dueling arguments");
+  B2RL_REQUIRE(B > 0 && K > 0 && K % 8 == 0 && A > 0 && A < HEAD_MAX_OUT, "need K % 8 == 0 and 0 < A < 32");
+  B2RL_REQUIRE((reinterpret_cast<uintptr_t>(phi) | reinterpret_cast<uintptr_t>(phi_t) | reinterpret_cast<uintptr_t>(phi_o) |
+                reinterpret_cast<uintptr_t>(Wa) | reinterpret_cast<uintptr_t>(Wv) | reinterpret_cast<uintptr_t>(Wa_t) |
+                reinterpret_cast<uintptr_t>(Wv_t)) % 16 == 0, "features and weights must be 16-byte aligned");
+  DqnHeadArgs a;
+  a.phi = reinterpret_cast<const __nv_bfloat16*>(phi); a.phi_t = reinterpret_cast<const __nv_bfloat16*>(phi_t);
+  a.phi_o = reinterpret_cast<const __nv_bfloat16*>(phi_o);
+  a.Wa = Wa; a.ba = ba; a.Wv = Wv; a.bv = bv; a.Wa_t = Wa_t; a.ba_t = ba_t; a.Wv_t = Wv_t; a.bv_t = bv_t;
+  a.action = action; a.reward = reward; a.mask = mask; a.gamma_n = gamma_n; a.B = B; a.K = K; a.A = A;
+  a.is_prob = is_prob; a.beta = beta; a.beta_dev = beta_dev; a.eps = eps; a.alpha = alpha;
+  a.gphi = reinterpret_cast<__nv_bfloat16*>(gphi); a.gWa = gWa; a.gba = gba; a.gWv = gWv; a.gbv = gbv; a.relu_colsum = relu_colsum;
+  a.q_out = q_out; a.delta_out = delta_out; a.prio_out = prio_out; a.loss_out = loss_out;
+  a.counter = reinterpret_cast<int*>(scratch); a.loss_partial = scratch + 4;
+  const int n_out = A + (Wv ? 1 : 0);
+  const dim3 grid((B + 3) / 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_out <= 8) launch_pdl(dqn_head_loss_kernel<8>, dim3(grid), dim3(128), 0, st, a, geff);
+  else if (n_out <= 19) launch_pdl(dqn_head_loss_kernel<19>, dim3(grid), dim3(128), 0, st, a, geff);
+  else launch_pdl(dqn_head_loss_kernel<HEAD_MAX_OUT>, dim3(grid), dim3(128), 0, st, a, geff);
+  int rc = check_launch("b2rl_dqn_head_two(loss)");
+  if (rc) return rc;
+  return head_bwd_impl(nullptr, phi, Wa, Wv, B, K, A, gphi, gWa, gba, gWv, gbv, relu_colsum, stream, geff);
 }

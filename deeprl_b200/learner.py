@@ -127,7 +127,7 @@ class GraphedDQNLearner:
 
     def _heads(self):
         """(online head modules, target head modules) when the DQN head can run in the fused head + loss + backward kernel."""
-        if self.kind != "dqn" or self.tail() is None or os.environ.get("B2RL_FUSED_HEAD", "0") == "0":
+        if self.kind != "dqn" or self.tail() is None or os.environ.get("B2RL_FUSED_HEAD", "1") == "0":
             return None
         out = []
         for n in (self.net, self.tgt):
@@ -297,7 +297,7 @@ class GraphedDQNLearner:
         cur.wait_stream(side)
         nature_tc.mark("fwd_joined")
         r = ops.dqn_head_fused(phi.detach(), phi_t, phi_o, heads[0], heads[1], t.action, t.reward, t.mask, self.gamma_n,
-                               tail.db4, **per)
+                               tail.db4, two=os.environ.get("B2RL_FUSED_HEAD", "1") != "one", **per)
         if self.per:
             if self.prefetch:                            # the sum tree is read by the prefetch branch: update after it
                 cur.wait_event(self._sampled_ev)

@@ -55,9 +55,9 @@ def dqn_loss_fused(q, q_next_target, q_next_online, action, reward, mask, gamma_
 
 
 def dqn_head_fused(phi, phi_t, phi_o, head, head_t, action, reward, mask, gamma_n, relu_colsum, is_prob=None, beta=0.0,
-                   eps=0.0, alpha=0.0, beta_dev=None, want_q=False):
-    """Head forward (online on s, target on s' [, online on s' for double-Q]) + ``dqn_loss_fused`` + head backward in ONE
-    launch (csrc/head.cu dqn_head_fused_kernel).  ``head`` / ``head_t`` = (fc_action_or_head, fc_value_or_None) modules of
+                   eps=0.0, alpha=0.0, beta_dev=None, want_q=False, two=True):
+    """Head forward (online on s, target on s' [, online on s' for double-Q]) + ``dqn_loss_fused`` + head backward in TWO
+    launches (``two``: a row kernel + the head backward, csrc/head.cu dqn_head_loss_kernel) or ONE (dqn_head_fused_kernel).  ``head`` / ``head_t`` = (fc_action_or_head, fc_value_or_None) modules of
     the online / target network (VanillaNet / DuelingNet, network_heads.py:11-37); their weight and bias gradients are
     accumulated into ``.grad`` (which must be fp32 contiguous tensors), ``relu_colsum`` [K] receives fc4's bias gradient.
     Returns dict(gphi = dLoss/dphi masked by phi > 0 (bf16), delta, priority, loss, q)."""
@@ -75,17 +75,18 @@ def dqn_head_fused(phi, phi_t, phi_o, head, head_t, action, reward, mask, gamma_
     prio = torch.empty(B, dtype=_f32, device=dev) if is_prob is not None else None
     loss = torch.empty(1, dtype=_f32, device=dev)
     q = torch.empty(B, A, dtype=_f32, device=dev) if want_q else None
-    scratch = _Scratch.get(dev, "dqn_head_scratch", (B + 15) // 16 + 8, _f32)
+    scratch = _Scratch.get(dev, "dqn_head_scratch2" if two else "dqn_head_scratch", (B + 3) // 4 + 8, _f32)
     w = lambda m: None if m is None else m.weight.detach()
     b = lambda m: None if m is None else m.bias.detach()
     g = lambda t: None if t is None else t.grad
-    _lib.call("b2rl_dqn_head_fused", _lib.ptr(phi), _lib.ptr(phi_t), _lib.ptr(phi_o), _lib.ptr(w(fa)), _lib.ptr(b(fa)),
+    extra = (_lib.ptr(_Scratch.get(dev, "dqn_head_geff", B * 33, _f32)),) if two else ()
+    _lib.call("b2rl_dqn_head_two" if two else "b2rl_dqn_head_fused", _lib.ptr(phi), _lib.ptr(phi_t), _lib.ptr(phi_o), _lib.ptr(w(fa)), _lib.ptr(b(fa)),
               _lib.ptr(w(fv)), _lib.ptr(b(fv)), _lib.ptr(w(ta)), _lib.ptr(b(ta)), _lib.ptr(w(tv)), _lib.ptr(b(tv)),
               _lib.ptr(_c(action, torch.int64)), _lib.ptr(_c(reward, _f32)), _lib.ptr(_c(mask, _f32)), float(gamma_n), B, K, A,
               _lib.ptr(_c(is_prob, _f32)), float(beta), _lib.ptr(beta_dev), float(eps), float(alpha), _lib.ptr(gphi),
               _lib.ptr(g(fa.weight)), _lib.ptr(g(fa.bias)), _lib.ptr(None if fv is None else g(fv.weight)),
               _lib.ptr(None if fv is None else g(fv.bias)), _lib.ptr(relu_colsum), _lib.ptr(q), _lib.ptr(delta), _lib.ptr(prio),
-              _lib.ptr(loss), _lib.ptr(scratch), _lib.stream())
+              _lib.ptr(loss), _lib.ptr(scratch), *extra, _lib.stream())
     return dict(gphi=gphi, delta=delta, priority=prio, loss=loss, q=q)
 
 

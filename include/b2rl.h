@@ -356,6 +356,15 @@ int b2rl_nature_fused_opt(const int32_t* units, int32_t n_units, float* param, f
  * norm_scratch[1] = min(max_norm / (norm + 1e-6), 1) * grad_scale. */
 int b2rl_grad_norm(const float* grad, int64_t n, float grad_scale, float max_norm, void* norm_scratch, void* stream);
 
+/* b2rl_dqn_head_fused in two launches (row kernel: one warp per batch row; then the head backward): same arguments plus
+ * geff = float scratch [B][33]; scratch: int32 counter + 12 bytes padding + float [ceil(B/4)], zero-initialised once. */
+int b2rl_dqn_head_two(const uint16_t* phi, const uint16_t* phi_t, const uint16_t* phi_o, const float* Wa, const float* ba,
+                      const float* Wv, const float* bv, const float* Wa_t, const float* ba_t, const float* Wv_t,
+                      const float* bv_t, const int64_t* action, const float* reward, const float* mask, float gamma_n, int32_t B,
+                      int32_t K, int32_t A, const float* is_prob, float beta, const float* beta_dev, float eps, float alpha,
+                      uint16_t* gphi, float* gWa, float* gba, float* gWv, float* gbv, float* relu_colsum, float* q_out,
+                      float* delta_out, float* prio_out, float* loss_out, float* scratch, float* geff, void* stream);
+
 /* Element-wise halves of the distributional heads (CategoricalNet / QuantileNet, network_heads.py:40-55, 89-102) around the
  * tcgen05 GEMMs: softmax + log_softmax over the N atoms of every (b, a) row (either output may be NULL), and the backward
  * preparation dlogits = dout - prob * sum_n dout (prob == NULL: dlogits = dout, QR-DQN) written as the bf16 GEMM operand

@@ -103,7 +103,8 @@ def test_tail_matches_unpack_clip_optimizer_pack(rl, kind, head):
 @pytest.mark.parametrize("per", [False, True])
 @pytest.mark.parametrize("double_q", [False, True])
 @pytest.mark.parametrize("B", [512, 37])
-def test_dqn_head_fused_matches_separate_kernels(rl, head, A, per, double_q, B):
+@pytest.mark.parametrize("two", [True, False])
+def test_dqn_head_fused_matches_separate_kernels(rl, head, A, per, double_q, B, two):
     from deeprl_b200 import _lib, ops
     dev = torch.device("cuda", 0)
     K = 512
@@ -141,7 +142,7 @@ def test_dqn_head_fused_matches_separate_kernels(rl, head, A, per, double_q, B):
               _lib.ptr(None if fv is None else fv.bias.grad), _lib.ptr(colsum_ref), _lib.stream())
     # ---- one launch
     colsum = torch.zeros(K, device=dev)
-    r = ops.dqn_head_fused(phi, phi_t, phi_o, heads(net), heads(tgt), action, reward, mask, 0.99, colsum, want_q=True, **pa)
+    r = ops.dqn_head_fused(phi, phi_t, phi_o, heads(net), heads(tgt), action, reward, mask, 0.99, colsum, want_q=True, two=two, **pa)
     torch.cuda.synchronize()
     assert torch.equal(r["q"], q), "same dot-product order as head_fwd: bit-identical q"
     assert torch.equal(r["delta"], ref["delta"])
@@ -153,7 +154,7 @@ def test_dqn_head_fused_matches_separate_kernels(rl, head, A, per, double_q, B):
     for pa_, pb_ in zip(net.parameters(), net2.parameters()):
         np.testing.assert_allclose(pa_.grad.cpu().numpy(), pb_.grad.cpu().numpy(), rtol=1e-4, atol=1e-6)
     # a second launch re-uses the self-resetting loss counter
-    r2 = ops.dqn_head_fused(phi, phi_t, phi_o, heads(net), heads(tgt), action, reward, mask, 0.99, colsum, **pa)
+    r2 = ops.dqn_head_fused(phi, phi_t, phi_o, heads(net), heads(tgt), action, reward, mask, 0.99, colsum, two=two, **pa)
     torch.cuda.synchronize()
     assert float(r2["loss"]) == float(r["loss"])
 
