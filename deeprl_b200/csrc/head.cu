@@ -315,14 +315,23 @@ __global__ void __launch_bounds__(128) dqn_head_loss_kernel(const DqnHeadArgs a,
   }
   if (lane == 0) s_loss[warp] = loss_r;
   __syncthreads();
-  if (threadIdx.x == 0 && a.loss_out) {
-    a.loss_partial[blockIdx.x] = (s_loss[0] + s_loss[1]) + (s_loss[2] + s_loss[3]);
-    __threadfence();
-    if (atomicAdd(a.counter, 1) == (int)gridDim.x - 1) {      // the last CTA adds the partials in a fixed order
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    s_last = false;
+    if (a.loss_out) {
+      a.loss_partial[blockIdx.x] = (s_loss[0] + s_loss[1]) + (s_loss[2] + s_loss[3]);
       __threadfence();
-      float tot = 0.0f;
-      for (int i = 0; i < (int)gridDim.x; ++i) tot += __ldcg(a.loss_partial + i);
-      a.loss_out[0] = tot * invB;
+      s_last = atomicAdd(a.counter, 1) == (int)gridDim.x - 1;
+    }
+  }
+  __syncthreads();
+  if (s_last) {            // the last CTA adds the partials: every thread loads a few (all in flight), fixed reduction tree
+    __threadfence();
+    float t = 0.0f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += __ldcg(a.loss_partial + i);
+    t = block_reduce(t, OpAdd(), 0.0f, s_red);
+    if (threadIdx.x == 0) {
+      a.loss_out[0] = t * invB;
       *a.counter = 0;
     }
   }

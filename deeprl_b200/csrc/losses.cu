@@ -266,8 +266,15 @@ __global__ void __launch_bounds__(256) qr_loss_kernel(const float* __restrict__ 
     __threadfence();
     float tot = 0.0f;
     for (int j = t; j < N; j += blockDim.x) {
-      float s = 0.0f;
-      for (int i = 0; i < B; ++i) s += __ldcg(partial + (int64_t)i * N + j);
+      // 8 interleaved partial sums (a fixed order: deterministic): 8 independent loads in flight instead of a chain of B
+      float p8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      int i = 0;
+      for (; i + 8 <= B; i += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) p8[k] += __ldcg(partial + (int64_t)(i + k) * N + j);
+      }
+      for (; i < B; ++i) p8[0] += __ldcg(partial + (int64_t)i * N + j);
+      float s = ((p8[0] + p8[1]) + (p8[2] + p8[3])) + ((p8[4] + p8[5]) + (p8[6] + p8[7]));
       s /= (float)B;                                                                     // .mean(1)
       if (vec_out) vec_out[j] = s;
       tot += s;
