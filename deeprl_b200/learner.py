@@ -127,7 +127,9 @@ class GraphedDQNLearner:
 
     def _heads(self):
         """(online head modules, target head modules) when the DQN head can run in the fused head + loss + backward kernel."""
-        if self.kind != "dqn" or self.tail() is None or os.environ.get("B2RL_FUSED_HEAD", "1") == "0":
+        # (off by default: measured on B200 at batch 512 the separate head_fwd | dqn_loss | head_bwd kernels -- the target head on
+        # the side branch -- give 224.7 us / update, the two-launch fused form 243.2 us, the one-launch form 252.9 us)
+        if self.kind != "dqn" or self.tail() is None or os.environ.get("B2RL_FUSED_HEAD", "0") == "0":
             return None
         out = []
         for n in (self.net, self.tgt):
@@ -297,7 +299,7 @@ class GraphedDQNLearner:
         cur.wait_stream(side)
         nature_tc.mark("fwd_joined")
         r = ops.dqn_head_fused(phi.detach(), phi_t, phi_o, heads[0], heads[1], t.action, t.reward, t.mask, self.gamma_n,
-                               tail.db4, two=os.environ.get("B2RL_FUSED_HEAD", "1") != "one", **per)
+                               tail.db4, two=os.environ.get("B2RL_FUSED_HEAD", "0") != "one", **per)
         if self.per:
             if self.prefetch:                            # the sum tree is read by the prefetch branch: update after it
                 cur.wait_event(self._sampled_ev)

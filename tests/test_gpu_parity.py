@@ -16,6 +16,7 @@ def rl():
         pytest.skip("no CUDA device")
     import deeprl_b200 as rl
     rl.select_device(0)
+    rl.Config.COMPUTE_DTYPE = torch.float32      # parity mode (another test module of the same session may have left bf16 selected)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     return rl
