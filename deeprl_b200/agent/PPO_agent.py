@@ -30,6 +30,7 @@ class PPOAgent(BaseAgent):
             self.critic_opt = config.critic_opt_fn(self.network.critic_params)
         self.total_steps = 0
         self.states = self.task.reset()
+        self._raw_states, self._raw_seen = self.states, True      # (device actor: un-normalised copy, already counted below)
         self.states = config.state_normalizer(self.states)
         if config.shared_repr:
             self.lr_scheduler = torch.optim.lr_scheduler.LambdaLR(self.opt, lambda step: 1 - step / config.max_steps)
@@ -41,8 +42,52 @@ class PPOAgent(BaseAgent):
             prediction = self.network(self.config.state_normalizer(state))
         return to_np(prediction["action"])
 
+    # ------------------------------------------------------------------ device-side actor (component/actor.py)
+    def _device_actor(self):
+        """One launch per env step for normaliser + network forward + sampling when the network / normaliser are the reference's
+        continuous-control configuration (examples.py:496-522) on a CUDA device (``config.device_actor = False`` turns it off)."""
+        if getattr(self, "_actor", None) is None:
+            from ..component import actor as dev_actor
+            cfg = self.config
+            ok = (getattr(cfg, "device_actor", True) and dev_actor.supported(self.network, cfg.state_normalizer)
+                  and cfg.num_workers <= 64 and type(cfg.reward_normalizer).__name__ == "RescaleNormalizer")
+            self._actor = dev_actor.DeviceGaussianActor(self.network, cfg.state_normalizer, cfg.num_workers) if ok else False
+        return self._actor or None
+
+    def _rollout_device(self, actor):
+        """``_rollout`` with the per-step normaliser / forward / sampling on the device: the raw observations go up through a
+        pinned double buffer, the actions come back for the host envs; everything else stays in HBM.  As in the reference, every
+        observation batch updates the running moments exactly once -- when it is first seen (the constructor counted the reset
+        batch on the host; the batch that ends a rollout is counted by its value forward and re-used, read-only, by the first
+        step of the next rollout)."""
+        config = self.config
+        storage = Storage(config.rollout_length)
+        raw, seen = self._raw_states, self._raw_seen
+        keys = ("action", "log_pi_a", "entropy", "mean", "v")
+        for _ in range(config.rollout_length):
+            pred = actor.step(raw, update=not seen)
+            raw, rewards, terminals, info = self.task.step(to_np(pred["action"]))
+            seen = False
+            self.record_online_return(info)
+            rewards = config.reward_normalizer(rewards)
+            storage.feed({k: pred[k] for k in keys})
+            storage.feed({"reward": tensor(rewards).unsqueeze(-1), "mask": tensor(1 - terminals).unsqueeze(-1),
+                          "state": pred["state"]})
+            self.total_steps += config.num_workers
+        pred = actor.step(raw, update=True)                 # value of the last state (PPO_agent.py:46-47)
+        self._raw_states, self._raw_seen = raw, True
+        storage.feed({k: pred[k] for k in keys})
+        storage.placeholder()
+        compute_advantages(storage, config, pred["v"], exact=self.gae_exact)
+        actor.pull_stats()                                  # the host normaliser object stays current (eval_step, save)
+        entries = storage.extract(["state", "action", "log_pi_a", "ret", "advantage"])
+        return type(entries)(*[x.detach().contiguous() for x in entries])
+
     def _rollout(self):
         config = self.config
+        actor = self._device_actor()
+        if actor is not None:
+            return self._rollout_device(actor)
         storage = Storage(config.rollout_length)
         states = self.states
         for _ in range(config.rollout_length):

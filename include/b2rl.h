@@ -365,6 +365,22 @@ int b2rl_dqn_head_two(const uint16_t* phi, const uint16_t* phi_t, const uint16_t
                       uint16_t* gphi, float* gWa, float* gba, float* gWv, float* gbv, float* relu_colsum, float* q_out,
                       float* delta_out, float* prio_out, float* loss_out, float* scratch, float* geff, void* stream);
 
+/* Device-side actor step of the on-policy agents (PPO_agent.py:45-50 between two task.step() calls) in one
+ * launch: MeanStdNormalizer (normalizer.py:36-51 over baselines' RunningMeanStd: float64 Chan merge of the batch moments into
+ * rm_mean / rm_var / rm_count -- all three NULL: no normalisation; update_stats 0: read-only -- then clip((x - mean) /
+ * sqrt(var + eps), +-clip) rounded once to float32), GaussianActorCriticNet.forward (network_heads.py:173-214) with two-layer
+ * tanh FCBody actor / critic bodies, and the Normal sample / log_prob / entropy.  obs [N][D]; weights in the reference's
+ * nn.Linear layouts ([out][in]); z: supplied standard normals [N][A] (parity mode) or NULL -> Philox4x32-10 (seed, *counter)
+ * with Box-Muller; given_action != NULL: log_prob of those actions instead of sampling.  Outputs: state_out [N][D] (normalised,
+ * may be NULL), action / mean [N][A] (mean may be NULL), log_pi_a / entropy / v [N].  Limits: N <= 64, D, hidden <= 128, A <= 32. */
+int b2rl_gaussian_actor_step(const float* obs, double* rm_mean, double* rm_var, double* rm_count, int32_t update_stats, double clip,
+                             double eps, const float* aw1, const float* ab1, const float* aw2, const float* ab2, const float* faw,
+                             const float* fab, const float* cw1, const float* cb1, const float* cw2, const float* cb2,
+                             const float* fcw, const float* fcb, const float* std_param, int32_t N, int32_t D, int32_t H1,
+                             int32_t H2, int32_t A, const float* z, uint64_t seed, int64_t* counter, const float* given_action,
+                             float* state_out, float* action, float* log_pi_a, float* entropy, float* mean, float* v,
+                             void* stream);
+
 /* Element-wise halves of the distributional heads (CategoricalNet / QuantileNet, network_heads.py:40-55, 89-102) around the
  * tcgen05 GEMMs: softmax + log_softmax over the N atoms of every (b, a) row (either output may be NULL), and the backward
  * preparation dlogits = dout - prob * sum_n dout (prob == NULL: dlogits = dout, QR-DQN) written as the bf16 GEMM operand
