@@ -93,7 +93,7 @@ def test_actor_philox_sampling_statistics(rl):
     assert int(actor.counter) == 200 * N * A
     assert abs(z.mean()) < 0.02 and abs(z.std() - 1.0) < 0.02
     assert abs(np.mean(z ** 3)) < 0.05 and abs(np.mean(z ** 4) - 3.0) < 0.15
-    assert len(np.unique(np.round(z, 6))) > 0.99 * z.size
+    assert len(np.unique(np.round(z, 6))) > 0.97 * z.size      # (birthday collisions of 76 800 draws at 1e-6 resolution)
 
 
 def test_ppo_agent_uses_the_device_actor(rl):
