@@ -265,12 +265,21 @@ class GraphedDQNLearner:
         nature_tc.mark("loss")
         if tail is None:
             self.opt.zero_grad()
-        with nature_tc.wgrad_stream(None if side is cur else side), nature_tc.grad_sink(tail):   # weight-gradient GEMMs on the side branch
-            head.backward(grad)
+        fired = []
+        if late and os.environ.get("B2RL_PREFETCH_AT", "dgrad") == "dgrad":
+            # the gather of the next batch is forked right after the last dgrad GEMM: it runs beside the conv2 / conv1
+            # weight-gradient GEMMs (whose CTAs leave room for one 35 KB gather CTA per SM) and the update tail
+            nature_tc.AFTER_DGRAD = lambda: (self._prefetch_branch(parity, "gather"), fired.append(1))
+        try:
+            with nature_tc.wgrad_stream(None if side is cur else side), nature_tc.grad_sink(tail):   # weight-gradient GEMMs on the side branch
+                head.backward(grad)
+        finally:
+            nature_tc.AFTER_DGRAD = None
         nature_tc.mark("bwd_done")
         self.loss.copy_(r["loss"])
         if late:
-            self._prefetch_branch(parity, "gather")
+            if not fired:
+                self._prefetch_branch(parity, "gather")
             self._late_join = True                       # joined after the optimizer kernels (_opt)
         elif self.prefetch:
             cur.wait_stream(pre)

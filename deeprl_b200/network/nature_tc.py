@@ -46,6 +46,8 @@ def mark(name, stream=None):
         TRACE.mark(name, stream)
 
 
+AFTER_DGRAD = None         # callable run once, on the current stream, right after the last dgrad GEMM of the backward pass was
+                           # launched (the learner forks its late prefetch branch there: beside the weight-gradient tail)
 SINK = None                # network/tail.py NatureTail while ``grad_sink`` is active: backward hands it the GEMM-layout gradients
 RELU_FEATURES = set()      # data_ptr of feature tensors y4 = relu(fc4(.)) produced by nature_body (for head_bwd_relu)
 PREMASKED = {}             # data_ptr of a feature gradient already masked by head_bwd_relu -> its column sums (= db4)
@@ -159,6 +161,8 @@ def _backward_fused(ctx, gy4):
     _lib.call("b2rl_conv_gemm_bwd_bf16", _lib.ptr(g2), B * 100, 64, _lib.ptr(w2d), 128, 4, 2, 10, _lib.ptr(g1), 32, 3, 21, 20,
               ctypes.byref(e1), 128, _lib.stream())
     mark("d_conv2")
+    if AFTER_DGRAD is not None:
+        AFTER_DGRAD()
     if ctx.ring is not None:
         gw1p, p1 = wgrad_partials_ring(ctx.ring, g1, 32, stream=_fork())
     else:
