@@ -266,9 +266,10 @@ class GraphedDQNLearner:
         if tail is None:
             self.opt.zero_grad()
         fired = []
-        if late and os.environ.get("B2RL_PREFETCH_AT", "dgrad") == "dgrad":
-            # the gather of the next batch is forked right after the last dgrad GEMM: it runs beside the conv2 / conv1
-            # weight-gradient GEMMs (whose CTAs leave room for one 35 KB gather CTA per SM) and the update tail
+        if late and os.environ.get("B2RL_PREFETCH_AT", "end") == "dgrad":
+            # option (B2RL_PREFETCH_AT=dgrad): fork the gather right after the last dgrad GEMM, beside the conv2 / conv1
+            # weight-gradient GEMMs.  Measured 227.6 us / update against 226.1 us for the fork after the backward pass (default):
+            # the gather slows the conv1 weight gradient and kernel A by as much as it gains
             nature_tc.AFTER_DGRAD = lambda: (self._prefetch_branch(parity, "gather"), fired.append(1))
         try:
             with nature_tc.wgrad_stream(None if side is cur else side), nature_tc.grad_sink(tail):   # weight-gradient GEMMs on the side branch
