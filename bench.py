@@ -222,8 +222,7 @@ def measure_learner(rl, workload, dev, rank, world, K, W, repeats, barrier, pref
     import gc
     learner = build_learner(rl, workload, dev, rank, world, prefetch=prefetch)
     if world > 1:                                          # parameters identical on every rank
-        import torch.distributed as dist
-        dist.broadcast(learner.opt.flat, 0)
+        rl.parallel.broadcast_parameters(learner.opt.flat, 0)
         learner.tgt.load_state_dict(learner.net.state_dict())
     learner.capture(warmup=3, with_h2d=False)
     for _ in range(W):
@@ -259,15 +258,10 @@ def measure_learner(rl, workload, dev, rank, world, K, W, repeats, barrier, pref
 
 
 def leave(world):
-    """End of a multi-rank run: every rank has printed / finished; a process group whose collectives were captured in CUDA
-    graphs can hang in its destructor (measured: the ranks never exit), so the ranks synchronise, flush and leave directly."""
+    """End of a multi-rank run (deeprl_b200.parallel.leave: barrier, flush, exit without the process group's destructor)."""
     if world > 1:
-        import torch.distributed as dist
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        sys.stdout.flush(), sys.stderr.flush()
-        os._exit(0)
+        from deeprl_b200 import parallel
+        parallel.leave()
 
 
 def free(*objs):

@@ -13,4 +13,4 @@ from .utils import *  # noqa: F401,F403
 from .component import *  # noqa: F401,F403
 from .network import *  # noqa: F401,F403
 from .agent import *  # noqa: F401,F403
-from . import ops  # noqa: F401
+from . import ops, parallel  # noqa: F401

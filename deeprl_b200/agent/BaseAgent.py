@@ -1,3 +1,11 @@
+#######################################################################
+# This file restates an interface of ShangtongZhang/DeepRL, whose     #
+# licence asks that the following declaration stay at the top:        #
+#                                                                     #
+# Copyright (C) 2017 Shangtong Zhang(zhangshangtong.cpp@gmail.com)    #
+# Permission given to modify the code as long as you keep this        #
+# declaration at the top                                              #
+#######################################################################
 """Agent base class and actor with the reference's interface (``deep_rl/agent/BaseAgent.py``:
 ``BaseAgent``:15 -- save / load / eval_step / eval_episodes / record_online_return / switch_task;
 ``BaseActor``:108 -- ``step()`` returns ``sgd_update_frequency`` transitions).

@@ -13,9 +13,8 @@ import sys
 
 import numpy as np
 import torch
-import torch.distributed as dist
 
-from . import _lib, ops
+from . import _lib, ops, parallel
 from .component.replay import PrioritizedReplay
 from .network import nature_tc
 from .network.fused import frame_scale
@@ -443,7 +442,7 @@ class GraphedDQNLearner:
         self._early_work = None
         if self._overlap:
             lo, hi = self._tail.early_slice
-            self._early_work = dist.all_reduce(self.opt.grad[lo:hi], async_op=True)
+            self._early_work = parallel.allreduce_gradients(self.opt.grad[lo:hi], async_op=True)
 
     def _allreduce(self):
         if self.world <= 1:
@@ -451,12 +450,12 @@ class GraphedDQNLearner:
         tail = self.tail()
         if tail is not None and self._overlap:
             for lo, hi in tail.late_slices:
-                dist.all_reduce(self.opt.grad[lo:hi])
+                parallel.allreduce_gradients(self.opt.grad[lo:hi])
             if getattr(self, "_early_work", None) is not None:
                 self._early_work.wait()
                 self._early_work = None
         else:
-            dist.all_reduce(self.opt.grad)
+            parallel.allreduce_gradients(self.opt.grad)
 
     def update(self):
         """One gradient update (graph replay).  Returns the device loss tensor (no sync)."""

@@ -1,3 +1,11 @@
+#######################################################################
+# This file restates an interface of ShangtongZhang/DeepRL, whose     #
+# licence asks that the following declaration stay at the top:        #
+#                                                                     #
+# Copyright (C) 2017 Shangtong Zhang(zhangshangtong.cpp@gmail.com)    #
+# Permission given to modify the code as long as you keep this        #
+# declaration at the top                                              #
+#######################################################################
 """Network heads returning the reference's output dicts (``deep_rl/network/network_heads.py``):
 ``VanillaNet``:11 / ``DuelingNet``:24 -> ``q``; ``CategoricalNet``:40 / ``RainbowNet``:57 -> ``prob, log_prob``;
 ``QuantileNet``:89 -> ``quantile``; ``GaussianActorCriticNet``:173 / ``CategoricalActorCriticNet``:217 ->

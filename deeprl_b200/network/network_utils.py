@@ -1,3 +1,11 @@
+#######################################################################
+# This file restates an interface of ShangtongZhang/DeepRL, whose     #
+# licence asks that the following declaration stay at the top:        #
+#                                                                     #
+# Copyright (C) 2017 Shangtong Zhang(zhangshangtong.cpp@gmail.com)    #
+# Permission given to modify the code as long as you keep this        #
+# declaration at the top                                              #
+#######################################################################
 """``layer_init`` / ``NoisyLinear`` / ``BaseNet`` with the reference's names
 (``deep_rl/network/network_utils.py:15-83``)."""
 import math

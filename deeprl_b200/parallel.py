@@ -33,11 +33,27 @@ def broadcast_parameters(flat, src=0):
     return flat
 
 
-def allreduce_gradients(flat_grad):
-    """SUM the flat gradient arena over ranks (the 1/world factor is folded into the clip kernel's grad_scale)."""
+def allreduce_gradients(flat_grad, async_op=False):
+    """SUM the flat gradient arena (or a slice of it) over ranks; the 1/world factor is folded into the clip kernel's
+    grad_scale.  ``async_op``: returns the work handle (the learner all-reduces fc4's slice beside the convolution backward and
+    waits for it before the optimizer kernels; inside a CUDA-graph capture the handle's wait() becomes a graph dependency)."""
     if dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
-    return flat_grad
+        return dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, async_op=async_op)
+    return None
+
+
+def leave():
+    """End of a multi-rank run whose collectives were captured in CUDA graphs: the process group's destructor can hang then
+    (measured), so the ranks synchronise, flush and exit directly."""
+    import sys
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        dist.barrier()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        sys.stdout.flush(), sys.stderr.flush()
+        os._exit(0)
 
 
 def grad_scale():

@@ -1,3 +1,11 @@
+#######################################################################
+# This file restates an interface of ShangtongZhang/DeepRL, whose     #
+# licence asks that the following declaration stay at the top:        #
+#                                                                     #
+# Copyright (C) 2017 Shangtong Zhang(zhangshangtong.cpp@gmail.com)    #
+# Permission given to modify the code as long as you keep this        #
+# declaration at the top                                              #
+#######################################################################
 """Thin logging facade with the reference's surface (``deep_rl/utils/logger.py:17-70``):
 ``get_logger(tag, log_level)`` -> object with ``info/debug/warning/add_scalar/add_histogram``.
 TensorBoard is created lazily and only if importable; ``tag=None`` writes no files."""

@@ -1,9 +1,14 @@
+#######################################################################
+# This file restates an interface of ShangtongZhang/DeepRL, whose     #
+# licence asks that the following declaration stay at the top:        #
+#                                                                     #
+# Copyright (C) 2017 Shangtong Zhang(zhangshangtong.cpp@gmail.com)    #
+# Permission given to modify the code as long as you keep this        #
+# declaration at the top                                              #
+#######################################################################
 """Driver loop and small host helpers (reference: ``deep_rl/utils/misc.py:19-84``)."""
 import datetime
-import itertools
 import time
-from collections import OrderedDict
-from collections.abc import Sequence
 from pathlib import Path
 
 import numpy as np
@@ -32,10 +37,6 @@ def run_steps(agent):
 
 def get_time_str():
     return datetime.datetime.now().strftime("%y%m%d-%H%M%S")
-
-
-def get_default_log_dir(name):
-    return "./log/%s-%s" % (name, get_time_str())
 
 
 def mkdir(path):
@@ -69,38 +70,3 @@ def generate_tag(params):
     run = params.pop("run", 0)
     parts = ["%s_%s" % (k, v if is_plain_type(v) else v.__name__) for k, v in sorted(params.items())]
     params.update(tag="%s-%s-run-%d" % (game, "-".join(parts), run), game=game, run=run)
-
-
-def translate(pattern):
-    return r"\.".join(pattern.split("."))
-
-
-def split(a, n):
-    k, m = divmod(len(a), n)
-    return (a[i * k + min(i, m):(i + 1) * k + min(i + 1, m)] for i in range(n))
-
-
-class HyperParameter:
-    def __init__(self, id, param):
-        self.id = id
-        self.param = {key: item for key, item in param}
-
-    def __str__(self):
-        return str(self.id)
-
-    def dict(self):
-        return self.param
-
-
-class HyperParameters(Sequence):
-    def __init__(self, ordered_params):
-        if not isinstance(ordered_params, OrderedDict):
-            raise NotImplementedError
-        axes = [[[key, item] for item in ordered_params[key]] for key in ordered_params]
-        self.params = list(itertools.product(*axes))
-
-    def __getitem__(self, index):
-        return HyperParameter(index, self.params[index])
-
-    def __len__(self):
-        return len(self.params)

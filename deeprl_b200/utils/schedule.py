@@ -1,3 +1,11 @@
+#######################################################################
+# This file restates an interface of ShangtongZhang/DeepRL, whose     #
+# licence asks that the following declaration stay at the top:        #
+#                                                                     #
+# Copyright (C) 2017 Shangtong Zhang(zhangshangtong.cpp@gmail.com)    #
+# Permission given to modify the code as long as you keep this        #
+# declaration at the top                                              #
+#######################################################################
 """Stateful scalar schedules (reference: ``deep_rl/utils/schedule.py:7-31``).  A
 ``LinearSchedule`` advances on EVERY call (schedule.py:28-31), so e.g. the PER beta moves once
 per gradient update (DQN_agent.py:125)."""
