@@ -426,9 +426,10 @@ def run_b2rl(args):
     if world > 1:
         barrier()
     if rank != 0:
-        leave(world)                                       # (its barrier waits for rank 0's single-rank extras: PPO, CPU baseline)
+        leave(world)                                       # (its barrier waits for rank 0 to print the line)
         return
-    if not args.no_extras:
+    single = world == 1                                    # PPO, the agent-API run and the CPU baseline are N=1 measurements
+    if not args.no_extras and single:
         try:
             extras["ppo"] = ppo_result(rl, args, quiet=True)
         except Exception as e:                             # noqa: BLE001 -- an extra must never take the headline line down
@@ -448,11 +449,13 @@ def run_b2rl(args):
                 traffic=traffic, traffic_source=traffic_src,
                 raw_u8_variant=dict(kernel="gather_raw_tma_kernel (uint8 stacks: exactly the SURVEY 8d bytes; UniformReplay.sample())",
                                     achieved=round(ach_u8, 1), frac=round(ach_u8 / hbm, 4), us_per_launch=round(gt["u8"] * 1e3, 2)))
-    try:
-        ag = agent_e2e(rl)
-    except Exception as e:                                 # noqa: BLE001
-        ag = dict(error=str(e).splitlines()[0][:200])
-    cpu = cpu_baseline(args.workload)                      # (selects the CPU device: last)
+    ag = cpu = None
+    if single:
+        try:
+            ag = agent_e2e(rl)
+        except Exception as e:                             # noqa: BLE001
+            ag = dict(error=str(e).splitlines()[0][:200])
+        cpu = cpu_baseline(args.workload)                  # (selects the CPU device: last)
     line = dict(
         metric="gradient-updates/sec (DQN batch 512, 84x84x4 synthetic)", value=main["value"], unit="updates/s",
         n_gpus=world, steps=K, warmup=W, repeats=R, ms_per_step=main["ms_per_step"], repeat_ms=main["repeat_ms"],
