@@ -4,3 +4,4 @@ from .CategoricalDQN_agent import *
 from .QuantileRegressionDQN_agent import *
 from .A2C_agent import *
 from .PPO_agent import *
+from .NStepDQN_agent import *

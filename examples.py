@@ -192,6 +192,32 @@ def a2c_continuous(**kwargs):
     run_steps(A2CAgent(config))
 
 
+# ------------------------------------------------------------------------------------------------ n-step DQN (examples.py:408-446)
+def n_step_dqn_feature(**kwargs):
+    config = _config(kwargs)
+    config.num_workers = kwargs.get("num_workers", 5)
+    config.task_fn = lambda: Task(config.game, num_envs=config.num_workers)
+    config.eval_env = Task(config.game)
+    config.optimizer_fn = lambda params: torch.optim.RMSprop(params, 0.001)
+    config.network_fn = lambda: VanillaNet(config.action_dim, FCBody(config.state_dim))
+    config.random_action_prob = LinearSchedule(1.0, 0.1, 1e4)
+    _apply(config, dict(discount=0.99, target_network_update_freq=200, rollout_length=5, gradient_clip=5))
+    run_steps(NStepDQNAgent(config))
+
+
+def n_step_dqn_pixel(**kwargs):
+    config = _config(kwargs)
+    config.num_workers = kwargs.get("num_workers", 16)
+    config.task_fn = lambda: Task(config.game, num_envs=config.num_workers)
+    config.eval_env = Task(config.game)
+    config.optimizer_fn = lambda params: torch.optim.RMSprop(params, lr=1e-4, alpha=0.99, eps=1e-5)
+    config.network_fn = lambda: VanillaNet(config.action_dim, NatureConvBody())
+    config.random_action_prob = LinearSchedule(1.0, 0.05, 1e6)
+    _apply(config, dict(state_normalizer=ImageNormalizer, reward_normalizer=SignNormalizer, discount=0.99,
+                        target_network_update_freq=10000, rollout_length=5, gradient_clip=5, max_steps=int(2e7)))
+    run_steps(NStepDQNAgent(config))
+
+
 # ------------------------------------------------------------------------------------------------ PPO (examples.py:496-550)
 def ppo_continuous(**kwargs):
     config = _config(kwargs)

@@ -151,3 +151,26 @@ def a2c_update(sd, params, opt, states, actions, rewards, masks, discount, tau, 
     clip_grad_norm(params, gradient_clip)
     opt.step()
     return adv, ret
+
+
+def nstep_dqn_update(sd, target_sd, params, opt, states, actions, rewards, masks, discount, gradient_clip, gate=F.relu):
+    """NStepDQN_agent.py:26-70 for one rollout whose env interaction is given: ``states`` (T+1,N,obs), ``actions`` (T,N),
+    ``rewards``/``masks`` (T,N,1).  The T forward passes keep their graphs (``storage.feed({'q': q})`` :40); the bootstrap is
+    ``max_a target(s_T)`` (:56-57); ``ret_t = r_t + discount * mask_t * ret_{t+1}`` (:58-60);
+    ``loss = 0.5 * mean((q[a] - ret)^2)`` (:63); clip + optimizer step (:64-67).  The target sync inside the rollout (:48-49)
+    is the caller's.  Returns (ret (T,N,1), loss)."""
+    T = actions.shape[0]
+    q = [nets.vanilla_q(sd, nets.fc_body(sd, states[t], "body.", gate)) for t in range(T)]
+    with torch.no_grad():
+        ret = nets.vanilla_q(target_sd, nets.fc_body(target_sd, states[T], "body.", gate)).max(dim=1, keepdim=True)[0]
+    rets = [None] * T
+    for i in reversed(range(T)):
+        ret = rewards[i] + discount * masks[i] * ret
+        rets[i] = ret
+    qa = torch.cat(q, dim=0).gather(1, actions.reshape(-1, 1).long())
+    loss = 0.5 * (qa - torch.cat(rets, dim=0)).pow(2).mean()
+    opt.zero_grad()
+    loss.backward()
+    clip_grad_norm(params, gradient_clip)
+    opt.step()
+    return torch.stack(rets), loss.detach()
