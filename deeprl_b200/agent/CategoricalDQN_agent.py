@@ -16,8 +16,8 @@ class CategoricalDQNActor(DQNActor):
     def _set_up(self):
         self.config.atoms = tensor(self.config.atoms)
 
-    def compute_q(self, prediction):
-        return to_np((prediction["prob"] * self.config.atoms).sum(-1))
+    def _q_tensor(self, prediction):
+        return (prediction["prob"] * self.config.atoms).sum(-1)
 
 
 class CategoricalDQNAgent(DQNAgent):

@@ -29,8 +29,24 @@ class DQNActor(BaseActor):
         self.config = config
         self.start()
 
+    def _q_tensor(self, prediction):
+        """Action values [num_envs, A] on the device (what ``compute_q`` converts to numpy)."""
+        return prediction["q"]
+
     def compute_q(self, prediction):
-        return to_np(prediction["q"])
+        return to_np(self._q_tensor(prediction))
+
+    def _graphed(self):
+        """``config.cuda_graph``: the forward pass below as one captured launch sequence (component/actor.py GraphedQActor).
+        Not for subclasses that redefine ``compute_q`` itself (they get the statements of the reference)."""
+        ga = getattr(self, "_graph_actor", None)
+        if ga is None:
+            from ..component import actor as device_actor
+            ok = (type(self).compute_q is DQNActor.compute_q and device_actor.q_actor_supported(self.config, self._network)
+                  and all(np.asarray(s).dtype == np.uint8 and np.asarray(s).shape == (4, 84, 84) for s in self._state))
+            ga = self._graph_actor = device_actor.GraphedQActor(
+                self._network, self._q_tensor, len(self._state), 4, (84, 84), self.config.state_normalizer.coef) if ok else False
+        return ga or None
 
     def _transition(self):
         """DQN_agent.py:24-45: epsilon-greedy on a forward pass of the shared network, one env step."""
@@ -39,9 +55,14 @@ class DQNActor(BaseActor):
         config = self.config
         if config.noisy_linear:
             self._network.reset_noise()
-        with config.lock, torch.no_grad():
-            prediction = self._network(config.state_normalizer(np.asarray([np.asarray(s) for s in self._state])))
-        q_values = self.compute_q(prediction)
+        ga = self._graphed() if getattr(config, "cuda_graph", False) else None
+        if ga is not None:
+            with config.lock:
+                q_values = ga.q_values(self._state)
+        else:
+            with config.lock, torch.no_grad():
+                prediction = self._network(config.state_normalizer(np.asarray([np.asarray(s) for s in self._state])))
+            q_values = self.compute_q(prediction)
         if config.noisy_linear:
             epsilon = 0
         elif self._total_steps < config.exploration_steps:

@@ -16,8 +16,8 @@ from .DQN_agent import DQNActor, DQNAgent
 
 
 class QuantileRegressionDQNActor(DQNActor):
-    def compute_q(self, prediction):
-        return to_np(prediction["quantile"].mean(-1))
+    def _q_tensor(self, prediction):
+        return prediction["quantile"].mean(-1)
 
 
 class QuantileRegressionDQNAgent(DQNAgent):

@@ -92,3 +92,94 @@ class DeviceGaussianActor:
                   _lib.ptr(out["state"]), _lib.ptr(out["action"]), _lib.ptr(out["log_pi_a"]), _lib.ptr(out["entropy"]),
                   _lib.ptr(out["mean"]), _lib.ptr(out["v"]), _lib.stream())
         return out
+
+
+class GraphedQActor:
+    """The DQN-family actor's forward pass (DQN_agent.py:29-31: ``network(state_normalizer(stack(state)))`` at batch
+    ``num_envs``, normally 1) as ONE CUDA-graph replay: pinned upload of the uint8 frame stacks -> frame-stack conversion to
+    the exact-integer bf16 space-to-depth layout (``b2rl_replay_gather`` on the staging buffer; ImageNormalizer's 1/255 is
+    folded into conv1 like in the learner) -> the network on the tcgen05 kernels -> action values -> pinned download.  The
+    epsilon-greedy draw stays on the host (``epsilon_greedy``: the reference's numpy stream, torch_utils.py:51-58).
+
+    The eager form of the same step is ~40 kernel / memcpy launches of Python-driven work per env step; this is one launch and
+    one stream synchronise."""
+
+    def __init__(self, network, q_fn, num_envs, history, frame_hw, scale):
+        p = next(network.parameters())
+        self.net, self.q_fn, self.dev = network, q_fn, p.device
+        self.N, self.hl, self.hw, self.scale = int(num_envs), int(history), tuple(frame_hw), float(scale)
+        self.row = self.hw[0] * self.hw[1]
+        rows = self.N * self.hl + 1                       # (+1: the gather kernel stages history + n_step rows)
+        self.h_frames = torch.zeros((rows, self.row), dtype=torch.uint8, pin_memory=True)
+        self.d_frames = torch.zeros((rows, self.row), dtype=torch.uint8, device=self.dev)
+        self._np_frames = self.h_frames.numpy()[:self.N * self.hl].reshape(self.N, self.hl, self.row)
+        self.idx = (torch.arange(self.N, dtype=torch.int64) * self.hl + self.hl - 1).to(self.dev)
+        self.d_action = torch.zeros(rows, dtype=torch.int32, device=self.dev)      # (scalar columns of the ring API: unused)
+        self.d_reward = torch.zeros(rows, dtype=torch.float64, device=self.dev)
+        self.d_mask = torch.ones(rows, dtype=torch.int32, device=self.dev)
+        self.x = torch.empty((self.N, self.hw[0] // 4, self.hw[1] // 4, 16 * self.hl), dtype=torch.bfloat16, device=self.dev)
+        self.d_q = self.h_q = None
+        self.graph, self._sig = None, None
+        self.replays = 0
+
+    def _signature(self):
+        """What the captured launch sequence depends on besides addresses: who re-packs the body's bf16 operands (the body per
+        forward, or the learner's optimizer kernel) and whether the distributional heads have their bf16 operand."""
+        body = getattr(self.net, "body", None)
+        heads = tuple(getattr(m, "_w16", None) is not None for m in self.net.children() if isinstance(m, torch.nn.Linear))
+        return (bool(getattr(body, "auto_repack", True)), heads)
+
+    def _forward(self):
+        from ..network.fused import frame_scale
+        self.d_frames.copy_(self.h_frames, non_blocking=True)
+        _lib.call("b2rl_replay_gather", _lib.ptr(self.d_frames), _lib.ptr(self.d_action), _lib.ptr(self.d_reward),
+                  _lib.ptr(self.d_mask), self.d_frames.shape[0], self.row, _lib.ptr(self.idx), self.N, self.hl, 1, 1.0, None,
+                  _lib.DTYPE_CODE[torch.bfloat16], 2, self.hw[1], _lib.ptr(self.x), None, None, None, None, _lib.stream())
+        with torch.no_grad(), frame_scale(self.scale):
+            q = self.q_fn(self.net(self.x.permute(0, 3, 1, 2))).float()
+        if self.d_q is None:
+            self.d_q = torch.empty_like(q)
+            self.h_q = torch.empty(q.shape, dtype=torch.float32, pin_memory=True)
+        self.d_q.copy_(q)
+        self.h_q.copy_(self.d_q, non_blocking=True)
+
+    def _capture(self):
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                     # eager warm-up (lazy allocations, cuBLAS workspaces of library heads)
+            self._forward()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._forward()
+        self._sig = self._signature()
+
+    def q_values(self, states):
+        """``states``: ``num_envs`` frame stacks (LazyFrames / uint8 arrays [history, H, W]).  Returns float32 [num_envs, A]."""
+        for i, s in enumerate(states):
+            a = np.asarray(s)
+            if a.dtype != np.uint8 or a.size != self.hl * self.row:
+                raise _lib.B2RLError("GraphedQActor expects uint8 frame stacks of %d x %s" % (self.hl, self.hw))
+            self._np_frames[i] = a.reshape(self.hl, self.row)
+        if self.graph is None or self._sig != self._signature():
+            self._capture()
+        self.graph.replay()
+        self.replays += 1
+        torch.cuda.current_stream().synchronize()
+        return self.h_q.numpy().copy()
+
+
+def q_actor_supported(config, network):
+    """``config.cuda_graph`` + synchronous actor + bf16 tcgen05 NatureConvBody on a CUDA device + ImageNormalizer-style rescale
+    of uint8 frames: the conditions under which the actor's forward is the captured device path."""
+    from ..network.network_bodies import NatureConvBody
+    from ..utils import Config
+    from ..utils.normalizer import RescaleNormalizer
+    body = getattr(network, "body", None)
+    return bool(getattr(config, "cuda_graph", False) and not config.async_actor and not config.noisy_linear
+                and isinstance(body, NatureConvBody) and not body.noisy_linear and body.conv1.weight.is_cuda
+                and body.conv1.in_channels == 4
+                and Config.COMPUTE_DTYPE == torch.bfloat16 and Config.DENSE_BACKEND == "tcgen05"
+                and isinstance(config.state_normalizer, RescaleNormalizer))
