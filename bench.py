@@ -335,8 +335,8 @@ def gather_traffic():
 
 def agent_e2e(rl, steps=48):
     """Updates/s through the reference's own seam: ``DQNAgent.step()`` (DQN_agent.py:101-138) with ``config.cuda_graph``:
-    per step the actor plays sgd_update_frequency = 4 env steps on the host (batch-1 forward each), the transitions are fed
-    to the HBM ring and ONE captured update runs.  Batch 512, 100k-transition ring, SyntheticAtari-v0."""
+    per step the actor plays sgd_update_frequency = 4 env steps on the host (batch-1 forward each, itself a captured launch
+    sequence), the transitions are fed to the HBM ring and ONE captured update runs.  Batch 512, 100k-transition ring, SyntheticAtari-v0."""
     c = rl.Config()
     c.merge(dict(tag=None))
     c.task_fn = lambda: rl.Task("SyntheticAtari-v0", seed=2)
@@ -364,8 +364,9 @@ def agent_e2e(rl, steps=48):
     ok = getattr(ag, "_learner", None) is not None
     ag.close()
     return dict(value=round(steps / dt, 1), unit="updates/s", steps=steps, graph_path=bool(ok),
-                note="DQNAgent.step() through run_steps' seam: 4 host env steps with a batch-1 actor forward each + feed + one "
-                     "captured update per step; wall clock (the host actor dominates)")
+                note="DQNAgent.step() through run_steps' seam: 4 host env steps, each with the actor's batch-1 forward as one captured "
+                     "launch sequence (GraphedQActor: pinned frame upload -> tcgen05 network -> pinned q download), + feed + one "
+                     "captured update per step; wall clock")
 
 
 def run_b2rl(args):
@@ -539,10 +540,12 @@ def ppo_result(rl, args, quiet=False):
                         timing="wall clock around whole iterations (host envs + eager launches), torch.cuda.synchronize on both sides"),
             env_steps_per_s=round(c.rollout_length * c.num_workers / dt, 1),
             minibatch_phase=(dict(updates_per_s=round(mb * K / sgd[0], 1), seconds_per_iteration=round(sgd[0] / K, 3),
-                                  form="one CUDA-graph replay per minibatch (GraphedPPOLearner), KL gate on the device")
+                                  form=("ONE persistent-kernel launch for all %d minibatch updates (PersistentPPOLearner: weights in shared "
+                                        "memory, KL gate on the device)" % mb if type(ag._graph).__name__ == "PersistentPPOLearner"
+                                        else "one CUDA-graph replay per minibatch (GraphedPPOLearner), KL gate on the device"))
                              if c.graph_minibatch else dict(form="eager loop (PPOAgent._minibatch)")),
             gpu_launches=int(rl._lib.launch_count() + (K * mb * ag._graph.launches_per_update if c.graph_minibatch else 0)),
-            gpu_launches_per_minibatch=(int(ag._graph.launches_per_update) if c.graph_minibatch else None))
+            gpu_launches_per_minibatch=(round(ag._graph.launches_per_update, 4) if c.graph_minibatch else None))
         ag.close()
         return res
     finally:

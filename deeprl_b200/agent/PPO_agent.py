@@ -187,15 +187,20 @@ class PPOAgent(BaseAgent):
         """``config.graph_minibatch = True``: the minibatch loop of PPO_agent.py:68-99 through ``GraphedPPOLearner``.  The
         torch optimizers built by ``actor_opt_fn`` / ``critic_opt_fn`` are replaced by flat-arena Adam with the same
         hyper-parameters on first use; the permutations come from ``np.random.permutation`` exactly as ``random_sample``."""
-        from ..learner import GraphedPPOLearner
+        from ..learner import GraphedPPOLearner, PersistentPPOLearner
         config = self.config
         rows, mb = entries.state.size(0), config.mini_batch_size
         if getattr(self, "_graph", None) is None:
             a = ops.FlatOptimizer.from_torch(self.actor_opt, self.network.actor_params)
             c = ops.FlatOptimizer.from_torch(self.critic_opt, self.network.critic_params)
-            self._graph = GraphedPPOLearner(self.network, a, c, rows, entries.state.shape[1], entries.action.shape[1], mb,
-                                            config.ppo_ratio_clip, config.entropy_weight, config.target_kl,
-                                            config.optimization_epochs * (rows // mb))
+            # one persistent kernel for the whole loop where the network is the examples' Gaussian MLP pair
+            # (config.persistent_minibatch = False keeps the one-graph-replay-per-minibatch form)
+            persistent = (getattr(config, "persistent_minibatch", True) and a.kind == "adam" and c.kind == "adam"
+                          and PersistentPPOLearner.supported(self.network, mb))
+            cls = PersistentPPOLearner if persistent else GraphedPPOLearner
+            self._graph = cls(self.network, a, c, rows, entries.state.shape[1], entries.action.shape[1], mb,
+                              config.ppo_ratio_clip, config.entropy_weight, config.target_kl,
+                              config.optimization_epochs * (rows // mb))
             self._graph.load(entries)
             self._graph.capture()
         g = self._graph

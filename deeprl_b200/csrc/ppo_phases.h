@@ -1,0 +1,463 @@
+// ppo_phases.h -- the PPO minibatch update (PPO_agent.py:73-99, non-shared representation) written as PHASES of a single
+// thread block: every function below takes (tid, NT) and is executed by all NT threads of the block, with a block barrier
+// between consecutive phases (the sequence is ppo_sequence.inc).  csrc/ppo_persistent.cu runs the sequence as ONE persistent
+// kernel over all minibatches of an iteration (weights in shared memory, Adam moments in L2); tests/host_emul/ppo_emul.cpp
+// compiles the SAME functions with g++ and runs the threads of a phase one after another, which is how the arithmetic is
+// checked against the oracle without a GPU.  Nothing here may depend on execution order inside a phase.
+//
+//   network   GaussianActorCriticNet (network_heads.py:173-214) with DummyBody phi, actor / critic FCBody(tanh) of two layers:
+//             mean = tanh(fc_action(actor_body(x))), v = fc_critic(critic_body(x)), std = softplus(std_param)
+//   losses    PPO_agent.py:79-88 (ratio, clipped surrogate, entropy bonus, value loss, approx_kl)
+//   updates   PPO_agent.py:94-99: actor Adam step iff approx_kl <= 1.5 * target_kl; critic Adam step always
+//             (torch.optim.Adam, _single_tensor_adam arithmetic, as csrc/optim.cu adam_kernel)
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define PPO_FN __device__ __forceinline__
+#define PPO_HD __host__ __device__ inline
+#else
+#define PPO_FN static inline
+#define PPO_HD static inline
+#endif
+
+namespace b2rl_ppo {
+
+struct PpoArgs {
+  // rollout rows (device): state [R][D], action [R][A], old log-prob / return / normalised advantage [R]
+  const float* state; const float* action; const float* old_logp; const float* ret; const float* adv;
+  int D, A, H1, H2, mb;
+  const int64_t* perm;        // [n_batches][mb] row indices (np.random.permutation rows, misc.py:55-62)
+  int n_batches;
+  // flat arenas of the two FlatOptimizers (ops.py): parameters, exp_avg, exp_avg_sq, step count; tensor offsets inside them
+  float* a_flat; float* a_m; float* a_v; int64_t* a_step; int a_off[7];     // w1 b1 w2 b2 fc_action.w fc_action.b std
+  float* c_flat; float* c_m; float* c_v; int64_t* c_step; int c_off[6];     // w1 b1 w2 b2 fc_critic.w fc_critic.b
+  float a_lr, a_b1, a_b2, a_eps, c_lr, c_b1, c_b2, c_eps;
+  float clip, ent_w, gate_max;
+  float* stats;               // [4]: policy loss, value loss, approx_kl of the LAST minibatch; actor steps taken in this call
+};
+
+struct PpoShared {
+  float *aw1, *ab1, *aw2, *ab2, *aw3, *ab3, *sdp;      // actor weights (aw3 = fc_action), std parameter
+  float *cw1, *cb1, *cw2, *cb2, *cw3, *cb3;            // critic weights (cw3 = fc_critic, one row)
+  float *xb, *actb, *oldlpb, *advb, *retb;             // double-buffered minibatch rows: buffer s at + s * (x|act|row)_stride
+  int x_stride, act_stride, row_stride;                // (no pointer arrays: a dynamically indexed member would push the struct to local memory)
+  float *ah1, *ah2, *ad1, *ad2;                        // actor  [mb][ldh] activations / pre-activation gradients
+  float *ch1, *ch2, *cd1, *cd2;                        // critic (the two networks run side by side, one half of the block each)
+  float *mu, *dmu, *dsd;                               // [mb][A]
+  float *v, *dv, *logp, *dlogp, *red;                  // [mb]; red [3*mb]
+  float *sdv, *lsd;                                    // [A] softplus(std), log of it
+  float *flag;                                         // [8]: 0 gate, 1 actor steps taken, 2 policy loss, 3 kl, 4 value loss
+  int* steps;                                          // [2] Adam step counts: actor, critic
+  int ld1, ldh;                                        // odd row strides (bank-conflict-free column walks)
+};
+
+PPO_HD int ppo_odd(int n) { return n | 1; }
+
+// carve the shared block (base may be a dummy when only the size is wanted); returns the number of floats used
+PPO_HD size_t ppo_carve(PpoShared& S, float* base, int D, int A, int H1, int H2, int mb) {
+  const int Hm = H1 > H2 ? H1 : H2;
+  S.ld1 = ppo_odd(D);
+  S.ldh = ppo_odd(Hm);
+  size_t off = 0;
+#define PPO_TAKE(n) (base + (off += ((size_t)(n) + 3) / 4 * 4) - ((size_t)(n) + 3) / 4 * 4)
+  const size_t w1 = (size_t)H1 * S.ld1, w2 = (size_t)H2 * S.ldh, act = (size_t)mb * S.ldh, ma = (size_t)mb * A;
+  S.aw1 = PPO_TAKE(w1); S.ab1 = PPO_TAKE(H1); S.aw2 = PPO_TAKE(w2); S.ab2 = PPO_TAKE(H2);
+  S.aw3 = PPO_TAKE((size_t)A * S.ldh); S.ab3 = PPO_TAKE(A); S.sdp = PPO_TAKE(A);
+  S.cw1 = PPO_TAKE(w1); S.cb1 = PPO_TAKE(H1); S.cw2 = PPO_TAKE(w2); S.cb2 = PPO_TAKE(H2);
+  S.cw3 = PPO_TAKE(S.ldh); S.cb3 = PPO_TAKE(1);
+  S.x_stride = (int)(((size_t)mb * S.ld1 + 3) / 4 * 4); S.act_stride = (int)((ma + 3) / 4 * 4); S.row_stride = (mb + 3) / 4 * 4;
+  S.xb = PPO_TAKE(2 * (size_t)S.x_stride); S.actb = PPO_TAKE(2 * (size_t)S.act_stride);
+  S.oldlpb = PPO_TAKE(2 * (size_t)S.row_stride); S.advb = PPO_TAKE(2 * (size_t)S.row_stride); S.retb = PPO_TAKE(2 * (size_t)S.row_stride);
+  S.ah1 = PPO_TAKE(act); S.ah2 = PPO_TAKE(act); S.ad1 = PPO_TAKE(act); S.ad2 = PPO_TAKE(act);
+  S.ch1 = PPO_TAKE(act); S.ch2 = PPO_TAKE(act); S.cd1 = PPO_TAKE(act); S.cd2 = PPO_TAKE(act);
+  S.mu = PPO_TAKE(ma); S.dmu = PPO_TAKE(ma); S.dsd = PPO_TAKE(ma);
+  S.v = PPO_TAKE(mb); S.dv = PPO_TAKE(mb); S.logp = PPO_TAKE(mb); S.dlogp = PPO_TAKE(mb); S.red = PPO_TAKE((size_t)3 * mb);
+  S.sdv = PPO_TAKE(A); S.lsd = PPO_TAKE(A);
+  S.flag = PPO_TAKE(8);
+  S.steps = reinterpret_cast<int*>(PPO_TAKE(4));
+#undef PPO_TAKE
+  return off;
+}
+
+// ------------------------------------------------------------------------------------------------ dense building blocks
+// Tiles are 4 rows x 4 INTERLEAVED columns (column c of tile t is t + tiles * c): consecutive threads walk consecutive
+// columns, so with odd row strides every shared-memory access of a warp is conflict-free or a broadcast.
+
+// out[n][j] = f(sum_k in[n][k] * W[j][k] + bias[j])       n < M (M % 4 == 0), j < J, k < K
+PPO_FN void dense_fwd(const float* in, int ldin, const float* W, int ldw, const float* bias, float* out, int ldout, int M,
+                      int K, int J, bool use_tanh, int tid, int NT) {
+  const int tjn = (J + 3) / 4, tiles = (M / 4) * tjn;
+  for (int t = tid; t < tiles; t += NT) {
+    const int tn = t / tjn, tj = t - tn * tjn;
+    int jj[4];
+    bool ok[4];
+    for (int c = 0; c < 4; ++c) {
+      jj[c] = tj + tjn * c;
+      ok[c] = jj[c] < J;
+      if (!ok[c]) jj[c] = J - 1;
+    }
+    float acc[4][4];
+    for (int i = 0; i < 4; ++i)
+      for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
+    const float* xr = in + (size_t)(4 * tn) * ldin;
+    for (int k = 0; k < K; ++k) {
+      float xv[4], wv[4];
+      for (int i = 0; i < 4; ++i) xv[i] = xr[i * ldin + k];
+      for (int c = 0; c < 4; ++c) wv[c] = W[jj[c] * ldw + k];
+      for (int i = 0; i < 4; ++i)
+        for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(xv[i], wv[c], acc[i][c]);
+    }
+    for (int i = 0; i < 4; ++i)
+      for (int c = 0; c < 4; ++c)
+        if (ok[c]) {
+          const float s = acc[i][c] + bias[jj[c]];
+          out[(size_t)(4 * tn + i) * ldout + jj[c]] = use_tanh ? tanhf(s) : s;
+        }
+  }
+}
+
+// out[n][k] = (sum_j d[n][j] * W[j][k]) * (1 - h[n][k]^2)       back through a tanh layer whose output is h
+PPO_FN void dense_bwd_data(const float* d, int ldd, const float* W, int ldw, const float* h, int ldhh, float* out, int ldout,
+                           int M, int J, int K, int tid, int NT) {
+  const int tkn = (K + 3) / 4, tiles = (M / 4) * tkn;
+  for (int t = tid; t < tiles; t += NT) {
+    const int tn = t / tkn, tk = t - tn * tkn;
+    int kk[4];
+    bool ok[4];
+    for (int c = 0; c < 4; ++c) {
+      kk[c] = tk + tkn * c;
+      ok[c] = kk[c] < K;
+      if (!ok[c]) kk[c] = K - 1;
+    }
+    float acc[4][4];
+    for (int i = 0; i < 4; ++i)
+      for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
+    const float* dr = d + (size_t)(4 * tn) * ldd;
+    for (int j = 0; j < J; ++j) {
+      float dv[4], wv[4];
+      for (int i = 0; i < 4; ++i) dv[i] = dr[i * ldd + j];
+      for (int c = 0; c < 4; ++c) wv[c] = W[j * ldw + kk[c]];
+      for (int i = 0; i < 4; ++i)
+        for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(dv[i], wv[c], acc[i][c]);
+    }
+    for (int i = 0; i < 4; ++i)
+      for (int c = 0; c < 4; ++c)
+        if (ok[c]) {
+          const float hv = h[(size_t)(4 * tn + i) * ldhh + kk[c]];
+          out[(size_t)(4 * tn + i) * ldout + kk[c]] = acc[i][c] * (1.0f - hv * hv);
+        }
+  }
+}
+
+struct AdamCoef {
+  float b1, b2, eps, step_size, bc2s;
+};
+
+// torch.optim.Adam, _single_tensor_adam (no amsgrad / weight decay / maximize): t = step count AFTER the increment
+PPO_FN AdamCoef adam_coef(float lr, float b1, float b2, float eps, int t) {
+  AdamCoef c;
+  const float bc1 = 1.0f - powf(b1, (float)t), bc2 = 1.0f - powf(b2, (float)t);
+  c.b1 = b1; c.b2 = b2; c.eps = eps;
+  c.step_size = lr / bc1;
+  c.bc2s = sqrtf(bc2);
+  return c;
+}
+
+PPO_FN float adam_elem(float p, float g, float* m, float* v, int idx, const AdamCoef& c) {
+  float mi = m[idx];
+  mi = mi + (1.0f - c.b1) * (g - mi);                              // exp_avg.lerp_(grad, 1 - beta1)
+  const float vi = c.b2 * v[idx] + (1.0f - c.b2) * g * g;          // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+  m[idx] = mi;
+  v[idx] = vi;
+  const float denom = sqrtf(vi) / c.bc2s + c.eps;
+  return p - c.step_size * (mi / denom);
+}
+
+// Number of 4 x 4 tiles of a [J][K] weight
+PPO_FN int wgrad_tiles(int J, int K) { return ((J + 3) / 4) * ((K + 3) / 4); }
+
+// tile `t` of: g[j][k] = sum_n d[n][j] * in[n][k], then Adam on element j*K + k of the tensor at arena offset `off`
+// (shared-memory copy W[j*ldw + k], master copy flat[off + j*K + k])
+PPO_FN void wgrad_adam_tile(int t, const float* d, int ldd, const float* in, int ldin, float* W, int ldw, int M, int J, int K,
+                            float* flat, float* m, float* v, int off, const AdamCoef& ac) {
+  const int tjn = (J + 3) / 4, tkn = (K + 3) / 4;
+  const int tj = t / tkn, tk = t - tj * tkn;
+  int jj[4], kk[4];
+  bool okj[4], okk[4];
+  for (int c = 0; c < 4; ++c) {
+    jj[c] = tj + tjn * c; okj[c] = jj[c] < J; if (!okj[c]) jj[c] = J - 1;
+    kk[c] = tk + tkn * c; okk[c] = kk[c] < K; if (!okk[c]) kk[c] = K - 1;
+  }
+  float acc[4][4];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+  for (int n = 0; n < M; ++n) {
+    float dv[4], xv[4];
+    for (int r = 0; r < 4; ++r) dv[r] = d[(size_t)n * ldd + jj[r]];
+    for (int c = 0; c < 4; ++c) xv[c] = in[(size_t)n * ldin + kk[c]];
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(dv[r], xv[c], acc[r][c]);
+  }
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c)
+      if (okj[r] && okk[c]) {
+        const int e = jj[r] * K + kk[c];
+        const float np_ = adam_elem(W[jj[r] * ldw + kk[c]], acc[r][c], m, v, off + e, ac);
+        W[jj[r] * ldw + kk[c]] = np_;
+        flat[off + e] = np_;
+      }
+}
+
+// element j of: g[j] = sum_n d[n][j], then Adam (bias vectors, the std parameter)
+PPO_FN void bias_adam_elem(int j, const float* d, int ldd, float* Bv, int M, float* flat, float* m, float* v, int off,
+                           const AdamCoef& ac) {
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+  int n = 0;
+  for (; n + 3 < M; n += 4) {
+    s0 += d[(size_t)n * ldd + j]; s1 += d[(size_t)(n + 1) * ldd + j];
+    s2 += d[(size_t)(n + 2) * ldd + j]; s3 += d[(size_t)(n + 3) * ldd + j];
+  }
+  for (; n < M; ++n) s0 += d[(size_t)n * ldd + j];
+  const float np_ = adam_elem(Bv[j], (s0 + s1) + (s2 + s3), m, v, off + j, ac);
+  Bv[j] = np_;
+  flat[off + j] = np_;
+}
+
+// all parameter gradients + Adam of one three-layer network, spread over the block as ONE index space:
+//   [W2 tiles | W1 tiles | W3 tiles | b1 | b2 | b3 | extra (std)]
+// d1 / d2 / d3: pre-activation gradients of the three layers; x / h1 / h2: their inputs
+PPO_FN void net_wgrad_adam(const float* x, int ldx, const float* h1, const float* h2, int ldh, const float* d1, const float* d2,
+                           const float* d3, int ld3, int M, int D, int H1, int H2, int O, float* w1, int ld1, float* b1,
+                           float* w2, float* b2, float* w3, float* b3, float* extra, const float* dextra, float* flat,
+                           float* m, float* v, const int* off, const AdamCoef& ac, int tid, int NT) {
+  const int t2 = wgrad_tiles(H2, H1), t1 = wgrad_tiles(H1, D), t3 = wgrad_tiles(O, H2);
+  const int nb = H1 + H2 + O + (extra ? O : 0);
+  const int total = t2 + t1 + t3 + nb;
+  for (int t = tid; t < total; t += NT) {
+    int u = t;
+    if (u < t2) { wgrad_adam_tile(u, d2, ldh, h1, ldh, w2, ldh, M, H2, H1, flat, m, v, off[2], ac); continue; }
+    u -= t2;
+    if (u < t1) { wgrad_adam_tile(u, d1, ldh, x, ldx, w1, ld1, M, H1, D, flat, m, v, off[0], ac); continue; }
+    u -= t1;
+    if (u < t3) { wgrad_adam_tile(u, d3, ld3, h2, ldh, w3, ldh, M, O, H2, flat, m, v, off[4], ac); continue; }
+    u -= t3;
+    if (u < H1) { bias_adam_elem(u, d1, ldh, b1, M, flat, m, v, off[1], ac); continue; }
+    u -= H1;
+    if (u < H2) { bias_adam_elem(u, d2, ldh, b2, M, flat, m, v, off[3], ac); continue; }
+    u -= H2;
+    if (u < O) { bias_adam_elem(u, d3, ld3, b3, M, flat, m, v, off[5], ac); continue; }
+    u -= O;
+    bias_adam_elem(u, dextra, O, extra, M, flat, m, v, off[6], ac);
+  }
+}
+
+PPO_FN float ppo_softplus(float x) { return x > 20.0f ? x : log1pf(expf(x)); }      // F.softplus (beta 1, threshold 20)
+
+// ------------------------------------------------------------------------------------------------ phases
+PPO_FN void copy_rows_in(float* dst, int ld, const float* src, int rows, int cols, int tid, int NT) {
+  for (int e = tid; e < rows * cols; e += NT) {
+    const int j = e / cols, k = e - j * cols;
+    dst[j * ld + k] = src[e];
+  }
+}
+
+PPO_FN void ph_load_weights(PpoShared& S, const PpoArgs& a, int tid, int NT) {
+  copy_rows_in(S.aw1, S.ld1, a.a_flat + a.a_off[0], a.H1, a.D, tid, NT);
+  copy_rows_in(S.ab1, a.H1, a.a_flat + a.a_off[1], 1, a.H1, tid, NT);
+  copy_rows_in(S.aw2, S.ldh, a.a_flat + a.a_off[2], a.H2, a.H1, tid, NT);
+  copy_rows_in(S.ab2, a.H2, a.a_flat + a.a_off[3], 1, a.H2, tid, NT);
+  copy_rows_in(S.aw3, S.ldh, a.a_flat + a.a_off[4], a.A, a.H2, tid, NT);
+  copy_rows_in(S.ab3, a.A, a.a_flat + a.a_off[5], 1, a.A, tid, NT);
+  copy_rows_in(S.sdp, a.A, a.a_flat + a.a_off[6], 1, a.A, tid, NT);
+  copy_rows_in(S.cw1, S.ld1, a.c_flat + a.c_off[0], a.H1, a.D, tid, NT);
+  copy_rows_in(S.cb1, a.H1, a.c_flat + a.c_off[1], 1, a.H1, tid, NT);
+  copy_rows_in(S.cw2, S.ldh, a.c_flat + a.c_off[2], a.H2, a.H1, tid, NT);
+  copy_rows_in(S.cb2, a.H2, a.c_flat + a.c_off[3], 1, a.H2, tid, NT);
+  copy_rows_in(S.cw3, S.ldh, a.c_flat + a.c_off[4], 1, a.H2, tid, NT);
+  copy_rows_in(S.cb3, 1, a.c_flat + a.c_off[5], 1, 1, tid, NT);
+  if (tid == 0) {
+    S.steps[0] = (int)*a.a_step;
+    S.steps[1] = (int)*a.c_step;
+    for (int i = 0; i < 8; ++i) S.flag[i] = 0.0f;
+  }
+}
+
+// minibatch b -> buffer b & 1, by the threads [t0, NT) of the block (the idle half during the dense phases)
+PPO_FN void ph_load_batch(PpoShared& S, const PpoArgs& a, int b, int tid, int NT, int t0) {
+  if (b >= a.n_batches || tid < t0) return;
+  const int s = b & 1, id = tid - t0, n_id = NT - t0;
+  const int64_t* rows = a.perm + (int64_t)b * a.mb;
+  for (int e = id; e < a.mb * a.D; e += n_id) {
+    const int n = e / a.D, k = e - n * a.D;
+    (S.xb + s * S.x_stride)[n * S.ld1 + k] = a.state[rows[n] * a.D + k];
+  }
+  for (int e = id; e < a.mb * a.A; e += n_id) {
+    const int n = e / a.A, k = e - n * a.A;
+    (S.actb + s * S.act_stride)[e] = a.action[rows[n] * a.A + k];
+  }
+  for (int n = id; n < a.mb; n += n_id) {
+    (S.oldlpb + s * S.row_stride)[n] = a.old_logp[rows[n]];
+    (S.advb + s * S.row_stride)[n] = a.adv[rows[n]];
+    (S.retb + s * S.row_stride)[n] = a.ret[rows[n]];
+  }
+}
+
+PPO_FN float sum_strided4(const float* p, int n) {       // fixed order, four independent chains
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+  int i = 0;
+  for (; i + 3 < n; i += 4) { s0 += p[i]; s1 += p[i + 1]; s2 += p[i + 2]; s3 += p[i + 3]; }
+  for (; i < n; ++i) s0 += p[i];
+  return (s0 + s1) + (s2 + s3);
+}
+
+// ---- the two networks side by side: threads [0, NT/2) run the actor, [NT/2, NT) the critic
+// P1: first layers (+ std = softplus(std_param), network_heads.py:205)
+PPO_FN void ph1_fwd1(PpoShared& S, const PpoArgs& a, int b, int tid, int NT) {
+  const int h = NT / 2, s = b & 1;
+  if (tid < h) {
+    dense_fwd((S.xb + s * S.x_stride), S.ld1, S.aw1, S.ld1, S.ab1, S.ah1, S.ldh, a.mb, a.D, a.H1, true, tid, h);
+    for (int j = tid; j < a.A; j += h) {
+      const float sd = ppo_softplus(S.sdp[j]);
+      S.sdv[j] = sd;
+      S.lsd[j] = logf(sd);
+    }
+  } else {
+    dense_fwd((S.xb + s * S.x_stride), S.ld1, S.cw1, S.ld1, S.cb1, S.ch1, S.ldh, a.mb, a.D, a.H1, true, tid - h, h);
+  }
+}
+// P2: second layers
+PPO_FN void ph2_fwd2(PpoShared& S, const PpoArgs& a, int b, int tid, int NT) {
+  const int h = NT / 2;
+  if (tid < h) dense_fwd(S.ah1, S.ldh, S.aw2, S.ldh, S.ab2, S.ah2, S.ldh, a.mb, a.H1, a.H2, true, tid, h);
+  else dense_fwd(S.ch1, S.ldh, S.cw2, S.ldh, S.cb2, S.ch2, S.ldh, a.mb, a.H1, a.H2, true, tid - h, h);
+}
+// P3: heads.  actor: mean = tanh(fc_action(.)); critic: v, value-loss terms, d value_loss / d v (PPO_agent.py:86) and the step
+// count of its (unconditional) update
+PPO_FN void ph3_heads(PpoShared& S, const PpoArgs& a, int b, int tid, int NT) {
+  const int h = NT / 2, s = b & 1;
+  if (tid < h) {
+    dense_fwd(S.ah2, S.ldh, S.aw3, S.ldh, S.ab3, S.mu, a.A, a.mb, a.H2, a.A, true, tid, h);
+    return;
+  }
+  const float invM = 1.0f / (float)a.mb;
+  for (int n = tid - h; n < a.mb; n += h) {
+    float acc = 0.0f;
+    for (int k = 0; k < a.H2; ++k) acc = fmaf(S.ch2[n * S.ldh + k], S.cw3[k], acc);
+    const float v = acc + S.cb3[0];
+    S.v[n] = v;
+    const float e = (S.retb + s * S.row_stride)[n] - v;
+    S.dv[n] = -e * invM;
+    S.red[2 * a.mb + n] = e * e;
+  }
+  if (tid == NT - 1) S.steps[1] += 1;
+}
+// P4: actor: per sample log pi(a|s), ratio, clipped surrogate and its gradient (PPO_agent.py:79-84, 88);
+//     critic: back through its head into layer 2
+PPO_FN void ph4_loss(PpoShared& S, const PpoArgs& a, int b, int tid, int NT) {
+  const int h = NT / 2, s = b & 1, A = a.A;
+  if (tid >= h) {
+    dense_bwd_data(S.dv, 1, S.cw3, S.ldh, S.ch2, S.ldh, S.cd2, S.ldh, a.mb, 1, a.H2, tid - h, h);
+    if (tid == NT - 1) S.flag[4] = 0.5f * (sum_strided4(S.red + 2 * a.mb, a.mb) / (float)a.mb);
+    return;
+  }
+  const float invM = 1.0f / (float)a.mb;
+  for (int n = tid; n < a.mb; n += h) {
+    float lp = 0.0f;
+    for (int j = 0; j < A; ++j) {
+      const float sd = S.sdv[j], t = (S.actb + s * S.act_stride)[n * A + j] - S.mu[n * A + j];
+      lp += -(t * t) / (2.0f * sd * sd) - S.lsd[j] - 0.91893853320467274178f;       // Normal.log_prob
+    }
+    S.logp[n] = lp;
+    const float old = (S.oldlpb + s * S.row_stride)[n], adv = (S.advb + s * S.row_stride)[n];
+    const float ratio = expf(lp - old);
+    const float obj = ratio * adv;
+    const float rc = fminf(fmaxf(ratio, 1.0f - a.clip), 1.0f + a.clip);
+    const float objc = rc * adv;
+    const bool inside = ratio >= 1.0f - a.clip && ratio <= 1.0f + a.clip;
+    float g;                                               // d min(obj, objc) / d log pi (torch.min splits ties evenly)
+    if (obj < objc) g = adv * ratio;
+    else if (obj > objc) g = inside ? adv * ratio : 0.0f;
+    else g = 0.5f * adv * ratio + (inside ? 0.5f * adv * ratio : 0.0f);
+    S.dlogp[n] = -g * invM;
+    S.red[n] = fminf(obj, objc);
+    S.red[a.mb + n] = old - lp;
+  }
+}
+// P5: actor: the reference's `if approx_kl <= 1.5 * target_kl` (PPO_agent.py:94), decided once for the block;
+//     critic: back into layer 1
+PPO_FN void ph5_gate(PpoShared& S, const PpoArgs& a, int b, int tid, int NT) {
+  const int h = NT / 2;
+  if (tid >= h) {
+    dense_bwd_data(S.cd2, S.ldh, S.cw2, S.ldh, S.ch1, S.ldh, S.cd1, S.ldh, a.mb, a.H2, a.H1, tid - h, h);
+    return;
+  }
+  if (tid != 0) return;
+  const float invM = 1.0f / (float)a.mb;
+  const float kl = sum_strided4(S.red + a.mb, a.mb) * invM;
+  float ent = 0.0f;
+  for (int j = 0; j < a.A; ++j) ent += 0.5f + 0.91893853320467274178f + S.lsd[j];    // Normal.entropy, summed over actions
+  const bool gate = kl <= a.gate_max;
+  S.flag[0] = gate ? 1.0f : 0.0f;
+  S.flag[2] = -(sum_strided4(S.red, a.mb) * invM) - a.ent_w * ent;
+  S.flag[3] = kl;
+  if (gate) {
+    S.steps[0] += 1;
+    S.flag[1] += 1.0f;
+  }
+}
+// P6: actor (if the gate is open): gradients at the policy head -- d / d pre-tanh mean, d / d std_param (through softplus);
+//     the critic half fetches the rows of the NEXT minibatch into the other buffer
+PPO_FN void ph6_head_bwd(PpoShared& S, const PpoArgs& a, int b, int tid, int NT) {
+  const int h = NT / 2, s = b & 1, A = a.A;
+  if (tid >= h) {
+    ph_load_batch(S, a, b + 1, tid, NT, h);
+    return;
+  }
+  if (S.flag[0] == 0.0f) return;
+  const float dent = -a.ent_w / (float)a.mb;             // d(-w * mean(entropy)) / d entropy_n
+  for (int e = tid; e < a.mb * A; e += h) {
+    const int n = e / A, j = e - n * A;
+    const float m_ = S.mu[e], sd = S.sdv[j], t = (S.actb + s * S.act_stride)[e] - m_, gl = S.dlogp[n];
+    S.dmu[e] = gl * (t / (sd * sd)) * (1.0f - m_ * m_);
+    const float p = S.sdp[j];
+    const float sig = p > 20.0f ? 1.0f : 1.0f / (1.0f + expf(-p));                  // softplus'
+    S.dsd[e] = (gl * ((t * t) / (sd * sd * sd) - 1.0f / sd) + dent * (1.0f / sd)) * sig;
+  }
+}
+// P7: actor (gate): back into layer 2; critic: all its parameter gradients + Adam (PPO_agent.py:97-99)
+PPO_FN void ph7_critic_update(PpoShared& S, const PpoArgs& a, int b, int tid, int NT) {
+  const int h = NT / 2;
+  if (tid < h) {
+    if (S.flag[0] != 0.0f) dense_bwd_data(S.dmu, a.A, S.aw3, S.ldh, S.ah2, S.ldh, S.ad2, S.ldh, a.mb, a.A, a.H2, tid, h);
+    return;
+  }
+  const AdamCoef ac = adam_coef(a.c_lr, a.c_b1, a.c_b2, a.c_eps, S.steps[1]);
+  net_wgrad_adam((S.xb + (b & 1) * S.x_stride), S.ld1, S.ch1, S.ch2, S.ldh, S.cd1, S.cd2, S.dv, 1, a.mb, a.D, a.H1, a.H2, 1, S.cw1, S.ld1, S.cb1,
+                 S.cw2, S.cb2, S.cw3, S.cb3, nullptr, nullptr, a.c_flat, a.c_m, a.c_v, a.c_off, ac, tid - h, h);
+}
+// P8: actor (gate): back into layer 1
+PPO_FN void ph8_actor_bwd1(PpoShared& S, const PpoArgs& a, int b, int tid, int NT) {
+  if (S.flag[0] == 0.0f) return;
+  dense_bwd_data(S.ad2, S.ldh, S.aw2, S.ldh, S.ah1, S.ldh, S.ad1, S.ldh, a.mb, a.H2, a.H1, tid, NT);
+}
+// P9: actor (gate): all its parameter gradients + Adam (PPO_agent.py:94-96), the whole block
+PPO_FN void ph9_actor_update(PpoShared& S, const PpoArgs& a, int b, int tid, int NT) {
+  if (S.flag[0] == 0.0f) return;
+  const AdamCoef ac = adam_coef(a.a_lr, a.a_b1, a.a_b2, a.a_eps, S.steps[0]);
+  net_wgrad_adam((S.xb + (b & 1) * S.x_stride), S.ld1, S.ah1, S.ah2, S.ldh, S.ad1, S.ad2, S.dmu, a.A, a.mb, a.D, a.H1, a.H2, a.A, S.aw1, S.ld1,
+                 S.ab1, S.aw2, S.ab2, S.aw3, S.ab3, S.sdp, S.dsd, a.a_flat, a.a_m, a.a_v, a.a_off, ac, tid, NT);
+}
+
+PPO_FN void ph_finish(PpoShared& S, const PpoArgs& a, int tid, int NT) {
+  if (tid != 0) return;
+  *a.a_step = (int64_t)S.steps[0];
+  *a.c_step = (int64_t)S.steps[1];
+  a.stats[0] = S.flag[2];
+  a.stats[1] = S.flag[4];
+  a.stats[2] = S.flag[3];
+  a.stats[3] = S.flag[1];
+}
+
+}  // namespace b2rl_ppo

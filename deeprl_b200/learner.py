@@ -580,3 +580,93 @@ class GraphedPPOLearner:
     def run(self, n_batches):
         for _ in range(n_batches):
             self.graph.replay()
+
+
+class PersistentPPOLearner:
+    """The whole minibatch loop of a PPO iteration (PPO_agent.py:68-99, non-shared representation) as ONE launch of one
+    persistent thread block (``b2rl_ppo_minibatch_updates``, csrc/ppo_persistent.cu): weights in shared memory, Adam moments in
+    L2, the rows of the next minibatch fetched during the current update, the KL gate decided on the device.  Same interface as
+    ``GraphedPPOLearner`` (which replays ~45 small kernels per update and remains the path for every network this kernel does
+    not cover)."""
+
+    KEYS = GraphedPPOLearner.KEYS
+    A_NAMES = ("actor_body.layers.0.weight", "actor_body.layers.0.bias", "actor_body.layers.1.weight",
+               "actor_body.layers.1.bias", "fc_action.weight", "fc_action.bias", "std")
+    C_NAMES = ("critic_body.layers.0.weight", "critic_body.layers.0.bias", "critic_body.layers.1.weight",
+               "critic_body.layers.1.bias", "fc_critic.weight", "fc_critic.bias")
+
+    @staticmethod
+    def supported(network, mini_batch_size):
+        """GaussianActorCriticNet with DummyBody phi and two-layer tanh FCBody actor / critic bodies of equal widths."""
+        from .network.network_bodies import DummyBody, FCBody
+        from .network.network_heads import GaussianActorCriticNet
+        if not isinstance(network, GaussianActorCriticNet) or not isinstance(network.phi_body, DummyBody):
+            return False
+        ab, cb = network.actor_body, network.critic_body
+        if not all(isinstance(b, FCBody) and len(b.layers) == 2 and b.gate is torch.tanh and not b.noisy_linear for b in (ab, cb)):
+            return False
+        dims = lambda b: (b.layers[0].in_features, b.layers[0].out_features, b.layers[1].out_features)
+        D, H1, H2 = dims(ab)
+        # (sizes whose weights + double-buffered rows + both networks' activations fit the 227 KB of one SM: the examples use
+        #  D = 17, hidden 64, A = 6, mini batch 64 -> 198 KB)
+        return (dims(cb) == (D, H1, H2) and D <= 64 and H1 <= 64 and H2 <= 64 and network.fc_action.out_features <= 32
+                and 4 <= mini_batch_size <= 64 and mini_batch_size % 4 == 0 and network.fc_action.weight.is_cuda)
+
+    def __init__(self, network, actor_opt, critic_opt, rows, state_dim, action_dim, mini_batch_size, ppo_ratio_clip,
+                 entropy_weight, target_kl, max_batches):
+        self.net, self.actor_opt, self.critic_opt = network, actor_opt, critic_opt
+        self.mb, self.clip, self.ent_w, self.target_kl = int(mini_batch_size), ppo_ratio_clip, entropy_weight, target_kl
+        if actor_opt.kind != "adam" or critic_opt.kind != "adam":
+            raise NotImplementedError("the persistent PPO kernel implements Adam (examples.py:508-509)")
+        dev = actor_opt.flat.device
+        self.dev = dev
+        f = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+        self.buf = dict(state=f(rows, state_dim), action=f(rows, action_dim), log_pi_a=f(rows, 1), ret=f(rows, 1),
+                        advantage=f(rows, 1))
+        self.perm = torch.zeros((max_batches, self.mb), dtype=torch.int64, device=dev)
+        self.stats = torch.zeros(4, dtype=torch.float32, device=dev)
+        named = dict(network.named_parameters())
+        self.a_off = self._offsets(actor_opt, [named[n] for n in self.A_NAMES])
+        self.c_off = self._offsets(critic_opt, [named[n] for n in self.C_NAMES])
+        ab = network.actor_body
+        self.D, self.H1, self.H2 = ab.layers[0].in_features, ab.layers[0].out_features, ab.layers[1].out_features
+        self.A = network.fc_action.out_features
+        self.launches_per_update = 0.0
+        self.n = 0
+
+    @staticmethod
+    def _offsets(opt, params):
+        """Element offsets of ``params`` inside the optimizer's arena (host int32 array for the kernel's argument block)."""
+        base = opt.flat.data_ptr()
+        offs = []
+        for p in params:
+            off = (p.data_ptr() - base) // 4
+            if not (0 <= off and off + p.numel() <= opt.n) or getattr(p, "_b2rl_flat_owner", None) != id(opt):
+                raise _lib.B2RLError("PersistentPPOLearner: a parameter does not live in the optimizer's arena")
+            offs.append(off)
+        return torch.tensor(offs, dtype=torch.int32)
+
+    def load(self, entries):
+        for k in self.KEYS:
+            self.buf[k].copy_(getattr(entries, k).reshape(self.buf[k].shape))
+
+    def set_batches(self, index_rows):
+        rows = np.stack([np.asarray(r, dtype=np.int64) for r in index_rows])
+        assert rows.shape[1] == self.mb and rows.shape[0] <= self.perm.shape[0]
+        self.perm[:rows.shape[0]].copy_(torch.from_numpy(rows), non_blocking=False)
+        return rows.shape[0]
+
+    def capture(self, warmup=0):
+        return self
+
+    def run(self, n_batches):
+        a, c, b = self.actor_opt, self.critic_opt, self.buf
+        _lib.call("b2rl_ppo_minibatch_updates", _lib.ptr(b["state"]), _lib.ptr(b["action"]), _lib.ptr(b["log_pi_a"]),
+                  _lib.ptr(b["ret"]), _lib.ptr(b["advantage"]), self.D, self.A, self.H1, self.H2, self.mb, _lib.ptr(self.perm),
+                  int(n_batches), _lib.ptr(a.flat), _lib.ptr(a.s1), _lib.ptr(a.s2), _lib.ptr(a.step_dev), _lib.ptr(self.a_off),
+                  _lib.ptr(c.flat), _lib.ptr(c.s1), _lib.ptr(c.s2), _lib.ptr(c.step_dev), _lib.ptr(self.c_off),
+                  float(a.lr), float(a.betas[0]), float(a.betas[1]), float(a.eps), float(c.lr), float(c.betas[0]),
+                  float(c.betas[1]), float(c.eps), float(self.clip), float(self.ent_w), float(1.5 * self.target_kl),
+                  _lib.ptr(self.stats), _lib.stream())
+        self.n = int(n_batches)         # (the one launch is counted by _lib.call itself; launches_per_update stays 0)
+

@@ -381,6 +381,25 @@ int b2rl_gaussian_actor_step(const float* obs, double* rm_mean, double* rm_var, 
                              float* state_out, float* action, float* log_pi_a, float* entropy, float* mean, float* v,
                              void* stream);
 
+/* Every minibatch update of one PPO iteration (PPO_agent.py:68-99, non-shared representation; optimization_epochs x
+ * rows / mini_batch_size updates) in ONE launch of one persistent thread block: per minibatch b the rows perm[b][0..mb) of the
+ * rollout (state [R][D], action [R][A], old_log_pi_a / ret / advantage [R], advantage already normalised, PPO_agent.py:66) go
+ * through GaussianActorCriticNet (network_heads.py:198-214: DummyBody phi, two-layer tanh FCBody actor / critic bodies,
+ * mean = tanh(fc_action), std = softplus(std)), the clipped-surrogate / entropy / value losses (PPO_agent.py:79-88), the
+ * backward pass, the actor Adam step iff approx_kl <= kl_gate (= 1.5 * target_kl, PPO_agent.py:94) and the critic Adam step
+ * (torch.optim.Adam arithmetic).  a_* / c_*: flat arenas holding the actor's / critic's parameters, exp_avg, exp_avg_sq
+ * (float32) and step count (int64 [1], device); a_off int32 [7] = element offsets of actor_body.layers.0.weight, .bias,
+ * layers.1.weight, .bias, fc_action.weight, fc_action.bias, std inside the actor arenas (host array); c_off int32 [6] likewise
+ * for critic_body.* and fc_critic.*.  stats float32 [4] = policy loss, value loss, approx_kl of the LAST minibatch and the
+ * number of actor steps taken.  Limits: D <= 256, A <= 32, hidden <= 128, mini batch <= 128 and a multiple of 4. */
+int b2rl_ppo_minibatch_updates(const float* state, const float* action, const float* old_log_pi_a, const float* ret,
+                               const float* advantage, int32_t D, int32_t A, int32_t H1, int32_t H2, int32_t mb,
+                               const int64_t* perm, int32_t n_batches, float* a_flat, float* a_exp_avg, float* a_exp_avg_sq,
+                               int64_t* a_step, const int32_t* a_off, float* c_flat, float* c_exp_avg, float* c_exp_avg_sq,
+                               int64_t* c_step, const int32_t* c_off, float a_lr, float a_beta1, float a_beta2, float a_eps,
+                               float c_lr, float c_beta1, float c_beta2, float c_eps, float ratio_clip, float entropy_weight,
+                               float kl_gate, float* stats, void* stream);
+
 /* Element-wise halves of the distributional heads (CategoricalNet / QuantileNet, network_heads.py:40-55, 89-102) around the
  * tcgen05 GEMMs: softmax + log_softmax over the N atoms of every (b, a) row (either output may be NULL), and the backward
  * preparation dlogits = dout - prob * sum_n dout (prob == NULL: dlogits = dout, QR-DQN) written as the bf16 GEMM operand

@@ -158,8 +158,10 @@ def test_dual_forward_matches_separate_forwards(env):
         assert float((g - r).abs().max()) <= 3e-2 * scale
 
 
-def test_graphed_ppo_minibatches_match_the_eager_loop(env):
-    """GraphedPPOLearner (one graph replay per minibatch, KL gate decided on the device by b2rl_clip_adam_gated) against
+@pytest.mark.parametrize("persistent", [False, True])
+def test_graphed_ppo_minibatches_match_the_eager_loop(env, persistent):
+    """GraphedPPOLearner (one graph replay per minibatch, KL gate decided on the device by b2rl_clip_adam_gated) and
+    PersistentPPOLearner (the whole loop in one persistent kernel, csrc/ppo_persistent.cu) against
     PPOAgent._minibatch (the eager loop with the host-side `if approx_kl <= 1.5 * target_kl`, PPO_agent.py:94) on the same
     rollout rows and the same permutations.  fp32 throughout: parameters agree to 1e-5 after 16 updates, and both took
     the same number of (gated) actor steps."""
@@ -185,6 +187,7 @@ def test_graphed_ppo_minibatches_match_the_eager_loop(env):
             c.rollout_length, c.optimization_epochs, c.mini_batch_size, c.ppo_ratio_clip = 8, 4, 64, 0.2
             c.target_kl = 2e-4                                             # small: some actor steps are skipped
             c.graph_minibatch = graph
+            c.persistent_minibatch = persistent
             return rl.PPOAgent(c)
 
         a, b = agent(False), agent(True)
@@ -205,6 +208,7 @@ def test_graphed_ppo_minibatches_match_the_eager_loop(env):
         np.random.seed(3)
         b._graphed_epochs(entries)
         torch.cuda.synchronize()
+        assert type(b._graph).__name__ == ("PersistentPPOLearner" if persistent else "GraphedPPOLearner")
         for (n, pa), pb in zip(a.network.named_parameters(), b.network.parameters()):
             np.testing.assert_allclose(pb.detach().cpu().numpy(), pa.detach().cpu().numpy(), rtol=1e-4, atol=1e-5, err_msg=n)
         steps_a = int(next(iter(a.actor_opt.state.values()))["step"])
