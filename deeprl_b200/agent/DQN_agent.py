@@ -236,14 +236,21 @@ class DQNAgent(BaseAgent):
     def step(self):
         config = self.config
         transitions = self.actor.step()
+        feeds = []
         for states, actions, rewards, next_states, dones, info in transitions:
             self.record_online_return(info)
             self.total_steps += 1
-            self.replay.feed(dict(
+            feeds.append(dict(
                 state=np.array([s[-1] if isinstance(s, LazyFrames) else s for s in states]),
                 action=actions,
                 reward=[config.reward_normalizer(r) for r in rewards],
                 mask=1 - np.asarray(dones, dtype=np.int32)))
+        feed_many = getattr(self.replay, "feed_many", None)
+        if feed_many is not None:                          # one staging upload for the env steps of this agent step;
+            feed_many(feeds)                               # ring / tree state as after feed(d) for d in feeds (replay.py:75-90)
+        else:
+            for d in feeds:
+                self.replay.feed(d)
 
         if self.total_steps > config.exploration_steps and self._graph_ok():
             self._graph_update()                           # config.cuda_graph: the whole update is one graph replay

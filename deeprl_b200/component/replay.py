@@ -106,18 +106,65 @@ class UniformReplay:
         self._torch_dtype = torch.from_numpy(np.zeros(1, self.item_dtype)).dtype
 
     def _staging(self, n):
+        """Pinned host + device staging for ``n`` items: the frame rows, and ONE block holding reward (float64) | action (int32)
+        | mask (int32) column after column, so that a feed is two host->device copies."""
         if self._stage is None or self._stage["n"] < n:
             cap = max(n, 16)
-            pin = dict(pin_memory=True)
+            hs = torch.empty(16 * cap, dtype=torch.uint8, pin_memory=True)
+            ds = torch.empty(16 * cap, dtype=torch.uint8, device=self.device)
+            cols = lambda t: (t[:8 * cap].view(torch.float64), t[8 * cap:12 * cap].view(torch.int32), t[12 * cap:].view(torch.int32))
+            hr, ha, hm = cols(hs)
+            dr, da, dm = cols(ds)
             self._stage = dict(
-                n=cap,
-                hf=torch.empty((cap, self.row_bytes), dtype=torch.uint8, **pin), ha=torch.empty(cap, dtype=torch.int32, **pin),
-                hr=torch.empty(cap, dtype=torch.float64, **pin), hm=torch.empty(cap, dtype=torch.int32, **pin),
-                df=torch.empty((cap, self.row_bytes), dtype=torch.uint8, device=self.device),
-                da=torch.empty(cap, dtype=torch.int32, device=self.device),
-                dr=torch.empty(cap, dtype=torch.float64, device=self.device),
-                dm=torch.empty(cap, dtype=torch.int32, device=self.device))
+                n=cap, hs=hs, ds=ds, hr=hr, ha=ha, hm=hm, dr=dr, da=da, dm=dm,
+                hf=torch.empty((cap, self.row_bytes), dtype=torch.uint8, pin_memory=True),
+                df=torch.empty((cap, self.row_bytes), dtype=torch.uint8, device=self.device))
         return self._stage
+
+    def _stage_rows(self, st, o, data):
+        """Write one feed() call's items into the pinned staging rows [o, o + n)."""
+        n = len(data["state"])
+        arr = np.ascontiguousarray(np.asarray(data["state"], dtype=self.item_dtype)).reshape(n, self.row_bytes // self.item_dtype.itemsize)
+        st["hf"][o:o + n].numpy()[...] = arr.view(np.uint8).reshape(n, self.row_bytes)
+        st["ha"][o:o + n].numpy()[...] = np.asarray(data["action"]).astype(np.int32).reshape(n)
+        st["hr"][o:o + n].numpy()[...] = np.asarray(data["reward"], dtype=np.float64).reshape(n)
+        st["hm"][o:o + n].numpy()[...] = np.asarray(data["mask"]).astype(np.int32).reshape(n)
+        return n
+
+    def _upload(self, st, total):
+        st["df"][:total].copy_(st["hf"][:total], non_blocking=True)
+        st["ds"].copy_(st["hs"], non_blocking=True)
+
+    def _feed_staged(self, st, o, n):
+        self.feed_device(st["df"][o:o + n], st["da"][o:o + n], st["dr"][o:o + n], st["dm"][o:o + n], n)
+
+    def feed_many(self, items):
+        """Several ``feed()`` calls -- the sgd_update_frequency env steps of one agent step, DQN_agent.py:104-112 -- with ONE
+        staging upload and one stream synchronise.  Ring (and, for PrioritizedReplay, tree) semantics are exactly those of
+        calling ``feed(d)`` for every ``d`` of ``items`` in order: one ring-write launch per original call (the reference's
+        multi-item quirk, replay.py:87, depends on the call boundaries)."""
+        for d in items:
+            for k in d:
+                if k not in self.keys:
+                    raise RuntimeError("Undefined key")
+        items = [d for d in items if len(d["state"])]
+        total = sum(len(d["state"]) for d in items)
+        if len(items) <= 1 or total > 1024:
+            for d in items:
+                self.feed(d)
+            return
+        if self.frames is None:
+            self._allocate(items[0]["state"][0])
+        st = self._staging(total)
+        o, spans = 0, []
+        for d in items:
+            n = self._stage_rows(st, o, d)
+            spans.append((o, n))
+            o += n
+        self._upload(st, total)
+        for o, n in spans:
+            self._feed_staged(st, o, n)
+        torch.cuda.current_stream().synchronize()       # the pinned staging buffers are reused by the next call
 
     def feed(self, data):
         """replay.py:75-90.  ``data``: dict of equal-length sequences for state / action / reward / mask."""
@@ -135,13 +182,8 @@ class UniformReplay:
         if self.frames is None:
             self._allocate(states[0])
         st = self._staging(n)
-        arr = np.ascontiguousarray(np.asarray(states, dtype=self.item_dtype)).reshape(n, self.row_bytes // self.item_dtype.itemsize)
-        st["hf"][:n].numpy()[...] = arr.view(np.uint8).reshape(n, self.row_bytes)
-        st["ha"][:n].numpy()[...] = np.asarray(data["action"]).astype(np.int32).reshape(n)
-        st["hr"][:n].numpy()[...] = np.asarray(data["reward"], dtype=np.float64).reshape(n)
-        st["hm"][:n].numpy()[...] = np.asarray(data["mask"]).astype(np.int32).reshape(n)
-        for h, d in (("hf", "df"), ("ha", "da"), ("hr", "dr"), ("hm", "dm")):
-            st[d][:n].copy_(st[h][:n], non_blocking=True)
+        self._stage_rows(st, 0, data)
+        self._upload(st, n)
         self.feed_device(st["df"], st["da"], st["dr"], st["dm"], n)
         torch.cuda.current_stream().synchronize()       # the pinned staging buffers are reused by the next call
 
@@ -385,6 +427,9 @@ class PrioritizedReplay(UniformReplay):
         if add_leaf:
             self.tree.add_n(1, self.max_priority_dev)
 
+    def _feed_staged(self, st, o, n):
+        self.feed_device(st["df"][o:o + n], st["da"][o:o + n], st["dr"][o:o + n], st["dm"][o:o + n], n, add_leaf=True)
+
     def load_synthetic(self, frames, action, reward, mask, pos, priorities=None):
         super().load_synthetic(frames, action, reward, mask, pos)
         cap = self.memory_size
@@ -476,6 +521,7 @@ class ReplayWrapper:
         if not self.async_:
             self.sample = self.replay.sample
             self.feed = self.replay.feed
+            self.feed_many = self.replay.feed_many
             self.update_priorities = self.replay.update_priorities
         else:
             self._side = torch.cuda.Stream(device=self.replay.device)
@@ -500,6 +546,10 @@ class ReplayWrapper:
 
     def feed(self, exp):
         self._on_side(self.replay.feed, exp)
+
+    def feed_many(self, exps):
+        """The feeds of one agent step with one staging upload (``UniformReplay.feed_many``)."""
+        self._on_side(self.replay.feed_many, exps)
 
     def sample(self):
         self._side.wait_stream(torch.cuda.current_stream())

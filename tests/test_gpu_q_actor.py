@@ -116,3 +116,28 @@ def test_agent_step_uses_the_graphed_actor(rl, agent_kind):
     q_ref = oracle_q(ag.network, kind, stacks, np.linspace(-10, 10, 51)).numpy()
     np.testing.assert_allclose(q, q_ref, rtol=0, atol=3e-2 * max(1.0, float(np.abs(q_ref).max())))
     ag.close()
+
+
+@pytest.mark.parametrize("replay_cls", ["UniformReplay", "PrioritizedReplay"])
+def test_feed_many_equals_sequential_feeds(rl, replay_cls):
+    """``feed_many`` (one staging upload per agent step) leaves ring, cursors and sum tree exactly as ``feed`` per env step
+    (replay.py:75-90, 160-162) -- including the wrap-around of a full ring and multi-item calls (the reference's quirk)."""
+    rng = np.random.default_rng(1)
+    cls = getattr(rl, replay_cls)
+    a = cls(memory_size=37, batch_size=8, n_step=1, discount=0.99, history_length=4)
+    b = cls(memory_size=37, batch_size=8, n_step=1, discount=0.99, history_length=4)
+    for step in range(30):
+        group = []
+        for _ in range(int(rng.integers(1, 6))):
+            n = int(rng.integers(1, 4))
+            group.append(dict(state=rng.integers(0, 256, (n, 84, 84), dtype=np.uint8), action=rng.integers(0, 4, n),
+                              reward=rng.normal(size=n), mask=rng.integers(0, 2, n)))
+        for d in group:
+            a.feed(d)
+        b.feed_many(group)
+        assert (a.pos, a._size) == (b.pos, b._size)
+    torch.cuda.synchronize()
+    for name in ("frames", "action", "reward", "mask", "ring_state"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    if replay_cls == "PrioritizedReplay":
+        assert torch.equal(a.tree.tree, b.tree.tree) and a.tree.n_entries == b.tree.n_entries
