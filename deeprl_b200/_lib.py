@@ -129,6 +129,8 @@ def lib():
         L.b2rl_version.restype = ctypes.c_int
         L.b2rl_last_error.restype = ctypes.c_char_p
         L.b2rl_launch_count.restype = ctypes.c_int64
+        L.b2rl_ppo_minibatch_smem_bytes.restype = ctypes.c_int64
+        L.b2rl_ppo_minibatch_smem_bytes.argtypes = [ctypes.c_int32] * 5
         L.b2rl_reset_launch_count.restype = None
         for name, args in SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError here = header / library mismatch: fail loudly

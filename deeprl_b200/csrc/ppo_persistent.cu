@@ -32,6 +32,12 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_minibatch_persistent_kernel(con
 
 using namespace b2rl;
 
+// dynamic shared memory the persistent kernel needs for these sizes (the caller checks it against the 227 KB of one SM)
+extern "C" int64_t b2rl_ppo_minibatch_smem_bytes(int32_t D, int32_t A, int32_t H1, int32_t H2, int32_t mb) {
+  b2rl_ppo::PpoShared probe;
+  return (int64_t)(b2rl_ppo::ppo_carve(probe, reinterpret_cast<float*>(uintptr_t(4096)), D, A, H1, H2, mb) * sizeof(float));
+}
+
 extern "C" int b2rl_ppo_minibatch_updates(const float* state, const float* action, const float* old_log_pi_a, const float* ret,
                                           const float* advantage, int32_t D, int32_t A, int32_t H1, int32_t H2, int32_t mb,
                                           const int64_t* perm, int32_t n_batches,
@@ -55,8 +61,7 @@ extern "C" int b2rl_ppo_minibatch_updates(const float* state, const float* actio
   a.a_lr = a_lr; a.a_b1 = a_beta1; a.a_b2 = a_beta2; a.a_eps = a_eps;
   a.c_lr = c_lr; a.c_b1 = c_beta1; a.c_b2 = c_beta2; a.c_eps = c_eps;
   a.clip = ratio_clip; a.ent_w = entropy_weight; a.gate_max = kl_gate; a.stats = stats;
-  b2rl_ppo::PpoShared probe;
-  const size_t smem = b2rl_ppo::ppo_carve(probe, reinterpret_cast<float*>(uintptr_t(4096)), D, A, H1, H2, mb) * sizeof(float);
+  const size_t smem = (size_t)b2rl_ppo_minibatch_smem_bytes(D, A, H1, H2, mb);
   B2RL_REQUIRE(smem <= 227 * 1024, "networks / minibatch too large for the shared memory of one SM");
   static size_t attr = 0;
   if (smem > attr) {

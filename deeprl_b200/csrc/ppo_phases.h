@@ -50,24 +50,30 @@ struct PpoShared {
   float *sdv, *lsd;                                    // [A] softplus(std), log of it
   float *flag;                                         // [8]: 0 gate, 1 actor steps taken, 2 policy loss, 3 kl, 4 value loss
   int* steps;                                          // [2] Adam step counts: actor, critic
-  int ld1, ldh;                                        // odd row strides (bank-conflict-free column walks)
+  int ld1, ldh, lda;                                   // row strides: multiples of 4 floats (16-byte rows for 128-bit loads); ld1 / ldh with an
+                                                       // odd number of 16-byte pieces, so that a walk down a column is bank-conflict-free
 };
 
-PPO_HD int ppo_odd(int n) { return n | 1; }
+PPO_HD int ppo_ld(int n) {                 // smallest multiple of 4 >= n whose quarter is odd (17 -> 20, 64 -> 68)
+  int q = (n + 3) / 4;
+  if ((q & 1) == 0) ++q;
+  return 4 * q;
+}
 
 // carve the shared block (base may be a dummy when only the size is wanted); returns the number of floats used
 PPO_HD size_t ppo_carve(PpoShared& S, float* base, int D, int A, int H1, int H2, int mb) {
   const int Hm = H1 > H2 ? H1 : H2;
-  S.ld1 = ppo_odd(D);
-  S.ldh = ppo_odd(Hm);
+  S.ld1 = ppo_ld(D);
+  S.ldh = ppo_ld(Hm);
+  S.lda = (A + 3) / 4 * 4;
   size_t off = 0;
 #define PPO_TAKE(n) (base + (off += ((size_t)(n) + 3) / 4 * 4) - ((size_t)(n) + 3) / 4 * 4)
-  const size_t w1 = (size_t)H1 * S.ld1, w2 = (size_t)H2 * S.ldh, act = (size_t)mb * S.ldh, ma = (size_t)mb * A;
+  const size_t w1 = (size_t)H1 * S.ld1, w2 = (size_t)H2 * S.ldh, act = (size_t)mb * S.ldh, ma = (size_t)mb * S.lda;
   S.aw1 = PPO_TAKE(w1); S.ab1 = PPO_TAKE(H1); S.aw2 = PPO_TAKE(w2); S.ab2 = PPO_TAKE(H2);
   S.aw3 = PPO_TAKE((size_t)A * S.ldh); S.ab3 = PPO_TAKE(A); S.sdp = PPO_TAKE(A);
   S.cw1 = PPO_TAKE(w1); S.cb1 = PPO_TAKE(H1); S.cw2 = PPO_TAKE(w2); S.cb2 = PPO_TAKE(H2);
   S.cw3 = PPO_TAKE(S.ldh); S.cb3 = PPO_TAKE(1);
-  S.x_stride = (int)(((size_t)mb * S.ld1 + 3) / 4 * 4); S.act_stride = (int)((ma + 3) / 4 * 4); S.row_stride = (mb + 3) / 4 * 4;
+  S.x_stride = (int)(((size_t)mb * S.ld1 + 3) / 4 * 4); S.act_stride = (int)(((size_t)mb * A + 3) / 4 * 4); S.row_stride = (mb + 3) / 4 * 4;
   S.xb = PPO_TAKE(2 * (size_t)S.x_stride); S.actb = PPO_TAKE(2 * (size_t)S.act_stride);
   S.oldlpb = PPO_TAKE(2 * (size_t)S.row_stride); S.advb = PPO_TAKE(2 * (size_t)S.row_stride); S.retb = PPO_TAKE(2 * (size_t)S.row_stride);
   S.ah1 = PPO_TAKE(act); S.ah2 = PPO_TAKE(act); S.ad1 = PPO_TAKE(act); S.ad2 = PPO_TAKE(act);
@@ -82,13 +88,22 @@ PPO_HD size_t ppo_carve(PpoShared& S, float* base, int D, int A, int H1, int H2,
 }
 
 // ------------------------------------------------------------------------------------------------ dense building blocks
-// Tiles are 4 rows x 4 INTERLEAVED columns (column c of tile t is t + tiles * c): consecutive threads walk consecutive
-// columns, so with odd row strides every shared-memory access of a warp is conflict-free or a broadcast.
+// Every operand row starts on a 16-byte boundary and the reduction index runs along rows, so the inner loops read 4 floats
+// per shared-memory load (LDS.128); a remainder of the reduction length (17 inputs, 6 actions) takes a scalar tail.  Tiles are
+// 4 x 4 outputs per thread: 8 vector loads feed 64 FMAs (shared-memory bandwidth, not the FMA pipe, bounded the scalar form).
+struct alignas(16) ppo_f4 { float x, y, z, w; };
+PPO_FN ppo_f4 ppo_ld4(const float* p) { return *reinterpret_cast<const ppo_f4*>(p); }
+PPO_FN void ppo_st4(float* p, const ppo_f4& v) { *reinterpret_cast<ppo_f4*>(p) = v; }
+PPO_FN float ppo_dot4(const ppo_f4& a, const ppo_f4& b, float acc) {
+  acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); return fmaf(a.w, b.w, acc);
+}
 
 // out[n][j] = f(sum_k in[n][k] * W[j][k] + bias[j])       n < M (M % 4 == 0), j < J, k < K
+// tile = rows 4tn..4tn+3 x INTERLEAVED columns tj + tiles_j * c: consecutive threads read consecutive rows of W, which with
+// an odd number of 16-byte pieces per row is conflict-free
 PPO_FN void dense_fwd(const float* in, int ldin, const float* W, int ldw, const float* bias, float* out, int ldout, int M,
                       int K, int J, bool use_tanh, int tid, int NT) {
-  const int tjn = (J + 3) / 4, tiles = (M / 4) * tjn;
+  const int tjn = (J + 3) / 4, tiles = (M / 4) * tjn, K4 = K & ~3;
   for (int t = tid; t < tiles; t += NT) {
     const int tn = t / tjn, tj = t - tn * tjn;
     int jj[4];
@@ -102,7 +117,14 @@ PPO_FN void dense_fwd(const float* in, int ldin, const float* W, int ldw, const 
     for (int i = 0; i < 4; ++i)
       for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
     const float* xr = in + (size_t)(4 * tn) * ldin;
-    for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < K4; k += 4) {
+      ppo_f4 xv[4], wv[4];
+      for (int i = 0; i < 4; ++i) xv[i] = ppo_ld4(xr + i * ldin + k);
+      for (int c = 0; c < 4; ++c) wv[c] = ppo_ld4(W + jj[c] * ldw + k);
+      for (int i = 0; i < 4; ++i)
+        for (int c = 0; c < 4; ++c) acc[i][c] = ppo_dot4(xv[i], wv[c], acc[i][c]);
+    }
+    for (int k = K4; k < K; ++k) {
       float xv[4], wv[4];
       for (int i = 0; i < 4; ++i) xv[i] = xr[i * ldin + k];
       for (int c = 0; c < 4; ++c) wv[c] = W[jj[c] * ldw + k];
@@ -119,35 +141,52 @@ PPO_FN void dense_fwd(const float* in, int ldin, const float* W, int ldw, const 
 }
 
 // out[n][k] = (sum_j d[n][j] * W[j][k]) * (1 - h[n][k]^2)       back through a tanh layer whose output is h
+// tile = rows 4tn..4tn+3 x CONSECUTIVE columns 4tk..4tk+3 (one 128-bit load per row of W); d rows 16-byte aligned unless ldd = 1
 PPO_FN void dense_bwd_data(const float* d, int ldd, const float* W, int ldw, const float* h, int ldhh, float* out, int ldout,
                            int M, int J, int K, int tid, int NT) {
-  const int tkn = (K + 3) / 4, tiles = (M / 4) * tkn;
+  const int tkn = (K + 3) / 4, tiles = (M / 4) * tkn, J4 = (ldd & 3) ? 0 : (J & ~3);
   for (int t = tid; t < tiles; t += NT) {
     const int tn = t / tkn, tk = t - tn * tkn;
-    int kk[4];
-    bool ok[4];
-    for (int c = 0; c < 4; ++c) {
-      kk[c] = tk + tkn * c;
-      ok[c] = kk[c] < K;
-      if (!ok[c]) kk[c] = K - 1;
-    }
     float acc[4][4];
     for (int i = 0; i < 4; ++i)
       for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
     const float* dr = d + (size_t)(4 * tn) * ldd;
-    for (int j = 0; j < J; ++j) {
-      float dv[4], wv[4];
-      for (int i = 0; i < 4; ++i) dv[i] = dr[i * ldd + j];
-      for (int c = 0; c < 4; ++c) wv[c] = W[j * ldw + kk[c]];
-      for (int i = 0; i < 4; ++i)
-        for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(dv[i], wv[c], acc[i][c]);
-    }
-    for (int i = 0; i < 4; ++i)
-      for (int c = 0; c < 4; ++c)
-        if (ok[c]) {
-          const float hv = h[(size_t)(4 * tn + i) * ldhh + kk[c]];
-          out[(size_t)(4 * tn + i) * ldout + kk[c]] = acc[i][c] * (1.0f - hv * hv);
+    const float* wc = W + 4 * tk;
+    for (int j = 0; j < J4; j += 4) {
+      ppo_f4 dv[4], wv[4];
+      for (int i = 0; i < 4; ++i) dv[i] = ppo_ld4(dr + i * ldd + j);
+      for (int q = 0; q < 4; ++q) wv[q] = ppo_ld4(wc + (j + q) * ldw);
+      for (int i = 0; i < 4; ++i) {
+        const float dq[4] = {dv[i].x, dv[i].y, dv[i].z, dv[i].w};
+        for (int q = 0; q < 4; ++q) {
+          acc[i][0] = fmaf(dq[q], wv[q].x, acc[i][0]); acc[i][1] = fmaf(dq[q], wv[q].y, acc[i][1]);
+          acc[i][2] = fmaf(dq[q], wv[q].z, acc[i][2]); acc[i][3] = fmaf(dq[q], wv[q].w, acc[i][3]);
         }
+      }
+    }
+    for (int j = J4; j < J; ++j) {
+      const ppo_f4 wv = ppo_ld4(wc + j * ldw);
+      for (int i = 0; i < 4; ++i) {
+        const float dq = dr[i * ldd + j];
+        acc[i][0] = fmaf(dq, wv.x, acc[i][0]); acc[i][1] = fmaf(dq, wv.y, acc[i][1]);
+        acc[i][2] = fmaf(dq, wv.z, acc[i][2]); acc[i][3] = fmaf(dq, wv.w, acc[i][3]);
+      }
+    }
+    for (int i = 0; i < 4; ++i) {
+      const size_t row = (size_t)(4 * tn + i);
+      const ppo_f4 hv = ppo_ld4(h + row * ldhh + 4 * tk);
+      ppo_f4 o;
+      o.x = acc[i][0] * (1.0f - hv.x * hv.x); o.y = acc[i][1] * (1.0f - hv.y * hv.y);
+      o.z = acc[i][2] * (1.0f - hv.z * hv.z); o.w = acc[i][3] * (1.0f - hv.w * hv.w);
+      float* op = out + row * ldout + 4 * tk;
+      if (4 * tk + 3 < K) {
+        ppo_st4(op, o);
+      } else {                                             // ragged last tile: only the valid columns
+        const float ov[4] = {o.x, o.y, o.z, o.w};
+        for (int c = 0; c < 4; ++c)
+          if (4 * tk + c < K) op[c] = ov[c];
+      }
+    }
   }
 }
 
@@ -179,35 +218,58 @@ PPO_FN float adam_elem(float p, float g, float* m, float* v, int idx, const Adam
 PPO_FN int wgrad_tiles(int J, int K) { return ((J + 3) / 4) * ((K + 3) / 4); }
 
 // tile `t` of: g[j][k] = sum_n d[n][j] * in[n][k], then Adam on element j*K + k of the tensor at arena offset `off`
-// (shared-memory copy W[j*ldw + k], master copy flat[off + j*K + k])
+// (shared-memory copy W[j*ldw + k], master copy flat[off + j*K + k]).  tile = rows 4tj..4tj+3 x columns 4tk..4tk+3 of the
+// weight: one 128-bit load of d and one of `in` per sample (rows 16-byte aligned; ldd = 1, the value head, takes scalars)
 PPO_FN void wgrad_adam_tile(int t, const float* d, int ldd, const float* in, int ldin, float* W, int ldw, int M, int J, int K,
                             float* flat, float* m, float* v, int off, const AdamCoef& ac) {
-  const int tjn = (J + 3) / 4, tkn = (K + 3) / 4;
+  const int tkn = (K + 3) / 4;
   const int tj = t / tkn, tk = t - tj * tkn;
-  int jj[4], kk[4];
-  bool okj[4], okk[4];
-  for (int c = 0; c < 4; ++c) {
-    jj[c] = tj + tjn * c; okj[c] = jj[c] < J; if (!okj[c]) jj[c] = J - 1;
-    kk[c] = tk + tkn * c; okk[c] = kk[c] < K; if (!okk[c]) kk[c] = K - 1;
-  }
   float acc[4][4];
   for (int r = 0; r < 4; ++r)
     for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
-  for (int n = 0; n < M; ++n) {
-    float dv[4], xv[4];
-    for (int r = 0; r < 4; ++r) dv[r] = d[(size_t)n * ldd + jj[r]];
-    for (int c = 0; c < 4; ++c) xv[c] = in[(size_t)n * ldin + kk[c]];
-    for (int r = 0; r < 4; ++r)
-      for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(dv[r], xv[c], acc[r][c]);
-  }
-  for (int r = 0; r < 4; ++r)
-    for (int c = 0; c < 4; ++c)
-      if (okj[r] && okk[c]) {
-        const int e = jj[r] * K + kk[c];
-        const float np_ = adam_elem(W[jj[r] * ldw + kk[c]], acc[r][c], m, v, off + e, ac);
-        W[jj[r] * ldw + kk[c]] = np_;
-        flat[off + e] = np_;
+  if ((ldd & 3) == 0) {
+    for (int n = 0; n < M; ++n) {
+      const ppo_f4 dv = ppo_ld4(d + (size_t)n * ldd + 4 * tj), xv = ppo_ld4(in + (size_t)n * ldin + 4 * tk);
+      const float dq[4] = {dv.x, dv.y, dv.z, dv.w};
+      for (int r = 0; r < 4; ++r) {
+        acc[r][0] = fmaf(dq[r], xv.x, acc[r][0]); acc[r][1] = fmaf(dq[r], xv.y, acc[r][1]);
+        acc[r][2] = fmaf(dq[r], xv.z, acc[r][2]); acc[r][3] = fmaf(dq[r], xv.w, acc[r][3]);
       }
+    }
+  } else {
+    for (int n = 0; n < M; ++n) {
+      const ppo_f4 xv = ppo_ld4(in + (size_t)n * ldin + 4 * tk);
+      for (int r = 0; r < 4; ++r) {
+        const float dq = 4 * tj + r < J ? d[(size_t)n * ldd + 4 * tj + r] : 0.0f;
+        acc[r][0] = fmaf(dq, xv.x, acc[r][0]); acc[r][1] = fmaf(dq, xv.y, acc[r][1]);
+        acc[r][2] = fmaf(dq, xv.z, acc[r][2]); acc[r][3] = fmaf(dq, xv.w, acc[r][3]);
+      }
+    }
+  }
+  // Adam: all moment loads first (independent L2 round trips), then the arithmetic, then the stores
+  float mo[4][4], vo[4][4];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) {
+      const bool ok = 4 * tj + r < J && 4 * tk + c < K;
+      const int e = ok ? off + (4 * tj + r) * K + 4 * tk + c : off;
+      mo[r][c] = m[e];
+      vo[r][c] = v[e];
+    }
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) {
+      if (!(4 * tj + r < J && 4 * tk + c < K)) continue;
+      const int e = off + (4 * tj + r) * K + 4 * tk + c;
+      const float g = acc[r][c];
+      const float mi = mo[r][c] + (1.0f - ac.b1) * (g - mo[r][c]);      // exp_avg.lerp_(grad, 1 - beta1)
+      const float vi = ac.b2 * vo[r][c] + (1.0f - ac.b2) * g * g;       // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+      const float denom = sqrtf(vi) / ac.bc2s + ac.eps;
+      float* wp = W + (4 * tj + r) * ldw + 4 * tk + c;
+      const float np_ = *wp - ac.step_size * (mi / denom);
+      m[e] = mi;
+      v[e] = vi;
+      *wp = np_;
+      flat[e] = np_;
+    }
 }
 
 // element j of: g[j] = sum_n d[n][j], then Adam (bias vectors, the std parameter)
@@ -249,7 +311,7 @@ PPO_FN void net_wgrad_adam(const float* x, int ldx, const float* h1, const float
     u -= H2;
     if (u < O) { bias_adam_elem(u, d3, ld3, b3, M, flat, m, v, off[5], ac); continue; }
     u -= O;
-    bias_adam_elem(u, dextra, O, extra, M, flat, m, v, off[6], ac);
+    bias_adam_elem(u, dextra, ld3, extra, M, flat, m, v, off[6], ac);
   }
 }
 
@@ -338,7 +400,7 @@ PPO_FN void ph2_fwd2(PpoShared& S, const PpoArgs& a, int b, int tid, int NT) {
 PPO_FN void ph3_heads(PpoShared& S, const PpoArgs& a, int b, int tid, int NT) {
   const int h = NT / 2, s = b & 1;
   if (tid < h) {
-    dense_fwd(S.ah2, S.ldh, S.aw3, S.ldh, S.ab3, S.mu, a.A, a.mb, a.H2, a.A, true, tid, h);
+    dense_fwd(S.ah2, S.ldh, S.aw3, S.ldh, S.ab3, S.mu, S.lda, a.mb, a.H2, a.A, true, tid, h);
     return;
   }
   const float invM = 1.0f / (float)a.mb;
@@ -366,7 +428,7 @@ PPO_FN void ph4_loss(PpoShared& S, const PpoArgs& a, int b, int tid, int NT) {
   for (int n = tid; n < a.mb; n += h) {
     float lp = 0.0f;
     for (int j = 0; j < A; ++j) {
-      const float sd = S.sdv[j], t = (S.actb + s * S.act_stride)[n * A + j] - S.mu[n * A + j];
+      const float sd = S.sdv[j], t = (S.actb + s * S.act_stride)[n * A + j] - S.mu[n * S.lda + j];
       lp += -(t * t) / (2.0f * sd * sd) - S.lsd[j] - 0.91893853320467274178f;       // Normal.log_prob
     }
     S.logp[n] = lp;
@@ -419,18 +481,18 @@ PPO_FN void ph6_head_bwd(PpoShared& S, const PpoArgs& a, int b, int tid, int NT)
   const float dent = -a.ent_w / (float)a.mb;             // d(-w * mean(entropy)) / d entropy_n
   for (int e = tid; e < a.mb * A; e += h) {
     const int n = e / A, j = e - n * A;
-    const float m_ = S.mu[e], sd = S.sdv[j], t = (S.actb + s * S.act_stride)[e] - m_, gl = S.dlogp[n];
-    S.dmu[e] = gl * (t / (sd * sd)) * (1.0f - m_ * m_);
+    const float m_ = S.mu[n * S.lda + j], sd = S.sdv[j], t = (S.actb + s * S.act_stride)[e] - m_, gl = S.dlogp[n];
+    S.dmu[n * S.lda + j] = gl * (t / (sd * sd)) * (1.0f - m_ * m_);
     const float p = S.sdp[j];
     const float sig = p > 20.0f ? 1.0f : 1.0f / (1.0f + expf(-p));                  // softplus'
-    S.dsd[e] = (gl * ((t * t) / (sd * sd * sd) - 1.0f / sd) + dent * (1.0f / sd)) * sig;
+    S.dsd[n * S.lda + j] = (gl * ((t * t) / (sd * sd * sd) - 1.0f / sd) + dent * (1.0f / sd)) * sig;
   }
 }
 // P7: actor (gate): back into layer 2; critic: all its parameter gradients + Adam (PPO_agent.py:97-99)
 PPO_FN void ph7_critic_update(PpoShared& S, const PpoArgs& a, int b, int tid, int NT) {
   const int h = NT / 2;
   if (tid < h) {
-    if (S.flag[0] != 0.0f) dense_bwd_data(S.dmu, a.A, S.aw3, S.ldh, S.ah2, S.ldh, S.ad2, S.ldh, a.mb, a.A, a.H2, tid, h);
+    if (S.flag[0] != 0.0f) dense_bwd_data(S.dmu, S.lda, S.aw3, S.ldh, S.ah2, S.ldh, S.ad2, S.ldh, a.mb, a.A, a.H2, tid, h);
     return;
   }
   const AdamCoef ac = adam_coef(a.c_lr, a.c_b1, a.c_b2, a.c_eps, S.steps[1]);
@@ -446,7 +508,7 @@ PPO_FN void ph8_actor_bwd1(PpoShared& S, const PpoArgs& a, int b, int tid, int N
 PPO_FN void ph9_actor_update(PpoShared& S, const PpoArgs& a, int b, int tid, int NT) {
   if (S.flag[0] == 0.0f) return;
   const AdamCoef ac = adam_coef(a.a_lr, a.a_b1, a.a_b2, a.a_eps, S.steps[0]);
-  net_wgrad_adam((S.xb + (b & 1) * S.x_stride), S.ld1, S.ah1, S.ah2, S.ldh, S.ad1, S.ad2, S.dmu, a.A, a.mb, a.D, a.H1, a.H2, a.A, S.aw1, S.ld1,
+  net_wgrad_adam((S.xb + (b & 1) * S.x_stride), S.ld1, S.ah1, S.ah2, S.ldh, S.ad1, S.ad2, S.dmu, S.lda, a.mb, a.D, a.H1, a.H2, a.A, S.aw1, S.ld1,
                  S.ab1, S.aw2, S.ab2, S.aw3, S.ab3, S.sdp, S.dsd, a.a_flat, a.a_m, a.a_v, a.a_off, ac, tid, NT);
 }
 

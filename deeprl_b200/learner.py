@@ -607,10 +607,13 @@ class PersistentPPOLearner:
             return False
         dims = lambda b: (b.layers[0].in_features, b.layers[0].out_features, b.layers[1].out_features)
         D, H1, H2 = dims(ab)
-        # (sizes whose weights + double-buffered rows + both networks' activations fit the 227 KB of one SM: the examples use
-        #  D = 17, hidden 64, A = 6, mini batch 64 -> 198 KB)
-        return (dims(cb) == (D, H1, H2) and D <= 64 and H1 <= 64 and H2 <= 64 and network.fc_action.out_features <= 32
-                and 4 <= mini_batch_size <= 64 and mini_batch_size % 4 == 0 and network.fc_action.weight.is_cuda)
+        A = network.fc_action.out_features
+        if not (dims(cb) == (D, H1, H2) and D <= 256 and H1 <= 128 and H2 <= 128 and A <= 32 and 4 <= mini_batch_size <= 128
+                and mini_batch_size % 4 == 0 and network.fc_action.weight.is_cuda):
+            return False
+        # weights + double-buffered rows + both networks' activations must fit the shared memory of one SM
+        # (examples.py:496-522: D = 17, hidden 64, A = 6, mini batch 64 -> 205 KB)
+        return int(_lib.lib().b2rl_ppo_minibatch_smem_bytes(D, A, H1, H2, int(mini_batch_size))) <= 227 * 1024
 
     def __init__(self, network, actor_opt, critic_opt, rows, state_dim, action_dim, mini_batch_size, ppo_ratio_clip,
                  entropy_weight, target_kl, max_batches):

@@ -82,7 +82,7 @@ def fp(x):
 @pytest.fixture(scope="module")
 def emul(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("ppo_emul") / "ppo_emul.so")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, os.path.join(ROOT, "tests", "host_emul", "ppo_emul.cpp")],
+    subprocess.run(["g++", "-O2", "-fno-strict-aliasing", "-std=c++17", "-shared", "-fPIC", "-o", out, os.path.join(ROOT, "tests", "host_emul", "ppo_emul.cpp")],
                    check=True)
     return ctypes.CDLL(out)
 
@@ -182,3 +182,11 @@ def test_cuda_kernel_matches_oracle(case):
                a_m=t["a_m"].cpu().numpy(), a_v=t["a_v"].cpu().numpy(), c_m=t["c_m"].cpu().numpy(), c_v=t["c_v"].cpu().numpy(),
                a_step=int(t["a_step"]), c_step=int(t["c_step"]), stats=stats.cpu().numpy(), n_batches=perm.shape[0])
     check_against_oracle(got, c, problem)
+
+
+def test_shared_memory_budget_of_the_example_sizes():
+    """The examples' sizes (examples.py:496-522) fit one SM; the learner falls back to the graph form when a network does not."""
+    from deeprl_b200 import _lib
+    L = _lib.lib()
+    assert 0 < L.b2rl_ppo_minibatch_smem_bytes(17, 6, 64, 64, 64) <= 227 * 1024
+    assert L.b2rl_ppo_minibatch_smem_bytes(64, 32, 128, 128, 128) > 227 * 1024
