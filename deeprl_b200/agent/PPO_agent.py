@@ -61,24 +61,49 @@ class PPOAgent(BaseAgent):
         batch on the host; the batch that ends a rollout is counted by its value forward and re-used, read-only, by the first
         step of the next rollout)."""
         config = self.config
-        storage = Storage(config.rollout_length)
+        T = config.rollout_length
+        storage = Storage(T)
         raw, seen = self._raw_states, self._raw_seen
         keys = ("action", "log_pi_a", "entropy", "mean", "v")
-        for _ in range(config.rollout_length):
-            pred = actor.step(raw, update=not seen)
-            raw, rewards, terminals, info = self.task.step(to_np(pred["action"]))
-            seen = False
-            self.record_online_return(info)
-            rewards = config.reward_normalizer(rewards)
+        if not getattr(config, "device_actor_arena", True):        # one set of output tensors and two small uploads per env step
+            for _ in range(T):
+                pred = actor.step(raw, update=not seen)
+                raw, rewards, terminals, info = self.task.step(to_np(pred["action"]))
+                seen = False
+                self.record_online_return(info)
+                rewards = config.reward_normalizer(rewards)
+                storage.feed({k: pred[k] for k in keys})
+                storage.feed({"reward": tensor(rewards).unsqueeze(-1), "mask": tensor(1 - terminals).unsqueeze(-1),
+                              "state": pred["state"]})
+                self.total_steps += config.num_workers
+            pred = actor.step(raw, update=True)             # value of the last state (PPO_agent.py:46-47)
+            self._raw_states, self._raw_seen = raw, True
             storage.feed({k: pred[k] for k in keys})
-            storage.feed({"reward": tensor(rewards).unsqueeze(-1), "mask": tensor(1 - terminals).unsqueeze(-1),
-                          "state": pred["state"]})
-            self.total_steps += config.num_workers
-        pred = actor.step(raw, update=True)                 # value of the last state (PPO_agent.py:46-47)
-        self._raw_states, self._raw_seen = raw, True
-        storage.feed({k: pred[k] for k in keys})
+            last_v = pred["v"]
+        else:
+            # the actor's outputs go straight into rollout-sized arenas; rewards / masks stay on the host until the rollout ends
+            N = config.num_workers
+            actor.begin_rollout(T)
+            rew, msk = np.empty((T, N), dtype=np.float32), np.empty((T, N), dtype=np.float32)
+            for t in range(T):
+                action = actor.step_into(t, raw, update=not seen)
+                raw, rewards, terminals, info = self.task.step(action)
+                seen = False
+                self.record_online_return(info)
+                rew[t] = np.asarray(config.reward_normalizer(rewards), dtype=np.float32)     # tensor(): float32 (torch_utils.py:20-25)
+                msk[t] = np.asarray(1 - terminals, dtype=np.float32)
+                self.total_steps += N
+            actor.step_into(T, raw, update=True)            # value of the last state (PPO_agent.py:46-47)
+            self._raw_states, self._raw_seen = raw, True
+            roll, dev = actor.roll, actor.dev
+            for k in keys:
+                setattr(storage, k, list(roll[k].unbind(0)))                                  # T + 1 entries, like feed()
+            storage.state = list(roll["state"][:T].unbind(0))
+            storage.reward = list(torch.from_numpy(rew).to(dev).unsqueeze(-1).unbind(0))
+            storage.mask = list(torch.from_numpy(msk).to(dev).unsqueeze(-1).unbind(0))
+            last_v = roll["v"][T]
         storage.placeholder()
-        compute_advantages(storage, config, pred["v"], exact=self.gae_exact)
+        compute_advantages(storage, config, last_v, exact=self.gae_exact)
         actor.pull_stats()                                  # the host normaliser object stays current (eval_step, save)
         entries = storage.extract(["state", "action", "log_pi_a", "ret", "advantage"])
         return type(entries)(*[x.detach().contiguous() for x in entries])

@@ -2,6 +2,8 @@
 two ``task.step()`` calls (PPO_agent.py:45-50) -- ``MeanStdNormalizer`` (normalizer.py:36-51), the ``GaussianActorCriticNet``
 forward (network_heads.py:173-214) and the Normal sample / log-prob / entropy -- as ONE launch of ``b2rl_gaussian_actor_step``
 (csrc/actor.cu) on a pinned, double-buffered observation upload.  The envs stay on the host (north_star)."""
+import ctypes
+
 import numpy as np
 import torch
 
@@ -92,6 +94,45 @@ class DeviceGaussianActor:
                   _lib.ptr(out["state"]), _lib.ptr(out["action"]), _lib.ptr(out["log_pi_a"]), _lib.ptr(out["entropy"]),
                   _lib.ptr(out["mean"]), _lib.ptr(out["v"]), _lib.stream())
         return out
+
+
+    # ---- rollout form: outputs written straight into rollout-sized arenas, weight addresses looked up once per rollout
+    KEYS = ("state", "action", "log_pi_a", "entropy", "mean", "v")
+
+    def begin_rollout(self, T):
+        """Arenas [T + 1, N, dim] for the six outputs of T + 1 actor steps (the last one is the bootstrap value forward) and
+        the argument block of the launches (the parameters' addresses change when an optimizer re-points them into its flat
+        arena, so they are read again at the start of every rollout)."""
+        n, N = self.net, self.N
+        if getattr(self, "_T", None) != T:
+            dims = dict(state=self.D, action=self.A, log_pi_a=1, entropy=1, mean=self.A, v=1)
+            self.roll = {k: torch.empty((T + 1, N, d), dtype=_f32, device=self.dev) for k, d in dims.items()}
+            self.h_action = torch.empty((N, self.A), dtype=_f32, pin_memory=True)
+            self._stride = {k: N * d * 4 for k, d in dims.items()}
+            self._T = T
+        self._base = {k: self.roll[k].data_ptr() for k in self.KEYS}
+        ab, cb = n.actor_body.layers, n.critic_body.layers
+        mods = (ab[0], ab[1], n.fc_action, cb[0], cb[1], n.fc_critic)
+        self._wptr = [_lib.ptr(t.detach()) for m in mods for t in (m.weight, m.bias)] + [_lib.ptr(n.std.detach())]
+        self._dims = (N, self.D, ab[0].out_features, ab[1].out_features, self.A)
+        self._obs_ptr = [_lib.ptr(t) for t in self.d_obs]
+        self._np_obs = [t.numpy() for t in self.h_obs]
+        self._fixed = (_lib.ptr(self.rm_mean), _lib.ptr(self.rm_var), _lib.ptr(self.rm_count))
+
+    def step_into(self, t, raw_obs, update):
+        """Actor step ``t`` of the rollout begun with ``begin_rollout``: outputs go to ``roll[key][t]``; returns the actions as
+        a host array (pinned download + one stream synchronise)."""
+        k = self.slot
+        self.slot = 1 - k
+        self._np_obs[k][...] = np.asarray(raw_obs, dtype=np.float32).reshape(self.N, self.D)
+        self.d_obs[k].copy_(self.h_obs[k], non_blocking=True)
+        at = lambda key: ctypes.c_void_p(self._base[key] + t * self._stride[key])
+        _lib.call("b2rl_gaussian_actor_step", self._obs_ptr[k], *self._fixed, int(bool(update)), float(self.norm.clip),
+                  float(self.norm.epsilon), *self._wptr, *self._dims, None, self.seed, _lib.ptr(self.counter), None,
+                  at("state"), at("action"), at("log_pi_a"), at("entropy"), at("mean"), at("v"), _lib.stream())
+        self.h_action.copy_(self.roll["action"][t], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.h_action.numpy().copy()
 
 
 class GraphedQActor:

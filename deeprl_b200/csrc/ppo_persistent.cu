@@ -23,7 +23,9 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_minibatch_persistent_kernel(con
   PpoShared S;
   ppo_carve(S, ppo_smem, a.D, a.A, a.H1, a.H2, a.mb);
   const int NT = PPO_NT;
-#define PPO_PHASE(stmt) { const int tid = threadIdx.x; stmt; } __syncthreads();
+  int clk_i = 0;                  // (profiling hook: thread 0 stamps the end of every phase when a clock buffer is installed)
+#define PPO_PHASE(stmt) { const int tid = threadIdx.x; stmt; } __syncthreads(); \
+  if (a.clk && threadIdx.x == 0) a.clk[clk_i++] = clock64();
 #include "ppo_sequence.inc"
 #undef PPO_PHASE
 }
@@ -31,6 +33,15 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_minibatch_persistent_kernel(con
 }  // namespace b2rl
 
 using namespace b2rl;
+
+static long long* g_ppo_clocks = nullptr;
+
+// Profiling hook: install (or with NULL remove) a device buffer of int64 [2 + 9 * n_batches] that the next launches fill with
+// clock64() of thread 0 after every phase barrier (scripts/ppo_phase_clocks.py turns it into cycles per phase).
+extern "C" int b2rl_ppo_set_phase_clocks(int64_t* clocks) {
+  g_ppo_clocks = reinterpret_cast<long long*>(clocks);
+  return 0;
+}
 
 // dynamic shared memory the persistent kernel needs for these sizes (the caller checks it against the 227 KB of one SM)
 extern "C" int64_t b2rl_ppo_minibatch_smem_bytes(int32_t D, int32_t A, int32_t H1, int32_t H2, int32_t mb) {
@@ -60,7 +71,7 @@ extern "C" int b2rl_ppo_minibatch_updates(const float* state, const float* actio
   for (int i = 0; i < 6; ++i) a.c_off[i] = c_off[i];
   a.a_lr = a_lr; a.a_b1 = a_beta1; a.a_b2 = a_beta2; a.a_eps = a_eps;
   a.c_lr = c_lr; a.c_b1 = c_beta1; a.c_b2 = c_beta2; a.c_eps = c_eps;
-  a.clip = ratio_clip; a.ent_w = entropy_weight; a.gate_max = kl_gate; a.stats = stats;
+  a.clip = ratio_clip; a.ent_w = entropy_weight; a.gate_max = kl_gate; a.stats = stats; a.clk = g_ppo_clocks;
   const size_t smem = (size_t)b2rl_ppo_minibatch_smem_bytes(D, A, H1, H2, mb);
   B2RL_REQUIRE(smem <= 227 * 1024, "networks / minibatch too large for the shared memory of one SM");
   static size_t attr = 0;

@@ -36,6 +36,7 @@ struct PpoArgs {
   float a_lr, a_b1, a_b2, a_eps, c_lr, c_b1, c_b2, c_eps;
   float clip, ent_w, gate_max;
   float* stats;               // [4]: policy loss, value loss, approx_kl of the LAST minibatch; actor steps taken in this call
+  long long* clk;             // profiling hook (device only, normally null): clock64() of thread 0 after every phase barrier
 };
 
 struct PpoShared {

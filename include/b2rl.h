@@ -392,6 +392,10 @@ int b2rl_gaussian_actor_step(const float* obs, double* rm_mean, double* rm_var, 
  * layers.1.weight, .bias, fc_action.weight, fc_action.bias, std inside the actor arenas (host array); c_off int32 [6] likewise
  * for critic_body.* and fc_critic.*.  stats float32 [4] = policy loss, value loss, approx_kl of the LAST minibatch and the
  * number of actor steps taken.  Limits: D <= 256, A <= 32, hidden <= 128, mini batch <= 128 and a multiple of 4. */
+/* Profiling hook of b2rl_ppo_minibatch_updates: install (NULL: remove) a device buffer int64 [2 + 9 * n_batches] that the next
+ * launches fill with clock64() of thread 0 after every phase barrier (scripts/ppo_phase_clocks.py). */
+int b2rl_ppo_set_phase_clocks(int64_t* clocks);
+
 /* Dynamic shared memory (bytes) b2rl_ppo_minibatch_updates needs for these sizes; it must fit the 227 KB of one SM. */
 int64_t b2rl_ppo_minibatch_smem_bytes(int32_t D, int32_t A, int32_t H1, int32_t H2, int32_t mb);
 

@@ -26,7 +26,7 @@ extern "C" int ppo_emul_minibatch_updates(const float* state, const float* actio
   for (int i = 0; i < 6; ++i) a.c_off[i] = c_off[i];
   a.a_lr = a_lr; a.a_b1 = a_beta1; a.a_b2 = a_beta2; a.a_eps = a_eps;
   a.c_lr = c_lr; a.c_b1 = c_beta1; a.c_b2 = c_beta2; a.c_eps = c_eps;
-  a.clip = ratio_clip; a.ent_w = entropy_weight; a.gate_max = kl_gate; a.stats = stats;
+  a.clip = ratio_clip; a.ent_w = entropy_weight; a.gate_max = kl_gate; a.stats = stats; a.clk = nullptr;
   PpoShared S;
   float dummy[4];
   const size_t n = ppo_carve(S, dummy, D, A, H1, H2, mb);
@@ -58,7 +58,7 @@ extern "C" int ppo_emul_minibatch_updates_reversed(const float* state, const flo
   for (int i = 0; i < 6; ++i) a.c_off[i] = c_off[i];
   a.a_lr = a_lr; a.a_b1 = a_beta1; a.a_b2 = a_beta2; a.a_eps = a_eps;
   a.c_lr = c_lr; a.c_b1 = c_beta1; a.c_b2 = c_beta2; a.c_eps = c_eps;
-  a.clip = ratio_clip; a.ent_w = entropy_weight; a.gate_max = kl_gate; a.stats = stats;
+  a.clip = ratio_clip; a.ent_w = entropy_weight; a.gate_max = kl_gate; a.stats = stats; a.clk = nullptr;
   PpoShared S;
   float dummy[4];
   const size_t n = ppo_carve(S, dummy, D, A, H1, H2, mb);

@@ -119,3 +119,37 @@ def test_ppo_agent_uses_the_device_actor(rl):
     assert abs(c.state_normalizer.rms.count - (1e-4 + 8 * (1 + 2 * 64))) < 1e-6
     assert all(torch.isfinite(p).all() for p in ag.network.parameters())
     ag.close()
+
+
+def test_arena_rollout_equals_the_per_step_rollout(rl):
+    """``PPOAgent._rollout_device`` writing the actor's outputs into rollout-sized arenas (and uploading rewards / masks once)
+    returns exactly the entries of the per-step form (same launches, same Philox stream, same env seeds)."""
+    def agent(arena):
+        torch.manual_seed(0), np.random.seed(0)
+        c = rl.Config()
+        c.merge(dict(tag=None))
+        c.num_workers = 8
+        c.task_fn = lambda: rl.Task("SyntheticCheetah-v0", num_envs=8, seed=3)
+        c.eval_env = rl.Task("SyntheticCheetah-v0", seed=3)
+        c.network_fn = lambda: rl.GaussianActorCriticNet(c.state_dim, c.action_dim,
+                                                         actor_body=rl.FCBody(c.state_dim, gate=torch.tanh),
+                                                         critic_body=rl.FCBody(c.state_dim, gate=torch.tanh))
+        c.actor_opt_fn = lambda p: torch.optim.Adam(p, 3e-4)
+        c.critic_opt_fn = lambda p: torch.optim.Adam(p, 1e-3)
+        c.discount, c.use_gae, c.gae_tau, c.gradient_clip = 0.99, True, 0.95, 0.5
+        c.rollout_length, c.optimization_epochs, c.mini_batch_size, c.ppo_ratio_clip, c.target_kl = 48, 2, 64, 0.2, 0.01
+        c.state_normalizer = rl.MeanStdNormalizer()
+        c.device_actor_arena = arena
+        return rl.PPOAgent(c)
+
+    a, b = agent(False), agent(True)
+    for it in range(3):                                    # (the second / third rollout start from a state seen before)
+        ea, eb = a._rollout(), b._rollout()
+        torch.cuda.synchronize()
+        for name, x, y in zip(ea._fields, ea, eb):
+            assert torch.equal(x, y), (it, name)
+        assert a.total_steps == b.total_steps
+        ra, rb = a.config.state_normalizer.rms, b.config.state_normalizer.rms
+        assert np.array_equal(ra.mean, rb.mean) and np.array_equal(ra.var, rb.var) and ra.count == rb.count
+    assert a._device_actor() is not None and b._device_actor() is not None
+    a.close(), b.close()
