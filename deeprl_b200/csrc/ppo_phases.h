@@ -17,9 +17,17 @@
 #ifdef __CUDACC__
 #define PPO_FN __device__ __forceinline__
 #define PPO_HD __host__ __device__ inline
+// the dense building blocks are called from several phases: ONE copy each (the kernel runs as a single block, and with every
+// block inlined into every phase its code was 400 KB -- an order of magnitude beyond the 32 KB instruction cache; measured:
+// 52 us per update, 35 % of it in one phase).  Their pointer arguments are shared-memory addresses at every call site, which
+// the compiler propagates into the one copy (LDS, not generic loads).
+#define PPO_SUB __device__ __noinline__
+#define PPO_LOOP _Pragma("unroll 1")
 #else
 #define PPO_FN static inline
 #define PPO_HD static inline
+#define PPO_SUB static
+#define PPO_LOOP
 #endif
 
 namespace b2rl_ppo {
@@ -95,6 +103,7 @@ PPO_HD size_t ppo_carve(PpoShared& S, float* base, int D, int A, int H1, int H2,
 struct alignas(16) ppo_f4 { float x, y, z, w; };
 PPO_FN ppo_f4 ppo_ld4(const float* p) { return *reinterpret_cast<const ppo_f4*>(p); }
 PPO_FN void ppo_st4(float* p, const ppo_f4& v) { *reinterpret_cast<ppo_f4*>(p) = v; }
+PPO_SUB float ppo_tanh(float x) { return tanhf(x); }
 PPO_FN float ppo_dot4(const ppo_f4& a, const ppo_f4& b, float acc) {
   acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); return fmaf(a.w, b.w, acc);
 }
@@ -105,6 +114,7 @@ PPO_FN float ppo_dot4(const ppo_f4& a, const ppo_f4& b, float acc) {
 PPO_FN void dense_fwd(const float* in, int ldin, const float* W, int ldw, const float* bias, float* out, int ldout, int M,
                       int K, int J, bool use_tanh, int tid, int NT) {
   const int tjn = (J + 3) / 4, tiles = (M / 4) * tjn, K4 = K & ~3;
+  PPO_LOOP
   for (int t = tid; t < tiles; t += NT) {
     const int tn = t / tjn, tj = t - tn * tjn;
     int jj[4];
@@ -118,6 +128,7 @@ PPO_FN void dense_fwd(const float* in, int ldin, const float* W, int ldw, const 
     for (int i = 0; i < 4; ++i)
       for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
     const float* xr = in + (size_t)(4 * tn) * ldin;
+    PPO_LOOP
     for (int k = 0; k < K4; k += 4) {
       ppo_f4 xv[4], wv[4];
       for (int i = 0; i < 4; ++i) xv[i] = ppo_ld4(xr + i * ldin + k);
@@ -125,6 +136,7 @@ PPO_FN void dense_fwd(const float* in, int ldin, const float* W, int ldw, const 
       for (int i = 0; i < 4; ++i)
         for (int c = 0; c < 4; ++c) acc[i][c] = ppo_dot4(xv[i], wv[c], acc[i][c]);
     }
+    PPO_LOOP
     for (int k = K4; k < K; ++k) {
       float xv[4], wv[4];
       for (int i = 0; i < 4; ++i) xv[i] = xr[i * ldin + k];
@@ -136,7 +148,7 @@ PPO_FN void dense_fwd(const float* in, int ldin, const float* W, int ldw, const 
       for (int c = 0; c < 4; ++c)
         if (ok[c]) {
           const float s = acc[i][c] + bias[jj[c]];
-          out[(size_t)(4 * tn + i) * ldout + jj[c]] = use_tanh ? tanhf(s) : s;
+          out[(size_t)(4 * tn + i) * ldout + jj[c]] = use_tanh ? ppo_tanh(s) : s;
         }
   }
 }
@@ -146,6 +158,7 @@ PPO_FN void dense_fwd(const float* in, int ldin, const float* W, int ldw, const 
 PPO_FN void dense_bwd_data(const float* d, int ldd, const float* W, int ldw, const float* h, int ldhh, float* out, int ldout,
                            int M, int J, int K, int tid, int NT) {
   const int tkn = (K + 3) / 4, tiles = (M / 4) * tkn, J4 = (ldd & 3) ? 0 : (J & ~3);
+  PPO_LOOP
   for (int t = tid; t < tiles; t += NT) {
     const int tn = t / tkn, tk = t - tn * tkn;
     float acc[4][4];
@@ -153,6 +166,7 @@ PPO_FN void dense_bwd_data(const float* d, int ldd, const float* W, int ldw, con
       for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
     const float* dr = d + (size_t)(4 * tn) * ldd;
     const float* wc = W + 4 * tk;
+    PPO_LOOP
     for (int j = 0; j < J4; j += 4) {
       ppo_f4 dv[4], wv[4];
       for (int i = 0; i < 4; ++i) dv[i] = ppo_ld4(dr + i * ldd + j);
@@ -165,6 +179,7 @@ PPO_FN void dense_bwd_data(const float* d, int ldd, const float* W, int ldw, con
         }
       }
     }
+    PPO_LOOP
     for (int j = J4; j < J; ++j) {
       const ppo_f4 wv = ppo_ld4(wc + j * ldw);
       for (int i = 0; i < 4; ++i) {
@@ -219,16 +234,17 @@ PPO_FN float adam_elem(float p, float g, float* m, float* v, int idx, const Adam
 PPO_FN int wgrad_tiles(int J, int K) { return ((J + 3) / 4) * ((K + 3) / 4); }
 
 // tile `t` of: g[j][k] = sum_n d[n][j] * in[n][k], then Adam on element j*K + k of the tensor at arena offset `off`
-// (shared-memory copy W[j*ldw + k], master copy flat[off + j*K + k]).  tile = rows 4tj..4tj+3 x columns 4tk..4tk+3 of the
+// (shared-memory copy W[j*ldw + k]; moments m / v [off + j*K + k]).  tile = rows 4tj..4tj+3 x columns 4tk..4tk+3 of the
 // weight: one 128-bit load of d and one of `in` per sample (rows 16-byte aligned; ldd = 1, the value head, takes scalars)
 PPO_FN void wgrad_adam_tile(int t, const float* d, int ldd, const float* in, int ldin, float* W, int ldw, int M, int J, int K,
-                            float* flat, float* m, float* v, int off, const AdamCoef& ac) {
+                            float* m, float* v, int off, const AdamCoef& ac) {
   const int tkn = (K + 3) / 4;
   const int tj = t / tkn, tk = t - tj * tkn;
   float acc[4][4];
   for (int r = 0; r < 4; ++r)
     for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
   if ((ldd & 3) == 0) {
+    PPO_LOOP
     for (int n = 0; n < M; ++n) {
       const ppo_f4 dv = ppo_ld4(d + (size_t)n * ldd + 4 * tj), xv = ppo_ld4(in + (size_t)n * ldin + 4 * tk);
       const float dq[4] = {dv.x, dv.y, dv.z, dv.w};
@@ -238,6 +254,7 @@ PPO_FN void wgrad_adam_tile(int t, const float* d, int ldd, const float* in, int
       }
     }
   } else {
+    PPO_LOOP
     for (int n = 0; n < M; ++n) {
       const ppo_f4 xv = ppo_ld4(in + (size_t)n * ldin + 4 * tk);
       for (int r = 0; r < 4; ++r) {
@@ -247,35 +264,56 @@ PPO_FN void wgrad_adam_tile(int t, const float* d, int ldd, const float* in, int
       }
     }
   }
-  // Adam: all moment loads first (independent L2 round trips), then the arithmetic, then the stores
+  // Adam.  The master copy `flat` is written once, when the kernel ends (ph_finish); the moments live in L2.  All moment
+  // loads are issued before the arithmetic (independent round trips); rows of a weight whose K is a multiple of 4 are read
+  // and written 128 bits at a time -- a warp then touches whole 32-byte sectors (the scalar form's 16-byte-strided stores
+  // kept the load/store unit busy long into the NEXT phase: 36 k cycles of a 6 k-cycle phase, measured with the phase clocks)
   float mo[4][4], vo[4][4];
-  for (int r = 0; r < 4; ++r)
-    for (int c = 0; c < 4; ++c) {
-      const bool ok = 4 * tj + r < J && 4 * tk + c < K;
-      const int e = ok ? off + (4 * tj + r) * K + 4 * tk + c : off;
-      mo[r][c] = m[e];
-      vo[r][c] = v[e];
+  const bool vec = (K & 3) == 0;
+  for (int r = 0; r < 4; ++r) {
+    const int j = 4 * tj + r < J ? 4 * tj + r : J - 1;
+    if (vec) {
+      const ppo_f4 mv = ppo_ld4(m + off + j * K + 4 * tk), vv = ppo_ld4(v + off + j * K + 4 * tk);
+      mo[r][0] = mv.x; mo[r][1] = mv.y; mo[r][2] = mv.z; mo[r][3] = mv.w;
+      vo[r][0] = vv.x; vo[r][1] = vv.y; vo[r][2] = vv.z; vo[r][3] = vv.w;
+    } else {
+      for (int c = 0; c < 4; ++c) {
+        const int e = off + j * K + (4 * tk + c < K ? 4 * tk + c : K - 1);
+        mo[r][c] = m[e];
+        vo[r][c] = v[e];
+      }
     }
-  for (int r = 0; r < 4; ++r)
+  }
+  for (int r = 0; r < 4; ++r) {
+    if (4 * tj + r >= J) continue;
+    float* wp = W + (4 * tj + r) * ldw + 4 * tk;
+    float wn[4], mn[4], vn[4];
     for (int c = 0; c < 4; ++c) {
-      if (!(4 * tj + r < J && 4 * tk + c < K)) continue;
-      const int e = off + (4 * tj + r) * K + 4 * tk + c;
       const float g = acc[r][c];
-      const float mi = mo[r][c] + (1.0f - ac.b1) * (g - mo[r][c]);      // exp_avg.lerp_(grad, 1 - beta1)
-      const float vi = ac.b2 * vo[r][c] + (1.0f - ac.b2) * g * g;       // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
-      const float denom = sqrtf(vi) / ac.bc2s + ac.eps;
-      float* wp = W + (4 * tj + r) * ldw + 4 * tk + c;
-      const float np_ = *wp - ac.step_size * (mi / denom);
-      m[e] = mi;
-      v[e] = vi;
-      *wp = np_;
-      flat[e] = np_;
+      mn[c] = mo[r][c] + (1.0f - ac.b1) * (g - mo[r][c]);             // exp_avg.lerp_(grad, 1 - beta1)
+      vn[c] = ac.b2 * vo[r][c] + (1.0f - ac.b2) * g * g;              // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+      const float denom = sqrtf(vn[c]) / ac.bc2s + ac.eps;
+      wn[c] = (4 * tk + c < K ? wp[c] : 0.0f) - ac.step_size * (mn[c] / denom);
     }
+    const int e = off + (4 * tj + r) * K + 4 * tk;
+    if (vec) {
+      ppo_f4 t;
+      t.x = mn[0]; t.y = mn[1]; t.z = mn[2]; t.w = mn[3]; ppo_st4(m + e, t);
+      t.x = vn[0]; t.y = vn[1]; t.z = vn[2]; t.w = vn[3]; ppo_st4(v + e, t);
+      t.x = wn[0]; t.y = wn[1]; t.z = wn[2]; t.w = wn[3]; ppo_st4(wp, t);
+    } else {
+      for (int c = 0; c < 4; ++c)
+        if (4 * tk + c < K) {
+          m[e + c] = mn[c];
+          v[e + c] = vn[c];
+          wp[c] = wn[c];
+        }
+    }
+  }
 }
 
 // element j of: g[j] = sum_n d[n][j], then Adam (bias vectors, the std parameter)
-PPO_FN void bias_adam_elem(int j, const float* d, int ldd, float* Bv, int M, float* flat, float* m, float* v, int off,
-                           const AdamCoef& ac) {
+PPO_FN void bias_adam_elem(int j, const float* d, int ldd, float* Bv, int M, float* m, float* v, int off, const AdamCoef& ac) {
   float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
   int n = 0;
   for (; n + 3 < M; n += 4) {
@@ -283,9 +321,7 @@ PPO_FN void bias_adam_elem(int j, const float* d, int ldd, float* Bv, int M, flo
     s2 += d[(size_t)(n + 2) * ldd + j]; s3 += d[(size_t)(n + 3) * ldd + j];
   }
   for (; n < M; ++n) s0 += d[(size_t)n * ldd + j];
-  const float np_ = adam_elem(Bv[j], (s0 + s1) + (s2 + s3), m, v, off + j, ac);
-  Bv[j] = np_;
-  flat[off + j] = np_;
+  Bv[j] = adam_elem(Bv[j], (s0 + s1) + (s2 + s3), m, v, off + j, ac);
 }
 
 // all parameter gradients + Adam of one three-layer network, spread over the block as ONE index space:
@@ -293,26 +329,30 @@ PPO_FN void bias_adam_elem(int j, const float* d, int ldd, float* Bv, int M, flo
 // d1 / d2 / d3: pre-activation gradients of the three layers; x / h1 / h2: their inputs
 PPO_FN void net_wgrad_adam(const float* x, int ldx, const float* h1, const float* h2, int ldh, const float* d1, const float* d2,
                            const float* d3, int ld3, int M, int D, int H1, int H2, int O, float* w1, int ld1, float* b1,
-                           float* w2, float* b2, float* w3, float* b3, float* extra, const float* dextra, float* flat,
-                           float* m, float* v, const int* off, const AdamCoef& ac, int tid, int NT) {
+                           float* w2, float* b2, float* w3, float* b3, float* extra, const float* dextra, float* m, float* v,
+                           const int* off, const AdamCoef& ac, int tid, int NT) {
   const int t2 = wgrad_tiles(H2, H1), t1 = wgrad_tiles(H1, D), t3 = wgrad_tiles(O, H2);
-  const int nb = H1 + H2 + O + (extra ? O : 0);
-  const int total = t2 + t1 + t3 + nb;
-  for (int t = tid; t < total; t += NT) {
-    int u = t;
-    if (u < t2) { wgrad_adam_tile(u, d2, ldh, h1, ldh, w2, ldh, M, H2, H1, flat, m, v, off[2], ac); continue; }
-    u -= t2;
-    if (u < t1) { wgrad_adam_tile(u, d1, ldh, x, ldx, w1, ld1, M, H1, D, flat, m, v, off[0], ac); continue; }
-    u -= t1;
-    if (u < t3) { wgrad_adam_tile(u, d3, ld3, h2, ldh, w3, ldh, M, O, H2, flat, m, v, off[4], ac); continue; }
-    u -= t3;
-    if (u < H1) { bias_adam_elem(u, d1, ldh, b1, M, flat, m, v, off[1], ac); continue; }
-    u -= H1;
-    if (u < H2) { bias_adam_elem(u, d2, ldh, b2, M, flat, m, v, off[3], ac); continue; }
-    u -= H2;
-    if (u < O) { bias_adam_elem(u, d3, ld3, b3, M, flat, m, v, off[5], ac); continue; }
-    u -= O;
-    bias_adam_elem(u, dextra, ld3, extra, M, flat, m, v, off[6], ac);
+  const int nt = t2 + t1 + t3, nb = H1 + H2 + O + (extra ? O : 0);
+  PPO_LOOP
+  for (int t = tid; t < nt + nb; t += NT) {
+    if (t < nt) {                                          // a 4 x 4 tile of one of the three weights: ONE copy of the tile code
+      const float *d, *in;
+      float* W;
+      int u = t, ldd, ldin, ldw, J, K, o;
+      if (u < t2) { d = d2; ldd = ldh; in = h1; ldin = ldh; W = w2; ldw = ldh; J = H2; K = H1; o = off[2]; }
+      else if (u < t2 + t1) { u -= t2; d = d1; ldd = ldh; in = x; ldin = ldx; W = w1; ldw = ld1; J = H1; K = D; o = off[0]; }
+      else { u -= t2 + t1; d = d3; ldd = ld3; in = h2; ldin = ldh; W = w3; ldw = ldh; J = O; K = H2; o = off[4]; }
+      wgrad_adam_tile(u, d, ldd, in, ldin, W, ldw, M, J, K, m, v, o, ac);
+    } else {                                               // an element of a bias vector / the std parameter
+      const float* d;
+      float* Bv;
+      int u = t - nt, ldd, o;
+      if (u < H1) { d = d1; ldd = ldh; Bv = b1; o = off[1]; }
+      else if (u < H1 + H2) { u -= H1; d = d2; ldd = ldh; Bv = b2; o = off[3]; }
+      else if (u < H1 + H2 + O) { u -= H1 + H2; d = d3; ldd = ld3; Bv = b3; o = off[5]; }
+      else { u -= H1 + H2 + O; d = dextra; ldd = ld3; Bv = extra; o = off[6]; }
+      bias_adam_elem(u, d, ldd, Bv, M, m, v, o, ac);
+    }
   }
 }
 
@@ -498,7 +538,7 @@ PPO_FN void ph7_critic_update(PpoShared& S, const PpoArgs& a, int b, int tid, in
   }
   const AdamCoef ac = adam_coef(a.c_lr, a.c_b1, a.c_b2, a.c_eps, S.steps[1]);
   net_wgrad_adam((S.xb + (b & 1) * S.x_stride), S.ld1, S.ch1, S.ch2, S.ldh, S.cd1, S.cd2, S.dv, 1, a.mb, a.D, a.H1, a.H2, 1, S.cw1, S.ld1, S.cb1,
-                 S.cw2, S.cb2, S.cw3, S.cb3, nullptr, nullptr, a.c_flat, a.c_m, a.c_v, a.c_off, ac, tid - h, h);
+                 S.cw2, S.cb2, S.cw3, S.cb3, nullptr, nullptr, a.c_m, a.c_v, a.c_off, ac, tid - h, h);
 }
 // P8: actor (gate): back into layer 1
 PPO_FN void ph8_actor_bwd1(PpoShared& S, const PpoArgs& a, int b, int tid, int NT) {
@@ -510,10 +550,31 @@ PPO_FN void ph9_actor_update(PpoShared& S, const PpoArgs& a, int b, int tid, int
   if (S.flag[0] == 0.0f) return;
   const AdamCoef ac = adam_coef(a.a_lr, a.a_b1, a.a_b2, a.a_eps, S.steps[0]);
   net_wgrad_adam((S.xb + (b & 1) * S.x_stride), S.ld1, S.ah1, S.ah2, S.ldh, S.ad1, S.ad2, S.dmu, S.lda, a.mb, a.D, a.H1, a.H2, a.A, S.aw1, S.ld1,
-                 S.ab1, S.aw2, S.ab2, S.aw3, S.ab3, S.sdp, S.dsd, a.a_flat, a.a_m, a.a_v, a.a_off, ac, tid, NT);
+                 S.ab1, S.aw2, S.ab2, S.aw3, S.ab3, S.sdp, S.dsd, a.a_m, a.a_v, a.a_off, ac, tid, NT);
 }
 
+PPO_FN void copy_rows_out(float* dst, const float* src, int ld, int rows, int cols, int tid, int NT) {
+  for (int e = tid; e < rows * cols; e += NT) {
+    const int j = e / cols, k = e - j * cols;
+    dst[e] = src[j * ld + k];
+  }
+}
+
+// the master copies of the parameters (the optimizers' arenas), the step counts and the statistics of the last minibatch
 PPO_FN void ph_finish(PpoShared& S, const PpoArgs& a, int tid, int NT) {
+  copy_rows_out(a.a_flat + a.a_off[0], S.aw1, S.ld1, a.H1, a.D, tid, NT);
+  copy_rows_out(a.a_flat + a.a_off[1], S.ab1, a.H1, 1, a.H1, tid, NT);
+  copy_rows_out(a.a_flat + a.a_off[2], S.aw2, S.ldh, a.H2, a.H1, tid, NT);
+  copy_rows_out(a.a_flat + a.a_off[3], S.ab2, a.H2, 1, a.H2, tid, NT);
+  copy_rows_out(a.a_flat + a.a_off[4], S.aw3, S.ldh, a.A, a.H2, tid, NT);
+  copy_rows_out(a.a_flat + a.a_off[5], S.ab3, a.A, 1, a.A, tid, NT);
+  copy_rows_out(a.a_flat + a.a_off[6], S.sdp, a.A, 1, a.A, tid, NT);
+  copy_rows_out(a.c_flat + a.c_off[0], S.cw1, S.ld1, a.H1, a.D, tid, NT);
+  copy_rows_out(a.c_flat + a.c_off[1], S.cb1, a.H1, 1, a.H1, tid, NT);
+  copy_rows_out(a.c_flat + a.c_off[2], S.cw2, S.ldh, a.H2, a.H1, tid, NT);
+  copy_rows_out(a.c_flat + a.c_off[3], S.cb2, a.H2, 1, a.H2, tid, NT);
+  copy_rows_out(a.c_flat + a.c_off[4], S.cw3, S.ldh, 1, a.H2, tid, NT);
+  copy_rows_out(a.c_flat + a.c_off[5], S.cb3, 1, 1, 1, tid, NT);
   if (tid != 0) return;
   *a.a_step = (int64_t)S.steps[0];
   *a.c_step = (int64_t)S.steps[1];
