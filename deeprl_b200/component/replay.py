@@ -92,6 +92,7 @@ class UniformReplay:
         self.mask = torch.zeros(self.memory_size, dtype=torch.int32, device=dev)
         self._status = torch.zeros(2, dtype=torch.int32, device=dev)
         self._stage = None
+        self._device_cursor = False            # set by a learner whose captured graph feeds the ring: pos / size live on the device
         self._lut_cache = {}
         self._bufs = {}
 
@@ -136,7 +137,7 @@ class UniformReplay:
         st["ds"].copy_(st["hs"], non_blocking=True)
 
     def _feed_staged(self, st, o, n):
-        self.feed_device(st["df"][o:o + n], st["da"][o:o + n], st["dr"][o:o + n], st["dm"][o:o + n], n)
+        UniformReplay.feed_device(self, st["df"][o:o + n], st["da"][o:o + n], st["dr"][o:o + n], st["dm"][o:o + n], n)
 
     def feed_many(self, items):
         """Several ``feed()`` calls -- the sgd_update_frequency env steps of one agent step, DQN_agent.py:104-112 -- with ONE
@@ -184,7 +185,7 @@ class UniformReplay:
         st = self._staging(n)
         self._stage_rows(st, 0, data)
         self._upload(st, n)
-        self.feed_device(st["df"], st["da"], st["dr"], st["dm"], n)
+        UniformReplay.feed_device(self, st["df"], st["da"], st["dr"], st["dm"], n)      # (a subclass adds its leaf in feed())
         torch.cuda.current_stream().synchronize()       # the pinned staging buffers are reused by the next call
 
     def feed_device(self, frames, action, reward, mask, n):
@@ -224,6 +225,7 @@ class UniformReplay:
         host mirrors.  ``torch.save``-able."""
         if self.frames is None:
             return dict(empty=True)
+        self._sync_cursor()
         st = self.ring_state.cpu()
         return dict(empty=False, frames=self.frames.cpu(), action=self.action.cpu(), reward=self.reward.cpu(), mask=self.mask.cpu(),
                     ring_state=st, item_shape=tuple(self.item_shape), item_dtype=np.dtype(self.item_dtype).str,
@@ -243,14 +245,23 @@ class UniformReplay:
         self.pos, self._size = int(sd["ring_state"][0]), int(sd["ring_state"][1])
         self._bufs = {}
 
+    def _sync_cursor(self):
+        """The host mirror of the ring cursor follows host-side feeds only; when a learner feeds the ring inside a captured
+        graph (``_device_cursor``) the truth is ``ring_state`` on the device (one small synchronising read)."""
+        if self._device_cursor:
+            self.pos, self._size = (int(x) for x in self.ring_state[:2].tolist())
+
     def size(self):
+        self._sync_cursor()
         return self._size
 
     def full(self):
+        self._sync_cursor()
         return self._size == self.memory_size
 
     def valid_index(self, index):
         """replay.py:105-110 (host arithmetic on the mirrored cursor; the kernels apply the same rule)."""
+        self._sync_cursor()
         hl, n = self.history_length, self.n_step
         if index - hl + 1 >= 0 and index + n < self.pos:
             return True
@@ -422,7 +433,9 @@ class PrioritizedReplay(UniformReplay):
         if len(data["state"]):
             self.tree.add_n(1, self.max_priority_dev)
 
-    def feed_device(self, frames, action, reward, mask, n, add_leaf=False):
+    def feed_device(self, frames, action, reward, mask, n, *, add_leaf):
+        """``add_leaf`` is explicit: transitions fed without a tree leaf have priority zero and are never sampled -- only a
+        caller that adds the leaves itself (the learner: ``tree.add_n(feeds)``) passes False."""
         super().feed_device(frames, action, reward, mask, n)
         if add_leaf:
             self.tree.add_n(1, self.max_priority_dev)

@@ -153,10 +153,13 @@ class GraphedDQNLearner:
         # call with each item in its own slot (reference_feed_quirk off) plus `feeds` tree.add(max_priority) -- one launch
         if self.feeds and phase != "gather":
             quirk, rp.quirk = rp.quirk, False
-            rp.feed_device(self.d_frames, self.d_action, self.d_reward, self.d_mask, self.feeds)
-            rp.quirk = quirk
+            rp._device_cursor = True                     # (a captured feed advances the device cursor only)
             if self.per:
+                rp.feed_device(self.d_frames, self.d_action, self.d_reward, self.d_mask, self.feeds, add_leaf=False)
                 rp.tree.add_n(self.feeds, rp.max_priority_dev)
+            else:
+                rp.feed_device(self.d_frames, self.d_action, self.d_reward, self.d_mask, self.feeds)
+            rp.quirk = quirk
         if self.dtype == torch.bfloat16:
             # exact integer frames, space-to-depth layout; ImageNormalizer's scale is folded into conv1's weights.
             # K1 (self.ring): no batch at all -- conv1 reads the sampled stacks from the uint8 ring (synchronous replay only:
