@@ -116,16 +116,20 @@ def test_host_cursor_follows_feeds_captured_in_the_graph(rl, workload):
     then read the cursor from the device (replay.py:80-90 keeps it on the host; ours lives in ``ring_state``)."""
     import bench
     bench.CAP = 30_000
-    lr = bench.build_learner(rl, workload, torch.device("cuda", 0), 0, 1, prefetch=False)
-    rp = lr.replay
-    lr.capture(warmup=2)
-    rp.size()
-    pos0 = rp.pos
-    for _ in range(7):
-        lr.update()
-    torch.cuda.synchronize()
-    assert rp.size() == rp.memory_size and rp.full()
-    assert (rp.pos, rp._size) == tuple(int(x) for x in rp.ring_state[:2].tolist())
-    assert rp.pos == (pos0 + 7 * lr.feeds) % rp.memory_size and lr.feeds == 4
-    assert int(rp.state_dict()["ring_state"][0]) == rp.pos
-    assert rp.valid_index(rp.pos - 1) is False and rp.valid_index(rp.pos - 2) is True     # next state of pos-1 is the write slot
+    rl.Config.COMPUTE_DTYPE = torch.bfloat16             # (the learner bench.py builds: bf16 tcgen05 body)
+    try:
+        lr = bench.build_learner(rl, workload, torch.device("cuda", 0), 0, 1, prefetch=False)
+        rp = lr.replay
+        lr.capture(warmup=2)
+        rp.size()
+        pos0 = rp.pos
+        for _ in range(7):
+            lr.update()
+        torch.cuda.synchronize()
+        assert rp.size() == rp.memory_size and rp.full()
+        assert (rp.pos, rp._size) == tuple(int(x) for x in rp.ring_state[:2].tolist())
+        assert rp.pos == (pos0 + 7 * lr.feeds) % rp.memory_size and lr.feeds == 4
+        assert int(rp.state_dict()["ring_state"][0]) == rp.pos
+        assert rp.valid_index(rp.pos - 1) is False and rp.valid_index(rp.pos - 2) is True   # next state of pos-1 is the write slot
+    finally:
+        rl.Config.COMPUTE_DTYPE = torch.float32
