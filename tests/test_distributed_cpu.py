@@ -77,3 +77,33 @@ def test_two_rank_gradient_allreduce_keeps_parameters_identical():
         opt.step()
     ref = torch.cat([p.detach().reshape(-1) for p in params]).numpy()
     np.testing.assert_allclose(a, ref, rtol=1e-5, atol=1e-6)
+
+
+def _worker_async_and_leave(rank, world, port, out):
+    """The learner's overlapped form of the exchange (learner.py `_allreduce_early` / `_allreduce`): the large slice of the arena
+    is all-reduced asynchronously, the remainder afterwards, then the handle is waited for; and ``parallel.leave()`` ends the
+    run with every rank at exit code 0 (it must return normally when there is nothing to tear down around: world 1)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    from deeprl_b200 import parallel
+    parallel.init("gloo")
+    g = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    early = parallel.allreduce_gradients(g[100:900], async_op=True)     # "fc4's slice"
+    for lo, hi in ((0, 100), (900, 1000)):                               # "the late slices"
+        parallel.allreduce_gradients(g[lo:hi])
+    early.wait()
+    want = torch.arange(1000, dtype=torch.float32) * sum(r + 1 for r in range(world))
+    out[rank] = bool(torch.equal(g, want))
+    parallel.leave()                                                     # barrier, flush, os._exit(0)
+    raise AssertionError("leave() returned in a multi-rank run")
+
+
+def test_sliced_async_allreduce_and_leave():
+    from deeprl_b200 import parallel
+    assert parallel.allreduce_gradients(torch.ones(4)) is None           # no process group: nothing to do, nothing to wait for
+    parallel.leave()                                                     # single process: returns
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_async_and_leave, args=(world, port, out), nprocs=world, join=True)    # raises if a rank exits non-zero
+    assert out[0] is True and out[1] is True
