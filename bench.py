@@ -448,6 +448,9 @@ def run_b2rl(args):
                 algorithmic_bytes_definition="SURVEY 8d: 512 samples x (5 unique frames read + 2 x 4 frames written) x 7056 B = 91 728 B "
                                              "per sample (this variant writes bf16, i.e. twice the write bytes, most of which stay in L2)",
                 traffic=traffic, traffic_source=traffic_src,
+                limited_by="not DRAM (traffic is below the algorithmic bytes: the bf16 batch stays in L2): 512 CTAs x 35 KB staging, "
+                           "u8->bf16 conversion and 16-byte stores through shared memory; the uint8 variant below moves exactly the "
+                           "SURVEY-8d bytes and is the HBM-bound form of the same gather",
                 raw_u8_variant=dict(kernel="gather_raw_tma_kernel (uint8 stacks: exactly the SURVEY 8d bytes; UniformReplay.sample())",
                                     achieved=round(ach_u8, 1), frac=round(ach_u8 / hbm, 4), us_per_launch=round(gt["u8"] * 1e3, 2)))
     ag = cpu = None
